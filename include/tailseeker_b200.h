@@ -1,0 +1,251 @@
+/*
+ * tailseeker_b200.h -- C ABI of the B200-native TAIL-seq signal-processing hot path.
+ *
+ * This is the drop-in boundary.  The reference (hyeshik/tailseeker 3.2.1) has no
+ * plugin/FFI API: its two native programs are driven by argv + files.  The seam this
+ * library replaces sits one call level below those programs' main():
+ *
+ *   tailseq-import:       distribute_processing(cfg, intensities, basecalls, firstclusterno)
+ *                         -> run_spot_processing -> process_spots(...)
+ *                         (reference src/importer/tailseq-import.c:516-565, :414-513,
+ *                          src/importer/spotanalyzer.c:617-755)
+ *   tailseq-polya-ruler:  process_polya_ruling(...) -> measure_polya_length(...)
+ *                         (reference src/polyaruler/polyaruler.c:201-314, :104-152)
+ *   cutoff estimator:     calculate_optimal_cutoffs / find_eqodds_point
+ *                         (reference scripts/calculate-optimal-parameters.py:57-171)
+ *
+ * Conventions follow that seam: every function returns 0 on success and -1 on error
+ * (message via tsk_last_error()), the caller owns every buffer it passes, parameters
+ * are a read-only POD mirror of the reference's config structs
+ * (src/importer/tailseq-import.h:172-215,220-274).  No torch / C++ types appear here.
+ *
+ * There is NO CPU fallback: every entry point that computes runs CUDA kernels built for
+ * sm_100a and fails with -1 when no such device is usable.
+ */
+#ifndef TAILSEEKER_B200_H
+#define TAILSEEKER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSK_ABI_VERSION          1
+
+#define TSK_NUM_CHANNELS         4      /* tailseq-import.h:40 */
+#define TSK_MAX_SAMPLES          64
+#define TSK_MAX_SEQ              32     /* longest index / delimiter / fingerprint */
+#define TSK_T_SCORE_BINS         200    /* T_INTENSITY_SCORE_BINS, tailseq-import.h:206 */
+#define TSK_SCORE_MAX            ((1u << 24) - 1u)   /* signal-packs.h:36-37 */
+#define TSK_MAX_CUTOFF_CYCLES    1024   /* MAX_NUM_CYCLES, polyaruler.c:39 */
+
+/* PAFLAG_* bits, src/sigproc-flags.h:30-43 (same values, same meaning). */
+#define TSK_PAFLAG_POLYA_DETECTED              0x0001
+#define TSK_PAFLAG_DELIMITER_HAS_MISMATCH      0x0002
+#define TSK_PAFLAG_HAVE_3P_MODIFICATION        0x0004
+#define TSK_PAFLAG_MEASURED_FROM_FLUORESCENCE  0x0008
+#define TSK_PAFLAG_BARCODE_HAS_MISMATCHES      0x0010
+#define TSK_PAFLAG_DELIMITER_IS_SHIFTED        0x0020
+#define TSK_PAFLAG_DARKCYCLE_EXISTS            0x0040
+#define TSK_PAFLAG_DELIMITER_NOT_FOUND         0x0080
+#define TSK_PAFLAG_BALANCER_CALL_QUALITY_BAD   0x0100
+#define TSK_PAFLAG_BALANCER_BIASED             0x0200
+#define TSK_PAFLAG_BALANCER_SIGNAL_BAD         0x0400
+#define TSK_PAFLAG_DARKCYCLE_OVER_THRESHOLD    0x0800
+
+/* One entry of the sample list, in the reference's list order after
+ * compute_derived_values() (parseconfig.c:575-641): entry 0 is "Unknown", entry 1 is
+ * the PhiX pseudo-sample when a control is configured, then the [sample:*] sections in
+ * REVERSE file order (LIFO, parseconfig.c:407-409).  Positions are absolute 0-based
+ * cycles (delimiter_pos already rebased by threep_start, parseconfig.c:638-639). */
+typedef struct tsk_sample {
+    char    index[TSK_MAX_SEQ];          /* NUL-terminated, "XXXXXX" for pseudo-samples */
+    char    delimiter[TSK_MAX_SEQ];      /* IUPAC, "" when none */
+    char    fingerprint[TSK_MAX_SEQ];    /* "" when none */
+    int32_t maximum_index_mismatches;
+    int32_t delimiter_pos;               /* -1 when none */
+    int32_t delimiter_length;
+    int32_t maximum_delimiter_mismatches;
+    int32_t fingerprint_pos;
+    int32_t fingerprint_length;
+    int32_t maximum_fingerprint_mismatches;
+    int32_t umi_ranges_count;            /* only ">0" matters on this path (spotanalyzer.c:697) */
+    int32_t limit_threep_processing;     /* 0 = no limit */
+    int32_t signal_dump_length;          /* parseconfig.c:630-636 */
+} tsk_sample;
+
+/* POD mirror of BalancerParameters / PolyASeederParameters / PolyAFinderParameters /
+ * PolyARulerParameters and the read layout (tailseq-import.h:172-215,226-236). */
+typedef struct tsk_params {
+    int32_t abi_version;                 /* = TSK_ABI_VERSION */
+
+    /* [read_format] -- 0-based starts */
+    int32_t total_cycles;
+    int32_t index_start, index_length;
+    int32_t threep_start, threep_length;
+
+    /* [options] */
+    int32_t keep_no_delimiter;
+    int32_t keep_low_quality_balancer;
+
+    /* [control]: 1 when the PhiX pseudo-sample (list entry 1) exists */
+    int32_t has_control;
+
+    /* [balancer] */
+    int32_t balancer_start, balancer_length;   /* end = start + length */
+    int32_t balancer_min_quality;
+    int32_t balancer_min_bases_passes;         /* (int)(length * min_fraction), parseconfig.c:544 */
+    int32_t balancer_minimum_occurrence;
+    int32_t balancer_num_positive_samples;
+    int32_t balancer_num_negative_samples;
+
+    /* [polyA_seeder] */
+    int32_t seed_trigger_polya_length;
+    int32_t negative_sample_polya_length;
+    int32_t max_cctr_scan_left_space, max_cctr_scan_right_space;
+    float   required_cdf_contrast;
+    int32_t polya_boundary_pos, polya_sampling_gap;
+    int32_t dist_sampling_bins;
+    int32_t fair_sampling_fingerprint_length;
+    int32_t fair_sampling_hash_space_size;
+    int32_t fair_sampling_max_count;           /* uint8_t in the reference */
+
+    /* [polyA_finder]: weights indexed A,C,G,T,N */
+    int32_t weights_polyA[5];
+    int32_t weights_nonA[5];
+    int32_t max_terminal_modifications;
+    int32_t min_polya_length;
+    int32_t sigproc_trigger_polya_length;
+
+    /* [polyA_ruler] */
+    float   dark_cycles_threshold;
+    int32_t max_dark_cycles;
+    float   maximum_entropy;                       /* signalproc.c:54-64,73 (host libm) */
+    float   t_intensity_score[TSK_T_SCORE_BINS + 1]; /* signalproc.c:75-81 (host libm expf) */
+
+    int32_t num_samples;
+    tsk_sample samples[TSK_MAX_SAMPLES];
+} tsk_params;
+
+/* Per-cluster call, the data the reference keeps in locals of process_spots()
+ * (spotanalyzer.c:641-643) and hands to write_measurements_to_buffers() (:725-727). */
+typedef struct tsk_call {
+    int16_t  sample;         /* list index (numindex); always valid */
+    uint16_t flags;          /* procflags, TSK_PAFLAG_* */
+    int16_t  delimiter_end;  /* absolute cycle, -1 = none */
+    int16_t  polya_len;      /* polya_status: seed poly(A) length, or -1 */
+    int16_t  terminal_mods;  /* -1 when process_polya_signal() was not reached */
+    uint8_t  written;        /* 1 = reference writes taginfo/seqqual lines for it */
+    uint8_t  emitted;        /* 1 = a sigpack record exists for it */
+    uint32_t record_slot;    /* slot within its sample's record array (valid if emitted) */
+} tsk_call;                  /* 16 bytes */
+
+/* Per-sample demultiplexing counters (tailseq-import.h:126-131, CSV tailseq-import.c:698-709). */
+typedef struct tsk_counters {
+    uint32_t clusters_mm0, clusters_mm1, clusters_mm2plus;
+    uint32_t clusters_nodelim, clusters_fpmismatch, clusters_qcfailed;
+} tsk_counters;
+
+typedef struct tsk_ctx tsk_ctx;
+
+/* Last error message of the calling thread ("" if none). */
+const char *tsk_last_error(void);
+
+/* Library / device probe: returns ABI version, or -1 if no sm_100-class device is usable. */
+int tsk_probe(int device);
+
+/* ---- context ------------------------------------------------------------------- */
+/* Replaces parse_config()'s product (a read-only TailseekerConfig shared by all workers,
+ * tailseq-import.c:741, parseconfig.c:683-708): validates and uploads the parameters. */
+int tsk_ctx_create(tsk_ctx **out, int device, const tsk_params *params);
+int tsk_ctx_destroy(tsk_ctx *ctx);
+
+/* ---- importer path --------------------------------------------------------------- */
+/* Replaces load_intensities_and_basecalls()'s buffers (tailseq-import.c:203-228) minus the
+ * AoS transpose of cifreader.c:163-164: data stay in the files' native layouts,
+ *   bcl[total_cycles][bcl_pitch] u8,   cif[threep_length][4][cif_pitch] i16  (A,C,G,T planes)
+ * pitches in ELEMENTS, >= nclusters.  on_device != 0: the pointers are device pointers that
+ * the caller keeps alive until the next upload (zero copy); otherwise they are host
+ * pointers (pinned or pageable) and are copied to HBM on the context's stream.
+ * invmatrix = inverse colour matrix (load_color_matrix(), signalproc.c:345-375). */
+int tsk_tile_upload(tsk_ctx *ctx, const uint8_t *bcl, size_t bcl_pitch,
+                    const int16_t *cif, size_t cif_pitch,
+                    const float invmatrix[16],
+                    uint32_t nclusters, uint32_t firstclusterno, int on_device);
+
+/* Replaces distribute_processing() (tailseq-import.c:516-565): runs the per-cluster path
+ * for the uploaded block.  Like prepare_split_jobs() (:340-392) it starts from zeroed
+ * pos/neg histograms and a zeroed fair-sampling table; counters accumulate across calls
+ * (they live in SampleInfo in the reference) until tsk_counters_reset(). */
+int tsk_tile_process(tsk_ctx *ctx);
+
+/* Results of the last tsk_tile_process().  All copies are synchronous w.r.t. the call. */
+int tsk_tile_get_calls(tsk_ctx *ctx, tsk_call *calls /* [nclusters] */);
+/* Number of record slots of one sample (some may be invalid, see below). */
+int tsk_tile_get_record_count(tsk_ctx *ctx, int sample, uint32_t *nslots);
+/* Record slots of one sample in cluster order, each (2 + signal_dump_length) u32 words:
+ * SignalRecordHeader {u32 clusterno; i16 first_cycle; i16 valid_cycle_count} followed by
+ * signal_dump_length packets (bit0 downhill, bits1-24 score), signal-packs.h:30-41.
+ * A slot whose valid_cycle_count is negative was withdrawn (the reference returns before
+ * write_polya_score() on a dark-cycle abort, spotanalyzer.c:561-565) and must be skipped. */
+int tsk_tile_get_records(tsk_ctx *ctx, int sample, uint32_t *records, size_t capacity_words);
+int tsk_get_counters(tsk_ctx *ctx, tsk_counters *counters /* [num_samples] */);
+int tsk_counters_reset(tsk_ctx *ctx);
+/* pos / neg score histograms u32[total_cycles][dist_sampling_bins]
+ * (GloballyAggregatedOutput, tailseq-import.h:291-294). */
+int tsk_get_hist(tsk_ctx *ctx, uint32_t *pos, uint32_t *neg);
+/* Device addresses of the same histograms and counters, for an in-place all-reduce by the
+ * caller (NCCL / torch.distributed) -- the cross-tile sum of
+ * calculate-optimal-parameters.py:139-140 and stats-merge-demultiplexing-counts.py:33-53. */
+int tsk_get_device_ptrs(tsk_ctx *ctx, void **pos_hist, void **neg_hist, void **counters,
+                        void **ruler_pos_hist);
+
+/* ---- ruler path -------------------------------------------------------------------- */
+/* load_score_cutoffs()'s float->24-bit conversion (polyaruler.c:93-96) for one value. */
+uint32_t tsk_cutoff_to_packed(double cutoff);
+
+/* Replaces process_polya_ruling()+measure_polya_length() (polyaruler.c:201-314,104-152) for
+ * `nrecords` record slots of `dump_len` packets each.  records: host pointer, or (on_device)
+ * device pointer.  Outputs: polya_len_out[i] per slot (-1 when below minimum_polya_len or
+ * withdrawn slot; host pointer), and the positive-sample histogram
+ * u32[ncutoffs][dist_sampling_bins] ADDED into the context's ruler histogram
+ * (zero it with tsk_ruler_hist_reset()). */
+int tsk_ruler_records(tsk_ctx *ctx, const uint32_t *records, size_t nrecords, int dump_len,
+                      const uint32_t *cutoffs, int ncutoffs,
+                      int minimum_polya_len, float downhill_ext_weight,
+                      int dist_sampling_bins, float dist_sampling_gap,
+                      int16_t *polya_len_out, int on_device);
+/* Same, on the resident record slots of `sample` from the last tsk_tile_process(). */
+int tsk_ruler_tile(tsk_ctx *ctx, int sample, const uint32_t *cutoffs, int ncutoffs,
+                   int minimum_polya_len, float downhill_ext_weight,
+                   int dist_sampling_bins, float dist_sampling_gap,
+                   int16_t *polya_len_out /* [nslots] host */);
+int tsk_ruler_hist_reset(tsk_ctx *ctx, int ncutoffs, int dist_sampling_bins);
+int tsk_ruler_get_hist(tsk_ctx *ctx, uint32_t *pos /* [ncutoffs][bins] */);
+
+/* ---- cutoff estimation --------------------------------------------------------------- */
+/* Replaces find_all_eqodds_point() (calculate-optimal-parameters.py:57-78): for every
+ * cycle with >= min_spots positive and negative samples, the root of the weighted-KDE
+ * log-likelihood ratio found by bisection in [low, high[k]] (first k whose bracket has a
+ * sign change and whose root lies strictly inside).  pos/neg: u64[cycles][bins] host.
+ * cutoffs_out[c] = root, or NaN when the cycle has too few spots or no root. */
+int tsk_fit_cutoffs(tsk_ctx *ctx, const uint64_t *pos, const uint64_t *neg,
+                    int cycles, int bins, uint64_t min_spots, double kde_bandwidth,
+                    double search_low, const double *search_high, int nsearch_high,
+                    double *cutoffs_out);
+
+/* ---- stream control (for callers that overlap copies and kernels) -------------------- */
+int tsk_synchronize(tsk_ctx *ctx);
+/* Timed re-run of the kernels of tsk_tile_process() on the resident tile: CUDA events on the
+ * context's stream, `iters` back-to-back runs, returns mean ms per run per stage in
+ * ms_out[4] = {decode_demux_seed, slot scan, normalise_score_pack(+fixups), total}. */
+int tsk_tile_process_timed(tsk_ctx *ctx, int iters, float ms_out[4]);
+/* Number of kernel launches issued by this context so far. */
+uint64_t tsk_launch_count(tsk_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAILSEEKER_B200_H */
