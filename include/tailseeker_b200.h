@@ -245,6 +245,11 @@ int tsk_tile_process_timed(tsk_ctx *ctx, int iters, float ms_out[4]);
 /* Number of kernel launches issued by this context so far. */
 uint64_t tsk_launch_count(tsk_ctx *ctx);
 
+/* Self-test: out[i] = the device's logf(in[i]) (finite in[i] > 0), which must equal the host
+ * libm's logf bit for bit because shannon_entropy() (signalproc.c:39-51) feeds 24-bit
+ * truncated scores.  Host pointers. */
+int tsk_selftest_logf(tsk_ctx *ctx, const float *in, float *out, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

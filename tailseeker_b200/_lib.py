@@ -1,0 +1,78 @@
+"""ctypes binding of libtailseeker_b200.so -- exactly the symbols of include/tailseeker_b200.h.
+
+There is no fallback: if the shared library (CUDA kernels for sm_100a) is missing or no
+B200-class device is usable, calls raise."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from .config import CCall, CParams
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtailseeker_b200.so")
+
+# every symbol include/tailseeker_b200.h declares (tests check the library exports them all)
+SYMBOLS = [
+    "tsk_last_error", "tsk_probe", "tsk_ctx_create", "tsk_ctx_destroy", "tsk_tile_upload",
+    "tsk_tile_process", "tsk_tile_get_calls", "tsk_tile_get_record_count", "tsk_tile_get_records",
+    "tsk_get_counters", "tsk_counters_reset", "tsk_get_hist", "tsk_get_device_ptrs",
+    "tsk_cutoff_to_packed", "tsk_ruler_records", "tsk_ruler_tile", "tsk_ruler_hist_reset",
+    "tsk_ruler_get_hist", "tsk_fit_cutoffs", "tsk_synchronize", "tsk_tile_process_timed",
+    "tsk_launch_count", "tsk_selftest_logf",
+]
+
+_lib = None
+
+
+class TskError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TskError("libtailseeker_b200.so is not built (run `python -m tailseeker_b200.build` "
+                       "or __graft_entry__.build()); there is no CPU fallback")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, u32, sz, f32, f64 = (ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_size_t,
+                                  ctypes.c_float, ctypes.c_double)
+    L.tsk_last_error.restype = ctypes.c_char_p
+    L.tsk_probe.argtypes = [i32]
+    L.tsk_ctx_create.argtypes = [ctypes.POINTER(vp), i32, ctypes.POINTER(CParams)]
+    L.tsk_ctx_destroy.argtypes = [vp]
+    L.tsk_tile_upload.argtypes = [vp, vp, sz, vp, sz, vp, u32, u32, i32]
+    L.tsk_tile_process.argtypes = [vp]
+    L.tsk_tile_get_calls.argtypes = [vp, vp]
+    L.tsk_tile_get_record_count.argtypes = [vp, i32, ctypes.POINTER(u32)]
+    L.tsk_tile_get_records.argtypes = [vp, i32, vp, sz]
+    L.tsk_get_counters.argtypes = [vp, vp]
+    L.tsk_counters_reset.argtypes = [vp]
+    L.tsk_get_hist.argtypes = [vp, vp, vp]
+    L.tsk_get_device_ptrs.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                      ctypes.POINTER(vp)]
+    L.tsk_cutoff_to_packed.argtypes = [f64]
+    L.tsk_cutoff_to_packed.restype = u32
+    L.tsk_ruler_records.argtypes = [vp, vp, sz, i32, vp, i32, i32, f32, i32, f32, vp, i32]
+    L.tsk_ruler_tile.argtypes = [vp, i32, vp, i32, i32, f32, i32, f32, vp]
+    L.tsk_ruler_hist_reset.argtypes = [vp, i32, i32]
+    L.tsk_ruler_get_hist.argtypes = [vp, vp]
+    L.tsk_fit_cutoffs.argtypes = [vp, vp, vp, i32, i32, ctypes.c_uint64, f64, f64, vp, i32, vp]
+    L.tsk_synchronize.argtypes = [vp]
+    L.tsk_tile_process_timed.argtypes = [vp, i32, vp]
+    L.tsk_launch_count.argtypes = [vp]
+    L.tsk_launch_count.restype = ctypes.c_uint64
+    L.tsk_selftest_logf.argtypes = [vp, vp, vp, sz]
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is ctypes.c_int and name not in ("tsk_probe",):
+            pass
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise TskError(load().tsk_last_error().decode() or "tailseeker_b200 call failed")

@@ -1,0 +1,549 @@
+/*
+ * tsk_capi.cu -- the extern "C" boundary of libtailseeker_b200.so (include/tailseeker_b200.h).
+ * Host-side plumbing only: parameter validation/upload, HBM buffers, stream, result copies.
+ */
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "tsk_internal.h"
+
+static thread_local char g_err[512] = "";
+
+void tsk_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *tsk_last_error(void) { return g_err; }
+
+extern "C" int tsk_probe(int device)
+{
+    int count = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        tsk_set_error("no CUDA device %d (found %d); this library has no CPU path", device, count);
+        return -1;
+    }
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        tsk_set_error("device %d is not an sm_100-class GPU; kernels are built for sm_100a only", device);
+        return -1;
+    }
+    return TSK_ABI_VERSION;
+}
+
+/* ---- parameter translation ----------------------------------------------------------- */
+static int base_code_of(char c)
+{
+    switch (c) {
+    case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3;
+    case 'N': return 4; default: return 7;
+    }
+}
+
+static int iupac_mask(char c)    /* bits over A,C,G,T; spotanalyzer.c:35-62 */
+{
+    switch (c) {
+    case 'A': return 1;  case 'C': return 2;  case 'G': return 4;  case 'T': case 'U': return 8;
+    case 'B': return 14; case 'D': return 13; case 'H': return 11; case 'V': return 7;
+    case 'K': return 12; case 'M': return 3;  case 'R': return 5;  case 'S': return 6;
+    case 'W': return 9;  case 'Y': return 10; case 'N': case 'X': return 15;
+    default:  return 0;
+    }
+}
+
+static int build_device_params(const tsk_params *p, DevParams *d, DevSample *ds)
+{
+    if (p->abi_version != TSK_ABI_VERSION) { tsk_set_error("tsk_params.abi_version mismatch"); return -1; }
+    if (p->num_samples < 1 || p->num_samples > TSK_MAX_SAMPLES) { tsk_set_error("bad num_samples"); return -1; }
+    if (p->total_cycles < 1 || p->total_cycles > TSK_MAX_CUTOFF_CYCLES) { tsk_set_error("bad total_cycles"); return -1; }
+    if (p->threep_start < 0 || p->threep_length < 1 ||
+        p->threep_start + p->threep_length > p->total_cycles) { tsk_set_error("3' read outside the run"); return -1; }
+    if (p->index_length < 0 || p->index_length >= TSK_MAX_SEQ || p->index_start < 0 ||
+        p->index_start + p->index_length > p->total_cycles) { tsk_set_error("bad index read"); return -1; }
+    if (p->balancer_start != 0) {
+        /* the reference indexes a balancer_len-long array with absolute balancer.start
+         * (signalproc.c:152-156 vs spotanalyzer.c:534-536): only start = 1 is defined */
+        tsk_set_error("balancer start != 1 is undefined behaviour in the reference; refused");
+        return -1;
+    }
+    if (p->balancer_length < 0 || p->balancer_length > p->threep_length ||
+        p->balancer_length > p->total_cycles) { tsk_set_error("bad balancer length"); return -1; }
+    if (p->balancer_num_positive_samples < 1 || p->balancer_num_positive_samples > TSK_MAX_RANK ||
+        p->balancer_num_negative_samples < 1 || p->balancer_num_negative_samples > TSK_MAX_RANK) {
+        tsk_set_error("balancer num-positive/negative-samples must be 1..%d", TSK_MAX_RANK); return -1;
+    }
+    if (p->max_terminal_modifications < 0 || p->max_terminal_modifications >= TSK_MAX_MODS) {
+        tsk_set_error("maximum-modifications must be < %d", TSK_MAX_MODS); return -1;
+    }
+    if (p->dist_sampling_bins < 1 || p->dist_sampling_bins > 65536) { tsk_set_error("bad dist-sampling-bins"); return -1; }
+    if (p->fair_sampling_hash_space_size < 1) { tsk_set_error("bad fair-sampling-hash-space-size"); return -1; }
+    if (p->fair_sampling_fingerprint_length < 0) { tsk_set_error("bad fair-sampling-fingerprint-length"); return -1; }
+    if (p->max_cctr_scan_left_space < 1 || p->max_cctr_scan_right_space < 1) { tsk_set_error("bad cctr scan space"); return -1; }
+    if (p->has_control) {
+        tsk_set_error("PhiX control alignment (controlaligner.c) is not part of this library yet; "
+                      "configure no [control] section");
+        return -1;
+    }
+
+    memset(d, 0, sizeof(*d));
+    d->total_cycles = p->total_cycles; d->index_start = p->index_start; d->index_length = p->index_length;
+    d->threep_start = p->threep_start; d->threep_length = p->threep_length;
+    d->keep_no_delimiter = p->keep_no_delimiter; d->keep_low_quality_balancer = p->keep_low_quality_balancer;
+    d->balancer_start = p->balancer_start; d->balancer_length = p->balancer_length;
+    d->balancer_min_quality = p->balancer_min_quality;
+    d->balancer_min_bases_passes = p->balancer_min_bases_passes;
+    d->balancer_minimum_occurrence = p->balancer_minimum_occurrence;
+    d->npos = p->balancer_num_positive_samples; d->nneg = p->balancer_num_negative_samples;
+    d->seed_trigger = p->seed_trigger_polya_length; d->neg_polya_len = p->negative_sample_polya_length;
+    d->cctr_left = p->max_cctr_scan_left_space; d->cctr_right = p->max_cctr_scan_right_space;
+    d->required_contrast = p->required_cdf_contrast;
+    d->boundary_pos = p->polya_boundary_pos; d->sampling_gap = p->polya_sampling_gap;
+    d->bins = p->dist_sampling_bins;
+    d->fair_fp_len = p->fair_sampling_fingerprint_length;
+    d->fair_hash_size = p->fair_sampling_hash_space_size;
+    d->fair_max_count = p->fair_sampling_max_count & 0xff;
+    for (int i = 0; i < 5; i++) { d->w_polyA[i] = p->weights_polyA[i]; d->w_nonA[i] = p->weights_nonA[i]; }
+    d->max_mods = p->max_terminal_modifications; d->min_polya_len = p->min_polya_length;
+    d->sigproc_trigger = p->sigproc_trigger_polya_length;
+    d->dark_threshold = p->dark_cycles_threshold; d->max_dark_cycles = p->max_dark_cycles;
+    d->maximum_entropy = p->maximum_entropy;
+    d->num_samples = p->num_samples;
+    d->index_words = (p->index_length + 9) / 10;
+    if (d->index_words > 4) { tsk_set_error("index too long"); return -1; }
+
+    for (int s = 0; s < p->num_samples; s++) {
+        const tsk_sample *hs = &p->samples[s];
+        DevSample *o = &ds[s];
+        memset(o, 0, sizeof(*o));
+        if ((int)strnlen(hs->index, TSK_MAX_SEQ) != p->index_length) {
+            tsk_set_error("sample %d: index length differs from index-length", s); return -1;
+        }
+        for (int k = 0; k < p->index_length; k++)
+            o->index_pk[k / 10] |= (uint32_t)(base_code_of(hs->index[k]) & 7) << (3 * (k % 10));
+        if (hs->delimiter_length < 0 || hs->delimiter_length >= TSK_MAX_SEQ ||
+            hs->fingerprint_length < 0 || hs->fingerprint_length >= TSK_MAX_SEQ) {
+            tsk_set_error("sample %d: delimiter/fingerprint too long", s); return -1;
+        }
+        if (hs->delimiter_length > 0 &&
+            (hs->delimiter_pos < 1 || hs->delimiter_pos + hs->delimiter_length + 1 > p->total_cycles ||
+             hs->delimiter_pos + hs->delimiter_length - 1 < p->threep_start)) {
+            tsk_set_error("sample %d: delimiter window outside the read", s); return -1;
+        }
+        if (hs->fingerprint_length > 0 &&
+            (hs->fingerprint_pos < 0 || hs->fingerprint_pos + hs->fingerprint_length > p->total_cycles)) {
+            tsk_set_error("sample %d: fingerprint outside the read", s); return -1;
+        }
+        for (int k = 0; k < hs->delimiter_length; k++) o->delim_mask[k] = (uint8_t)iupac_mask(hs->delimiter[k]);
+        for (int k = 0; k < hs->fingerprint_length; k++) o->fingerprint[k] = (uint8_t)base_code_of(hs->fingerprint[k]);
+        o->max_index_mm = (int16_t)hs->maximum_index_mismatches;
+        o->delimiter_pos = (int16_t)hs->delimiter_pos; o->delimiter_length = (int16_t)hs->delimiter_length;
+        o->max_delim_mm = (int16_t)hs->maximum_delimiter_mismatches;
+        o->fp_pos = (int16_t)hs->fingerprint_pos; o->fp_len = (int16_t)hs->fingerprint_length;
+        o->max_fp_mm = (int16_t)hs->maximum_fingerprint_mismatches;
+        o->has_umi = (int16_t)(hs->umi_ranges_count > 0);
+        o->limit_threep = (int16_t)hs->limit_threep_processing;
+        if (hs->signal_dump_length < 0 || hs->signal_dump_length > p->threep_length + 1) {
+            tsk_set_error("sample %d: bad signal_dump_length", s); return -1;
+        }
+        o->dump_len = (int16_t)hs->signal_dump_length;
+    }
+    return 0;
+}
+
+/* ---- context --------------------------------------------------------------------------- */
+extern "C" int tsk_ctx_create(tsk_ctx **out, int device, const tsk_params *params)
+{
+    if (!out || !params) { tsk_set_error("null argument"); return -1; }
+    *out = NULL;
+    if (tsk_probe(device) < 0) return -1;
+    DevSample hs[TSK_MAX_SAMPLES];
+    tsk_ctx *ctx = (tsk_ctx *)calloc(1, sizeof(tsk_ctx));
+    if (!ctx) { tsk_set_error("out of memory"); return -1; }
+    if (build_device_params(params, &ctx->dp, hs) != 0) { free(ctx); return -1; }
+    ctx->device = device;
+    ctx->hp = *params;
+    ctx->maxdump = 0;
+    for (int s = 0; s < params->num_samples; s++)
+        if (params->samples[s].signal_dump_length > ctx->maxdump) ctx->maxdump = params->samples[s].signal_dump_length;
+
+    TSK_CUDA(cudaSetDevice(device));
+    TSK_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    const int S = params->num_samples;
+    const size_t histbytes = sizeof(uint32_t) * (size_t)params->total_cycles * params->dist_sampling_bins;
+    TSK_CUDA(cudaMalloc(&ctx->d_samples, sizeof(DevSample) * S));
+    TSK_CUDA(cudaMemcpy(ctx->d_samples, hs, sizeof(DevSample) * S, cudaMemcpyHostToDevice));
+    TSK_CUDA(cudaMalloc(&ctx->d_tscore, sizeof(float) * (TSK_T_SCORE_BINS + 1)));
+    TSK_CUDA(cudaMemcpy(ctx->d_tscore, params->t_intensity_score, sizeof(float) * (TSK_T_SCORE_BINS + 1),
+                        cudaMemcpyHostToDevice));
+    TSK_CUDA(cudaMalloc(&ctx->d_pos, histbytes));
+    TSK_CUDA(cudaMalloc(&ctx->d_neg, histbytes));
+    TSK_CUDA(cudaMemset(ctx->d_pos, 0, histbytes));
+    TSK_CUDA(cudaMemset(ctx->d_neg, 0, histbytes));
+    TSK_CUDA(cudaMalloc(&ctx->d_counters, sizeof(uint32_t) * S * TSK_NCOUNT));
+    TSK_CUDA(cudaMemset(ctx->d_counters, 0, sizeof(uint32_t) * S * TSK_NCOUNT));
+    TSK_CUDA(cudaMalloc(&ctx->d_fair, sizeof(uint32_t) * (size_t)params->fair_sampling_hash_space_size));
+    TSK_CUDA(cudaMalloc(&ctx->d_totals, sizeof(uint32_t) * (TSK_MAX_SAMPLES + 1)));
+    TSK_CUDA(cudaMalloc(&ctx->d_recbase, sizeof(uint64_t) * (TSK_MAX_SAMPLES + 1)));
+    TSK_CUDA(cudaMalloc(&ctx->d_cutoffs, sizeof(uint32_t) * TSK_MAX_CUTOFF_CYCLES));
+    *out = ctx;
+    return 0;
+}
+
+extern "C" int tsk_ctx_destroy(tsk_ctx *ctx)
+{
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    void *ptrs[] = {ctx->d_samples, ctx->d_tscore, ctx->d_bcl_own, ctx->d_cif_own, ctx->d_calls, ctx->d_kind,
+                    ctx->d_bucket, ctx->d_worklist, ctx->d_blkcnt, ctx->d_totals, ctx->d_recbase,
+                    ctx->d_records, ctx->d_scratch, ctx->d_pos, ctx->d_neg, ctx->d_counters, ctx->d_fair,
+                    ctx->d_lists, ctx->d_ruler_pos, ctx->d_cutoffs, ctx->d_rlen};
+    for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)
+        if (ptrs[i]) cudaFree(ptrs[i]);
+    cudaStreamDestroy(ctx->stream);
+    free(ctx);
+    return 0;
+}
+
+template <typename T>
+static int ensure(T **ptr, size_t *cap, size_t need)
+{
+    if (*cap >= need && *ptr) return 0;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = NULL; *cap = 0;
+    TSK_CUDA(cudaMalloc(ptr, need * sizeof(T)));
+    *cap = need;
+    return 0;
+}
+
+static int ensure_cluster_buffers(tsk_ctx *ctx, uint32_t n)
+{
+    if (n <= ctx->cap_clusters && ctx->d_calls) return 0;
+    /* round the capacity up so consecutive tiles of similar size do not reallocate */
+    uint32_t cap = (n + 4095u) & ~4095u;
+    if (cap < 4096) cap = 4096;
+    const int S = ctx->dp.num_samples;
+    void *old[] = {ctx->d_calls, ctx->d_kind, ctx->d_bucket, ctx->d_worklist, ctx->d_blkcnt,
+                   ctx->d_records, ctx->d_scratch, ctx->d_lists};
+    for (size_t i = 0; i < sizeof(old) / sizeof(old[0]); i++) if (old[i]) cudaFree(old[i]);
+    ctx->d_calls = NULL; ctx->d_kind = NULL; ctx->d_bucket = NULL; ctx->d_worklist = NULL;
+    ctx->d_blkcnt = NULL; ctx->d_records = NULL; ctx->d_scratch = NULL; ctx->d_lists = NULL;
+    ctx->cap_clusters = 0;
+    const size_t nblk = (cap + TSK_K1_THREADS - 1) / TSK_K1_THREADS;
+    const int maxinsert = ctx->dp.threep_length + 1;
+    TSK_CUDA(cudaMalloc(&ctx->d_calls, sizeof(tsk_call) * (size_t)cap));
+    TSK_CUDA(cudaMalloc(&ctx->d_kind, (size_t)cap));
+    TSK_CUDA(cudaMalloc(&ctx->d_bucket, sizeof(uint32_t) * (size_t)cap));
+    TSK_CUDA(cudaMalloc(&ctx->d_worklist, sizeof(uint32_t) * (size_t)cap));
+    TSK_CUDA(cudaMalloc(&ctx->d_blkcnt, sizeof(uint32_t) * nblk * (S + 1)));
+    ctx->rec_cap_words = (size_t)cap * (size_t)(2 + ctx->maxdump);
+    TSK_CUDA(cudaMalloc(&ctx->d_records, sizeof(uint32_t) * ctx->rec_cap_words));
+    ctx->scratch_cap = (size_t)cap * (size_t)maxinsert;
+    TSK_CUDA(cudaMalloc(&ctx->d_scratch, sizeof(float) * ctx->scratch_cap));
+    TSK_CUDA(cudaMalloc(&ctx->d_lists, sizeof(uint32_t) * (16 + 3 * (size_t)cap)));
+    ctx->cap_clusters = cap;
+    return 0;
+}
+
+/* ---- importer path ----------------------------------------------------------------------- */
+extern "C" int tsk_tile_upload(tsk_ctx *ctx, const uint8_t *bcl, size_t bcl_pitch,
+                               const int16_t *cif, size_t cif_pitch, const float invmatrix[16],
+                               uint32_t nclusters, uint32_t firstclusterno, int on_device)
+{
+    if (!ctx || !invmatrix || (nclusters && (!bcl || !cif))) { tsk_set_error("null argument"); return -1; }
+    if (bcl_pitch < nclusters || cif_pitch < nclusters) { tsk_set_error("pitch smaller than nclusters"); return -1; }
+    if (nclusters >= 0x7fffffffu) { tsk_set_error("too many clusters in one block"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    if (ensure_cluster_buffers(ctx, nclusters) != 0) return -1;
+    const int T = ctx->dp.total_cycles, L3 = ctx->dp.threep_length;
+    ctx->processed = 0;
+    memcpy(ctx->dp.inv, invmatrix, sizeof(float) * 16);
+    ctx->tile.nclusters = nclusters;
+    ctx->tile.firstclusterno = firstclusterno;
+    if (on_device) {
+        ctx->tile.bcl = bcl; ctx->tile.bcl_pitch = bcl_pitch;
+        ctx->tile.cif = cif; ctx->tile.cif_pitch = cif_pitch;
+        return 0;
+    }
+    /* own HBM copy; rows padded to 128 B so every row starts on a full line */
+    const size_t bpitch = ((size_t)nclusters + 127) & ~(size_t)127;
+    const size_t cpitch = ((size_t)nclusters + 63) & ~(size_t)63;
+    if (ensure(&ctx->d_bcl_own, &ctx->bcl_cap, bpitch * T + 128) != 0) return -1;
+    if (ensure(&ctx->d_cif_own, &ctx->cif_cap, cpitch * 4 * L3 + 64) != 0) return -1;
+    if (nclusters) {
+        TSK_CUDA(cudaMemcpy2DAsync(ctx->d_bcl_own, bpitch, bcl, bcl_pitch, nclusters, T,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+        TSK_CUDA(cudaMemcpy2DAsync(ctx->d_cif_own, cpitch * sizeof(int16_t), cif, cif_pitch * sizeof(int16_t),
+                                   (size_t)nclusters * sizeof(int16_t), (size_t)4 * L3,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->tile.bcl = ctx->d_bcl_own; ctx->tile.bcl_pitch = bpitch;
+    ctx->tile.cif = ctx->d_cif_own; ctx->tile.cif_pitch = cpitch;
+    return 0;
+}
+
+static int fetch_totals(tsk_ctx *ctx)
+{
+    const int S = ctx->dp.num_samples;
+    TSK_CUDA(cudaMemcpyAsync(ctx->h_totals, ctx->d_totals, sizeof(uint32_t) * (S + 1),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    TSK_CUDA(cudaMemcpyAsync(ctx->h_recbase, ctx->d_recbase, sizeof(uint64_t) * (S + 1),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    TSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int tsk_tile_process(tsk_ctx *ctx)
+{
+    if (!ctx || !ctx->d_calls) { tsk_set_error("no tile uploaded"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    if (tsk_launch_import(ctx, NULL) != 0) return -1;
+    if (fetch_totals(ctx) != 0) return -1;
+    ctx->processed = 1;
+    return 0;
+}
+
+extern "C" int tsk_tile_process_timed(tsk_ctx *ctx, int iters, float ms_out[4])
+{
+    if (!ctx || !ctx->d_calls || iters < 1) { tsk_set_error("bad argument"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    cudaEvent_t ev[4];
+    for (int i = 0; i < 4; i++) TSK_CUDA(cudaEventCreate(&ev[i]));
+    const int S = ctx->dp.num_samples;
+    double acc[4] = {0, 0, 0, 0};
+    uint32_t *saved = (uint32_t *)malloc(sizeof(uint32_t) * S * TSK_NCOUNT);
+    for (int it = 0; it < iters; it++) {
+        /* counters accumulate across calls by contract; keep them unchanged by the re-runs */
+        TSK_CUDA(cudaMemcpyAsync(saved, ctx->d_counters, sizeof(uint32_t) * S * TSK_NCOUNT,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+        TSK_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (tsk_launch_import(ctx, ev) != 0) { free(saved); return -1; }
+        TSK_CUDA(cudaStreamSynchronize(ctx->stream));
+        float a, b, c, t;
+        cudaEventElapsedTime(&a, ev[0], ev[1]);
+        cudaEventElapsedTime(&b, ev[1], ev[2]);
+        cudaEventElapsedTime(&c, ev[2], ev[3]);
+        cudaEventElapsedTime(&t, ev[0], ev[3]);
+        acc[0] += a; acc[1] += b; acc[2] += c; acc[3] += t;
+        if (ctx->processed || it > 0) {
+            TSK_CUDA(cudaMemcpyAsync(ctx->d_counters, saved, sizeof(uint32_t) * S * TSK_NCOUNT,
+                                     cudaMemcpyHostToDevice, ctx->stream));
+            TSK_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    free(saved);
+    for (int i = 0; i < 4; i++) { ms_out[i] = (float)(acc[i] / iters); cudaEventDestroy(ev[i]); }
+    if (fetch_totals(ctx) != 0) return -1;
+    ctx->processed = 1;
+    return 0;
+}
+
+static int need_processed(tsk_ctx *ctx)
+{
+    if (!ctx || !ctx->processed) { tsk_set_error("tsk_tile_process() has not run on this tile"); return -1; }
+    return cudaSetDevice(ctx->device) == cudaSuccess ? 0 : -1;
+}
+
+extern "C" int tsk_tile_get_calls(tsk_ctx *ctx, tsk_call *calls)
+{
+    if (need_processed(ctx) != 0) return -1;
+    TSK_CUDA(cudaMemcpyAsync(calls, ctx->d_calls, sizeof(tsk_call) * (size_t)ctx->tile.nclusters,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    TSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int tsk_tile_get_record_count(tsk_ctx *ctx, int sample, uint32_t *nslots)
+{
+    if (need_processed(ctx) != 0) return -1;
+    if (sample < 0 || sample >= ctx->dp.num_samples) { tsk_set_error("bad sample"); return -1; }
+    *nslots = ctx->h_totals[sample];
+    return 0;
+}
+
+extern "C" int tsk_tile_get_records(tsk_ctx *ctx, int sample, uint32_t *records, size_t capacity_words)
+{
+    if (need_processed(ctx) != 0) return -1;
+    if (sample < 0 || sample >= ctx->dp.num_samples) { tsk_set_error("bad sample"); return -1; }
+    const size_t words = (size_t)ctx->h_totals[sample] * (size_t)(2 + ctx->hp.samples[sample].signal_dump_length);
+    if (capacity_words < words) { tsk_set_error("record buffer too small"); return -1; }
+    if (words) {
+        TSK_CUDA(cudaMemcpyAsync(records, ctx->d_records + ctx->h_recbase[sample], sizeof(uint32_t) * words,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+        TSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+extern "C" int tsk_get_counters(tsk_ctx *ctx, tsk_counters *counters)
+{
+    if (!ctx) { tsk_set_error("null ctx"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    TSK_CUDA(cudaMemcpyAsync(counters, ctx->d_counters, sizeof(uint32_t) * ctx->dp.num_samples * TSK_NCOUNT,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    TSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int tsk_counters_reset(tsk_ctx *ctx)
+{
+    if (!ctx) { tsk_set_error("null ctx"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    TSK_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(uint32_t) * ctx->dp.num_samples * TSK_NCOUNT, ctx->stream));
+    return 0;
+}
+
+extern "C" int tsk_get_hist(tsk_ctx *ctx, uint32_t *pos, uint32_t *neg)
+{
+    if (!ctx) { tsk_set_error("null ctx"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    const size_t histbytes = sizeof(uint32_t) * (size_t)ctx->dp.total_cycles * ctx->dp.bins;
+    if (pos) TSK_CUDA(cudaMemcpyAsync(pos, ctx->d_pos, histbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (neg) TSK_CUDA(cudaMemcpyAsync(neg, ctx->d_neg, histbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    TSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int tsk_get_device_ptrs(tsk_ctx *ctx, void **pos_hist, void **neg_hist, void **counters,
+                                   void **ruler_pos_hist)
+{
+    if (!ctx) { tsk_set_error("null ctx"); return -1; }
+    if (pos_hist) *pos_hist = ctx->d_pos;
+    if (neg_hist) *neg_hist = ctx->d_neg;
+    if (counters) *counters = ctx->d_counters;
+    if (ruler_pos_hist) *ruler_pos_hist = ctx->d_ruler_pos;
+    return 0;
+}
+
+extern "C" int tsk_synchronize(tsk_ctx *ctx)
+{
+    if (!ctx) { tsk_set_error("null ctx"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    TSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" uint64_t tsk_launch_count(tsk_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+/* ---- ruler path ---------------------------------------------------------------------------- */
+extern "C" uint32_t tsk_cutoff_to_packed(double cutoff)
+{
+    /* polyaruler.c:93-96; "nan" -> (int)NaN = INT_MIN on x86-64 -> 0x80000001 -> clamped */
+    const double scaled = cutoff * (double)(TSK_SCORE_MAX - 1);
+    uint32_t v;
+    if (!(scaled > -2147483649.0 && scaled < 2147483648.0)) v = 0x80000001u;
+    else v = 1u + (uint32_t)(int)scaled;
+    if (v >= TSK_SCORE_MAX) v = TSK_SCORE_MAX;
+    return v;
+}
+
+extern "C" int tsk_ruler_hist_reset(tsk_ctx *ctx, int ncutoffs, int dist_sampling_bins)
+{
+    if (!ctx || ncutoffs < 1 || ncutoffs > TSK_MAX_CUTOFF_CYCLES || dist_sampling_bins < 1) {
+        tsk_set_error("bad argument"); return -1;
+    }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    const size_t words = (size_t)ncutoffs * dist_sampling_bins;
+    if (ensure(&ctx->d_ruler_pos, &ctx->ruler_pos_words, words) != 0) return -1;
+    TSK_CUDA(cudaMemsetAsync(ctx->d_ruler_pos, 0, sizeof(uint32_t) * ctx->ruler_pos_words, ctx->stream));
+    return 0;
+}
+
+extern "C" int tsk_ruler_get_hist(tsk_ctx *ctx, uint32_t *pos)
+{
+    if (!ctx || !ctx->d_ruler_pos) { tsk_set_error("no ruler histogram"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    TSK_CUDA(cudaMemcpyAsync(pos, ctx->d_ruler_pos, sizeof(uint32_t) * ctx->ruler_pos_words,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    TSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int ruler_common(tsk_ctx *ctx, const uint32_t *d_records, size_t nrecords, int dump_len,
+                        const uint32_t *cutoffs, int ncutoffs, int min_len, float weight, int bins,
+                        float gap, int16_t *polya_len_out)
+{
+    if (ncutoffs < 1 || ncutoffs > TSK_MAX_CUTOFF_CYCLES || bins < 1 || dump_len < 0 || !cutoffs) {
+        tsk_set_error("bad ruler argument"); return -1;
+    }
+    if (!ctx->d_ruler_pos || ctx->ruler_pos_words < (size_t)ncutoffs * bins) {
+        if (tsk_ruler_hist_reset(ctx, ncutoffs, bins) != 0) return -1;
+    }
+    TSK_CUDA(cudaMemcpyAsync(ctx->d_cutoffs, cutoffs, sizeof(uint32_t) * ncutoffs, cudaMemcpyHostToDevice,
+                             ctx->stream));
+    if (ensure(&ctx->d_rlen, &ctx->rlen_cap, nrecords ? nrecords : 1) != 0) return -1;
+    if (nrecords) {
+        if (tsk_launch_ruler(ctx, d_records, nrecords, dump_len, ncutoffs, min_len, weight, bins, gap,
+                             ctx->d_rlen) != 0) return -1;
+        TSK_CUDA(cudaMemcpyAsync(polya_len_out, ctx->d_rlen, sizeof(int16_t) * nrecords,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    TSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int tsk_ruler_records(tsk_ctx *ctx, const uint32_t *records, size_t nrecords, int dump_len,
+                                 const uint32_t *cutoffs, int ncutoffs, int minimum_polya_len,
+                                 float downhill_ext_weight, int dist_sampling_bins, float dist_sampling_gap,
+                                 int16_t *polya_len_out, int on_device)
+{
+    if (!ctx || (nrecords && (!records || !polya_len_out))) { tsk_set_error("null argument"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t *d_rec = records;
+    uint32_t *tmp = NULL;
+    if (!on_device && nrecords) {
+        const size_t bytes = sizeof(uint32_t) * nrecords * (size_t)(2 + dump_len);
+        TSK_CUDA(cudaMalloc(&tmp, bytes));
+        TSK_CUDA(cudaMemcpyAsync(tmp, records, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_rec = tmp;
+    }
+    const int rc = ruler_common(ctx, d_rec, nrecords, dump_len, cutoffs, ncutoffs, minimum_polya_len,
+                                downhill_ext_weight, dist_sampling_bins, dist_sampling_gap, polya_len_out);
+    if (tmp) cudaFree(tmp);
+    return rc;
+}
+
+extern "C" int tsk_ruler_tile(tsk_ctx *ctx, int sample, const uint32_t *cutoffs, int ncutoffs,
+                              int minimum_polya_len, float downhill_ext_weight, int dist_sampling_bins,
+                              float dist_sampling_gap, int16_t *polya_len_out)
+{
+    if (need_processed(ctx) != 0) return -1;
+    if (sample < 0 || sample >= ctx->dp.num_samples) { tsk_set_error("bad sample"); return -1; }
+    return ruler_common(ctx, ctx->d_records + ctx->h_recbase[sample], ctx->h_totals[sample],
+                        ctx->hp.samples[sample].signal_dump_length, cutoffs, ncutoffs, minimum_polya_len,
+                        downhill_ext_weight, dist_sampling_bins, dist_sampling_gap, polya_len_out);
+}
+
+/* ---- cutoff estimation ----------------------------------------------------------------------- */
+extern "C" int tsk_fit_cutoffs(tsk_ctx *ctx, const uint64_t *pos, const uint64_t *neg, int cycles, int bins,
+                               uint64_t min_spots, double kde_bandwidth, double search_low,
+                               const double *search_high, int nsearch_high, double *cutoffs_out)
+{
+    if (!ctx || !pos || !neg || !cutoffs_out || cycles < 1 || bins < 2 || nsearch_high < 1 ||
+        nsearch_high > 8 || !search_high) { tsk_set_error("bad argument"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    uint64_t *d_pos = NULL, *d_neg = NULL;
+    double *d_out = NULL;
+    const size_t hb = sizeof(uint64_t) * (size_t)cycles * bins;
+    TSK_CUDA(cudaMalloc(&d_pos, hb));
+    TSK_CUDA(cudaMalloc(&d_neg, hb));
+    TSK_CUDA(cudaMalloc(&d_out, sizeof(double) * cycles));
+    TSK_CUDA(cudaMemcpyAsync(d_pos, pos, hb, cudaMemcpyHostToDevice, ctx->stream));
+    TSK_CUDA(cudaMemcpyAsync(d_neg, neg, hb, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = tsk_launch_fit(ctx, d_pos, d_neg, cycles, bins, min_spots, kde_bandwidth, search_low,
+                            search_high, nsearch_high, d_out);
+    if (rc == 0) {
+        cudaError_t e = cudaMemcpyAsync(cutoffs_out, d_out, sizeof(double) * cycles, cudaMemcpyDeviceToHost,
+                                        ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { tsk_set_error("fit copy back: %s", cudaGetErrorString(e)); rc = -1; }
+    }
+    cudaFree(d_pos); cudaFree(d_neg); cudaFree(d_out);
+    return rc;
+}

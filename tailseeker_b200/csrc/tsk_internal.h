@@ -1,0 +1,121 @@
+/* Internal declarations shared by the CUDA translation units of libtailseeker_b200.so. */
+#ifndef TSK_INTERNAL_H
+#define TSK_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/tailseeker_b200.h"
+
+#define TSK_K1_THREADS   128     /* clusters per decode_demux_seed CTA */
+#define TSK_K2_THREADS   128
+#define TSK_MAX_MODS     64      /* upper bound on max_terminal_modifications */
+#define TSK_MAX_RANK     8       /* upper bound on balancer num-positive/negative samples */
+#define TSK_NCOUNT       6       /* counters per sample */
+
+/* cluster kinds produced by decode_demux_seed (bit field, one byte per cluster) */
+#define KIND_PROCESS   0x01      /* reaches process_polya_signal() and passes the balancer check */
+#define KIND_EMIT      0x02      /* seed poly(A) >= signal-analysis-trigger: owns a record slot */
+#define KIND_POS       0x04      /* seed poly(A) >= seed-trigger: contrast test / positive sampling */
+#define KIND_NEG       0x08      /* negative-sampling candidate (before fair sampling) */
+
+/* Device-side sample descriptor (128 bytes), built by the host from tsk_sample. */
+struct DevSample {
+    uint32_t index_pk[4];        /* index read as 3-bit base codes, 10 per word */
+    uint8_t  delim_mask[TSK_MAX_SEQ];   /* per delimiter position: IUPAC bit mask over A,C,G,T */
+    uint8_t  fingerprint[TSK_MAX_SEQ];  /* base codes (0-4), 7 = matches nothing */
+    int16_t  max_index_mm;
+    int16_t  delimiter_pos, delimiter_length, max_delim_mm;
+    int16_t  fp_pos, fp_len, max_fp_mm;
+    int16_t  has_umi;
+    int16_t  limit_threep, dump_len;
+    int16_t  pad_[14];
+};
+static_assert(sizeof(DevSample) == 128, "DevSample must be 128 bytes");
+
+/* Scalar parameters, passed to kernels by value (__grid_constant__). */
+struct DevParams {
+    int32_t total_cycles, index_start, index_length, threep_start, threep_length;
+    int32_t keep_no_delimiter, keep_low_quality_balancer;
+    int32_t balancer_start, balancer_length, balancer_min_quality, balancer_min_bases_passes;
+    int32_t balancer_minimum_occurrence, npos, nneg;
+    int32_t seed_trigger, neg_polya_len, cctr_left, cctr_right;
+    float   required_contrast;
+    int32_t boundary_pos, sampling_gap, bins;
+    int32_t fair_fp_len, fair_hash_size, fair_max_count;
+    int32_t w_polyA[5], w_nonA[5];
+    int32_t max_mods, min_polya_len, sigproc_trigger;
+    float   dark_threshold;
+    int32_t max_dark_cycles;
+    float   maximum_entropy;
+    int32_t num_samples;
+    int32_t index_words;         /* ceil(index_length / 10) */
+    float   inv[16];             /* inverse colour matrix of the resident tile */
+};
+
+/* Work descriptors of the resident tile (device pointers). */
+struct TileView {
+    const uint8_t *bcl;  size_t bcl_pitch;
+    const int16_t *cif;  size_t cif_pitch;     /* elements */
+    uint32_t nclusters, firstclusterno;
+};
+
+struct tsk_ctx {
+    int device;
+    cudaStream_t stream;
+    tsk_params hp;               /* host copy of the parameters */
+    DevParams dp;
+    DevSample *d_samples;        /* [num_samples] */
+    float *d_tscore;             /* [201] */
+    int maxdump;                 /* max signal_dump_length over samples */
+
+    /* resident tile */
+    TileView tile;
+    uint8_t *d_bcl_own;  size_t bcl_cap;
+    int16_t *d_cif_own;  size_t cif_cap;
+    uint32_t cap_clusters;       /* capacity of the per-cluster buffers below */
+
+    tsk_call *d_calls;           /* [N] */
+    uint8_t  *d_kind;            /* [N] */
+    uint32_t *d_bucket;          /* [N] fair-sampling hash bucket of KIND_NEG clusters */
+    uint32_t *d_worklist;        /* [N] clusters with KIND_PROCESS, ascending */
+    uint32_t *d_blkcnt;          /* [nblk][num_samples+1] per-CTA counts, then exclusive bases */
+    uint32_t *d_totals;          /* [num_samples+1] */
+    uint64_t *d_recbase;         /* [num_samples+1] word offset of each sample's slots */
+    uint32_t *d_records;  size_t rec_cap_words;
+    float    *d_scratch;  size_t scratch_cap;   /* [maxinsert][N] scores of KIND_POS clusters */
+    uint32_t *d_pos, *d_neg;     /* [T][bins] */
+    uint32_t *d_counters;        /* [num_samples][6] */
+    uint32_t *d_fair;            /* [hash_size] candidate counts per bucket */
+    uint32_t *d_lists;           /* undo / contended / accepted lists + their counters */
+    uint32_t *d_ruler_pos;  size_t ruler_pos_words;
+    uint32_t *d_cutoffs;         /* [TSK_MAX_CUTOFF_CYCLES] */
+    int16_t  *d_rlen;  size_t rlen_cap;
+
+    /* host mirrors filled by tsk_tile_process() */
+    uint32_t h_totals[TSK_MAX_SAMPLES + 1];
+    uint64_t h_recbase[TSK_MAX_SAMPLES + 1];
+    int processed;
+    uint64_t launches;
+};
+
+void tsk_set_error(const char *fmt, ...);
+#define TSK_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e_ = (call);                                                    \
+        if (e_ != cudaSuccess) {                                                    \
+            tsk_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                          __FILE__, __LINE__);                                      \
+            return -1;                                                              \
+        }                                                                           \
+    } while (0)
+
+/* kernel launchers (tsk_kernels.cu / tsk_ruler.cu / tsk_fit.cu) */
+int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev /* optional [4] */);
+int tsk_launch_ruler(tsk_ctx *ctx, const uint32_t *d_records, size_t nrecords, int dump_len,
+                     int ncutoffs, int min_len, float weight, int bins, float gap,
+                     int16_t *d_len_out);
+int tsk_launch_fit(tsk_ctx *ctx, const uint64_t *d_pos, const uint64_t *d_neg, int cycles, int bins,
+                   uint64_t min_spots, double bw, double low, const double *high, int nhigh,
+                   double *d_out);
+
+#endif

@@ -1,0 +1,745 @@
+/*
+ * tsk_kernels.cu -- sm_100a kernels of the importer path (decode / demultiplex / seed,
+ * slot scan, normalise / score / pack, fair-sampling fix-ups).
+ *
+ * One thread per cluster.  Inputs stay in the files' cycle-major layouts, so consecutive
+ * lanes read consecutive bytes (BCL) or int16 (CIF planes): every request is coalesced.
+ * All per-cluster state lives in registers; nothing here is a dense contraction, so no
+ * tensor cores.  Compiled with -fmad=false: the reference is built without FMA
+ * contraction and parity of the packed scores needs separately rounded IEEE operations.
+ *
+ * Reference behaviour restated here (cited per function): src/importer/spotanalyzer.c,
+ * signalproc.c, findpolya.c, bclreader.c of hyeshik/tailseeker 3.2.1.
+ */
+#include <math_constants.h>
+#include "tsk_internal.h"
+#include "tsk_device.cuh"
+
+#define FULL_MASK 0xffffffffu
+
+/* =======================================================================================
+ * K1  decode_demux_seed : BCL bytes -> per-cluster call, kind, fair-sampling bucket
+ *   format_basecalls (bclreader.c:146-166), assign_barcode (spotanalyzer.c:67-103),
+ *   counters + fingerprint + balancer QC + delimiter (spotanalyzer.c:648-715,106-203),
+ *   find_polya (findpolya.c:35-84), check_balance_minimum (signalproc.c:106-129),
+ *   fair-sampling hash (spotanalyzer.c:460-474)
+ * ===================================================================================== */
+__device__ __forceinline__ int mismatch3(uint32_t a, uint32_t b)
+{
+    uint32_t x = a ^ b;
+    x = (x | (x >> 1) | (x >> 2)) & 0x09249249u;
+    return __popc(x);
+}
+
+__global__ void __launch_bounds__(TSK_K1_THREADS)
+k_decode_demux_seed(const __grid_constant__ DevParams P, const TileView tv,
+                    const DevSample *__restrict__ g_samples,
+                    tsk_call *__restrict__ calls, uint8_t *__restrict__ kind,
+                    uint32_t *__restrict__ bucket, uint32_t *__restrict__ blkcnt,
+                    uint32_t *__restrict__ counters, uint32_t *__restrict__ fair)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = P.num_samples;
+    DevSample *s_samples = reinterpret_cast<DevSample *>(smem_raw);
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem_raw + sizeof(DevSample) * S); /* [S][6] */
+    uint32_t *s_wcnt = s_cnt + S * TSK_NCOUNT;       /* [warps][S+1] */
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwarps = TSK_K1_THREADS / 32;
+
+    for (int i = tid; i < (int)(sizeof(DevSample) / 4) * S; i += TSK_K1_THREADS)
+        reinterpret_cast<uint32_t *>(s_samples)[i] = reinterpret_cast<const uint32_t *>(g_samples)[i];
+    for (int i = tid; i < S * TSK_NCOUNT + nwarps * (S + 1); i += TSK_K1_THREADS)
+        s_cnt[i] = 0;
+    __syncthreads();
+
+    const uint32_t n = blockIdx.x * TSK_K1_THREADS + tid;
+    const bool active = n < tv.nclusters;
+    const size_t pitch = tv.bcl_pitch;
+    const uint8_t *col = tv.bcl + n;
+    auto rd = [&](int c) -> uint32_t { return (uint32_t)__ldg(col + (size_t)c * pitch); };
+
+    int sample = 0, flags = 0, de = -1, status = -1, mods = -1;
+    int written = 0;
+    uint32_t kd = 0, bk = 0;
+
+    if (active) {
+        const int ts = P.threep_start, tl = P.threep_length;
+        bool dropped = false;
+
+        /* ---- barcode ---- */
+        uint32_t rpk[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            if (w < P.index_words) {
+                const int k0 = w * 10;
+                const int kn = min(10, P.index_length - k0);
+                uint32_t acc = 0;
+                for (int k = 0; k < kn; k++)
+                    acc |= tsk_base_code(rd(P.index_start + k0 + k)) << (3 * k);
+                rpk[w] = acc;
+            }
+        }
+        int best = -1, bestmm = P.index_length + 1;
+        bool tie = false;
+        for (int s = 1; s < S; s++) {
+            int mm = 0;
+#pragma unroll
+            for (int w = 0; w < 4; w++)
+                if (w < P.index_words) mm += mismatch3(rpk[w], s_samples[s].index_pk[w]);
+            if (mm < bestmm) { best = s; bestmm = mm; tie = false; }
+            else if (mm == bestmm) tie = true;
+        }
+        int mismatches;
+        if (best < 0 || tie || bestmm > s_samples[best].max_index_mm) { mismatches = -1; sample = 0; }
+        else { mismatches = bestmm; sample = best; }
+        const DevSample &sm = s_samples[sample];
+
+        if (mismatches <= 0) atomicAdd(&s_cnt[sample * TSK_NCOUNT + 0], 1u);
+        else {
+            flags |= TSK_PAFLAG_BARCODE_HAS_MISMATCHES;
+            atomicAdd(&s_cnt[sample * TSK_NCOUNT + (mismatches == 1 ? 1 : 2)], 1u);
+        }
+
+        /* ---- fingerprint ---- */
+        if (sm.fp_len > 0) {
+            int mm = 0;
+            for (int k = 0; k < sm.fp_len; k++)
+                mm += tsk_base_code(rd(sm.fp_pos + k)) != sm.fingerprint[k];
+            if (mm > sm.max_fp_mm) {
+                atomicAdd(&s_cnt[sample * TSK_NCOUNT + 4], 1u);
+                dropped = true;
+            }
+        }
+
+        /* ---- balancer base-call quality (whole-read indices) ---- */
+        if (!dropped && sm.has_umi > 0 && P.balancer_min_bases_passes > 0) {
+            int pass = 0;
+            for (int j = P.balancer_start; j < P.balancer_start + P.balancer_length; j++)
+                pass += (int)tsk_base_qual(rd(j)) >= P.balancer_min_quality;
+            if (pass < P.balancer_min_bases_passes) {
+                flags |= TSK_PAFLAG_BALANCER_CALL_QUALITY_BAD;
+                atomicAdd(&s_cnt[sample * TSK_NCOUNT + 5], 1u);
+                if (!P.keep_low_quality_balancer) dropped = true;
+            }
+        }
+
+        if (!dropped) {
+            written = 1;
+            if (sm.delimiter_length > 0) {
+                /* ---- delimiter: offsets 0, -1, +1 ---- */
+                int found = -1, foundshift = 0, foundmm = 0;
+#pragma unroll
+                for (int t = 0; t < 3; t++) {
+                    const int shift = (t == 0) ? 0 : (t == 1 ? -1 : 1);
+                    if (found < 0) {
+                        int nd = 0;
+                        for (int k = 0; k < sm.delimiter_length; k++) {
+                            const uint32_t code = tsk_base_code(rd(sm.delimiter_pos + shift + k));
+                            nd += !((sm.delim_mask[k] >> code) & 1u);
+                        }
+                        if (nd <= sm.max_delim_mm) { found = t; foundshift = shift; foundmm = nd; }
+                    }
+                }
+                if (found < 0) {
+                    flags |= TSK_PAFLAG_DELIMITER_NOT_FOUND;
+                    atomicAdd(&s_cnt[sample * TSK_NCOUNT + 3], 1u);
+                    if (!P.keep_no_delimiter) written = 0;
+                } else {
+                    if (foundmm > 0) flags |= TSK_PAFLAG_DELIMITER_HAS_MISMATCH;
+                    if (foundshift != 0) flags |= TSK_PAFLAG_DELIMITER_IS_SHIFTED;
+                    de = sm.delimiter_pos + sm.delimiter_length + foundshift;
+
+                    /* ---- sequence seed: find_polya as one backward pass ----
+                     * score(i,j) = V(i) + S(i) - S(j+1), S(k) = sum_{m>=k} polyA_w[seq m],
+                     * V(i) = sum_{m<i} nonA_w[seq m]; the reference's (i asc, j asc, strict >)
+                     * scan ends on the lexicographically first maximum, which is: per i the
+                     * smallest j >= i+minlen-1 minimising S(j+1), then the first i maximising. */
+                    const int L = ts + tl - de;
+                    const int M = min(P.max_mods, L);
+                    const int mlen = max(P.min_polya_len, 1);
+                    int candS[TSK_MAX_MODS], candJ[TSK_MAX_MODS], sfull[TSK_MAX_MODS];
+                    uint8_t codes[TSK_MAX_MODS];
+                    {
+                        int Srun = 0, minS = 0x3fffffff, argj = -1;
+                        const int captop = M + mlen - 1;    /* j below this may be a j_min(i) */
+                        for (int j = L - 1; j >= 0; j--) {
+                            const uint32_t code = tsk_base_code(rd(de + j));
+                            if (Srun <= minS) { minS = Srun; argj = j; }
+                            if (j < captop) {
+                                const int i = j - (mlen - 1);
+                                if (i >= 0 && i < M) { candS[i] = minS; candJ[i] = argj; }
+                            }
+                            Srun += P.w_polyA[code];
+                            if (j < M) { sfull[j] = Srun; codes[j] = (uint8_t)code; }
+                        }
+                    }
+                    int bi = -1, bj = -1, bscore = -1, V = 0;
+                    for (int i = 0; i < M; i++) {
+                        if (i + mlen - 1 <= L - 1) {
+                            const int sc = V + sfull[i] - candS[i];
+                            if (sc > bscore) { bscore = sc; bi = i; bj = candJ[i]; }
+                        }
+                        V += P.w_nonA[codes[i]];
+                    }
+                    int ps = 0, plen = 0;
+                    if (bi >= 0 && bscore >= 1 && (bj - bi + 1) >= P.min_polya_len) {
+                        ps = bi; plen = bj + 1 - bi;
+                    }
+                    mods = ps;
+                    if (ps > 0) flags |= TSK_PAFLAG_HAVE_3P_MODIFICATION;
+                    if (plen > 0) flags |= TSK_PAFLAG_POLYA_DETECTED;
+
+                    /* ---- balancer composition ---- */
+                    int blen = de - ts;
+                    if (blen > P.balancer_length) blen = P.balancer_length;
+                    uint32_t comp = 0;          /* four byte counters A,C,G,T */
+                    for (int c = P.balancer_start; c < P.balancer_start + blen; c++) {
+                        const uint32_t code = tsk_base_code(rd(ts + c));
+                        if (code < 4) comp += 1u << (8 * code);
+                    }
+                    const int mo = P.balancer_minimum_occurrence;
+                    if ((int)(comp & 255) < mo || (int)((comp >> 8) & 255) < mo ||
+                        (int)((comp >> 16) & 255) < mo || (int)(comp >> 24) < mo) {
+                        flags |= TSK_PAFLAG_BALANCER_BIASED;
+                        status = -1;
+                    } else {
+                        status = plen;
+                        kd = KIND_PROCESS;
+                        int insert_len = L;
+                        if (sm.limit_threep > 0 && sm.limit_threep < insert_len)
+                            insert_len = sm.limit_threep;
+                        const int scan_len = insert_len - ps;
+                        if (scan_len > 0) {
+                            if (plen >= P.seed_trigger) kd |= KIND_POS;
+                            else if (plen <= P.neg_polya_len && scan_len >= P.fair_fp_len) {
+                                /* 63-bit rolling hash of the first bases after the seed start */
+                                unsigned long long v = 0;
+                                for (int k = 0; k < P.fair_fp_len; k++) {
+                                    const uint32_t code = tsk_base_code(rd(de + ps + k));
+                                    /* 'A','C','G','T','N' & 7 */
+                                    const unsigned long long ch = (0x64731ull >> (4 * code)) & 7ull;
+                                    v = ((v << 3) | (ch ^ (v >> 60))) & 0x7fffffffffffffffull;
+                                }
+                                bk = (uint32_t)(v % (unsigned long long)P.fair_hash_size);
+                                kd |= KIND_NEG;
+                                atomicAdd(&fair[bk], 1u);
+                            }
+                            if (plen >= P.sigproc_trigger) kd |= KIND_EMIT;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    /* ---- order-preserving ranks inside the CTA: record slots per sample, work items ---- */
+    const int ekey = (kd & KIND_EMIT) ? sample : -1;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned peers = __match_any_sync(FULL_MASK, ekey);
+    int erank = __popc(peers & lt);
+    if (ekey >= 0 && erank == 0) s_wcnt[warp * (S + 1) + ekey] = __popc(peers);
+    const unsigned pb = __ballot_sync(FULL_MASK, (kd & KIND_PROCESS) != 0);
+    int prank = __popc(pb & lt);
+    if (lane == 0) s_wcnt[warp * (S + 1) + S] = __popc(pb);
+    __syncthreads();
+    for (int w = 0; w < warp; w++) {
+        if (ekey >= 0) erank += s_wcnt[w * (S + 1) + ekey];
+        prank += s_wcnt[w * (S + 1) + S];
+    }
+    if (tid <= S) {
+        uint32_t tot = 0;
+        for (int w = 0; w < nwarps; w++) tot += s_wcnt[w * (S + 1) + tid];
+        blkcnt[(size_t)blockIdx.x * (S + 1) + tid] = tot;
+    }
+    for (int i = tid; i < S * TSK_NCOUNT; i += TSK_K1_THREADS)
+        if (s_cnt[i]) atomicAdd(&counters[i], s_cnt[i]);
+
+    if (active) {
+        tsk_call c;
+        c.sample = (int16_t)sample;
+        c.flags = (uint16_t)flags;
+        c.delimiter_end = (int16_t)de;
+        c.polya_len = (int16_t)status;
+        c.terminal_mods = (int16_t)mods;
+        c.written = (uint8_t)written;
+        c.emitted = (kd & KIND_EMIT) ? 1 : 0;
+        c.record_slot = ((uint32_t)prank << 16) | (uint32_t)erank;   /* CTA-local, see k_assign */
+        *reinterpret_cast<uint4 *>(&calls[n]) = *reinterpret_cast<const uint4 *>(&c);
+        kind[n] = (uint8_t)kd;
+        bucket[n] = bk;
+    }
+}
+
+/* Exclusive scan of the per-CTA counts, one CTA per column (sample 0..S-1 = record slots,
+ * column S = work items). */
+__global__ void __launch_bounds__(256)
+k_scan_blocks(uint32_t *__restrict__ blkcnt, uint32_t *__restrict__ totals, int nblk, int ncol)
+{
+    __shared__ uint32_t s_part[256];
+    const int col = blockIdx.x, tid = threadIdx.x;
+    const int per = (nblk + 255) / 256;
+    const int b0 = min(nblk, tid * per), b1 = min(nblk, b0 + per);
+    uint32_t sum = 0;
+    for (int b = b0; b < b1; b++) sum += blkcnt[(size_t)b * ncol + col];
+    s_part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (int i = 0; i < 256; i++) { uint32_t v = s_part[i]; s_part[i] = run; run += v; }
+        totals[col] = run;
+    }
+    __syncthreads();
+    uint32_t run = s_part[tid];
+    for (int b = b0; b < b1; b++) {
+        uint32_t v = blkcnt[(size_t)b * ncol + col];
+        blkcnt[(size_t)b * ncol + col] = run;
+        run += v;
+    }
+}
+
+__global__ void k_record_bases(const uint32_t *__restrict__ totals, const DevSample *__restrict__ samples,
+                               uint64_t *__restrict__ recbase, int S)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        uint64_t at = 0;
+        for (int s = 0; s < S; s++) {
+            recbase[s] = at;
+            at += (uint64_t)totals[s] * (uint64_t)(2 + samples[s].dump_len);
+        }
+        recbase[S] = at;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_assign(const TileView tv, tsk_call *__restrict__ calls, const uint8_t *__restrict__ kind,
+         const uint32_t *__restrict__ blkbase, uint32_t *__restrict__ worklist, int S)
+{
+    const uint32_t n = blockIdx.x * 256 + threadIdx.x;
+    if (n >= tv.nclusters) return;
+    const uint32_t kd = kind[n];
+    const uint32_t tmp = calls[n].record_slot;
+    const size_t row = (size_t)(n / TSK_K1_THREADS) * (S + 1);
+    uint32_t slot = 0;
+    if (kd & KIND_EMIT) slot = blkbase[row + calls[n].sample] + (tmp & 0xffffu);
+    if (kd & KIND_PROCESS) worklist[blkbase[row + S] + (tmp >> 16)] = n;
+    calls[n].record_slot = slot;
+}
+
+/* =======================================================================================
+ * K2  normalise_score_pack
+ *   probe_signal_ranges (signalproc.c:132-201), decrosstalk_intensity (:85-103),
+ *   compute_polya_score + normalize_signals + shannon_entropy (:269-342,246-266,39-51),
+ *   find_max_cumulative_contrast (:378-412), sampling policy and add_polya_score_sample
+ *   (spotanalyzer.c:574-599,441-457), write_polya_score (spotanalyzer.c:389-438)
+ * ===================================================================================== */
+struct ScoreShared {
+    double2 logtab[16];
+    float   tscore[TSK_T_SCORE_BINS + 1];
+    int16_t limit[TSK_MAX_SAMPLES];
+    int16_t dump[TSK_MAX_SAMPLES];
+};
+
+__device__ __forceinline__ void load_score_shared(ScoreShared &sh, const float *__restrict__ tscore,
+                                                  const DevSample *__restrict__ samples, int S)
+{
+    for (int i = threadIdx.x; i < 16; i += blockDim.x)
+        sh.logtab[i] = make_double2(c_logf_tab[i][0], c_logf_tab[i][1]);
+    for (int i = threadIdx.x; i <= TSK_T_SCORE_BINS; i += blockDim.x) sh.tscore[i] = tscore[i];
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        sh.limit[i] = samples[i].limit_threep;
+        sh.dump[i] = samples[i].dump_len;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void decrosstalk(float sig[4], const int16_t *__restrict__ p, size_t pitch,
+                                            const float *inv)
+{
+    const float v0 = (float)__ldg(p), v1 = (float)__ldg(p + pitch);
+    const float v2 = (float)__ldg(p + 2 * pitch), v3 = (float)__ldg(p + 3 * pitch);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        float a = __fmul_rn(inv[4 * j + 0], v0);
+        a = __fadd_rn(a, __fmul_rn(inv[4 * j + 1], v1));
+        a = __fadd_rn(a, __fmul_rn(inv[4 * j + 2], v2));
+        sig[j] = __fadd_rn(a, __fmul_rn(inv[4 * j + 3], v3));
+    }
+}
+
+/* low / bandwidth of the four channels over the balancer cycles.  Generic in npos / nneg
+ * (<= TSK_MAX_RANK); the bubble-insert keeps earlier elements on ties like the reference. */
+__device__ __forceinline__ void probe_ranges(const DevParams &P, const int16_t *__restrict__ cifcol,
+                                             size_t pitch, int blen, float low[4], float bw[4])
+{
+    float top[4][TSK_MAX_RANK], bot[4][TSK_MAX_RANK];
+    const int npos = P.npos, nneg = P.nneg;
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++)
+#pragma unroll
+        for (int r = 0; r < TSK_MAX_RANK; r++) { top[ch][r] = -CUDART_INF_F; bot[ch][r] = CUDART_INF_F; }
+    for (int c = P.balancer_start; c < P.balancer_start + blen; c++) {
+        float sig[4];
+        decrosstalk(sig, cifcol + (size_t)c * 4 * pitch, pitch, P.inv);
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++) {
+            float carry = sig[ch];
+#pragma unroll
+            for (int r = 0; r < TSK_MAX_RANK; r++)
+                if (r < npos && carry > top[ch][r]) { const float t = top[ch][r]; top[ch][r] = carry; carry = t; }
+            carry = sig[ch];
+#pragma unroll
+            for (int r = 0; r < TSK_MAX_RANK; r++)
+                if (r < nneg && carry < bot[ch][r]) { const float t = bot[ch][r]; bot[ch][r] = carry; carry = t; }
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) {
+        float acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < TSK_MAX_RANK; r++) if (r < nneg) acc = __fadd_rn(acc, bot[ch][r]);
+        low[ch] = __fdiv_rn(acc, (float)nneg);
+        acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < TSK_MAX_RANK; r++) if (r < npos) acc = __fadd_rn(acc, top[ch][r]);
+        bw[ch] = __fsub_rn(__fdiv_rn(acc, (float)npos), low[ch]);
+    }
+}
+
+/* One cycle of compute_polya_score().  Returns false for a dark cycle. */
+__device__ __forceinline__ bool score_cycle(const DevParams &P, const ScoreShared &sh,
+                                            const int16_t *__restrict__ p, size_t pitch,
+                                            const float low[4], const float bw[4],
+                                            float &entropy_score, float &score)
+{
+    float sig[4], nrm[4];
+    decrosstalk(sig, p, pitch, P.inv);
+    float total = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++)
+        if (sig[ch] > 0.f) total = __fadd_rn(total, sig[ch]);
+    if (total < P.dark_threshold) return false;
+    total = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) {
+        float v = __fdiv_rn(__fsub_rn(sig[ch], low[ch]), bw[ch]);
+        if (v < 0.f) v = 0.f;
+        nrm[ch] = v;
+        total = __fadd_rn(total, v);
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) nrm[ch] = __fdiv_rn(nrm[ch], total);
+    if (nrm[0] != nrm[0]) return false;
+    float h = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++)
+        if (nrm[ch] > 0.f) h = __fsub_rn(h, __fmul_rn(nrm[ch], tsk_logf(nrm[ch], sh.logtab)));
+    entropy_score = __fsub_rn(1.f, __fdiv_rn(h, P.maximum_entropy));
+    int ti = __float2int_rz(__fmul_rn(nrm[3], (float)TSK_T_SCORE_BINS));
+    ti = max(0, min(TSK_T_SCORE_BINS, ti));      /* the reference indexes unchecked (UB outside) */
+    score = __fmul_rn(entropy_score, sh.tscore[ti]);
+    return true;
+}
+
+__device__ __forceinline__ int score_bin(float score, int bins)
+{
+    int b = __float2int_rz(__fmul_rn(score, (float)bins));
+    return b >= bins ? bins - 1 : b;
+}
+
+/* list area layout (u32): [0] undo count, [1] contended count, [2] accepted count,
+ * then three arrays of `cap` entries */
+__device__ __forceinline__ uint32_t *list_array(uint32_t *lists, int which, uint32_t cap)
+{
+    return lists + 16 + (size_t)which * cap;
+}
+
+__global__ void __launch_bounds__(TSK_K2_THREADS)
+k_normalise_score_pack(const __grid_constant__ DevParams P, const TileView tv,
+                       const DevSample *__restrict__ samples, const float *__restrict__ g_tscore,
+                       tsk_call *__restrict__ calls, const uint8_t *__restrict__ kind,
+                       const uint32_t *__restrict__ bucket, const uint32_t *__restrict__ worklist,
+                       const uint32_t *__restrict__ totals, const uint64_t *__restrict__ recbase,
+                       uint32_t *__restrict__ records, float *__restrict__ scratch, size_t spitch,
+                       uint32_t *__restrict__ pos, uint32_t *__restrict__ neg,
+                       const uint32_t *__restrict__ fair, uint32_t *__restrict__ lists, uint32_t listcap)
+{
+    __shared__ ScoreShared sh;
+    const int S = P.num_samples;
+    load_score_shared(sh, g_tscore, samples, S);
+
+    const uint32_t w = blockIdx.x * TSK_K2_THREADS + threadIdx.x;
+    if (w >= totals[S]) return;
+    const uint32_t n = worklist[w];
+    const uint4 craw = *reinterpret_cast<const uint4 *>(&calls[n]);
+    tsk_call call = *reinterpret_cast<const tsk_call *>(&craw);
+    const uint32_t kd = kind[n];
+    const int ts = P.threep_start, tl = P.threep_length, bins = P.bins;
+    const int de = call.delimiter_end, ps = call.terminal_mods;
+    const int sample = call.sample;
+    const size_t pitch = tv.cif_pitch;
+    const int16_t *cifcol = tv.cif + n;
+
+    int blen = de - ts;
+    if (blen > P.balancer_length) blen = P.balancer_length;
+    float low[4], bw[4];
+    probe_ranges(P, cifcol, pitch, blen, low, bw);
+
+    int insert_len = ts + tl - de;
+    const int limit = sh.limit[sample], dump = sh.dump[sample];
+    if (limit > 0 && limit < insert_len) insert_len = limit;
+    const int scan_len = insert_len - ps;
+    const int valid = min(scan_len, dump);
+
+    /* record slot */
+    uint32_t *rec = nullptr;
+    if (kd & KIND_EMIT) {
+        rec = records + recbase[sample] + (size_t)call.record_slot * (size_t)(2 + dump);
+        rec[0] = tv.firstclusterno + n;
+        rec[1] = (uint32_t)(uint16_t)(int16_t)(de + ps) | ((uint32_t)(uint16_t)(int16_t)valid << 16);
+    }
+    /* negative sampling: inline when the bucket cannot overflow */
+    bool neg_inline = false;
+    if (kd & KIND_NEG)
+        neg_inline = (P.fair_max_count == 0) || (fair[bucket[n]] <= (uint32_t)P.fair_max_count);
+
+    int ndark = 0;
+    float prev_entropy = CUDART_NAN_F;
+    unsigned long long dhwin = 0;          /* bit k = downhill of cycle (c - k) */
+    const int16_t *p = cifcol + (size_t)(de - ts) * 4 * pitch;
+    const uint32_t rowbase = (uint32_t)de;  /* histogram row of score index c is de + c */
+
+    for (int c = 0; c < insert_len; c++, p += 4 * pitch) {
+        float es, score;
+        const bool lit = score_cycle(P, sh, p, pitch, low, bw, es, score);
+        uint32_t dh = 0;
+        if (lit) {
+            dh = (es < prev_entropy) ? 1u : 0u;
+            prev_entropy = es;
+        } else {
+            ndark++;
+            score = CUDART_NAN_F;
+            prev_entropy = CUDART_NAN_F;
+        }
+        dhwin = (dhwin << 1) | dh;
+        const int j = c - ps;
+        if (j >= 0) {
+            if (rec != nullptr && j < valid) {
+                uint32_t word = 0;
+                if (lit) {
+                    uint32_t s = 1u + (uint32_t)__float2int_rz(__fmul_rn(score, (float)(TSK_SCORE_MAX - 1)));
+                    if (s >= TSK_SCORE_MAX) s = TSK_SCORE_MAX;
+                    /* the reference passes the UN-offset downhill array: packet j carries
+                     * downhill[j], not downhill[ps + j] (spotanalyzer.c:604-606) */
+                    word = (s << 1) | (uint32_t)((dhwin >> ps) & 1ull);
+                }
+                rec[2 + j] = word;
+            }
+            if (kd & KIND_POS) scratch[(size_t)j * spitch + w] = score;
+            if (neg_inline && lit && !isinf(score))
+                atomicAdd(&neg[(size_t)(rowbase + c) * bins + score_bin(score, bins)], 1u);
+        }
+    }
+    if (rec != nullptr)
+        for (int j = max(valid, 0); j < dump; j++) rec[2 + j] = 0;
+
+    bool aborted = false;
+    if (ndark > 0) {
+        call.flags |= TSK_PAFLAG_DARKCYCLE_EXISTS;
+        if (ndark >= P.max_dark_cycles) {
+            call.flags |= TSK_PAFLAG_DARKCYCLE_OVER_THRESHOLD;
+            call.polya_len = -1;
+            call.emitted = 0;
+            aborted = true;
+            if (rec != nullptr) rec[1] |= 0xffff0000u;     /* withdraw the slot: valid = -1 */
+        }
+        *reinterpret_cast<uint4 *>(&calls[n]) = *reinterpret_cast<const uint4 *>(&call);
+    } else if ((kd & KIND_EMIT) && scan_len <= 0) {
+        call.emitted = 0;   /* unreachable: KIND_EMIT implies scan_len > 0 */
+    }
+
+    if (kd & KIND_NEG) {
+        if (aborted && neg_inline)
+            list_array(lists, 0, listcap)[atomicAdd(&lists[0], 1u)] = n;
+        else if (!aborted && !neg_inline)
+            list_array(lists, 1, listcap)[atomicAdd(&lists[1], 1u)] = n;
+    }
+
+    /* contrast test and positive sampling */
+    if ((kd & KIND_POS) && !aborted && scan_len > 0 && P.cctr_left + P.cctr_right < scan_len) {
+        const float *col = scratch + w;
+        double total = 0.;
+        for (int i = 0; i < scan_len; i++) total = __dadd_rn(total, (double)col[(size_t)i * spitch]);
+        double cum = 0., best = 0.;
+        int at = -1;
+        const int last = scan_len - P.cctr_right;
+        for (int i = 0; i <= last; i++) {
+            cum = __dadd_rn(cum, (double)col[(size_t)i * spitch]);
+            if (i >= P.cctr_left - 1) {
+                const double v = __dsub_rn(__ddiv_rn(cum, (double)i),
+                                           __ddiv_rn(__dsub_rn(total, cum), (double)(scan_len - i)));
+                if (i == P.cctr_left - 1) { best = v; at = i; }
+                else if (v > best) { best = v; at = i; }
+            }
+        }
+        const float contrast = (float)best;
+        if (at + 1 >= P.boundary_pos && contrast >= P.required_contrast) {
+            const int take = -ps + min(scan_len, P.boundary_pos - P.sampling_gap);
+            for (int i = 0; i < take; i++) {
+                const float sc = col[(size_t)i * spitch];
+                if (!isnan(sc) && !isinf(sc))
+                    atomicAdd(&pos[(size_t)(rowbase + ps + i) * bins + score_bin(sc, bins)], 1u);
+            }
+        }
+    }
+}
+
+/* Fair sampling among the clusters of over-subscribed buckets: the reference accepts, per
+ * bucket, the first fair_max_count eligible clusters in cluster order (spotanalyzer.c:476-484
+ * with threads=1).  One CTA; per round every still-waiting entry bids its cluster number
+ * with atomicMin, the winner of each bucket is accepted.  `fair` is reused as the bid table. */
+__global__ void __launch_bounds__(1024)
+k_fair_resolve(uint32_t *__restrict__ fair, const uint32_t *__restrict__ bucket,
+               uint32_t *__restrict__ lists, uint32_t listcap, int max_count)
+{
+    const uint32_t cnt = lists[1];
+    uint32_t *cont = list_array(lists, 1, listcap);
+    uint32_t *acc = list_array(lists, 2, listcap);
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) fair[bucket[cont[i] & 0x7fffffffu]] = 0xffffffffu;
+    __syncthreads();
+    for (int round = 0; round < max_count; round++) {
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const uint32_t e = cont[i];
+            if (!(e & 0x80000000u)) atomicMin(&fair[bucket[e]], e);
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const uint32_t e = cont[i];
+            if (!(e & 0x80000000u) && fair[bucket[e]] == e) {
+                acc[atomicAdd(&lists[2], 1u)] = e;
+                cont[i] = e | 0x80000000u;
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
+            fair[bucket[cont[i] & 0x7fffffffu]] = 0xffffffffu;
+        __syncthreads();
+    }
+}
+
+/* Recompute the scores of the listed clusters and add `delta` (+1 / -1, as u32) to the
+ * negative histogram: accepted clusters of over-subscribed buckets (+1), and inline-sampled
+ * clusters that later aborted on dark cycles (-1). */
+__global__ void __launch_bounds__(TSK_K2_THREADS)
+k_resample_neg(const __grid_constant__ DevParams P, const TileView tv,
+               const DevSample *__restrict__ samples, const float *__restrict__ g_tscore,
+               const tsk_call *__restrict__ calls, uint32_t *__restrict__ neg,
+               const uint32_t *__restrict__ lists, uint32_t listcap, int which, uint32_t delta)
+{
+    __shared__ ScoreShared sh;
+    load_score_shared(sh, g_tscore, samples, P.num_samples);
+    const uint32_t cnt = lists[which];
+    const uint32_t *arr = list_array(const_cast<uint32_t *>(lists), which, listcap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        const uint32_t n = arr[i] & 0x7fffffffu;
+        const tsk_call call = calls[n];
+        const int ts = P.threep_start, tl = P.threep_length, bins = P.bins;
+        const int de = call.delimiter_end, ps = call.terminal_mods;
+        const size_t pitch = tv.cif_pitch;
+        const int16_t *cifcol = tv.cif + n;
+        int blen = de - ts;
+        if (blen > P.balancer_length) blen = P.balancer_length;
+        float low[4], bw[4];
+        probe_ranges(P, cifcol, pitch, blen, low, bw);
+        int insert_len = ts + tl - de;
+        const int limit = sh.limit[call.sample];
+        if (limit > 0 && limit < insert_len) insert_len = limit;
+        const int16_t *p = cifcol + (size_t)(de - ts) * 4 * pitch;
+        for (int c = 0; c < insert_len; c++, p += 4 * pitch) {
+            float es, score;
+            if (score_cycle(P, sh, p, pitch, low, bw, es, score) && c >= ps && !isinf(score))
+                atomicAdd(&neg[(size_t)(de + c) * bins + score_bin(score, bins)], delta);
+        }
+    }
+}
+
+/* self-test hook: device logf over an array (tests pin it against the host libm) */
+__global__ void k_logf_probe(const float *__restrict__ in, float *__restrict__ out, size_t n)
+{
+    __shared__ double2 tab[16];
+    if (threadIdx.x < 16) tab[threadIdx.x] = make_double2(c_logf_tab[threadIdx.x][0], c_logf_tab[threadIdx.x][1]);
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = tsk_logf(in[i], tab);
+}
+
+extern "C" int tsk_selftest_logf(tsk_ctx *ctx, const float *in, float *out, size_t n)
+{
+    if (!ctx || !in || !out) { tsk_set_error("null argument"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    float *d_in = NULL, *d_out = NULL;
+    TSK_CUDA(cudaMalloc(&d_in, sizeof(float) * n));
+    TSK_CUDA(cudaMalloc(&d_out, sizeof(float) * n));
+    TSK_CUDA(cudaMemcpyAsync(d_in, in, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+    k_logf_probe<<<148 * 8, 256, 0, ctx->stream>>>(d_in, d_out, n);
+    ctx->launches++;
+    TSK_CUDA(cudaMemcpyAsync(out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    TSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_in); cudaFree(d_out);
+    return 0;
+}
+
+/* ===================================================================================== */
+int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev)
+{
+    const DevParams &P = ctx->dp;
+    const TileView &tv = ctx->tile;
+    const int S = P.num_samples;
+    const uint32_t N = tv.nclusters;
+    const int nblk = (int)((N + TSK_K1_THREADS - 1) / TSK_K1_THREADS);
+    cudaStream_t st = ctx->stream;
+    const size_t histbytes = sizeof(uint32_t) * (size_t)P.total_cycles * P.bins;
+    const uint32_t listcap = ctx->cap_clusters;
+
+    TSK_CUDA(cudaMemsetAsync(ctx->d_pos, 0, histbytes, st));
+    TSK_CUDA(cudaMemsetAsync(ctx->d_neg, 0, histbytes, st));
+    TSK_CUDA(cudaMemsetAsync(ctx->d_fair, 0, sizeof(uint32_t) * (size_t)P.fair_hash_size, st));
+    TSK_CUDA(cudaMemsetAsync(ctx->d_lists, 0, sizeof(uint32_t) * 16, st));
+    if (ev) TSK_CUDA(cudaEventRecord(ev[0], st));
+
+    if (N > 0) {
+        const size_t smem1 = sizeof(DevSample) * S +
+                             sizeof(uint32_t) * (S * TSK_NCOUNT + (TSK_K1_THREADS / 32) * (S + 1));
+        k_decode_demux_seed<<<nblk, TSK_K1_THREADS, smem1, st>>>(
+            P, tv, ctx->d_samples, ctx->d_calls, ctx->d_kind, ctx->d_bucket, ctx->d_blkcnt,
+            ctx->d_counters, ctx->d_fair);
+        ctx->launches++;
+    }
+    if (ev) TSK_CUDA(cudaEventRecord(ev[1], st));
+    if (N > 0) {
+        k_scan_blocks<<<S + 1, 256, 0, st>>>(ctx->d_blkcnt, ctx->d_totals, nblk, S + 1);
+        k_record_bases<<<1, 32, 0, st>>>(ctx->d_totals, ctx->d_samples, ctx->d_recbase, S);
+        k_assign<<<(N + 255) / 256, 256, 0, st>>>(tv, ctx->d_calls, ctx->d_kind, ctx->d_blkcnt,
+                                                  ctx->d_worklist, S);
+        ctx->launches += 3;
+    } else {
+        TSK_CUDA(cudaMemsetAsync(ctx->d_totals, 0, sizeof(uint32_t) * (S + 1), st));
+        TSK_CUDA(cudaMemsetAsync(ctx->d_recbase, 0, sizeof(uint64_t) * (S + 1), st));
+    }
+    if (ev) TSK_CUDA(cudaEventRecord(ev[2], st));
+    if (N > 0) {
+        k_normalise_score_pack<<<(N + TSK_K2_THREADS - 1) / TSK_K2_THREADS, TSK_K2_THREADS, 0, st>>>(
+            P, tv, ctx->d_samples, ctx->d_tscore, ctx->d_calls, ctx->d_kind, ctx->d_bucket,
+            ctx->d_worklist, ctx->d_totals, ctx->d_recbase, ctx->d_records, ctx->d_scratch,
+            (size_t)ctx->cap_clusters, ctx->d_pos, ctx->d_neg, ctx->d_fair, ctx->d_lists, listcap);
+        k_fair_resolve<<<1, 1024, 0, st>>>(ctx->d_fair, ctx->d_bucket, ctx->d_lists, listcap,
+                                           P.fair_max_count);
+        k_resample_neg<<<148, TSK_K2_THREADS, 0, st>>>(P, tv, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
+                                                      ctx->d_neg, ctx->d_lists, listcap, 2, 1u);
+        k_resample_neg<<<148, TSK_K2_THREADS, 0, st>>>(P, tv, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
+                                                      ctx->d_neg, ctx->d_lists, listcap, 0, 0xffffffffu);
+        ctx->launches += 4;
+    }
+    if (ev) TSK_CUDA(cudaEventRecord(ev[3], st));
+    TSK_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,121 @@
+/*
+ * tsk_ruler.cu -- polya_ruler kernel: per-record poly(A) length from packed signal records.
+ *
+ * One WARP per record: the 32 lanes read 32 consecutive packets (one 128-byte line), so the
+ * AoS record layout of signal-packs.h is read fully coalesced; the +-1 cumulative sum, its
+ * first strict maximum and the downhill extension are warp scans / ballots held in registers.
+ *
+ * Restates measure_polya_length() (src/polyaruler/polyaruler.c:104-152), the length gate and
+ * positive resampling of process_polya_ruling() (:289-299) and add_polya_score_sample()
+ * (:154-172).
+ */
+#include "tsk_internal.h"
+
+#define FULL_MASK 0xffffffffu
+#define RULER_THREADS 256
+
+__global__ void __launch_bounds__(RULER_THREADS)
+k_polya_ruler(const uint32_t *__restrict__ records, size_t nrecords, int dump_len,
+              const uint32_t *__restrict__ g_cutoffs, int ncut, int min_len, float weight,
+              int bins, float gap, int16_t *__restrict__ len_out, uint32_t *__restrict__ pos)
+{
+    __shared__ uint32_t s_cut[TSK_MAX_CUTOFF_CYCLES];
+    for (int i = threadIdx.x; i < ncut; i += RULER_THREADS) s_cut[i] = g_cutoffs[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const size_t warps_total = (size_t)gridDim.x * (RULER_THREADS / 32);
+    const size_t words = 2 + (size_t)dump_len;
+
+    for (size_t r = (size_t)blockIdx.x * (RULER_THREADS / 32) + (threadIdx.x >> 5); r < nrecords;
+         r += warps_total) {
+        const uint32_t *rec = records + r * words;
+        const uint32_t hdr = __ldg(rec + 1);
+        const int first = (int16_t)(hdr & 0xffffu);
+        const int valid = (int16_t)(hdr >> 16);
+        int len = 0;
+
+        if (valid > 0) {
+            /* ---- +-1 cumulative sum and its first strict maximum ---- */
+            int carry = 0;
+            int bestkey = INT_MIN;
+            for (int base = 0; base < valid; base += 32) {
+                const int i = base + lane;
+                const int cyc = first + i;
+                int v = 0;
+                if (i < valid && cyc < ncut) {
+                    const uint32_t cut = s_cut[cyc];
+                    if (cut != 0) {
+                        const uint32_t sc = (__ldg(rec + 2 + i) >> 1) & TSK_SCORE_MAX;
+                        v = (sc >= cut) ? 1 : -1;
+                    }
+                }
+                int pre = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(FULL_MASK, pre, d);
+                    if (lane >= d) pre += o;
+                }
+                const int cum = carry + pre;
+                /* larger cumsum wins, then the smaller cycle index */
+                const int key = ((cum + 2048) << 16) | (0xffff - i);
+                if (i < valid) bestkey = max(bestkey, key);
+                carry = __shfl_sync(FULL_MASK, cum, 31);
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) bestkey = max(bestkey, __shfl_xor_sync(FULL_MASK, bestkey, d));
+            const int maxcum = (bestkey >> 16) - 2048;
+            const int argmax = (maxcum > 0) ? (0xffff - (bestkey & 0xffff)) : -1;
+
+            /* ---- downhill extension ---- */
+            int ext = -1;
+            if (argmax >= 0) {
+                for (int base = ((argmax + 1) >> 5) << 5; base < valid; base += 32) {
+                    const int i = base + lane;
+                    uint32_t x = 0;
+                    if (i < valid && i > argmax) x = __ldg(rec + 2 + i);
+                    const bool lit = ((x >> 1) & TSK_SCORE_MAX) != 0;
+                    const unsigned stop = __ballot_sync(FULL_MASK, lit && !(x & 1u));
+                    unsigned go = __ballot_sync(FULL_MASK, lit && (x & 1u));
+                    if (stop) {
+                        go &= (1u << (__ffs(stop) - 1)) - 1u;
+                        if (go) ext = base + 31 - __clz(go);
+                        break;
+                    }
+                    if (go) ext = base + 31 - __clz(go);
+                }
+            }
+            len = argmax + 1;
+            if (ext >= 0) len += (int)roundf(__fmul_rn((float)(ext - argmax), weight));
+        }
+
+        const bool pass = len >= min_len;
+        if (lane == 0) len_out[r] = pass ? (int16_t)len : (int16_t)-1;
+        if (pass) {
+            const int take = len - __float2int_rz(__fmul_rn((float)len, gap));
+            for (int i = lane; i < take; i += 32) {
+                const uint32_t sc = (__ldg(rec + 2 + i) >> 1) & TSK_SCORE_MAX;
+                if (sc > 0) {
+                    int b = __double2int_rz(__dmul_rn(__ddiv_rn(__dsub_rn((double)sc, 1.0),
+                                                               (double)(TSK_SCORE_MAX - 1)), (double)bins));
+                    if (b >= bins) b = bins - 1;
+                    atomicAdd(&pos[(size_t)(first + i) * bins + b], 1u);
+                }
+            }
+        }
+    }
+}
+
+int tsk_launch_ruler(tsk_ctx *ctx, const uint32_t *d_records, size_t nrecords, int dump_len,
+                     int ncutoffs, int min_len, float weight, int bins, float gap, int16_t *d_len_out)
+{
+    size_t blocks = (nrecords + (RULER_THREADS / 32) - 1) / (RULER_THREADS / 32);
+    const size_t maxblocks = 148 * 8 * 4;       /* persistent-ish: a few waves of 148 SMs x 8 CTAs */
+    if (blocks > maxblocks) blocks = maxblocks;
+    k_polya_ruler<<<(unsigned)blocks, RULER_THREADS, 0, ctx->stream>>>(
+        d_records, nrecords, dump_len, ctx->d_cutoffs, ncutoffs, min_len, weight, bins, gap,
+        d_len_out, ctx->d_ruler_pos);
+    ctx->launches++;
+    TSK_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,206 @@
+"""Host-side mirror of the reference importer / ruler / estimator seam, on top of the C ABI.
+
+`TileProcessor` plays the role of tailseq-import's process() loop body
+(src/importer/tailseq-import.c:568-682): upload one block of CIF/BCL data, run the
+per-cluster path on the GPU (distribute_processing, :516-565), hand back the same products
+the reference writes to disk.  `ruler()` is tailseq-polya-ruler's process_polya_ruling()
+(src/polyaruler/polyaruler.c:201-314); `fit_cutoffs()` is find_all_eqodds_point()
+(scripts/calculate-optimal-parameters.py:73-78).
+
+PyTorch is not needed here; device memory is owned by the library.  Callers that already
+hold the tile in HBM (bench.py, torch tensors) pass raw device pointers with on_device=True.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .config import CALL_DTYPE, CParams, ImporterConfig
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return ctypes.c_void_p(a)
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def invert_colormatrix(m: np.ndarray) -> np.ndarray:
+    """inverse_4x4_matrix() (src/contrib/misc.c:11-58): float cofactor expansion, same term
+    order, so the inverse is bit-identical to the reference's load_color_matrix()."""
+    m = np.asarray(m, dtype=np.float32).reshape(16)
+    terms = ((+1, -1, 0, 0, -1, +1), (+1, +1, 0, -1, -1, 0), (-1, -1, +1, 0, 0, +1),
+             (-1, -1, 0, 0, +1, +1), (-1, +1, 0, -1, +1, 0), (+1, -1, -1, 0, 0, +1))
+    adj = np.zeros(16, dtype=np.float32)
+    f32 = np.float32
+    for i in range(4):
+        for j in range(4):
+            o = 2 + (j - i)
+            ci, rj = i + 4 + o, j + 4 - o
+            acc = f32(0)
+            for t, (a1, b1, a2, b2, a3, b3) in enumerate(terms):
+                e1 = m[((rj + b1) % 4) * 4 + ((ci + a1) % 4)]
+                e2 = m[((rj + b2) % 4) * 4 + ((ci + a2) % 4)]
+                e3 = m[((rj + b3) % 4) * 4 + ((ci + a3) % 4)]
+                prod = f32(f32(e1 * e2) * e3)
+                acc = prod if t == 0 else (f32(acc + prod) if t < 3 else f32(acc - prod))
+            adj[j * 4 + i] = acc if (o % 2) else f32(-acc)
+    det = f32(0)
+    for k in range(4):
+        det = f32(det + f32(m[k] * adj[k * 4]))
+    if det == 0:
+        raise ValueError("Color matrix could not be inverted.")
+    det = f32(1.0 / float(det))
+    return (adj * det).astype(np.float32)
+
+
+class TileProcessor:
+    def __init__(self, cfg: ImporterConfig, device: int = 0, params: Optional[CParams] = None):
+        self.cfg = cfg
+        self.params = params if params is not None else cfg.to_cparams()
+        self.lib = _lib.load()
+        self._ctx = ctypes.c_void_p()
+        _lib.check(self.lib.tsk_ctx_create(ctypes.byref(self._ctx), device, ctypes.byref(self.params)))
+        self.nclusters = 0
+        self._keep = None
+
+    def close(self):
+        if self._ctx:
+            self.lib.tsk_ctx_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ importer path
+    def upload(self, bcl, cif, invmatrix: np.ndarray, nclusters: Optional[int] = None,
+               firstclusterno: int = 0, on_device: bool = False,
+               bcl_pitch: Optional[int] = None, cif_pitch: Optional[int] = None):
+        """bcl u8[T][pitch], cif i16[L3][4][pitch]: numpy arrays (host) or raw device
+        addresses (ints) with on_device=True."""
+        inv = np.ascontiguousarray(invmatrix, dtype=np.float32).reshape(16)
+        if not on_device:
+            bcl = np.ascontiguousarray(bcl, dtype=np.uint8)
+            cif = np.ascontiguousarray(cif, dtype=np.int16)
+            nclusters = bcl.shape[1] if nclusters is None else nclusters
+            bcl_pitch = bcl.shape[1]
+            cif_pitch = cif.shape[2]
+        self._keep = (bcl, cif)
+        _lib.check(self.lib.tsk_tile_upload(self._ctx, _ptr(bcl), bcl_pitch, _ptr(cif), cif_pitch,
+                                            _ptr(inv), nclusters, firstclusterno, int(on_device)))
+        self.nclusters = int(nclusters)
+
+    def process(self):
+        _lib.check(self.lib.tsk_tile_process(self._ctx))
+
+    def process_timed(self, iters: int = 1) -> np.ndarray:
+        ms = np.zeros(4, dtype=np.float32)
+        _lib.check(self.lib.tsk_tile_process_timed(self._ctx, iters, _ptr(ms)))
+        return ms
+
+    def calls(self) -> np.ndarray:
+        out = np.zeros(self.nclusters, dtype=CALL_DTYPE)
+        _lib.check(self.lib.tsk_tile_get_calls(self._ctx, _ptr(out)))
+        return out
+
+    def record_count(self, sample: int) -> int:
+        n = ctypes.c_uint32()
+        _lib.check(self.lib.tsk_tile_get_record_count(self._ctx, sample, ctypes.byref(n)))
+        return n.value
+
+    def records(self, sample: int, drop_withdrawn: bool = True) -> np.ndarray:
+        """u32 [nslots][2 + signal_dump_length] record slots of one sample, cluster order."""
+        w = 2 + self.params.samples[sample].signal_dump_length
+        n = self.record_count(sample)
+        out = np.zeros((n, w), dtype=np.uint32)
+        _lib.check(self.lib.tsk_tile_get_records(self._ctx, sample, _ptr(out), out.size))
+        if drop_withdrawn and n:
+            valid = (out[:, 1] >> 16).astype(np.uint16).view(np.int16) >= 0
+            out = out[valid]
+        return out
+
+    def counters(self) -> np.ndarray:
+        out = np.zeros((self.params.num_samples, 6), dtype=np.uint32)
+        _lib.check(self.lib.tsk_get_counters(self._ctx, _ptr(out)))
+        return out
+
+    def reset_counters(self):
+        _lib.check(self.lib.tsk_counters_reset(self._ctx))
+
+    def hist(self):
+        shape = (self.params.total_cycles, self.params.dist_sampling_bins)
+        pos = np.zeros(shape, dtype=np.uint32)
+        neg = np.zeros(shape, dtype=np.uint32)
+        _lib.check(self.lib.tsk_get_hist(self._ctx, _ptr(pos), _ptr(neg)))
+        return pos, neg
+
+    def device_ptrs(self) -> Dict[str, int]:
+        p = [ctypes.c_void_p() for _ in range(4)]
+        _lib.check(self.lib.tsk_get_device_ptrs(self._ctx, *[ctypes.byref(x) for x in p]))
+        return dict(pos=p[0].value, neg=p[1].value, counters=p[2].value, ruler_pos=p[3].value)
+
+    def synchronize(self):
+        _lib.check(self.lib.tsk_synchronize(self._ctx))
+
+    def launch_count(self) -> int:
+        return int(self.lib.tsk_launch_count(self._ctx))
+
+    # ------------------------------------------------------------------ ruler path
+    def cutoffs_to_packed(self, cutoffs: Sequence[float]) -> np.ndarray:
+        return np.array([self.lib.tsk_cutoff_to_packed(float(c)) for c in cutoffs], dtype=np.uint32)
+
+    def ruler_reset(self, ncutoffs: int, bins: Optional[int] = None):
+        bins = self.cfg.dist_sampling_bins if bins is None else bins
+        _lib.check(self.lib.tsk_ruler_hist_reset(self._ctx, ncutoffs, bins))
+        self._ruler_shape = (ncutoffs, bins)
+
+    def ruler_records(self, records: np.ndarray, cutoffs_packed: np.ndarray, min_polya: int = 8,
+                      downhill_w: float = 0.49, bins: int = 1000, gap: float = 0.1) -> np.ndarray:
+        records = np.ascontiguousarray(records, dtype=np.uint32)
+        n, w = records.shape
+        cut = np.ascontiguousarray(cutoffs_packed, dtype=np.uint32)
+        out = np.full(n, -1, dtype=np.int16)
+        _lib.check(self.lib.tsk_ruler_records(self._ctx, _ptr(records), n, w - 2, _ptr(cut), cut.size,
+                                              min_polya, downhill_w, bins, gap, _ptr(out), 0))
+        return out
+
+    def ruler_tile(self, sample: int, cutoffs_packed: np.ndarray, min_polya: int = 8,
+                   downhill_w: float = 0.49, bins: int = 1000, gap: float = 0.1) -> np.ndarray:
+        cut = np.ascontiguousarray(cutoffs_packed, dtype=np.uint32)
+        out = np.full(self.record_count(sample), -1, dtype=np.int16)
+        _lib.check(self.lib.tsk_ruler_tile(self._ctx, sample, _ptr(cut), cut.size, min_polya,
+                                           downhill_w, bins, gap, _ptr(out)))
+        return out
+
+    def ruler_hist(self) -> np.ndarray:
+        out = np.zeros(self._ruler_shape, dtype=np.uint32)
+        _lib.check(self.lib.tsk_ruler_get_hist(self._ctx, _ptr(out)))
+        return out
+
+    def selftest_logf(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.empty_like(x)
+        _lib.check(self.lib.tsk_selftest_logf(self._ctx, _ptr(x), _ptr(out), x.size))
+        return out
+
+    # ------------------------------------------------------------------ estimator
+    def fit_cutoffs(self, pos: np.ndarray, neg: np.ndarray) -> np.ndarray:
+        """Per-cycle equal-odds cutoffs (NaN where undetermined) for one histogram pair."""
+        pos = np.ascontiguousarray(pos, dtype=np.uint64)
+        neg = np.ascontiguousarray(neg, dtype=np.uint64)
+        cycles, bins = pos.shape
+        highs = np.array(self.cfg.cutoff_score_search_high, dtype=np.float64)
+        out = np.zeros(cycles, dtype=np.float64)
+        _lib.check(self.lib.tsk_fit_cutoffs(
+            self._ctx, _ptr(pos), _ptr(neg), cycles, bins,
+            ctypes.c_uint64(self.cfg.minimum_spots_for_dist_sampling),
+            float(self.cfg.kde_bandwidth_for_dist), float(self.cfg.cutoff_score_search_low),
+            _ptr(highs), highs.size, _ptr(out)))
+        return out

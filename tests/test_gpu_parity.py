@@ -1,0 +1,164 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle
+on the same seeded inputs.  Bar: bit-exact calls, flags, record packets, histograms, counters."""
+import numpy as np
+import pytest
+
+from helpers import compare_tile
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def proc(stock_cfg):
+    from tailseeker_b200.importer import TileProcessor
+    p = TileProcessor(stock_cfg)
+    yield p
+    p.close()
+
+
+def _run(proc, cfg, oracle, n, seed, **tilekw):
+    from tailseeker_b200.synth import make_tile
+    from tailseeker_b200.importer import invert_colormatrix
+    tile = make_tile(cfg, n, seed=seed, **tilekw)
+    inv = invert_colormatrix(tile.matrix)
+    assert (inv == oracle.invert_matrix(tile.matrix)).all()
+    proc.reset_counters()
+    proc.upload(tile.bcl, tile.cif, inv)
+    proc.process()
+    o = oracle.process(cfg, tile.bcl, tile.cif, inv)
+    return tile, o
+
+
+def test_logf_exact(proc, oracle):
+    """Device logf == host libm logf, bit for bit, on (0,1]: dense near 1, every binade,
+    subnormals, and 4M pseudo-random floats (SURVEY appendix C re-checked on this box)."""
+    rng = np.random.default_rng(7)
+    bits = [rng.integers(1, 0x3f800001, size=1 << 22, dtype=np.uint32),
+            np.arange(0x3f800000 - (1 << 18), 0x3f800001, dtype=np.uint32),
+            np.arange(1, 1 << 14, dtype=np.uint32),
+            (np.arange(1, 128, dtype=np.uint32) << 23)[:, None].repeat(64, 1).ravel()
+            + rng.integers(0, 1 << 23, size=127 * 64, dtype=np.uint32)]
+    x = np.concatenate(bits).astype(np.uint32).view(np.float32)
+    got = proc.selftest_logf(x)
+    import ctypes
+    want = np.empty_like(x)
+    lib = oracle.lib()
+    # vectorised host logf through the oracle's exported libm wrapper
+    f = lib.tsk_oracle_logf
+    step = 1 << 16
+    for i in range(0, x.size, step):   # keep the python loop cheap: sample every 8th value
+        blk = x[i:i + step:8]
+        want[i:i + step:8] = [f(ctypes.c_float(float(v))) for v in blk]
+    sel = np.zeros(x.size, dtype=bool)
+    sel[::8] = True
+    assert (got[sel].view(np.uint32) == want[sel].view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("n,seed", [(20000, 1), (4099, 2), (129, 3), (1, 4)])
+def test_tile_matches_oracle(proc, stock_cfg, oracle, n, seed):
+    _, o = _run(proc, stock_cfg, oracle, n, seed)
+    compare_tile(proc, stock_cfg, None, o)
+
+
+def test_empty_tile(proc, stock_cfg):
+    T, L3 = stock_cfg.total_cycles, stock_cfg.threep_length
+    proc.reset_counters()
+    proc.upload(np.zeros((T, 0), np.uint8), np.zeros((L3, 4, 0), np.int16), np.eye(4, dtype=np.float32))
+    proc.process()
+    assert proc.calls().size == 0
+    assert proc.counters().sum() == 0
+    pos, neg = proc.hist()
+    assert pos.sum() == 0 and neg.sum() == 0
+
+
+def test_dark_and_lowdiversity_heavy(proc, stock_cfg, oracle):
+    """Many dark clusters (withdrawn record slots, undo of inline negative sampling) and many
+    identical inserts (over-subscribed fair-sampling buckets)."""
+    _, o = _run(proc, stock_cfg, oracle, 12000, 11, dark_cluster_frac=0.08, dark_cycle_frac=0.01,
+                lowdiv_frac=0.25)
+    calls = compare_tile(proc, stock_cfg, None, o)
+    assert (calls["flags"] & 0x800).sum() > 50
+
+
+def test_keep_options_and_hiseq_layout(oracle):
+    from tailseeker_b200.config import stock_config
+    from tailseeker_b200.importer import TileProcessor
+    cfg = stock_config("hiseq", keep_no_delimiter=1, keep_low_quality_balancer=1)
+    p = TileProcessor(cfg)
+    try:
+        _, o = _run(p, cfg, oracle, 6000, 5)
+        compare_tile(p, cfg, None, o)
+    finally:
+        p.close()
+
+
+def test_nondefault_parameters(oracle):
+    """Other trigger lengths / weights / sampling parameters than conf/defaults.conf."""
+    from tailseeker_b200.config import stock_config
+    from tailseeker_b200.importer import TileProcessor
+    cfg = stock_config("miseq", seed_trigger_polya_length=6, signal_analysis_trigger=12,
+                       negative_sample_polya_length=5, minimum_polya_length=3,
+                       maximum_modifications=10, polya_boundary_pos=60, polya_sampling_gap=5,
+                       max_cctr_scan_left_space=10, max_cctr_scan_right_space=15,
+                       fair_sampling_max_count=2, fair_sampling_hash_space_size=1000003,
+                       dist_sampling_bins=500, maximum_dark_cycles=3, dark_cycles_threshold=25,
+                       balancer_num_positive_samples=3, balancer_num_negative_samples=5,
+                       t_intensity_k=20.0, t_intensity_center=0.75)
+    p = TileProcessor(cfg)
+    try:
+        _, o = _run(p, cfg, oracle, 8000, 6, lowdiv_frac=0.05)
+        compare_tile(p, cfg, None, o)
+    finally:
+        p.close()
+
+
+def test_firstclusterno_and_pitch(stock_cfg, oracle):
+    """Second read block of a tile (global cluster numbers) and padded row pitches."""
+    from tailseeker_b200.synth import make_tile
+    from tailseeker_b200.importer import TileProcessor, invert_colormatrix
+    tile = make_tile(stock_cfg, 3000, seed=8)
+    inv = invert_colormatrix(tile.matrix)
+    p = TileProcessor(stock_cfg)
+    try:
+        p.upload(tile.bcl, tile.cif, inv, firstclusterno=123456)
+        p.process()
+        o = oracle.process(stock_cfg, tile.bcl, tile.cif, inv, firstclusterno=123456)
+        compare_tile(p, stock_cfg, None, o, firstclusterno=123456)
+    finally:
+        p.close()
+
+
+def test_ruler_matches_oracle(proc, stock_cfg, oracle):
+    tile, o = _run(proc, stock_cfg, oracle, 20000, 9)
+    T = stock_cfg.total_cycles
+    rng = np.random.default_rng(3)
+    cut = np.clip(0.25 + 0.1 * rng.standard_normal(T), 0.01, 0.9)
+    cut[rng.random(T) < 0.05] = np.nan          # "nan" cycles
+    packed = proc.cutoffs_to_packed(cut)
+    assert (packed == oracle.cutoffs_to_packed(cut)).all()
+    proc.ruler_reset(T)
+    want_hist = np.zeros((T, stock_cfg.dist_sampling_bins), dtype=np.uint32)
+    nmeasured = 0
+    for s in range(proc.params.num_samples):
+        recs = o["records"][s]
+        if recs.shape[0] == 0:
+            continue
+        want, want_hist = oracle.ruler(recs, packed, pos=want_hist)
+        # (a) on host-provided records (the tailseq-polya-ruler binary's path)
+        got = proc.ruler_records(recs, packed)
+        assert (got == want).all()
+        nmeasured += int((want >= 0).sum())
+    assert nmeasured > 1000
+    assert (proc.ruler_hist() == want_hist).all()
+    # (b) on the resident record slots of the tile (fused pipeline), incl. withdrawn slots
+    proc.ruler_reset(T)
+    for s in range(proc.params.num_samples):
+        slots = proc.records(s, drop_withdrawn=False)
+        if slots.shape[0] == 0:
+            continue
+        got = proc.ruler_tile(s, packed)
+        valid = (slots[:, 1] >> 16).astype(np.uint16).view(np.int16) >= 0
+        want, _ = oracle.ruler(o["records"][s], packed)
+        assert (got[valid] == want).all()
+        assert (got[~valid] == -1).all()
+    assert (proc.ruler_hist() == want_hist).all()
