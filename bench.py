@@ -1,0 +1,456 @@
+#!/usr/bin/env python
+"""bench.py -- clusters/sec of the TAIL-seq signal-processing hot path on B200.
+
+Metric (BASELINE.json): clusters/sec for decode + normalise + poly(A) call; HBM GB/s vs peak.
+Workload at every N: BASELINE.json configs[1] -- a MiSeq v2 full run, 14 tiles of ~1.07 M
+clusters (15 M clusters, 51+251 cycles, 4 experimental + 7 spike-in samples) PER GPU (weak
+scaling: tiles and lanes are independent, one tile set per GPU, no data-path collective;
+the only exchange is the all-reduce of the QC histograms / counters at the end of a step).
+
+A step = one pass of the hot path over the whole tile set:
+  per tile : decode_demux_seed -> slot scan -> normalise_score_pack (+ fair-sampling fix-ups)
+             -> polya_ruler over every sample's records with the previous round's cutoffs
+  per step : all-reduce (N>1) of the summed pos/neg histograms and demux counters,
+             fit_cutoffs on the run-wide histograms
+`value`  : inputs resident in HBM when the timed region starts.
+`e2e`    : the same step through the C ABI with HOST (pinned) buffers: H2D of every tile and
+           D2H of calls / poly(A) lengths / histograms inside the timed region.
+--impl reference : the reference's own CPU implementation (oracle/_ref binaries built from
+           the unmodified sources) on the box's host cores, on a bounded sample of the same
+           workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TILES_PER_GPU = 14
+CLUSTERS_PER_TILE = 1_070_000
+METRIC = "clusters/sec for decode+normalise+poly(A) call"
+UNIT = "clusters/s"
+WORKLOAD = ("MiSeq v2 full run: %d tiles x %d clusters, 51+251 cycles, 4 exp + 7 spike-in samples "
+            "(BASELINE.json configs[1]) per GPU" % (TILES_PER_GPU, CLUSTERS_PER_TILE))
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+        os.close(fd)
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        try:
+            rows = [r.strip().split(", ") for r in open(self.path) if r.strip()]
+            os.unlink(self.path)
+        except OSError:
+            rows = []
+        sm, reasons = [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the unmodified reference binaries on host cores
+# ------------------------------------------------------------------------------------------
+def reference_sample_run(cfg, bcl, cif, matrix_text, threads, cutoffs):
+    """One pass of the reference's CPU path (tailseq-import, then tailseq-polya-ruler per
+    sample) over a host tile.  Returns (clusters, seconds of the binaries' wall time)."""
+    from oracle import refrun
+    from tailseeker_b200.synth import Tile
+
+    tile = Tile(bcl=bcl, cif=cif, matrix_text=matrix_text, nclusters=bcl.shape[1],
+                truth_sample=np.zeros(0, np.int32))
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    work = tempfile.mkdtemp(prefix="tskbench_", dir=base)
+    try:
+        r = refrun.run_import(cfg, tile, workdir=work, threads=threads, gz_level=1)
+        secs = r["wall_s"]
+        tid = cfg.tile_id
+        cpath = os.path.join(work, "cutoffs.txt")
+        refrun.write_cutoffs_file(cpath, tid, list(cutoffs))
+        for s in cfg.samples:
+            rr = refrun.run_ruler(tid, os.path.join(work, "signals", "%s_%s.sigpack" % (s.name, tid)),
+                                  cpath, os.path.join(work, "taginfo", "%s_%s.txt.gz" % (s.name, tid)),
+                                  os.path.join(work, "sigdist_%s.gz" % s.name))
+            secs += rr["wall_s"]
+        return tile.nclusters, secs
+    finally:
+        import shutil
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def default_cutoffs(T):
+    return np.full(T, 0.25, dtype=np.float64)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import refrun
+    from tailseeker_b200.config import stock_config
+    from tailseeker_b200.synth import make_tile
+    cfg = stock_config("miseq")
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD}}
+    if not refrun.available():
+        line["unavailable"] = "oracle/_ref binaries are not built (run __graft_entry__.build() where /root/reference exists)"
+        print(json.dumps(line))
+        return 0
+    cores = os.cpu_count() or 1
+    nsample = args.ref_clusters
+    tile = make_tile(cfg, nsample, seed=1234)
+    cut = default_cutoffs(cfg.total_cycles)
+    times = []
+    for it in range(args.warmup + args.steps):
+        n, secs = reference_sample_run(cfg, tile.bcl, tile.cif, tile.matrix_text, cores, cut)
+        if it >= args.warmup:
+            times.append(secs)
+    value = nsample / (sum(times) / len(times))
+    sample = ("%d-cluster MiSeq-shaped tile per step: tailseq-import (threads=%d, one read block, "
+              "zlib level 1 instead of BGZF) + tailseq-polya-ruler per sample, files on /dev/shm; "
+              "wall time of the binaries (file read + compute + compress + write)" % (nsample, cores))
+    line.update({"value": value, "ms_per_step": 1e3 * sum(times) / len(times),
+                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                                  "sample": sample},
+                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "gpu_launches": 0})
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+# device arm
+# ------------------------------------------------------------------------------------------
+class DevView:
+    """Expose raw device memory of the library to torch (CUDA array interface)."""
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False),
+                                         "version": 2}
+
+
+def algorithmic_bytes(cfg, params, calls, nclusters, slot_counts):
+    """bytes that must move per tile (stated in DESIGN.md).
+    K1 decode_demux_seed   : N*T (BCL) + N*16 (call written)
+    K2 normalise_score_pack: per processed cluster 8*(balancer_len + insert_len) CIF bytes
+                             + 16 (call read) + per record slot (8 + 4*dump_len) written
+    ruler                  : per record slot (8 + 4*dump_len) read + 2 (int16 length) written"""
+    T, L3, ts = cfg.total_cycles, cfg.threep_length, cfg.threep_start - 1
+    de = calls["delimiter_end"].astype(np.int64)
+    proc = (calls["written"] == 1) & (de >= 0) & ((calls["flags"] & 0x200) == 0)
+    limit = np.array([params.samples[s].limit_threep_processing for s in range(params.num_samples)])
+    dump = np.array([params.samples[s].signal_dump_length for s in range(params.num_samples)])
+    smp = calls["sample"].astype(np.int64)
+    ins = ts + L3 - de
+    lim = limit[smp]
+    ins = np.where((lim > 0) & (lim < ins), lim, ins)
+    blen = np.minimum(de - ts, cfg.balancer_length)
+    k2 = int((8 * (blen + ins) + 16)[proc].sum())
+    nslots = int(sum(slot_counts))
+    recbytes = int(sum(c * (8 + 4 * int(d)) for c, d in zip(slot_counts, dump)))
+    k1 = nclusters * (T + 16)
+    return {"k1": k1, "k2": k2 + recbytes, "ruler": recbytes + 2 * nslots,
+            "total": k1 + k2 + 2 * recbytes + 2 * nslots, "records": nslots,
+            "processed": int(proc.sum())}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--tiles", type=int, default=TILES_PER_GPU)
+    ap.add_argument("--clusters-per-tile", type=int, default=CLUSTERS_PER_TILE)
+    ap.add_argument("--ref-clusters", type=int, default=100_000,
+                    help="clusters in the bounded CPU sample (reference arm / cpu_baseline)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from tailseeker_b200.config import stock_config
+    from tailseeker_b200.importer import TileProcessor, invert_colormatrix
+    from tailseeker_b200.synth_torch import make_tile_device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = stock_config("miseq")
+    T, L3, bins = cfg.total_cycles, cfg.threep_length, cfg.dist_sampling_bins
+    ntiles, N = args.tiles, args.clusters_per_tile
+
+    proc = TileProcessor(cfg, device=local_rank)
+    stream = torch.cuda.current_stream()
+    proc.set_stream(stream.cuda_stream)
+    S = proc.params.num_samples
+
+    # ---- synthetic tile set, generated in HBM (one lane's worth per rank) -------------------
+    tiles = []
+    for t in range(ntiles):
+        bcl, cif, mtext, pitch = make_tile_device(cfg, N, seed=1000 * (rank + 1) + t, device=dev)
+        mtx = np.array([np.float32(x) for x in mtext.split()], dtype=np.float32)
+        tiles.append((bcl, cif, invert_colormatrix(mtx), pitch, mtext))
+    torch.cuda.synchronize()
+
+    cut = default_cutoffs(T)
+    packed = proc.cutoffs_to_packed(cut)
+    acc_pos = torch.zeros((T, bins), dtype=torch.int64, device=dev)
+    acc_neg = torch.zeros((T, bins), dtype=torch.int64, device=dev)
+    ptrs = None
+
+    def lib_views():
+        p = proc.device_ptrs()
+        return (torch.as_tensor(DevView(p["pos"], (T, bins), "<i4"), device=dev),
+                torch.as_tensor(DevView(p["neg"], (T, bins), "<i4"), device=dev),
+                torch.as_tensor(DevView(p["counters"], (S, 6), "<i4"), device=dev))
+
+    def finish_step(host_fit: bool):
+        """run-wide statistics: all-reduce (N>1) + cutoff fit on the summed histograms"""
+        cnt = lib_views()[2].to(torch.int64)
+        if world > 1:
+            dist.all_reduce(acc_pos)
+            dist.all_reduce(acc_neg)
+            dist.all_reduce(cnt)
+        hp = acc_pos.cpu().numpy().astype(np.uint64)
+        hn = acc_neg.cpu().numpy().astype(np.uint64)
+        return proc.fit_cutoffs(hp, hn), cnt
+
+    def device_step():
+        acc_pos.zero_(); acc_neg.zero_()
+        proc.reset_counters()
+        measured = 0
+        for (bcl, cif, inv, pitch, _) in tiles:
+            proc.upload(bcl.data_ptr(), cif.data_ptr(), inv, nclusters=N, on_device=True,
+                        bcl_pitch=pitch, cif_pitch=pitch)
+            proc.process()
+            vp, vn, _ = lib_views()
+            acc_pos.add_(vp); acc_neg.add_(vn)
+            for s in range(S):
+                if proc.record_count(s):
+                    lens = proc.ruler_tile(s, packed)
+                    measured += int((lens >= 0).sum())
+        fit, _ = finish_step(True)
+        return measured, fit
+
+    # ---- warm-up, then K timed steps (device-resident inputs) --------------------------------
+    proc.ruler_reset(T)
+    for _ in range(args.warmup):
+        measured, fit = device_step()
+    # byte accounting + per-stage timing from a representative pass (tile 0 calls)
+    calls0 = proc.calls()       # last tile processed
+    ab = algorithmic_bytes(cfg, proc.params, calls0, N, [proc.record_count(s) for s in range(S)])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    proc.profile(True)
+    launches0 = proc.launch_count()
+    sampler = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    e0.record(stream)
+    for _ in range(args.steps):
+        measured, fit = device_step()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = proc.launch_count() - launches0
+    stage_ms, stage_runs = proc.profile_get()
+    proc.profile(False)
+    tms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_step = float(tms.item()) / args.steps
+    clusters_step = ntiles * N * world
+    value = clusters_step / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (normalise_score_pack) -------------------------------
+    peak, peak_src = measured_peaks()
+    k2_ms = stage_ms[2] / max(1, int(stage_runs[2]))
+    k2_gbs = ab["k2"] / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
+    roof = {"bound": "hbm", "kernel": "k_normalise_score_pack", "achieved": k2_gbs, "peak": peak,
+            "unit": "GB/s", "frac": k2_gbs / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": ab["k2"], "ms_per_launch": k2_ms,
+            "stages_ms_per_tile": {
+                "decode_demux_seed": stage_ms[0] / max(1, int(stage_runs[0])),
+                "slot_scan_assign": stage_ms[1] / max(1, int(stage_runs[1])),
+                "normalise_score_pack": k2_ms,
+                "fair_sampling_fixups": stage_ms[3] / max(1, int(stage_runs[3])),
+                "polya_ruler_per_sample": stage_ms[4] / max(1, int(stage_runs[4])),
+                "fit_cutoffs": stage_ms[5] / max(1, int(stage_runs[5]))},
+            "pipeline_algorithmic_gbs_per_gpu": ab["total"] * ntiles / (ms_step * 1e-3) / 1e9,
+            "processed_fraction": ab["processed"] / N, "record_slots_per_tile": ab["records"],
+            "note": "K1 %.0f GB/s algorithmic" % (
+                ab["k1"] / (1e-3 * stage_ms[0] / max(1, int(stage_runs[0]))) / 1e9 if stage_ms[0] > 0 else 0)}
+    tfile = os.path.join(ROOT, "profiles", "k2_traffic.json")
+    if os.path.exists(tfile):
+        try:
+            roof["traffic"] = json.load(open(tfile)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- end-to-end: host (pinned) buffers through the C ABI ----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        nhost = min(2, ntiles)
+        host_tiles = []
+        for i in range(nhost):
+            bcl, cif, inv, pitch, _ = tiles[i]
+            hb = torch.empty((T, N), dtype=torch.uint8, pin_memory=True)
+            hc = torch.empty((L3, 4, N), dtype=torch.int16, pin_memory=True)
+            hb.copy_(bcl[:, :N]); hc.copy_(cif[:, :, :N])
+            host_tiles.append((hb.numpy(), hc.numpy(), inv))
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            acc_pos.zero_(); acc_neg.zero_()
+            proc.reset_counters()
+            d2h = 0
+            for t in range(ntiles):
+                hb, hc, inv = host_tiles[t % nhost]
+                proc.upload(hb, hc, inv)                     # H2D of the tile (pinned -> HBM)
+                proc.process()
+                calls = proc.calls()                          # D2H 16 B / cluster
+                d2h += calls.nbytes
+                vp, vn, _ = lib_views()
+                acc_pos.add_(vp); acc_neg.add_(vn)
+                for s in range(S):
+                    if proc.record_count(s):
+                        lens = proc.ruler_tile(s, packed)     # D2H 2 B / record slot
+                        d2h += lens.nbytes
+            fit, cnt = finish_step(True)                      # D2H of the two histograms
+            cnt.cpu()
+            d2h += 2 * T * bins * 8 + S * 6 * 8
+            return d2h
+
+        for _ in range(1):
+            e2e_step()
+        barrier()
+        esteps = max(1, min(args.steps, 3))
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record(stream)
+        for _ in range(esteps):
+            d2h_bytes = e2e_step()
+        e3.record(stream)
+        barrier()
+        dt = e2.elapsed_time(e3) * 1e-3 / esteps
+        tdt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+        e2e = {"value": clusters_step / float(tdt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(ntiles * N * (T + 8 * L3)),
+               "d2h_bytes_per_step": int(d2h_bytes), "steps": esteps,
+               "note": "serial upload->process->download per tile on one stream; 2 distinct pinned host tiles cycled"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) --------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import refrun
+        if refrun.available():
+            ns = args.ref_clusters
+            bcl, cif, inv, pitch, mtext = tiles[0]
+            hb = bcl[:, :ns].contiguous().cpu().numpy()
+            hc = cif[:, :, :ns].contiguous().cpu().numpy()
+            cores = os.cpu_count() or 1
+            n, secs = reference_sample_run(cfg, hb, hc, mtext, cores, cut)
+            cpu = {"value": n / secs, "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": "first %d clusters of tile 0: reference tailseq-import (threads=%d, zlib level 1) "
+                             "+ tailseq-polya-ruler per sample, files on /dev/shm, binaries' wall time" % (ns, cores)}
+        else:
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                   "sample": "oracle/_ref not built"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "tiles_per_gpu": ntiles, "clusters_per_tile": N,
+                           "l2": "inputs_larger_than_L2 (2.5 GB per tile, streamed once)",
+                           "polya_called_per_step": int(measured) * world,
+                           "cutoffs_fitted": int(np.isfinite(fit).sum())},
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"],
+                           "reasons": clocks["reasons"], "samples": clocks["samples"]}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    proc.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -239,9 +239,19 @@ int tsk_fit_cutoffs(tsk_ctx *ctx, const uint64_t *pos, const uint64_t *neg,
 /* ---- stream control (for callers that overlap copies and kernels) -------------------- */
 int tsk_synchronize(tsk_ctx *ctx);
 /* Timed re-run of the kernels of tsk_tile_process() on the resident tile: CUDA events on the
- * context's stream, `iters` back-to-back runs, returns mean ms per run per stage in
- * ms_out[4] = {decode_demux_seed, slot scan, normalise_score_pack(+fixups), total}. */
-int tsk_tile_process_timed(tsk_ctx *ctx, int iters, float ms_out[4]);
+ * context's stream (the stream the kernels are launched on), `iters` back-to-back runs,
+ * mean ms per run per stage in ms_out[5] = {decode_demux_seed, slot scan + assign,
+ * normalise_score_pack, fair-sampling fix-ups, total}.  Counters are left as one run
+ * leaves them. */
+int tsk_tile_process_timed(tsk_ctx *ctx, int iters, float ms_out[5]);
+/* Use the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream) for every copy
+ * and kernel of this context instead of the context's own stream. */
+int tsk_set_stream(tsk_ctx *ctx, void *cuda_stream);
+/* Per-stage device time, accumulated with CUDA events on the context's stream while
+ * enabled: stage_ms[6] / stage_runs[6] = {decode_demux_seed, slot scan + assign,
+ * normalise_score_pack, fair-sampling fix-ups, polya_ruler, fit_cutoffs}.  Enabling resets. */
+int tsk_profile_enable(tsk_ctx *ctx, int on);
+int tsk_profile_get(tsk_ctx *ctx, double stage_ms[6], uint64_t stage_runs[6]);
 /* Number of kernel launches issued by this context so far. */
 uint64_t tsk_launch_count(tsk_ctx *ctx);
 
@@ -249,6 +259,15 @@ uint64_t tsk_launch_count(tsk_ctx *ctx);
  * libm's logf bit for bit because shannon_entropy() (signalproc.c:39-51) feeds 24-bit
  * truncated scores.  Host pointers. */
 int tsk_selftest_logf(tsk_ctx *ctx, const float *in, float *out, size_t n);
+/* Self-test sweeps on the device: (1) the FMA form of logf used by the fast scoring kernel
+ * against the separately-rounded form above on EVERY normal float in (0,1]; (2) the
+ * reciprocal-multiply-and-correct division against IEEE division on `div_pairs` pseudo-random
+ * operand pairs.  Both mismatch counts must be 0. */
+int tsk_selftest_sweeps(tsk_ctx *ctx, uint64_t div_pairs, uint64_t *logf_mismatches,
+                        uint64_t *div_mismatches);
+/* Debug: run normalise_score_pack with the literal operation-by-operation kernel for every
+ * cluster instead of the fast kernel (tests pin one against the other and the oracle). */
+int tsk_debug_force_generic(tsk_ctx *ctx, int on);
 
 #ifdef __cplusplus
 }

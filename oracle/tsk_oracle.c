@@ -237,7 +237,13 @@ static int score_cycles(const tsk_params *p, const int16_t *cif, size_t pitch, u
         for (int ch = 0; ch < 4; ch++)
             if (norm[ch] > 0.f) h -= norm[ch] * logf(norm[ch]);
         float entropy_score = 1.f - h / p->maximum_entropy;
-        float tscore = p->t_intensity_score[(int)(norm[3] * TSK_T_SCORE_BINS)];
+        /* the reference indexes unchecked: (int)(norm[3] * 200) is undefined behaviour (and an
+         * out-of-bounds read) when norm[3] is NaN/Inf, which needs a zero signal bandwidth
+         * (SURVEY quirk 7).  Defined here, and in the CUDA kernels, as NaN -> 0 and a clamp to
+         * [0, 200]; identical to the reference wherever the reference is defined. */
+        float tpos = norm[3] * TSK_T_SCORE_BINS;
+        int ti = (tpos >= 0.f) ? (tpos > (float)TSK_T_SCORE_BINS ? TSK_T_SCORE_BINS : (int)tpos) : 0;
+        float tscore = p->t_intensity_score[ti];
 
         scores[c] = entropy_score * tscore;
         downhill[c] = (char)(entropy_score < prev_entropy);

@@ -19,7 +19,8 @@ SYMBOLS = [
     "tsk_get_counters", "tsk_counters_reset", "tsk_get_hist", "tsk_get_device_ptrs",
     "tsk_cutoff_to_packed", "tsk_ruler_records", "tsk_ruler_tile", "tsk_ruler_hist_reset",
     "tsk_ruler_get_hist", "tsk_fit_cutoffs", "tsk_synchronize", "tsk_tile_process_timed",
-    "tsk_launch_count", "tsk_selftest_logf",
+    "tsk_launch_count", "tsk_selftest_logf", "tsk_set_stream", "tsk_profile_enable", "tsk_profile_get",
+    "tsk_selftest_sweeps", "tsk_debug_force_generic",
 ]
 
 _lib = None
@@ -65,6 +66,11 @@ def load():
     L.tsk_launch_count.argtypes = [vp]
     L.tsk_launch_count.restype = ctypes.c_uint64
     L.tsk_selftest_logf.argtypes = [vp, vp, vp, sz]
+    L.tsk_selftest_sweeps.argtypes = [vp, ctypes.c_uint64, vp, vp]
+    L.tsk_debug_force_generic.argtypes = [vp, i32]
+    L.tsk_set_stream.argtypes = [vp, vp]
+    L.tsk_profile_enable.argtypes = [vp, i32]
+    L.tsk_profile_get.argtypes = [vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is ctypes.c_int and name not in ("tsk_probe",):

@@ -174,6 +174,7 @@ extern "C" int tsk_ctx_create(tsk_ctx **out, int device, const tsk_params *param
 
     TSK_CUDA(cudaSetDevice(device));
     TSK_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = 1;
     const int S = params->num_samples;
     const size_t histbytes = sizeof(uint32_t) * (size_t)params->total_cycles * params->dist_sampling_bins;
     TSK_CUDA(cudaMalloc(&ctx->d_samples, sizeof(DevSample) * S));
@@ -206,7 +207,8 @@ extern "C" int tsk_ctx_destroy(tsk_ctx *ctx)
                     ctx->d_lists, ctx->d_ruler_pos, ctx->d_cutoffs, ctx->d_rlen};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)
         if (ptrs[i]) cudaFree(ptrs[i]);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->profile) for (int i = 0; i < 7; i++) cudaEventDestroy(ctx->pev[i]);
     free(ctx);
     return 0;
 }
@@ -246,7 +248,7 @@ static int ensure_cluster_buffers(tsk_ctx *ctx, uint32_t n)
     TSK_CUDA(cudaMalloc(&ctx->d_records, sizeof(uint32_t) * ctx->rec_cap_words));
     ctx->scratch_cap = (size_t)cap * (size_t)maxinsert;
     TSK_CUDA(cudaMalloc(&ctx->d_scratch, sizeof(float) * ctx->scratch_cap));
-    TSK_CUDA(cudaMalloc(&ctx->d_lists, sizeof(uint32_t) * (16 + 3 * (size_t)cap)));
+    TSK_CUDA(cudaMalloc(&ctx->d_lists, sizeof(uint32_t) * (16 + 4 * (size_t)cap)));
     ctx->cap_clusters = cap;
     return 0;
 }
@@ -303,20 +305,65 @@ extern "C" int tsk_tile_process(tsk_ctx *ctx)
 {
     if (!ctx || !ctx->d_calls) { tsk_set_error("no tile uploaded"); return -1; }
     TSK_CUDA(cudaSetDevice(ctx->device));
-    if (tsk_launch_import(ctx, NULL) != 0) return -1;
+    if (tsk_launch_import(ctx, ctx->profile ? ctx->pev : NULL) != 0) return -1;
     if (fetch_totals(ctx) != 0) return -1;
+    if (ctx->profile)
+        for (int i = 0; i < 4; i++) {
+            float ms = 0.f;
+            TSK_CUDA(cudaEventElapsedTime(&ms, ctx->pev[i], ctx->pev[i + 1]));
+            ctx->stage_ms[i] += ms;
+            ctx->stage_runs[i]++;
+        }
     ctx->processed = 1;
     return 0;
 }
 
-extern "C" int tsk_tile_process_timed(tsk_ctx *ctx, int iters, float ms_out[4])
+extern "C" int tsk_set_stream(tsk_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) { tsk_set_error("null ctx"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    TSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = 0;
+    return 0;
+}
+
+extern "C" int tsk_debug_force_generic(tsk_ctx *ctx, int on)
+{
+    if (!ctx) { tsk_set_error("null ctx"); return -1; }
+    ctx->force_generic = on ? 1 : 0;
+    return 0;
+}
+
+extern "C" int tsk_profile_enable(tsk_ctx *ctx, int on)
+{
+    if (!ctx) { tsk_set_error("null ctx"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    if (on && !ctx->profile)
+        for (int i = 0; i < 7; i++) TSK_CUDA(cudaEventCreate(&ctx->pev[i]));
+    if (!on && ctx->profile)
+        for (int i = 0; i < 7; i++) cudaEventDestroy(ctx->pev[i]);
+    ctx->profile = on ? 1 : 0;
+    for (int i = 0; i < 6; i++) { ctx->stage_ms[i] = 0.; ctx->stage_runs[i] = 0; }
+    return 0;
+}
+
+extern "C" int tsk_profile_get(tsk_ctx *ctx, double stage_ms[6], uint64_t stage_runs[6])
+{
+    if (!ctx) { tsk_set_error("null ctx"); return -1; }
+    for (int i = 0; i < 6; i++) { stage_ms[i] = ctx->stage_ms[i]; stage_runs[i] = ctx->stage_runs[i]; }
+    return 0;
+}
+
+extern "C" int tsk_tile_process_timed(tsk_ctx *ctx, int iters, float ms_out[5])
 {
     if (!ctx || !ctx->d_calls || iters < 1) { tsk_set_error("bad argument"); return -1; }
     TSK_CUDA(cudaSetDevice(ctx->device));
-    cudaEvent_t ev[4];
-    for (int i = 0; i < 4; i++) TSK_CUDA(cudaEventCreate(&ev[i]));
+    cudaEvent_t ev[5];
+    for (int i = 0; i < 5; i++) TSK_CUDA(cudaEventCreate(&ev[i]));
     const int S = ctx->dp.num_samples;
-    double acc[4] = {0, 0, 0, 0};
+    double acc[5] = {0, 0, 0, 0, 0};
     uint32_t *saved = (uint32_t *)malloc(sizeof(uint32_t) * S * TSK_NCOUNT);
     for (int it = 0; it < iters; it++) {
         /* counters accumulate across calls by contract; keep them unchanged by the re-runs */
@@ -325,12 +372,13 @@ extern "C" int tsk_tile_process_timed(tsk_ctx *ctx, int iters, float ms_out[4])
         TSK_CUDA(cudaStreamSynchronize(ctx->stream));
         if (tsk_launch_import(ctx, ev) != 0) { free(saved); return -1; }
         TSK_CUDA(cudaStreamSynchronize(ctx->stream));
-        float a, b, c, t;
+        float a, b, c, d, t;
         cudaEventElapsedTime(&a, ev[0], ev[1]);
         cudaEventElapsedTime(&b, ev[1], ev[2]);
         cudaEventElapsedTime(&c, ev[2], ev[3]);
-        cudaEventElapsedTime(&t, ev[0], ev[3]);
-        acc[0] += a; acc[1] += b; acc[2] += c; acc[3] += t;
+        cudaEventElapsedTime(&d, ev[3], ev[4]);
+        cudaEventElapsedTime(&t, ev[0], ev[4]);
+        acc[0] += a; acc[1] += b; acc[2] += c; acc[3] += d; acc[4] += t;
         if (ctx->processed || it > 0) {
             TSK_CUDA(cudaMemcpyAsync(ctx->d_counters, saved, sizeof(uint32_t) * S * TSK_NCOUNT,
                                      cudaMemcpyHostToDevice, ctx->stream));
@@ -338,7 +386,7 @@ extern "C" int tsk_tile_process_timed(tsk_ctx *ctx, int iters, float ms_out[4])
         }
     }
     free(saved);
-    for (int i = 0; i < 4; i++) { ms_out[i] = (float)(acc[i] / iters); cudaEventDestroy(ev[i]); }
+    for (int i = 0; i < 5; i++) { ms_out[i] = (float)(acc[i] / iters); cudaEventDestroy(ev[i]); }
     if (fetch_totals(ctx) != 0) return -1;
     ctx->processed = 1;
     return 0;
@@ -479,12 +527,20 @@ static int ruler_common(tsk_ctx *ctx, const uint32_t *d_records, size_t nrecords
                              ctx->stream));
     if (ensure(&ctx->d_rlen, &ctx->rlen_cap, nrecords ? nrecords : 1) != 0) return -1;
     if (nrecords) {
+        if (ctx->profile) TSK_CUDA(cudaEventRecord(ctx->pev[5], ctx->stream));
         if (tsk_launch_ruler(ctx, d_records, nrecords, dump_len, ncutoffs, min_len, weight, bins, gap,
                              ctx->d_rlen) != 0) return -1;
+        if (ctx->profile) TSK_CUDA(cudaEventRecord(ctx->pev[6], ctx->stream));
         TSK_CUDA(cudaMemcpyAsync(polya_len_out, ctx->d_rlen, sizeof(int16_t) * nrecords,
                                  cudaMemcpyDeviceToHost, ctx->stream));
     }
     TSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (nrecords && ctx->profile) {
+        float ms = 0.f;
+        TSK_CUDA(cudaEventElapsedTime(&ms, ctx->pev[5], ctx->pev[6]));
+        ctx->stage_ms[4] += ms;
+        ctx->stage_runs[4]++;
+    }
     return 0;
 }
 
@@ -536,13 +592,22 @@ extern "C" int tsk_fit_cutoffs(tsk_ctx *ctx, const uint64_t *pos, const uint64_t
     TSK_CUDA(cudaMalloc(&d_out, sizeof(double) * cycles));
     TSK_CUDA(cudaMemcpyAsync(d_pos, pos, hb, cudaMemcpyHostToDevice, ctx->stream));
     TSK_CUDA(cudaMemcpyAsync(d_neg, neg, hb, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->profile) cudaEventRecord(ctx->pev[5], ctx->stream);
     int rc = tsk_launch_fit(ctx, d_pos, d_neg, cycles, bins, min_spots, kde_bandwidth, search_low,
                             search_high, nsearch_high, d_out);
+    if (ctx->profile) cudaEventRecord(ctx->pev[6], ctx->stream);
     if (rc == 0) {
         cudaError_t e = cudaMemcpyAsync(cutoffs_out, d_out, sizeof(double) * cycles, cudaMemcpyDeviceToHost,
                                         ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { tsk_set_error("fit copy back: %s", cudaGetErrorString(e)); rc = -1; }
+        else if (ctx->profile) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ctx->pev[5], ctx->pev[6]) == cudaSuccess) {
+                ctx->stage_ms[5] += ms;
+                ctx->stage_runs[5]++;
+            }
+        }
     }
     cudaFree(d_pos); cudaFree(d_neg); cudaFree(d_out);
     return rc;

@@ -96,6 +96,12 @@ struct tsk_ctx {
     uint64_t h_recbase[TSK_MAX_SAMPLES + 1];
     int processed;
     uint64_t launches;
+
+    /* optional per-stage device timing (tsk_profile_enable) */
+    int profile, own_stream, force_generic;
+    cudaEvent_t pev[7];
+    double stage_ms[6];          /* decode, scan, normalise/score/pack, fix-ups, ruler, fit */
+    uint64_t stage_runs[6];
 };
 
 void tsk_set_error(const char *fmt, ...);
@@ -110,7 +116,9 @@ void tsk_set_error(const char *fmt, ...);
     } while (0)
 
 /* kernel launchers (tsk_kernels.cu / tsk_ruler.cu / tsk_fit.cu) */
-int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev /* optional [4] */);
+int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev /* optional [5] */);
+int tsk_launch_score(tsk_ctx *ctx);
+int tsk_launch_fixups(tsk_ctx *ctx);
 int tsk_launch_ruler(tsk_ctx *ctx, const uint32_t *d_records, size_t nrecords, int dump_len,
                      int ncutoffs, int min_len, float weight, int bins, float gap,
                      int16_t *d_len_out);

@@ -325,369 +325,6 @@ k_assign(const TileView tv, tsk_call *__restrict__ calls, const uint8_t *__restr
     calls[n].record_slot = slot;
 }
 
-/* =======================================================================================
- * K2  normalise_score_pack
- *   probe_signal_ranges (signalproc.c:132-201), decrosstalk_intensity (:85-103),
- *   compute_polya_score + normalize_signals + shannon_entropy (:269-342,246-266,39-51),
- *   find_max_cumulative_contrast (:378-412), sampling policy and add_polya_score_sample
- *   (spotanalyzer.c:574-599,441-457), write_polya_score (spotanalyzer.c:389-438)
- * ===================================================================================== */
-struct ScoreShared {
-    double2 logtab[16];
-    float   tscore[TSK_T_SCORE_BINS + 1];
-    int16_t limit[TSK_MAX_SAMPLES];
-    int16_t dump[TSK_MAX_SAMPLES];
-};
-
-__device__ __forceinline__ void load_score_shared(ScoreShared &sh, const float *__restrict__ tscore,
-                                                  const DevSample *__restrict__ samples, int S)
-{
-    for (int i = threadIdx.x; i < 16; i += blockDim.x)
-        sh.logtab[i] = make_double2(c_logf_tab[i][0], c_logf_tab[i][1]);
-    for (int i = threadIdx.x; i <= TSK_T_SCORE_BINS; i += blockDim.x) sh.tscore[i] = tscore[i];
-    for (int i = threadIdx.x; i < S; i += blockDim.x) {
-        sh.limit[i] = samples[i].limit_threep;
-        sh.dump[i] = samples[i].dump_len;
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ void decrosstalk(float sig[4], const int16_t *__restrict__ p, size_t pitch,
-                                            const float *inv)
-{
-    const float v0 = (float)__ldg(p), v1 = (float)__ldg(p + pitch);
-    const float v2 = (float)__ldg(p + 2 * pitch), v3 = (float)__ldg(p + 3 * pitch);
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        float a = __fmul_rn(inv[4 * j + 0], v0);
-        a = __fadd_rn(a, __fmul_rn(inv[4 * j + 1], v1));
-        a = __fadd_rn(a, __fmul_rn(inv[4 * j + 2], v2));
-        sig[j] = __fadd_rn(a, __fmul_rn(inv[4 * j + 3], v3));
-    }
-}
-
-/* low / bandwidth of the four channels over the balancer cycles.  Generic in npos / nneg
- * (<= TSK_MAX_RANK); the bubble-insert keeps earlier elements on ties like the reference. */
-__device__ __forceinline__ void probe_ranges(const DevParams &P, const int16_t *__restrict__ cifcol,
-                                             size_t pitch, int blen, float low[4], float bw[4])
-{
-    float top[4][TSK_MAX_RANK], bot[4][TSK_MAX_RANK];
-    const int npos = P.npos, nneg = P.nneg;
-#pragma unroll
-    for (int ch = 0; ch < 4; ch++)
-#pragma unroll
-        for (int r = 0; r < TSK_MAX_RANK; r++) { top[ch][r] = -CUDART_INF_F; bot[ch][r] = CUDART_INF_F; }
-    for (int c = P.balancer_start; c < P.balancer_start + blen; c++) {
-        float sig[4];
-        decrosstalk(sig, cifcol + (size_t)c * 4 * pitch, pitch, P.inv);
-#pragma unroll
-        for (int ch = 0; ch < 4; ch++) {
-            float carry = sig[ch];
-#pragma unroll
-            for (int r = 0; r < TSK_MAX_RANK; r++)
-                if (r < npos && carry > top[ch][r]) { const float t = top[ch][r]; top[ch][r] = carry; carry = t; }
-            carry = sig[ch];
-#pragma unroll
-            for (int r = 0; r < TSK_MAX_RANK; r++)
-                if (r < nneg && carry < bot[ch][r]) { const float t = bot[ch][r]; bot[ch][r] = carry; carry = t; }
-        }
-    }
-#pragma unroll
-    for (int ch = 0; ch < 4; ch++) {
-        float acc = 0.f;
-#pragma unroll
-        for (int r = 0; r < TSK_MAX_RANK; r++) if (r < nneg) acc = __fadd_rn(acc, bot[ch][r]);
-        low[ch] = __fdiv_rn(acc, (float)nneg);
-        acc = 0.f;
-#pragma unroll
-        for (int r = 0; r < TSK_MAX_RANK; r++) if (r < npos) acc = __fadd_rn(acc, top[ch][r]);
-        bw[ch] = __fsub_rn(__fdiv_rn(acc, (float)npos), low[ch]);
-    }
-}
-
-/* One cycle of compute_polya_score().  Returns false for a dark cycle. */
-__device__ __forceinline__ bool score_cycle(const DevParams &P, const ScoreShared &sh,
-                                            const int16_t *__restrict__ p, size_t pitch,
-                                            const float low[4], const float bw[4],
-                                            float &entropy_score, float &score)
-{
-    float sig[4], nrm[4];
-    decrosstalk(sig, p, pitch, P.inv);
-    float total = 0.f;
-#pragma unroll
-    for (int ch = 0; ch < 4; ch++)
-        if (sig[ch] > 0.f) total = __fadd_rn(total, sig[ch]);
-    if (total < P.dark_threshold) return false;
-    total = 0.f;
-#pragma unroll
-    for (int ch = 0; ch < 4; ch++) {
-        float v = __fdiv_rn(__fsub_rn(sig[ch], low[ch]), bw[ch]);
-        if (v < 0.f) v = 0.f;
-        nrm[ch] = v;
-        total = __fadd_rn(total, v);
-    }
-#pragma unroll
-    for (int ch = 0; ch < 4; ch++) nrm[ch] = __fdiv_rn(nrm[ch], total);
-    if (nrm[0] != nrm[0]) return false;
-    float h = 0.f;
-#pragma unroll
-    for (int ch = 0; ch < 4; ch++)
-        if (nrm[ch] > 0.f) h = __fsub_rn(h, __fmul_rn(nrm[ch], tsk_logf(nrm[ch], sh.logtab)));
-    entropy_score = __fsub_rn(1.f, __fdiv_rn(h, P.maximum_entropy));
-    int ti = __float2int_rz(__fmul_rn(nrm[3], (float)TSK_T_SCORE_BINS));
-    ti = max(0, min(TSK_T_SCORE_BINS, ti));      /* the reference indexes unchecked (UB outside) */
-    score = __fmul_rn(entropy_score, sh.tscore[ti]);
-    return true;
-}
-
-__device__ __forceinline__ int score_bin(float score, int bins)
-{
-    int b = __float2int_rz(__fmul_rn(score, (float)bins));
-    return b >= bins ? bins - 1 : b;
-}
-
-/* list area layout (u32): [0] undo count, [1] contended count, [2] accepted count,
- * then three arrays of `cap` entries */
-__device__ __forceinline__ uint32_t *list_array(uint32_t *lists, int which, uint32_t cap)
-{
-    return lists + 16 + (size_t)which * cap;
-}
-
-__global__ void __launch_bounds__(TSK_K2_THREADS)
-k_normalise_score_pack(const __grid_constant__ DevParams P, const TileView tv,
-                       const DevSample *__restrict__ samples, const float *__restrict__ g_tscore,
-                       tsk_call *__restrict__ calls, const uint8_t *__restrict__ kind,
-                       const uint32_t *__restrict__ bucket, const uint32_t *__restrict__ worklist,
-                       const uint32_t *__restrict__ totals, const uint64_t *__restrict__ recbase,
-                       uint32_t *__restrict__ records, float *__restrict__ scratch, size_t spitch,
-                       uint32_t *__restrict__ pos, uint32_t *__restrict__ neg,
-                       const uint32_t *__restrict__ fair, uint32_t *__restrict__ lists, uint32_t listcap)
-{
-    __shared__ ScoreShared sh;
-    const int S = P.num_samples;
-    load_score_shared(sh, g_tscore, samples, S);
-
-    const uint32_t w = blockIdx.x * TSK_K2_THREADS + threadIdx.x;
-    if (w >= totals[S]) return;
-    const uint32_t n = worklist[w];
-    const uint4 craw = *reinterpret_cast<const uint4 *>(&calls[n]);
-    tsk_call call = *reinterpret_cast<const tsk_call *>(&craw);
-    const uint32_t kd = kind[n];
-    const int ts = P.threep_start, tl = P.threep_length, bins = P.bins;
-    const int de = call.delimiter_end, ps = call.terminal_mods;
-    const int sample = call.sample;
-    const size_t pitch = tv.cif_pitch;
-    const int16_t *cifcol = tv.cif + n;
-
-    int blen = de - ts;
-    if (blen > P.balancer_length) blen = P.balancer_length;
-    float low[4], bw[4];
-    probe_ranges(P, cifcol, pitch, blen, low, bw);
-
-    int insert_len = ts + tl - de;
-    const int limit = sh.limit[sample], dump = sh.dump[sample];
-    if (limit > 0 && limit < insert_len) insert_len = limit;
-    const int scan_len = insert_len - ps;
-    const int valid = min(scan_len, dump);
-
-    /* record slot */
-    uint32_t *rec = nullptr;
-    if (kd & KIND_EMIT) {
-        rec = records + recbase[sample] + (size_t)call.record_slot * (size_t)(2 + dump);
-        rec[0] = tv.firstclusterno + n;
-        rec[1] = (uint32_t)(uint16_t)(int16_t)(de + ps) | ((uint32_t)(uint16_t)(int16_t)valid << 16);
-    }
-    /* negative sampling: inline when the bucket cannot overflow */
-    bool neg_inline = false;
-    if (kd & KIND_NEG)
-        neg_inline = (P.fair_max_count == 0) || (fair[bucket[n]] <= (uint32_t)P.fair_max_count);
-
-    int ndark = 0;
-    float prev_entropy = CUDART_NAN_F;
-    unsigned long long dhwin = 0;          /* bit k = downhill of cycle (c - k) */
-    const int16_t *p = cifcol + (size_t)(de - ts) * 4 * pitch;
-    const uint32_t rowbase = (uint32_t)de;  /* histogram row of score index c is de + c */
-
-    for (int c = 0; c < insert_len; c++, p += 4 * pitch) {
-        float es, score;
-        const bool lit = score_cycle(P, sh, p, pitch, low, bw, es, score);
-        uint32_t dh = 0;
-        if (lit) {
-            dh = (es < prev_entropy) ? 1u : 0u;
-            prev_entropy = es;
-        } else {
-            ndark++;
-            score = CUDART_NAN_F;
-            prev_entropy = CUDART_NAN_F;
-        }
-        dhwin = (dhwin << 1) | dh;
-        const int j = c - ps;
-        if (j >= 0) {
-            if (rec != nullptr && j < valid) {
-                uint32_t word = 0;
-                if (lit) {
-                    uint32_t s = 1u + (uint32_t)__float2int_rz(__fmul_rn(score, (float)(TSK_SCORE_MAX - 1)));
-                    if (s >= TSK_SCORE_MAX) s = TSK_SCORE_MAX;
-                    /* the reference passes the UN-offset downhill array: packet j carries
-                     * downhill[j], not downhill[ps + j] (spotanalyzer.c:604-606) */
-                    word = (s << 1) | (uint32_t)((dhwin >> ps) & 1ull);
-                }
-                rec[2 + j] = word;
-            }
-            if (kd & KIND_POS) scratch[(size_t)j * spitch + w] = score;
-            if (neg_inline && lit && !isinf(score))
-                atomicAdd(&neg[(size_t)(rowbase + c) * bins + score_bin(score, bins)], 1u);
-        }
-    }
-    if (rec != nullptr)
-        for (int j = max(valid, 0); j < dump; j++) rec[2 + j] = 0;
-
-    bool aborted = false;
-    if (ndark > 0) {
-        call.flags |= TSK_PAFLAG_DARKCYCLE_EXISTS;
-        if (ndark >= P.max_dark_cycles) {
-            call.flags |= TSK_PAFLAG_DARKCYCLE_OVER_THRESHOLD;
-            call.polya_len = -1;
-            call.emitted = 0;
-            aborted = true;
-            if (rec != nullptr) rec[1] |= 0xffff0000u;     /* withdraw the slot: valid = -1 */
-        }
-        *reinterpret_cast<uint4 *>(&calls[n]) = *reinterpret_cast<const uint4 *>(&call);
-    } else if ((kd & KIND_EMIT) && scan_len <= 0) {
-        call.emitted = 0;   /* unreachable: KIND_EMIT implies scan_len > 0 */
-    }
-
-    if (kd & KIND_NEG) {
-        if (aborted && neg_inline)
-            list_array(lists, 0, listcap)[atomicAdd(&lists[0], 1u)] = n;
-        else if (!aborted && !neg_inline)
-            list_array(lists, 1, listcap)[atomicAdd(&lists[1], 1u)] = n;
-    }
-
-    /* contrast test and positive sampling */
-    if ((kd & KIND_POS) && !aborted && scan_len > 0 && P.cctr_left + P.cctr_right < scan_len) {
-        const float *col = scratch + w;
-        double total = 0.;
-        for (int i = 0; i < scan_len; i++) total = __dadd_rn(total, (double)col[(size_t)i * spitch]);
-        double cum = 0., best = 0.;
-        int at = -1;
-        const int last = scan_len - P.cctr_right;
-        for (int i = 0; i <= last; i++) {
-            cum = __dadd_rn(cum, (double)col[(size_t)i * spitch]);
-            if (i >= P.cctr_left - 1) {
-                const double v = __dsub_rn(__ddiv_rn(cum, (double)i),
-                                           __ddiv_rn(__dsub_rn(total, cum), (double)(scan_len - i)));
-                if (i == P.cctr_left - 1) { best = v; at = i; }
-                else if (v > best) { best = v; at = i; }
-            }
-        }
-        const float contrast = (float)best;
-        if (at + 1 >= P.boundary_pos && contrast >= P.required_contrast) {
-            const int take = -ps + min(scan_len, P.boundary_pos - P.sampling_gap);
-            for (int i = 0; i < take; i++) {
-                const float sc = col[(size_t)i * spitch];
-                if (!isnan(sc) && !isinf(sc))
-                    atomicAdd(&pos[(size_t)(rowbase + ps + i) * bins + score_bin(sc, bins)], 1u);
-            }
-        }
-    }
-}
-
-/* Fair sampling among the clusters of over-subscribed buckets: the reference accepts, per
- * bucket, the first fair_max_count eligible clusters in cluster order (spotanalyzer.c:476-484
- * with threads=1).  One CTA; per round every still-waiting entry bids its cluster number
- * with atomicMin, the winner of each bucket is accepted.  `fair` is reused as the bid table. */
-__global__ void __launch_bounds__(1024)
-k_fair_resolve(uint32_t *__restrict__ fair, const uint32_t *__restrict__ bucket,
-               uint32_t *__restrict__ lists, uint32_t listcap, int max_count)
-{
-    const uint32_t cnt = lists[1];
-    uint32_t *cont = list_array(lists, 1, listcap);
-    uint32_t *acc = list_array(lists, 2, listcap);
-    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) fair[bucket[cont[i] & 0x7fffffffu]] = 0xffffffffu;
-    __syncthreads();
-    for (int round = 0; round < max_count; round++) {
-        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-            const uint32_t e = cont[i];
-            if (!(e & 0x80000000u)) atomicMin(&fair[bucket[e]], e);
-        }
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-            const uint32_t e = cont[i];
-            if (!(e & 0x80000000u) && fair[bucket[e]] == e) {
-                acc[atomicAdd(&lists[2], 1u)] = e;
-                cont[i] = e | 0x80000000u;
-            }
-        }
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
-            fair[bucket[cont[i] & 0x7fffffffu]] = 0xffffffffu;
-        __syncthreads();
-    }
-}
-
-/* Recompute the scores of the listed clusters and add `delta` (+1 / -1, as u32) to the
- * negative histogram: accepted clusters of over-subscribed buckets (+1), and inline-sampled
- * clusters that later aborted on dark cycles (-1). */
-__global__ void __launch_bounds__(TSK_K2_THREADS)
-k_resample_neg(const __grid_constant__ DevParams P, const TileView tv,
-               const DevSample *__restrict__ samples, const float *__restrict__ g_tscore,
-               const tsk_call *__restrict__ calls, uint32_t *__restrict__ neg,
-               const uint32_t *__restrict__ lists, uint32_t listcap, int which, uint32_t delta)
-{
-    __shared__ ScoreShared sh;
-    load_score_shared(sh, g_tscore, samples, P.num_samples);
-    const uint32_t cnt = lists[which];
-    const uint32_t *arr = list_array(const_cast<uint32_t *>(lists), which, listcap);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-        const uint32_t n = arr[i] & 0x7fffffffu;
-        const tsk_call call = calls[n];
-        const int ts = P.threep_start, tl = P.threep_length, bins = P.bins;
-        const int de = call.delimiter_end, ps = call.terminal_mods;
-        const size_t pitch = tv.cif_pitch;
-        const int16_t *cifcol = tv.cif + n;
-        int blen = de - ts;
-        if (blen > P.balancer_length) blen = P.balancer_length;
-        float low[4], bw[4];
-        probe_ranges(P, cifcol, pitch, blen, low, bw);
-        int insert_len = ts + tl - de;
-        const int limit = sh.limit[call.sample];
-        if (limit > 0 && limit < insert_len) insert_len = limit;
-        const int16_t *p = cifcol + (size_t)(de - ts) * 4 * pitch;
-        for (int c = 0; c < insert_len; c++, p += 4 * pitch) {
-            float es, score;
-            if (score_cycle(P, sh, p, pitch, low, bw, es, score) && c >= ps && !isinf(score))
-                atomicAdd(&neg[(size_t)(de + c) * bins + score_bin(score, bins)], delta);
-        }
-    }
-}
-
-/* self-test hook: device logf over an array (tests pin it against the host libm) */
-__global__ void k_logf_probe(const float *__restrict__ in, float *__restrict__ out, size_t n)
-{
-    __shared__ double2 tab[16];
-    if (threadIdx.x < 16) tab[threadIdx.x] = make_double2(c_logf_tab[threadIdx.x][0], c_logf_tab[threadIdx.x][1]);
-    __syncthreads();
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        out[i] = tsk_logf(in[i], tab);
-}
-
-extern "C" int tsk_selftest_logf(tsk_ctx *ctx, const float *in, float *out, size_t n)
-{
-    if (!ctx || !in || !out) { tsk_set_error("null argument"); return -1; }
-    TSK_CUDA(cudaSetDevice(ctx->device));
-    float *d_in = NULL, *d_out = NULL;
-    TSK_CUDA(cudaMalloc(&d_in, sizeof(float) * n));
-    TSK_CUDA(cudaMalloc(&d_out, sizeof(float) * n));
-    TSK_CUDA(cudaMemcpyAsync(d_in, in, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
-    k_logf_probe<<<148 * 8, 256, 0, ctx->stream>>>(d_in, d_out, n);
-    ctx->launches++;
-    TSK_CUDA(cudaMemcpyAsync(out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    TSK_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_in); cudaFree(d_out);
-    return 0;
-}
-
 /* ===================================================================================== */
 int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev)
 {
@@ -698,8 +335,6 @@ int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev)
     const int nblk = (int)((N + TSK_K1_THREADS - 1) / TSK_K1_THREADS);
     cudaStream_t st = ctx->stream;
     const size_t histbytes = sizeof(uint32_t) * (size_t)P.total_cycles * P.bins;
-    const uint32_t listcap = ctx->cap_clusters;
-
     TSK_CUDA(cudaMemsetAsync(ctx->d_pos, 0, histbytes, st));
     TSK_CUDA(cudaMemsetAsync(ctx->d_neg, 0, histbytes, st));
     TSK_CUDA(cudaMemsetAsync(ctx->d_fair, 0, sizeof(uint32_t) * (size_t)P.fair_hash_size, st));
@@ -726,20 +361,10 @@ int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev)
         TSK_CUDA(cudaMemsetAsync(ctx->d_recbase, 0, sizeof(uint64_t) * (S + 1), st));
     }
     if (ev) TSK_CUDA(cudaEventRecord(ev[2], st));
-    if (N > 0) {
-        k_normalise_score_pack<<<(N + TSK_K2_THREADS - 1) / TSK_K2_THREADS, TSK_K2_THREADS, 0, st>>>(
-            P, tv, ctx->d_samples, ctx->d_tscore, ctx->d_calls, ctx->d_kind, ctx->d_bucket,
-            ctx->d_worklist, ctx->d_totals, ctx->d_recbase, ctx->d_records, ctx->d_scratch,
-            (size_t)ctx->cap_clusters, ctx->d_pos, ctx->d_neg, ctx->d_fair, ctx->d_lists, listcap);
-        k_fair_resolve<<<1, 1024, 0, st>>>(ctx->d_fair, ctx->d_bucket, ctx->d_lists, listcap,
-                                           P.fair_max_count);
-        k_resample_neg<<<148, TSK_K2_THREADS, 0, st>>>(P, tv, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
-                                                      ctx->d_neg, ctx->d_lists, listcap, 2, 1u);
-        k_resample_neg<<<148, TSK_K2_THREADS, 0, st>>>(P, tv, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
-                                                      ctx->d_neg, ctx->d_lists, listcap, 0, 0xffffffffu);
-        ctx->launches += 4;
-    }
+    if (tsk_launch_score(ctx) != 0) return -1;
     if (ev) TSK_CUDA(cudaEventRecord(ev[3], st));
+    if (tsk_launch_fixups(ctx) != 0) return -1;
+    if (ev) TSK_CUDA(cudaEventRecord(ev[4], st));
     TSK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -1,0 +1,876 @@
+/*
+ * tsk_score.cu -- normalise_score_pack: CIF intensities -> poly(A) scores -> packed signal
+ * records + positive / negative score histograms, and the fair-sampling fix-up kernels.
+ *
+ * Restates (bit for bit) probe_signal_ranges (signalproc.c:132-201), decrosstalk_intensity
+ * (:85-103), compute_polya_score + normalize_signals + shannon_entropy (:269-342,246-266,
+ * 39-51), find_max_cumulative_contrast (:378-412), the sampling policy and
+ * add_polya_score_sample (spotanalyzer.c:574-599,441-457), write_polya_score (:389-438).
+ *
+ * Two code paths, both exact:
+ *   k_normalise_score_pack          the fast path: one thread per cluster, a branch-free
+ *       cycle step; the nine IEEE divisions per cycle become multiplications by hoisted
+ *       correctly rounded reciprocals plus two FMA residual corrections (Markstein), logf is
+ *       the host's table algorithm in fp64 FMAs, packed record words are transposed through
+ *       shared memory so every record is written with full 128-byte lines.
+ *   k_normalise_score_pack_generic  the literal operation-by-operation restatement
+ *       (__fdiv_rn everywhere); runs only for the clusters the fast path hands over because
+ *       its preconditions do not hold (degenerate signal bandwidths), and is what the fast
+ *       path is tested against.
+ */
+#include <math_constants.h>
+#include "tsk_internal.h"
+#include "tsk_device.cuh"
+
+#define FULL_MASK 0xffffffffu
+#define CONTRAST_MAXLEN 288          /* reciprocal table length (scan_len <= threep_length + 1) */
+
+struct ScoreShared {
+    double2 logtab[16];
+    double  rcp[CONTRAST_MAXLEN];     /* 1.0 / i */
+    float   tscore[TSK_T_SCORE_BINS + 1];
+    int16_t limit[TSK_MAX_SAMPLES];
+    int16_t dump[TSK_MAX_SAMPLES];
+};
+
+__device__ __forceinline__ void load_score_shared(ScoreShared &sh, const float *__restrict__ tscore,
+                                                  const DevSample *__restrict__ samples, int S)
+{
+    for (int i = threadIdx.x; i < 16; i += blockDim.x)
+        sh.logtab[i] = make_double2(c_logf_tab[i][0], c_logf_tab[i][1]);
+    for (int i = threadIdx.x; i < CONTRAST_MAXLEN; i += blockDim.x)
+        sh.rcp[i] = (i > 0) ? __drcp_rn((double)i) : 0.;
+    for (int i = threadIdx.x; i <= TSK_T_SCORE_BINS; i += blockDim.x) sh.tscore[i] = tscore[i];
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        sh.limit[i] = samples[i].limit_threep;
+        sh.dump[i] = samples[i].dump_len;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ int score_bin(float score, int bins)
+{
+    int b = __float2int_rz(__fmul_rn(score, (float)bins));
+    return b >= bins ? bins - 1 : b;
+}
+
+/* list area layout (u32): [0] undo count, [1] contended count, [2] accepted count,
+ * [3] slow-path count, then four arrays of `cap` entries */
+__device__ __forceinline__ uint32_t *list_array(uint32_t *lists, int which, uint32_t cap)
+{
+    return lists + 16 + (size_t)which * cap;
+}
+
+/* ======================================================================================
+ * generic path: literal restatement
+ * ==================================================================================== */
+__device__ __forceinline__ void decrosstalk(float sig[4], const int16_t *__restrict__ p, size_t pitch,
+                                            const float *inv)
+{
+    const float v0 = (float)__ldg(p), v1 = (float)__ldg(p + pitch);
+    const float v2 = (float)__ldg(p + 2 * pitch), v3 = (float)__ldg(p + 3 * pitch);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        float a = __fmul_rn(inv[4 * j + 0], v0);
+        a = __fadd_rn(a, __fmul_rn(inv[4 * j + 1], v1));
+        a = __fadd_rn(a, __fmul_rn(inv[4 * j + 2], v2));
+        sig[j] = __fadd_rn(a, __fmul_rn(inv[4 * j + 3], v3));
+    }
+}
+
+/* low / bandwidth of the four channels over the balancer cycles.  Generic in npos / nneg
+ * (<= TSK_MAX_RANK); the bubble-insert keeps earlier elements on ties like the reference. */
+__device__ __forceinline__ void probe_ranges(const DevParams &P, const int16_t *__restrict__ cifcol,
+                                             size_t pitch, int blen, float low[4], float bw[4])
+{
+    float top[4][TSK_MAX_RANK], bot[4][TSK_MAX_RANK];
+    const int npos = P.npos, nneg = P.nneg;
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++)
+#pragma unroll
+        for (int r = 0; r < TSK_MAX_RANK; r++) { top[ch][r] = -CUDART_INF_F; bot[ch][r] = CUDART_INF_F; }
+    for (int c = P.balancer_start; c < P.balancer_start + blen; c++) {
+        float sig[4];
+        decrosstalk(sig, cifcol + (size_t)c * 4 * pitch, pitch, P.inv);
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++) {
+            float carry = sig[ch];
+#pragma unroll
+            for (int r = 0; r < TSK_MAX_RANK; r++)
+                if (r < npos && carry > top[ch][r]) { const float t = top[ch][r]; top[ch][r] = carry; carry = t; }
+            carry = sig[ch];
+#pragma unroll
+            for (int r = 0; r < TSK_MAX_RANK; r++)
+                if (r < nneg && carry < bot[ch][r]) { const float t = bot[ch][r]; bot[ch][r] = carry; carry = t; }
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) {
+        float acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < TSK_MAX_RANK; r++) if (r < nneg) acc = __fadd_rn(acc, bot[ch][r]);
+        low[ch] = __fdiv_rn(acc, (float)nneg);
+        acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < TSK_MAX_RANK; r++) if (r < npos) acc = __fadd_rn(acc, top[ch][r]);
+        bw[ch] = __fsub_rn(__fdiv_rn(acc, (float)npos), low[ch]);
+    }
+}
+
+/* One cycle of compute_polya_score(), operation by operation.  Returns false for a dark cycle. */
+__device__ __forceinline__ bool score_cycle_generic(const DevParams &P, const ScoreShared &sh,
+                                                    const int16_t *__restrict__ p, size_t pitch,
+                                                    const float low[4], const float bw[4],
+                                                    float &entropy_score, float &score)
+{
+    float sig[4], nrm[4];
+    decrosstalk(sig, p, pitch, P.inv);
+    float total = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++)
+        if (sig[ch] > 0.f) total = __fadd_rn(total, sig[ch]);
+    if (total < P.dark_threshold) return false;
+    total = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) {
+        float v = __fdiv_rn(__fsub_rn(sig[ch], low[ch]), bw[ch]);
+        if (v < 0.f) v = 0.f;
+        nrm[ch] = v;
+        total = __fadd_rn(total, v);
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) nrm[ch] = __fdiv_rn(nrm[ch], total);
+    if (nrm[0] != nrm[0]) return false;
+    float h = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++)
+        if (nrm[ch] > 0.f) h = __fsub_rn(h, __fmul_rn(nrm[ch], tsk_logf(nrm[ch], sh.logtab)));
+    entropy_score = __fsub_rn(1.f, __fdiv_rn(h, P.maximum_entropy));
+    int ti = __float2int_rz(__fmul_rn(nrm[3], (float)TSK_T_SCORE_BINS));
+    ti = max(0, min(TSK_T_SCORE_BINS, ti));      /* the reference indexes unchecked (UB outside) */
+    score = __fmul_rn(entropy_score, sh.tscore[ti]);
+    return true;
+}
+
+/* find_max_cumulative_contrast(), exact scan (signalproc.c:378-412) over a scratch column. */
+__device__ __forceinline__ int contrast_exact(const float *__restrict__ col, size_t spitch, int len,
+                                              int left, int right, double total, float *contrast)
+{
+    double cum = 0., best = 0.;
+    int at = -1;
+    const int last = len - right;
+    for (int i = 0; i <= last; i++) {
+        cum = __dadd_rn(cum, (double)col[(size_t)i * spitch]);
+        if (i >= left - 1) {
+            const double v = __dsub_rn(__ddiv_rn(cum, (double)i),
+                                       __ddiv_rn(__dsub_rn(total, cum), (double)(len - i)));
+            if (i == left - 1) { best = v; at = i; }
+            else if (v > best) { best = v; at = i; }
+        }
+    }
+    *contrast = (float)best;
+    return at + 1;
+}
+
+__device__ __forceinline__ void sample_positive(const DevParams &P, const float *__restrict__ col,
+                                                size_t spitch, int scan_len, int ps, int firstrow,
+                                                uint32_t *__restrict__ pos)
+{
+    const int take = -ps + min(scan_len, P.boundary_pos - P.sampling_gap);
+    for (int i = 0; i < take; i++) {
+        const float sc = col[(size_t)i * spitch];
+        if (!isnan(sc) && !isinf(sc))
+            atomicAdd(&pos[(size_t)(firstrow + i) * P.bins + score_bin(sc, P.bins)], 1u);
+    }
+}
+
+struct ScoreArgs {
+    TileView tv;
+    const DevSample *samples;
+    const float *tscore;
+    tsk_call *calls;
+    const uint8_t *kind;
+    const uint32_t *bucket;
+    const uint32_t *worklist;
+    const uint32_t *totals;
+    const uint64_t *recbase;
+    uint32_t *records;
+    float *scratch;
+    size_t spitch;
+    uint32_t *pos, *neg;
+    const uint32_t *fair;
+    uint32_t *lists;
+    uint32_t listcap;
+};
+
+/* Everything the reference does for one cluster inside process_polya_signal() after the
+ * sequence seed, for work item w. */
+__device__ void process_item_generic(const DevParams &P, const ScoreShared &sh, const ScoreArgs &A,
+                                     uint32_t w)
+{
+    const TileView &tv = A.tv;
+    const uint32_t n = A.worklist[w];
+    const uint4 craw = *reinterpret_cast<const uint4 *>(&A.calls[n]);
+    tsk_call call = *reinterpret_cast<const tsk_call *>(&craw);
+    const uint32_t kd = A.kind[n];
+    const int ts = P.threep_start, tl = P.threep_length, bins = P.bins;
+    const int de = call.delimiter_end, ps = call.terminal_mods;
+    const int sample = call.sample;
+    const size_t pitch = tv.cif_pitch, spitch = A.spitch;
+    const int16_t *cifcol = tv.cif + n;
+
+    int blen = de - ts;
+    if (blen > P.balancer_length) blen = P.balancer_length;
+    float low[4], bw[4];
+    probe_ranges(P, cifcol, pitch, blen, low, bw);
+
+    int insert_len = ts + tl - de;
+    const int limit = sh.limit[sample], dump = sh.dump[sample];
+    if (limit > 0 && limit < insert_len) insert_len = limit;
+    const int scan_len = insert_len - ps;
+    const int valid = min(scan_len, dump);
+
+    uint32_t *rec = nullptr;
+    if (kd & KIND_EMIT) {
+        rec = A.records + A.recbase[sample] + (size_t)call.record_slot * (size_t)(2 + dump);
+        rec[0] = tv.firstclusterno + n;
+        rec[1] = (uint32_t)(uint16_t)(int16_t)(de + ps) | ((uint32_t)(uint16_t)(int16_t)valid << 16);
+    }
+    bool neg_inline = false;
+    if (kd & KIND_NEG)
+        neg_inline = (P.fair_max_count == 0) || (A.fair[A.bucket[n]] <= (uint32_t)P.fair_max_count);
+
+    int ndark = 0;
+    float prev_entropy = CUDART_NAN_F;
+    unsigned long long dhwin = 0;          /* bit k = downhill of cycle (c - k) */
+    const int16_t *p = cifcol + (size_t)(de - ts) * 4 * pitch;
+    const uint32_t rowbase = (uint32_t)de;  /* histogram row of score index c is de + c */
+
+    for (int c = 0; c < insert_len; c++, p += 4 * pitch) {
+        float es, score;
+        const bool lit = score_cycle_generic(P, sh, p, pitch, low, bw, es, score);
+        uint32_t dh = 0;
+        if (lit) {
+            dh = (es < prev_entropy) ? 1u : 0u;
+            prev_entropy = es;
+        } else {
+            ndark++;
+            score = CUDART_NAN_F;
+            prev_entropy = CUDART_NAN_F;
+        }
+        dhwin = (dhwin << 1) | dh;
+        const int j = c - ps;
+        if (j >= 0) {
+            if (rec != nullptr && j < valid) {
+                uint32_t word = 0;
+                if (lit) {
+                    uint32_t s = 1u + (uint32_t)__float2int_rz(__fmul_rn(score, (float)(TSK_SCORE_MAX - 1)));
+                    if (s >= TSK_SCORE_MAX) s = TSK_SCORE_MAX;
+                    /* the reference passes the UN-offset downhill array: packet j carries
+                     * downhill[j], not downhill[ps + j] (spotanalyzer.c:604-606) */
+                    word = (s << 1) | (uint32_t)((dhwin >> ps) & 1ull);
+                }
+                rec[2 + j] = word;
+            }
+            if (kd & KIND_POS) A.scratch[(size_t)j * spitch + w] = score;
+            if (neg_inline && lit && !isinf(score))
+                atomicAdd(&A.neg[(size_t)(rowbase + c) * bins + score_bin(score, bins)], 1u);
+        }
+    }
+    if (rec != nullptr)
+        for (int j = max(valid, 0); j < dump; j++) rec[2 + j] = 0;
+
+    bool aborted = false;
+    if (ndark > 0) {
+        call.flags |= TSK_PAFLAG_DARKCYCLE_EXISTS;
+        if (ndark >= P.max_dark_cycles) {
+            call.flags |= TSK_PAFLAG_DARKCYCLE_OVER_THRESHOLD;
+            call.polya_len = -1;
+            call.emitted = 0;
+            aborted = true;
+            if (rec != nullptr) rec[1] |= 0xffff0000u;     /* withdraw the slot: valid = -1 */
+        }
+        *reinterpret_cast<uint4 *>(&A.calls[n]) = *reinterpret_cast<const uint4 *>(&call);
+    }
+
+    if (kd & KIND_NEG) {
+        if (aborted && neg_inline)
+            list_array(A.lists, 0, A.listcap)[atomicAdd(&A.lists[0], 1u)] = n;
+        else if (!aborted && !neg_inline)
+            list_array(A.lists, 1, A.listcap)[atomicAdd(&A.lists[1], 1u)] = n;
+    }
+
+    if ((kd & KIND_POS) && !aborted && scan_len > 0 && P.cctr_left + P.cctr_right < scan_len) {
+        const float *col = A.scratch + w;
+        double total = 0.;
+        for (int i = 0; i < scan_len; i++) total = __dadd_rn(total, (double)col[(size_t)i * spitch]);
+        float contrast;
+        const int at = contrast_exact(col, spitch, scan_len, P.cctr_left, P.cctr_right, total, &contrast);
+        if (at >= P.boundary_pos && contrast >= P.required_contrast)
+            sample_positive(P, col, spitch, scan_len, ps, (int)rowbase + ps, A.pos);
+    }
+}
+
+__global__ void __launch_bounds__(TSK_K2_THREADS)
+k_normalise_score_pack_generic(const __grid_constant__ DevParams P, const ScoreArgs A, int all_items)
+{
+    __shared__ ScoreShared sh;
+    load_score_shared(sh, A.tscore, A.samples, P.num_samples);
+    /* all_items: every work item (used by tests to pin the fast path against this one);
+     * otherwise only the items the fast path handed over (list 3). */
+    const uint32_t cnt = all_items ? A.totals[P.num_samples] : A.lists[3];
+    const uint32_t *slow = list_array(A.lists, 3, A.listcap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x)
+        process_item_generic(P, sh, A, all_items ? i : slow[i]);
+}
+
+/* ======================================================================================
+ * fast path
+ * ==================================================================================== */
+/* a / b given y = RN(1/b): two residual corrections (Markstein).  After the first, q is a
+ * faithful quotient; the second then yields RN(a/b) exactly [Markstein 1990; Cornea, Harrison,
+ * Tang 2002, thm. on q' = RN(q + r*y) with r = a - b*q exact].  Preconditions (checked by the
+ * caller): b, y normal and finite, |a/b| far from the overflow/underflow thresholds.
+ * tests/test_gpu_parity.py::test_division_exact compares against __fdiv_rn on 2^31 pairs. */
+__device__ __forceinline__ float div_by_rcp(float a, float b, float y)
+{
+    float q = __fmul_rn(a, y);
+    float r = __fmaf_rn(-b, q, a);
+    q = __fmaf_rn(r, y, q);
+    r = __fmaf_rn(-b, q, a);
+    return __fmaf_rn(r, y, q);
+}
+
+/* host-libm logf in fp64 FMAs for x in (0, 1] given as raw bits (subnormals clamped to the
+ * smallest normal: their terms are < 2^-119 and cannot reach the float sum they feed). */
+__device__ __forceinline__ float logf_core(uint32_t ix, const double2 *__restrict__ tab)
+{
+    const uint32_t tmp = ix - 0x3f330000u;
+    const int i = (tmp >> 19) & 15;
+    const int k = (int32_t)tmp >> 23;
+    const uint32_t iz = ix - (tmp & 0xff800000u);
+    const double2 t = tab[i];
+    const double z = (double)__uint_as_float(iz);
+    /* (double)k without the conversion unit: 2^52 + 2^31 + k, minus the bias */
+    const double kd = __dsub_rn(__hiloint2double(0x43300000, (int)(0x80000000u ^ (uint32_t)k)),
+                                4503601774854144.0);
+    const double r = __fma_rn(z, t.x, -1.0);
+    const double y0 = __fma_rn(kd, 0x1.62e42fefa39efp-1, t.y);
+    const double r2 = __dmul_rn(r, r);
+    double y = __fma_rn(0x1.5575b0be00b6ap-2, r, -0x1.ffffef20a4123p-2);
+    y = __fma_rn(-0x1.00ea348b88334p-2, r2, y);
+    y = __fma_rn(y, r2, __dadd_rn(y0, r));
+    return (float)y;
+}
+
+/* top-npos / bottom-nneg probing with compile-time ranks (the stock configuration 2 / 4) */
+template <int NPOS, int NNEG>
+__device__ __forceinline__ void probe_ranges_fixed(const DevParams &P, const int16_t *__restrict__ cifcol,
+                                                   size_t pitch, int blen, float low[4], float bw[4])
+{
+    float top[4][NPOS], bot[4][NNEG];
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) {
+#pragma unroll
+        for (int r = 0; r < NPOS; r++) top[ch][r] = -CUDART_INF_F;
+#pragma unroll
+        for (int r = 0; r < NNEG; r++) bot[ch][r] = CUDART_INF_F;
+    }
+    const int16_t *p = cifcol + (size_t)P.balancer_start * 4 * pitch;
+    for (int c = 0; c < blen; c++, p += 4 * pitch) {
+        float sig[4];
+        decrosstalk(sig, p, pitch, P.inv);
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++) {
+            float carry = sig[ch];
+#pragma unroll
+            for (int r = 0; r < NPOS; r++) {
+                const bool sw = carry > top[ch][r];
+                const float t = top[ch][r];
+                top[ch][r] = sw ? carry : t;
+                carry = sw ? t : carry;
+            }
+            carry = sig[ch];
+#pragma unroll
+            for (int r = 0; r < NNEG; r++) {
+                const bool sw = carry < bot[ch][r];
+                const float t = bot[ch][r];
+                bot[ch][r] = sw ? carry : t;
+                carry = sw ? t : carry;
+            }
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) {
+        float acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < NNEG; r++) acc = __fadd_rn(acc, bot[ch][r]);
+        low[ch] = __fdiv_rn(acc, (float)NNEG);
+        acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < NPOS; r++) acc = __fadd_rn(acc, top[ch][r]);
+        bw[ch] = __fsub_rn(__fdiv_rn(acc, (float)NPOS), low[ch]);
+    }
+}
+
+__device__ __forceinline__ bool in_exp_range(float v, int lo_exp, int hi_exp)
+{   /* finite, positive, 2^lo_exp <= v < 2^hi_exp */
+    const int e = (int)(__float_as_uint(v) >> 23);       /* sign bit set -> e >= 256 */
+    return e >= 127 + lo_exp && e < 127 + hi_exp;
+}
+
+__global__ void __launch_bounds__(TSK_K2_THREADS, 4)
+k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, const float rcp_maxent)
+{
+    __shared__ ScoreShared sh;
+    __shared__ uint32_t s_tile[TSK_K2_THREADS / 32][32][33];   /* packed words, [lane][cycle & 31] */
+    const int S = P.num_samples;
+    load_score_shared(sh, A.tscore, A.samples, S);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t w = blockIdx.x * TSK_K2_THREADS + threadIdx.x;
+    const uint32_t nwork = A.totals[S];
+    if ((w & ~31u) >= nwork) return;                 /* whole warp past the end */
+    bool alive = w < nwork;
+
+    const TileView &tv = A.tv;
+    const int ts = P.threep_start, tl = P.threep_length, bins = P.bins;
+    const size_t pitch = tv.cif_pitch, spitch = A.spitch;
+
+    uint32_t n = 0, kd = 0;
+    tsk_call call;
+    int de = ts, ps = 0, sample = 0;
+    if (alive) {
+        n = A.worklist[w];
+        const uint4 craw = *reinterpret_cast<const uint4 *>(&A.calls[n]);
+        call = *reinterpret_cast<const tsk_call *>(&craw);
+        kd = A.kind[n];
+        de = call.delimiter_end; ps = call.terminal_mods; sample = call.sample;
+    }
+    const int16_t *cifcol = tv.cif + n;
+
+    /* ---- balancer: per-cluster dynamic range ---- */
+    float low[4] = {0.f, 0.f, 0.f, 0.f}, bw[4] = {1.f, 1.f, 1.f, 1.f}, ybw[4];
+    if (alive) {
+        int blen = de - ts;
+        if (blen > P.balancer_length) blen = P.balancer_length;
+        if (P.npos == 2 && P.nneg == 4) probe_ranges_fixed<2, 4>(P, cifcol, pitch, blen, low, bw);
+        else probe_ranges(P, cifcol, pitch, blen, low, bw);
+        /* fast-path preconditions; otherwise the generic kernel takes this cluster */
+        bool ok = true;
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++)
+            ok = ok && in_exp_range(bw[ch], -40, 40) && (fabsf(low[ch]) < 0x1p40f);
+        if (!ok) {
+            list_array(A.lists, 3, A.listcap)[atomicAdd(&A.lists[3], 1u)] = w;
+            alive = false;
+            kd = 0;
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) ybw[ch] = __frcp_rn(bw[ch]);
+
+    int insert_len = 0, dump = 0;
+    if (alive) {
+        insert_len = ts + tl - de;
+        const int limit = sh.limit[sample];
+        dump = sh.dump[sample];
+        if (limit > 0 && limit < insert_len) insert_len = limit;
+    }
+    const int scan_len = insert_len - ps;
+    const int valid = min(scan_len, dump);
+    const bool emit = (kd & KIND_EMIT) != 0;
+    const bool ispos = (kd & KIND_POS) != 0;
+
+    uint32_t *rec = nullptr;
+    if (emit) {
+        rec = A.records + A.recbase[sample] + (size_t)call.record_slot * (size_t)(2 + dump);
+        rec[0] = tv.firstclusterno + n;
+        rec[1] = (uint32_t)(uint16_t)(int16_t)(de + ps) | ((uint32_t)(uint16_t)(int16_t)valid << 16);
+    }
+    bool neg_inline = false;
+    if (kd & KIND_NEG)
+        neg_inline = (P.fair_max_count == 0) || (A.fair[A.bucket[n]] <= (uint32_t)P.fair_max_count);
+
+    /* the warp walks to the last cycle any of its lanes needs; an emitting lane needs
+     * record positions up to dump-1, i.e. cycle indices up to dump-1+ps (zero padding) */
+    int cend = emit ? max(insert_len, dump + ps) : insert_len;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cend = max(cend, __shfl_xor_sync(FULL_MASK, cend, d));
+    const unsigned emitmask = __ballot_sync(FULL_MASK, emit);
+    /* lane r's record parameters, fetched by shuffle during the flush */
+    const unsigned long long recaddr = (unsigned long long)(uintptr_t)rec;
+    const int recinfo = (ps & 0xffff) | (max(dump, 0) << 16);
+
+    int ndark = 0;
+    float prev_entropy = CUDART_NAN_F;
+    unsigned long long dhwin = 0;
+    const int16_t *p = cifcol + (size_t)(de - ts) * 4 * pitch;
+    const uint32_t rowbase = (uint32_t)de;
+    float *scr = A.scratch + w - (size_t)ps * spitch;       /* scr[c * spitch] = score of cycle c */
+    uint32_t (*tile)[33] = s_tile[warp];
+
+    for (int c = 0; c < cend; c++, p += 4 * pitch) {
+        uint32_t word = 0;
+        if (c < insert_len) {
+            /* ---- decrosstalk (signalproc.c:85-103) ---- */
+            const int i0 = __ldg(p), i1 = __ldg(p + pitch), i2 = __ldg(p + 2 * pitch), i3 = __ldg(p + 3 * pitch);
+            /* exact int16 -> float without the conversion unit: 2^23+2^22 + i, minus the bias */
+            const float v0 = __fsub_rn(__int_as_float(0x4B400000 + i0), 12582912.f);
+            const float v1 = __fsub_rn(__int_as_float(0x4B400000 + i1), 12582912.f);
+            const float v2 = __fsub_rn(__int_as_float(0x4B400000 + i2), 12582912.f);
+            const float v3 = __fsub_rn(__int_as_float(0x4B400000 + i3), 12582912.f);
+            float sig[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float a = __fmul_rn(P.inv[4 * j + 0], v0);
+                a = __fadd_rn(a, __fmul_rn(P.inv[4 * j + 1], v1));
+                a = __fadd_rn(a, __fmul_rn(P.inv[4 * j + 2], v2));
+                sig[j] = __fadd_rn(a, __fmul_rn(P.inv[4 * j + 3], v3));
+            }
+            /* ---- dark test: sum of the positive channels (x + 0 == x, so max(.,0) is exact) ---- */
+            float tot = fmaxf(sig[0], 0.f);
+            tot = __fadd_rn(tot, fmaxf(sig[1], 0.f));
+            tot = __fadd_rn(tot, fmaxf(sig[2], 0.f));
+            tot = __fadd_rn(tot, fmaxf(sig[3], 0.f));
+            bool lit = !(tot < P.dark_threshold);
+            /* ---- normalise into the cluster's dynamic range (signalproc.c:246-266) ---- */
+            float nrm[4];
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++)
+                nrm[ch] = fmaxf(div_by_rcp(__fsub_rn(sig[ch], low[ch]), bw[ch], ybw[ch]), 0.f);
+            float sum = __fadd_rn(__fadd_rn(__fadd_rn(nrm[0], nrm[1]), nrm[2]), nrm[3]);
+            float prob[4];
+            if (__builtin_expect(in_exp_range(sum, -60, 60), 1)) {
+                const float ys = __frcp_rn(sum);
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) prob[ch] = div_by_rcp(nrm[ch], sum, ys);
+            } else {
+                /* sum == 0 (0/0 -> NaN -> dark) or a pathological magnitude: IEEE division */
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) prob[ch] = __fdiv_rn(nrm[ch], sum);
+            }
+            lit = lit && (prob[0] == prob[0]);
+            /* ---- Shannon entropy: h -= p*logf(p) for p > 0; p <= 0 contributes p*logf(1) = +-0 ---- */
+            float h = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++) {
+                const int pbits = __float_as_int(prob[ch]);
+                const uint32_t ix = (pbits <= 0) ? 0x3f800000u : (uint32_t)max(pbits, 0x00800000);
+                h = __fsub_rn(h, __fmul_rn(prob[ch], logf_core(ix, sh.logtab)));
+            }
+            const float es = __fsub_rn(1.f, div_by_rcp(h, P.maximum_entropy, rcp_maxent));
+            int ti = __float2int_rz(__fmul_rn(prob[3], (float)TSK_T_SCORE_BINS));
+            ti = max(0, min(TSK_T_SCORE_BINS, ti));
+            const float score = lit ? __fmul_rn(es, sh.tscore[ti]) : CUDART_NAN_F;
+            const uint32_t dh = (lit && es < prev_entropy) ? 1u : 0u;
+            prev_entropy = lit ? es : CUDART_NAN_F;
+            ndark += lit ? 0 : 1;
+            dhwin = (dhwin << 1) | dh;
+
+            if (c >= ps) {
+                if (lit) {
+                    uint32_t s = 1u + (uint32_t)__float2int_rz(__fmul_rn(score, (float)(TSK_SCORE_MAX - 1)));
+                    s = min(s, TSK_SCORE_MAX);
+                    word = (s << 1) | (uint32_t)((dhwin >> ps) & 1ull);
+                }
+                if (ispos) scr[(size_t)c * spitch] = score;
+                if (neg_inline && lit && !isinf(score))
+                    atomicAdd(&A.neg[(size_t)(rowbase + c) * bins + score_bin(score, bins)], 1u);
+            }
+        }
+        /* ---- stage the packed word; every 32 cycles write the emitting lanes' records with
+         *      full lines: lane l carries cycle cbase + l of record r ---- */
+        tile[lane][c & 31] = word;
+        if ((c & 31) == 31 || c == cend - 1) {
+            __syncwarp();
+            const int cbase = c & ~31;
+            unsigned m = emitmask;
+            while (m) {
+                const int r = __ffs(m) - 1;
+                m &= m - 1;
+                const unsigned long long ra = __shfl_sync(FULL_MASK, recaddr, r);
+                const int ri = __shfl_sync(FULL_MASK, recinfo, r);
+                const int j = cbase + lane - (ri & 0xffff);
+                if (j >= 0 && j < (ri >> 16) && cbase + lane <= c)
+                    reinterpret_cast<uint32_t *>((uintptr_t)ra)[2 + j] = tile[r][lane];
+            }
+            __syncwarp();
+        }
+    }
+
+    if (!alive) return;
+    bool aborted = false;
+    if (ndark > 0) {
+        call.flags |= TSK_PAFLAG_DARKCYCLE_EXISTS;
+        if (ndark >= P.max_dark_cycles) {
+            call.flags |= TSK_PAFLAG_DARKCYCLE_OVER_THRESHOLD;
+            call.polya_len = -1;
+            call.emitted = 0;
+            aborted = true;
+            if (rec != nullptr) rec[1] |= 0xffff0000u;     /* withdraw the slot: valid = -1 */
+        }
+        *reinterpret_cast<uint4 *>(&A.calls[n]) = *reinterpret_cast<const uint4 *>(&call);
+    }
+    if (kd & KIND_NEG) {
+        if (aborted && neg_inline)
+            list_array(A.lists, 0, A.listcap)[atomicAdd(&A.lists[0], 1u)] = n;
+        else if (!aborted && !neg_inline)
+            list_array(A.lists, 1, A.listcap)[atomicAdd(&A.lists[1], 1u)] = n;
+    }
+
+    /* ---- contrast test (find_max_cumulative_contrast) and positive sampling ----
+     * f(i) = cum_i/i - (total-cum_i)/(len-i).  The divisions are replaced by table reciprocals
+     * to locate the maximum (error < 1.2e-15 per value, all terms <= 1 in magnitude); the
+     * exact IEEE value is evaluated only there.  If a second candidate lies within 1e-14 the
+     * exact scan decides, so ties resolve exactly like the reference's strict '>' scan. */
+    if (ispos && !aborted && scan_len > 0 && P.cctr_left + P.cctr_right < scan_len) {
+        const float *col = A.scratch + w;
+        const int left = P.cctr_left, last = scan_len - P.cctr_right;
+        double total = 0.;
+        for (int i = 0; i < scan_len; i++) total = __dadd_rn(total, (double)col[(size_t)i * spitch]);
+        if (total == total) {        /* a NaN anywhere makes the first candidate NaN: no sampling */
+            double cum = 0., m1 = -CUDART_INF, m2 = -CUDART_INF, cum1 = 0.;
+            int at = left - 1;
+            for (int i = 0; i <= last; i++) {
+                cum = __dadd_rn(cum, (double)col[(size_t)i * spitch]);
+                if (i >= left - 1) {
+                    const double v = __dsub_rn(__dmul_rn(cum, sh.rcp[i]),
+                                               __dmul_rn(__dsub_rn(total, cum), sh.rcp[scan_len - i]));
+                    if (v > m1) { m2 = m1; m1 = v; at = i; cum1 = cum; }
+                    else if (v > m2) m2 = v;
+                }
+            }
+            float contrast;
+            int atpos;
+            if (m1 - m2 > 1e-14 && at > 0) {
+                const double v = __dsub_rn(__ddiv_rn(cum1, (double)at),
+                                           __ddiv_rn(__dsub_rn(total, cum1), (double)(scan_len - at)));
+                contrast = (float)v;
+                atpos = at + 1;
+            } else {
+                atpos = contrast_exact(col, spitch, scan_len, left, P.cctr_right, total, &contrast);
+            }
+            if (atpos >= P.boundary_pos && contrast >= P.required_contrast)
+                sample_positive(P, col, spitch, scan_len, ps, (int)rowbase + ps, A.pos);
+        }
+    }
+}
+
+/* ======================================================================================
+ * fair-sampling fix-ups
+ * ==================================================================================== */
+/* Fair sampling among the clusters of over-subscribed buckets: the reference accepts, per
+ * bucket, the first fair_max_count eligible clusters in cluster order (spotanalyzer.c:476-484
+ * with threads=1).  One CTA; per round every still-waiting entry bids its cluster number
+ * with atomicMin, the winner of each bucket is accepted.  `fair` is reused as the bid table. */
+__global__ void __launch_bounds__(1024)
+k_fair_resolve(uint32_t *__restrict__ fair, const uint32_t *__restrict__ bucket,
+               uint32_t *__restrict__ lists, uint32_t listcap, int max_count)
+{
+    const uint32_t cnt = lists[1];
+    uint32_t *cont = list_array(lists, 1, listcap);
+    uint32_t *acc = list_array(lists, 2, listcap);
+    if (cnt == 0) return;
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) fair[bucket[cont[i] & 0x7fffffffu]] = 0xffffffffu;
+    __syncthreads();
+    for (int round = 0; round < max_count; round++) {
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const uint32_t e = cont[i];
+            if (!(e & 0x80000000u)) atomicMin(&fair[bucket[e]], e);
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const uint32_t e = cont[i];
+            if (!(e & 0x80000000u) && fair[bucket[e]] == e) {
+                acc[atomicAdd(&lists[2], 1u)] = e;
+                cont[i] = e | 0x80000000u;
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
+            fair[bucket[cont[i] & 0x7fffffffu]] = 0xffffffffu;
+        __syncthreads();
+    }
+}
+
+/* Recompute the scores of the listed clusters and add `delta` (+1 / -1, as u32) to the
+ * negative histogram: accepted clusters of over-subscribed buckets (+1), and inline-sampled
+ * clusters that later aborted on dark cycles (-1). */
+__global__ void __launch_bounds__(TSK_K2_THREADS)
+k_resample_neg(const __grid_constant__ DevParams P, const TileView tv,
+               const DevSample *__restrict__ samples, const float *__restrict__ g_tscore,
+               const tsk_call *__restrict__ calls, uint32_t *__restrict__ neg,
+               const uint32_t *__restrict__ lists, uint32_t listcap, int which, uint32_t delta)
+{
+    __shared__ ScoreShared sh;
+    load_score_shared(sh, g_tscore, samples, P.num_samples);
+    const uint32_t cnt = lists[which];
+    const uint32_t *arr = list_array(const_cast<uint32_t *>(lists), which, listcap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        const uint32_t n = arr[i] & 0x7fffffffu;
+        const tsk_call call = calls[n];
+        const int ts = P.threep_start, tl = P.threep_length, bins = P.bins;
+        const int de = call.delimiter_end, ps = call.terminal_mods;
+        const size_t pitch = tv.cif_pitch;
+        const int16_t *cifcol = tv.cif + n;
+        int blen = de - ts;
+        if (blen > P.balancer_length) blen = P.balancer_length;
+        float low[4], bw[4];
+        probe_ranges(P, cifcol, pitch, blen, low, bw);
+        int insert_len = ts + tl - de;
+        const int limit = sh.limit[call.sample];
+        if (limit > 0 && limit < insert_len) insert_len = limit;
+        const int16_t *p = cifcol + (size_t)(de - ts) * 4 * pitch;
+        for (int c = 0; c < insert_len; c++, p += 4 * pitch) {
+            float es, score;
+            if (score_cycle_generic(P, sh, p, pitch, low, bw, es, score) && c >= ps && !isinf(score))
+                atomicAdd(&neg[(size_t)(de + c) * bins + score_bin(score, bins)], delta);
+        }
+    }
+}
+
+/* ======================================================================================
+ * self-test hooks
+ * ==================================================================================== */
+__global__ void k_logf_probe(const float *__restrict__ in, float *__restrict__ out, size_t n, int variant)
+{
+    __shared__ double2 tab[16];
+    if (threadIdx.x < 16) tab[threadIdx.x] = make_double2(c_logf_tab[threadIdx.x][0], c_logf_tab[threadIdx.x][1]);
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float x = in[i];
+        if (variant == 0) out[i] = tsk_logf(x, tab);
+        else {
+            const int pbits = __float_as_int(x);
+            out[i] = logf_core((pbits <= 0) ? 0x3f800000u : (uint32_t)max(pbits, 0x00800000), tab);
+        }
+    }
+}
+
+/* all floats with bit patterns [first, first+count): counts where the FMA core differs from
+ * the separately-rounded restatement (must be 0 on normal inputs in (0,1]) */
+__global__ void k_logf_sweep(uint32_t first, uint64_t count, unsigned long long *mismatches)
+{
+    __shared__ double2 tab[16];
+    if (threadIdx.x < 16) tab[threadIdx.x] = make_double2(c_logf_tab[threadIdx.x][0], c_logf_tab[threadIdx.x][1]);
+    __syncthreads();
+    unsigned long long bad = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t ix = first + (uint32_t)i;
+        const float a = tsk_logf(__uint_as_float(ix), tab);
+        const float b = logf_core(ix, tab);
+        bad += __float_as_uint(a) != __float_as_uint(b);
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+/* pseudo-random (a, b) pairs: div_by_rcp(a, b, RN(1/b)) against __fdiv_rn(a, b) */
+__global__ void k_div_sweep(uint64_t seed, uint64_t count, int mode, unsigned long long *mismatches)
+{
+    unsigned long long bad = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t x = (i + seed) * 0x9E3779B97F4A7C15ull;
+        x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32;
+        uint32_t ab = (uint32_t)x, bb = (uint32_t)(x >> 32);
+        float a, b;
+        if (mode == 0) {            /* b in [2^-40, 2^40), a = +-[2^-60, 2^60) : arbitrary mantissas */
+            b = __uint_as_float(((127 - 40 + (bb >> 23) % 80) << 23) | (bb & 0x7fffffu));
+            a = __uint_as_float((ab & 0x80000000u) | ((127 - 60 + ((ab >> 23) & 0xff) % 120) << 23) | (ab & 0x7fffffu));
+        } else {                    /* probabilities: 0 <= a <= b, b in [2^-3, 2^3) */
+            b = __uint_as_float(((124 + (bb >> 23) % 6) << 23) | (bb & 0x7fffffu));
+            a = __fmul_rn(b, __uint_as_float(0x3f800000u | (ab & 0x7fffffu)) - 1.0f);
+        }
+        const float q = div_by_rcp(a, b, __frcp_rn(b));
+        const float want = __fdiv_rn(a, b);
+        bad += __float_as_uint(q) != __float_as_uint(want) && !(q == 0.f && want == 0.f);
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+extern "C" int tsk_selftest_logf(tsk_ctx *ctx, const float *in, float *out, size_t n)
+{
+    if (!ctx || !in || !out) { tsk_set_error("null argument"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    float *d_in = NULL, *d_out = NULL;
+    TSK_CUDA(cudaMalloc(&d_in, sizeof(float) * n));
+    TSK_CUDA(cudaMalloc(&d_out, sizeof(float) * n));
+    TSK_CUDA(cudaMemcpyAsync(d_in, in, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+    k_logf_probe<<<148 * 8, 256, 0, ctx->stream>>>(d_in, d_out, n, 0);
+    ctx->launches++;
+    TSK_CUDA(cudaMemcpyAsync(out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    TSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_in); cudaFree(d_out);
+    return 0;
+}
+
+extern "C" int tsk_selftest_sweeps(tsk_ctx *ctx, uint64_t div_pairs, uint64_t *logf_mismatches,
+                                   uint64_t *div_mismatches)
+{
+    if (!ctx || !logf_mismatches || !div_mismatches) { tsk_set_error("null argument"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    unsigned long long *d = NULL, h[2] = {0, 0};
+    TSK_CUDA(cudaMalloc(&d, sizeof(h)));
+    TSK_CUDA(cudaMemsetAsync(d, 0, sizeof(h), ctx->stream));
+    /* every normal float in (0, 1] */
+    k_logf_sweep<<<148 * 16, 256, 0, ctx->stream>>>(0x00800000u, (uint64_t)(0x3f800000u - 0x00800000u) + 1, d);
+    k_div_sweep<<<148 * 16, 256, 0, ctx->stream>>>(12345, div_pairs / 2, 0, d + 1);
+    k_div_sweep<<<148 * 16, 256, 0, ctx->stream>>>(98765, div_pairs / 2, 1, d + 1);
+    ctx->launches += 3;
+    TSK_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    TSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    *logf_mismatches = h[0];
+    *div_mismatches = h[1];
+    return 0;
+}
+
+/* ======================================================================================
+ * launchers
+ * ==================================================================================== */
+static ScoreArgs make_args(tsk_ctx *ctx)
+{
+    ScoreArgs a;
+    a.tv = ctx->tile; a.samples = ctx->d_samples; a.tscore = ctx->d_tscore; a.calls = ctx->d_calls;
+    a.kind = ctx->d_kind; a.bucket = ctx->d_bucket; a.worklist = ctx->d_worklist; a.totals = ctx->d_totals;
+    a.recbase = ctx->d_recbase; a.records = ctx->d_records; a.scratch = ctx->d_scratch;
+    a.spitch = (size_t)ctx->cap_clusters; a.pos = ctx->d_pos; a.neg = ctx->d_neg; a.fair = ctx->d_fair;
+    a.lists = ctx->d_lists; a.listcap = ctx->cap_clusters;
+    return a;
+}
+
+int tsk_launch_score(tsk_ctx *ctx)
+{
+    const uint32_t N = ctx->tile.nclusters;
+    if (N == 0) return 0;
+    const ScoreArgs a = make_args(ctx);
+    const unsigned grid = (N + TSK_K2_THREADS - 1) / TSK_K2_THREADS;
+    if (ctx->force_generic) {
+        k_normalise_score_pack_generic<<<grid, TSK_K2_THREADS, 0, ctx->stream>>>(ctx->dp, a, 1);
+        ctx->launches += 1;
+    } else {
+        const float rcp_maxent = 1.0f / ctx->dp.maximum_entropy;      /* IEEE RN on the host */
+        k_normalise_score_pack<<<grid, TSK_K2_THREADS, 0, ctx->stream>>>(ctx->dp, a, rcp_maxent);
+        k_normalise_score_pack_generic<<<8, TSK_K2_THREADS, 0, ctx->stream>>>(ctx->dp, a, 0);
+        ctx->launches += 2;
+    }
+    TSK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tsk_launch_fixups(tsk_ctx *ctx)
+{
+    const uint32_t N = ctx->tile.nclusters;
+    if (N == 0) return 0;
+    const DevParams &P = ctx->dp;
+    const uint32_t listcap = ctx->cap_clusters;
+    cudaStream_t st = ctx->stream;
+    k_fair_resolve<<<1, 1024, 0, st>>>(ctx->d_fair, ctx->d_bucket, ctx->d_lists, listcap, P.fair_max_count);
+    k_resample_neg<<<148, TSK_K2_THREADS, 0, st>>>(P, ctx->tile, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
+                                                  ctx->d_neg, ctx->d_lists, listcap, 2, 1u);
+    k_resample_neg<<<148, TSK_K2_THREADS, 0, st>>>(P, ctx->tile, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
+                                                  ctx->d_neg, ctx->d_lists, listcap, 0, 0xffffffffu);
+    ctx->launches += 3;
+    TSK_CUDA(cudaGetLastError());
+    return 0;
+}

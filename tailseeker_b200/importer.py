@@ -101,7 +101,7 @@ class TileProcessor:
         _lib.check(self.lib.tsk_tile_process(self._ctx))
 
     def process_timed(self, iters: int = 1) -> np.ndarray:
-        ms = np.zeros(4, dtype=np.float32)
+        ms = np.zeros(5, dtype=np.float32)
         _lib.check(self.lib.tsk_tile_process_timed(self._ctx, iters, _ptr(ms)))
         return ms
 
@@ -149,6 +149,19 @@ class TileProcessor:
     def synchronize(self):
         _lib.check(self.lib.tsk_synchronize(self._ctx))
 
+    def set_stream(self, cuda_stream: int):
+        """Run on the caller's stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        _lib.check(self.lib.tsk_set_stream(self._ctx, ctypes.c_void_p(cuda_stream)))
+
+    def profile(self, on: bool = True):
+        _lib.check(self.lib.tsk_profile_enable(self._ctx, int(on)))
+
+    def profile_get(self):
+        ms = np.zeros(6, dtype=np.float64)
+        runs = np.zeros(6, dtype=np.uint64)
+        _lib.check(self.lib.tsk_profile_get(self._ctx, _ptr(ms), _ptr(runs)))
+        return ms, runs
+
     def launch_count(self) -> int:
         return int(self.lib.tsk_launch_count(self._ctx))
 
@@ -189,6 +202,16 @@ class TileProcessor:
         out = np.empty_like(x)
         _lib.check(self.lib.tsk_selftest_logf(self._ctx, _ptr(x), _ptr(out), x.size))
         return out
+
+    def selftest_sweeps(self, div_pairs: int = 1 << 31):
+        a = ctypes.c_uint64()
+        b = ctypes.c_uint64()
+        _lib.check(self.lib.tsk_selftest_sweeps(self._ctx, ctypes.c_uint64(div_pairs),
+                                                ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def force_generic(self, on: bool = True):
+        _lib.check(self.lib.tsk_debug_force_generic(self._ctx, int(on)))
 
     # ------------------------------------------------------------------ estimator
     def fit_cutoffs(self, pos: np.ndarray, neg: np.ndarray) -> np.ndarray:

@@ -54,6 +54,48 @@ def test_logf_exact(proc, oracle):
     assert (got[sel].view(np.uint32) == want[sel].view(np.uint32)).all()
 
 
+def test_fast_arithmetic_sweeps(proc):
+    """(1) FMA logf == separately-rounded logf on every normal float in (0,1];
+    (2) reciprocal-multiply + 2 residual corrections == IEEE division on 2^31 operand pairs."""
+    logf_bad, div_bad = proc.selftest_sweeps(1 << 31)
+    assert logf_bad == 0
+    assert div_bad == 0
+
+
+def test_generic_kernel_matches_oracle(stock_cfg, oracle):
+    """The literal operation-by-operation scoring kernel (the fast kernel's fallback)."""
+    from tailseeker_b200.importer import TileProcessor
+    p = TileProcessor(stock_cfg)
+    try:
+        p.force_generic(True)
+        _, o = _run(p, stock_cfg, oracle, 9000, 21, dark_cluster_frac=0.03, lowdiv_frac=0.05)
+        compare_tile(p, stock_cfg, None, o)
+    finally:
+        p.close()
+
+
+def test_degenerate_bandwidth_handover(stock_cfg, oracle):
+    """Clusters whose balancer cycles are constant (zero signal bandwidth -> division by zero,
+    NaN/inf normalised signals) leave the fast kernel for the generic one; results still
+    equal the oracle's."""
+    from tailseeker_b200.synth import make_tile
+    from tailseeker_b200.importer import TileProcessor, invert_colormatrix
+    tile = make_tile(stock_cfg, 5000, seed=31)
+    rng = np.random.default_rng(5)
+    flat = rng.choice(5000, size=400, replace=False)
+    tile.cif[:20, :, flat[:200]] = 0                      # all-zero balancer: bandwidth 0 on all channels
+    tile.cif[:20, 1, flat[200:]] = 77                     # one constant channel
+    inv = invert_colormatrix(tile.matrix)
+    p = TileProcessor(stock_cfg)
+    try:
+        p.upload(tile.bcl, tile.cif, inv)
+        p.process()
+        o = oracle.process(stock_cfg, tile.bcl, tile.cif, inv)
+        compare_tile(p, stock_cfg, None, o)
+    finally:
+        p.close()
+
+
 @pytest.mark.parametrize("n,seed", [(20000, 1), (4099, 2), (129, 3), (1, 4)])
 def test_tile_matches_oracle(proc, stock_cfg, oracle, n, seed):
     _, o = _run(proc, stock_cfg, oracle, n, seed)
