@@ -182,6 +182,13 @@ extern "C" int tsk_ctx_create(tsk_ctx **out, int device, const tsk_params *param
     TSK_CUDA(cudaMalloc(&ctx->d_tscore, sizeof(float) * (TSK_T_SCORE_BINS + 1)));
     TSK_CUDA(cudaMemcpy(ctx->d_tscore, params->t_intensity_score, sizeof(float) * (TSK_T_SCORE_BINS + 1),
                         cudaMemcpyHostToDevice));
+    {
+        double rcp[288];
+        rcp[0] = 0.;
+        for (int i = 1; i < 288; i++) rcp[i] = 1.0 / (double)i;     /* IEEE RN on the host */
+        TSK_CUDA(cudaMalloc(&ctx->d_rcp, sizeof(rcp)));
+        TSK_CUDA(cudaMemcpy(ctx->d_rcp, rcp, sizeof(rcp), cudaMemcpyHostToDevice));
+    }
     TSK_CUDA(cudaMalloc(&ctx->d_pos, histbytes));
     TSK_CUDA(cudaMalloc(&ctx->d_neg, histbytes));
     TSK_CUDA(cudaMemset(ctx->d_pos, 0, histbytes));
@@ -201,7 +208,7 @@ extern "C" int tsk_ctx_destroy(tsk_ctx *ctx)
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    void *ptrs[] = {ctx->d_samples, ctx->d_tscore, ctx->d_bcl_own, ctx->d_cif_own, ctx->d_calls, ctx->d_kind,
+    void *ptrs[] = {ctx->d_samples, ctx->d_tscore, ctx->d_rcp, ctx->d_bcl_own, ctx->d_cif_own, ctx->d_calls, ctx->d_kind,
                     ctx->d_bucket, ctx->d_worklist, ctx->d_blkcnt, ctx->d_totals, ctx->d_recbase,
                     ctx->d_records, ctx->d_scratch, ctx->d_pos, ctx->d_neg, ctx->d_counters, ctx->d_fair,
                     ctx->d_lists, ctx->d_ruler_pos, ctx->d_cutoffs, ctx->d_rlen};
@@ -275,9 +282,9 @@ extern "C" int tsk_tile_upload(tsk_ctx *ctx, const uint8_t *bcl, size_t bcl_pitc
     }
     /* own HBM copy; rows padded to 128 B so every row starts on a full line */
     const size_t bpitch = ((size_t)nclusters + 127) & ~(size_t)127;
-    const size_t cpitch = ((size_t)nclusters + 63) & ~(size_t)63;
+    const size_t cpitch = ((size_t)nclusters + 127) & ~(size_t)127;   /* whole 128-cluster CTA windows */
     if (ensure(&ctx->d_bcl_own, &ctx->bcl_cap, bpitch * T + 128) != 0) return -1;
-    if (ensure(&ctx->d_cif_own, &ctx->cif_cap, cpitch * 4 * L3 + 64) != 0) return -1;
+    if (ensure(&ctx->d_cif_own, &ctx->cif_cap, cpitch * 4 * L3 + 128) != 0) return -1;
     if (nclusters) {
         TSK_CUDA(cudaMemcpy2DAsync(ctx->d_bcl_own, bpitch, bcl, bcl_pitch, nclusters, T,
                                    cudaMemcpyHostToDevice, ctx->stream));

@@ -66,6 +66,7 @@ struct tsk_ctx {
     DevParams dp;
     DevSample *d_samples;        /* [num_samples] */
     float *d_tscore;             /* [201] */
+    double *d_rcp;               /* [288] 1.0 / i for the contrast scan */
     int maxdump;                 /* max signal_dump_length over samples */
 
     /* resident tile */

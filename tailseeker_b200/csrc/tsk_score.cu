@@ -18,6 +18,7 @@
  *       its preconditions do not hold (degenerate signal bandwidths), and is what the fast
  *       path is tested against.
  */
+#include <cuda.h>
 #include <math_constants.h>
 #include "tsk_internal.h"
 #include "tsk_device.cuh"
@@ -27,7 +28,6 @@
 
 struct ScoreShared {
     double2 logtab[16];
-    double  rcp[CONTRAST_MAXLEN];     /* 1.0 / i */
     float   tscore[TSK_T_SCORE_BINS + 1];
     int16_t limit[TSK_MAX_SAMPLES];
     int16_t dump[TSK_MAX_SAMPLES];
@@ -38,8 +38,6 @@ __device__ __forceinline__ void load_score_shared(ScoreShared &sh, const float *
 {
     for (int i = threadIdx.x; i < 16; i += blockDim.x)
         sh.logtab[i] = make_double2(c_logf_tab[i][0], c_logf_tab[i][1]);
-    for (int i = threadIdx.x; i < CONTRAST_MAXLEN; i += blockDim.x)
-        sh.rcp[i] = (i > 0) ? __drcp_rn((double)i) : 0.;
     for (int i = threadIdx.x; i <= TSK_T_SCORE_BINS; i += blockDim.x) sh.tscore[i] = tscore[i];
     for (int i = threadIdx.x; i < S; i += blockDim.x) {
         sh.limit[i] = samples[i].limit_threep;
@@ -186,6 +184,7 @@ __device__ __forceinline__ void sample_positive(const DevParams &P, const float 
 
 struct ScoreArgs {
     TileView tv;
+    const double *rcp;            /* [CONTRAST_MAXLEN] 1.0 / i, correctly rounded */
     const DevSample *samples;
     const float *tscore;
     tsk_call *calls;
@@ -206,10 +205,10 @@ struct ScoreArgs {
 /* Everything the reference does for one cluster inside process_polya_signal() after the
  * sequence seed, for work item w. */
 __device__ void process_item_generic(const DevParams &P, const ScoreShared &sh, const ScoreArgs &A,
-                                     uint32_t w)
+                                     uint32_t n)
 {
     const TileView &tv = A.tv;
-    const uint32_t n = A.worklist[w];
+    const uint32_t w = n;                  /* scratch column of this cluster */
     const uint4 craw = *reinterpret_cast<const uint4 *>(&A.calls[n]);
     tsk_call call = *reinterpret_cast<const tsk_call *>(&craw);
     const uint32_t kd = A.kind[n];
@@ -321,7 +320,7 @@ k_normalise_score_pack_generic(const __grid_constant__ DevParams P, const ScoreA
     const uint32_t cnt = all_items ? A.totals[P.num_samples] : A.lists[3];
     const uint32_t *slow = list_array(A.lists, 3, A.listcap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x)
-        process_item_generic(P, sh, A, all_items ? i : slow[i]);
+        process_item_generic(P, sh, A, all_items ? A.worklist[i] : slow[i]);
 }
 
 /* ======================================================================================
@@ -341,8 +340,10 @@ __device__ __forceinline__ float div_by_rcp(float a, float b, float y)
     return __fmaf_rn(r, y, q);
 }
 
-/* host-libm logf in fp64 FMAs for x in (0, 1] given as raw bits (subnormals clamped to the
- * smallest normal: their terms are < 2^-119 and cannot reach the float sum they feed). */
+/* host-libm logf in fp64 FMAs for a NORMAL x in (0, 1] given as raw bits.  For zero, negative
+ * or subnormal bit patterns the result is a finite meaningless number: callers either discard
+ * it (p <= 0) or multiply it by a subnormal p, a term < 2^-119 that cannot reach the float sum
+ * it feeds (h is 0 or >= 2^-24 * |log|, and 1 - h/maxent rounds to 1 for h < 2^-25). */
 __device__ __forceinline__ float logf_core(uint32_t ix, const double2 *__restrict__ tab)
 {
     const uint32_t tmp = ix - 0x3f330000u;
@@ -376,10 +377,19 @@ __device__ __forceinline__ void probe_ranges_fixed(const DevParams &P, const int
 #pragma unroll
         for (int r = 0; r < NNEG; r++) bot[ch][r] = CUDART_INF_F;
     }
-    const int16_t *p = cifcol + (size_t)P.balancer_start * 4 * pitch;
+    const int16_t *p = cifcol;      /* first balancer cycle; plain loads: shared or global memory */
     for (int c = 0; c < blen; c++, p += 4 * pitch) {
         float sig[4];
-        decrosstalk(sig, p, pitch, P.inv);
+        {
+            const float v0 = (float)p[0], v1 = (float)p[pitch], v2 = (float)p[2 * pitch], v3 = (float)p[3 * pitch];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float a = __fmul_rn(P.inv[4 * j + 0], v0);
+                a = __fadd_rn(a, __fmul_rn(P.inv[4 * j + 1], v1));
+                a = __fadd_rn(a, __fmul_rn(P.inv[4 * j + 2], v2));
+                sig[j] = __fadd_rn(a, __fmul_rn(P.inv[4 * j + 3], v3));
+            }
+        }
 #pragma unroll
         for (int ch = 0; ch < 4; ch++) {
             float carry = sig[ch];
@@ -419,56 +429,123 @@ __device__ __forceinline__ bool in_exp_range(float v, int lo_exp, int hi_exp)
     return e >= 127 + lo_exp && e < 127 + hi_exp;
 }
 
-__global__ void __launch_bounds__(TSK_K2_THREADS, 4)
-k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, const float rcp_maxent)
+/* ---- TMA engine plumbing: bulk asynchronous copies global -> shared, completion on an mbarrier.
+ *      All helpers take 32-bit shared-window addresses computed once per thread. ---- */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    __shared__ ScoreShared sh;
-    __shared__ uint32_t s_tile[TSK_K2_THREADS / 32][32][33];   /* packed words, [lane][cycle & 31] */
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_drop(uint32_t bar)
+{   /* arrive for the current phase and leave the barrier for all later phases */
+    asm volatile("mbarrier.arrive_drop.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    /* try_wait suspends the thread in hardware up to the hint (ns) instead of spinning */
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+/* one TMA tensor copy: box {32 clusters, 4 channels, 1 cycle} of the CIF tensor -> shared */
+__device__ __forceinline__ void tma_cycle_g2s(uint32_t dst, const CUtensorMap *tmap, int x, int cyc, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tmap), "r"(x), "r"(0), "r"(cyc), "r"(bar) : "memory");
+}
+__device__ __forceinline__ int lds_s16(uint32_t addr)
+{
+    int v;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+#define K2_CL        TSK_K2_THREADS      /* clusters per CTA */
+#define K2_WARPS     (TSK_K2_THREADS / 32)
+#define K2_NSTAGE    8                   /* single-cycle stages per warp */
+#define K2_HEAD_MAX  24                  /* resident cycles [0, head): balancer + first scored cycles */
+#define K2_ROWB      (4 * 32 * 2)        /* bytes per cycle and warp: four channel rows of 32 int16 */
+#define K2_TILE_CYC  8                   /* record words staged per lane between flushes */
+#ifndef K2_MIN_CTAS
+#define K2_MIN_CTAS  5
+#endif
+
+struct __align__(128) K2Smem {
+    int16_t  head[K2_WARPS][K2_HEAD_MAX][4][32];
+    int16_t  stage[K2_WARPS][K2_NSTAGE][4][32];
+    uint32_t tile[K2_WARPS][32][K2_TILE_CYC + 1];
+    ScoreShared sh;
+    uint64_t bar_head[K2_WARPS], bar_full[K2_WARPS][K2_NSTAGE];
+};
+
+/* One warp = 32 consecutive clusters, one lane per cluster, and its own little pipeline: the four
+ * channel planes of every 3'-read cycle (4 x 64 bytes) are brought into shared memory by the TMA
+ * engine (bulk asynchronous copies completing on an mbarrier) -- cycles [0, head) once, then a
+ * ring of eight single-cycle stages that lane 0 refills right after the warp has consumed a
+ * cycle.  The arithmetic therefore never waits on a global load, no warp waits for another, and
+ * every DRAM request is a full, aligned 64-byte segment of a cycle-major plane. */
+__global__ void __launch_bounds__(TSK_K2_THREADS, K2_MIN_CTAS)
+k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, const float rcp_maxent,
+                       const int head, const __grid_constant__ CUtensorMap tmap)
+{
+    extern __shared__ __align__(128) unsigned char k2_smem_raw[];
+    K2Smem &sm = *reinterpret_cast<K2Smem *>(k2_smem_raw);
+    const ScoreShared &sh = sm.sh;
     const int S = P.num_samples;
-    load_score_shared(sh, A.tscore, A.samples, S);
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t w = blockIdx.x * TSK_K2_THREADS + threadIdx.x;
-    const uint32_t nwork = A.totals[S];
-    if ((w & ~31u) >= nwork) return;                 /* whole warp past the end */
-    bool alive = w < nwork;
-
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TileView &tv = A.tv;
     const int ts = P.threep_start, tl = P.threep_length, bins = P.bins;
-    const size_t pitch = tv.cif_pitch, spitch = A.spitch;
+    const size_t spitch = A.spitch;
+    const uint32_t n = blockIdx.x * K2_CL + tid;              /* my cluster */
+    const uint32_t a_head = smem_u32(&sm.head[warp][0][0][0]), a_stage = smem_u32(&sm.stage[warp][0][0][0]);
+    const uint32_t a_bhead = smem_u32(&sm.bar_head[warp]), a_full = smem_u32(&sm.bar_full[warp][0]);
+    const int x0 = (int)(n - lane);                           /* first cluster of this warp */
 
-    uint32_t n = 0, kd = 0;
+    if (lane == 0) {
+        mbar_init(a_bhead, 1);
+        for (int i = 0; i < K2_NSTAGE; i++) mbar_init(a_full + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    load_score_shared(sm.sh, A.tscore, A.samples, S);      /* ends with __syncthreads() */
+
+    /* ---- per-cluster descriptor ---- */
+    uint32_t kd = 0;
     tsk_call call;
     int de = ts, ps = 0, sample = 0;
-    if (alive) {
-        n = A.worklist[w];
-        const uint4 craw = *reinterpret_cast<const uint4 *>(&A.calls[n]);
-        call = *reinterpret_cast<const tsk_call *>(&craw);
+    bool alive = false;
+    if (n < tv.nclusters) {
         kd = A.kind[n];
-        de = call.delimiter_end; ps = call.terminal_mods; sample = call.sample;
-    }
-    const int16_t *cifcol = tv.cif + n;
-
-    /* ---- balancer: per-cluster dynamic range ---- */
-    float low[4] = {0.f, 0.f, 0.f, 0.f}, bw[4] = {1.f, 1.f, 1.f, 1.f}, ybw[4];
-    if (alive) {
-        int blen = de - ts;
-        if (blen > P.balancer_length) blen = P.balancer_length;
-        if (P.npos == 2 && P.nneg == 4) probe_ranges_fixed<2, 4>(P, cifcol, pitch, blen, low, bw);
-        else probe_ranges(P, cifcol, pitch, blen, low, bw);
-        /* fast-path preconditions; otherwise the generic kernel takes this cluster */
-        bool ok = true;
-#pragma unroll
-        for (int ch = 0; ch < 4; ch++)
-            ok = ok && in_exp_range(bw[ch], -40, 40) && (fabsf(low[ch]) < 0x1p40f);
-        if (!ok) {
-            list_array(A.lists, 3, A.listcap)[atomicAdd(&A.lists[3], 1u)] = w;
-            alive = false;
+        alive = (kd & KIND_PROCESS) != 0;
+        if (alive) {
+            const uint4 craw = *reinterpret_cast<const uint4 *>(&A.calls[n]);
+            call = *reinterpret_cast<const tsk_call *>(&craw);
+            de = call.delimiter_end; ps = call.terminal_mods; sample = call.sample;
+        } else {
             kd = 0;
         }
     }
-#pragma unroll
-    for (int ch = 0; ch < 4; ch++) ybw[ch] = __frcp_rn(bw[ch]);
+    if (!__any_sync(FULL_MASK, alive)) return;                /* nothing to do for these 32 clusters */
+    const int start = de - ts;                                /* first scored cycle (3'-read index) */
 
     int insert_len = 0, dump = 0;
     if (alive) {
@@ -477,10 +554,52 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
         dump = sh.dump[sample];
         if (limit > 0 && limit < insert_len) insert_len = limit;
     }
+    const int rdata_end = start + insert_len;                 /* this lane scores cycles [start, rdata_end) */
+    int rdata_w = alive ? rdata_end : 0;                      /* the warp needs data of cycles [0, rdata_w) */
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) rdata_w = max(rdata_w, __shfl_xor_sync(FULL_MASK, rdata_w, d));
+
+    /* ---- TMA: resident head cycles, then the first ring of streamed cycles ---- */
+    auto issue_cycle = [&](int r) {          /* lane 0 only: cycle r -> ring slot (r - head) % 8 */
+        const int slot = (r - head) & (K2_NSTAGE - 1);
+        mbar_arrive_expect_tx(a_full + 8 * slot, K2_ROWB);
+        tma_cycle_g2s(a_stage + slot * K2_ROWB, &tmap, x0, r, a_full + 8 * slot);
+    };
+    if (lane == 0) {
+        const int hrows = min(head, rdata_w);
+        mbar_arrive_expect_tx(a_bhead, (uint32_t)hrows * K2_ROWB);
+        for (int r = 0; r < hrows; r++) tma_cycle_g2s(a_head + r * K2_ROWB, &tmap, x0, r, a_bhead);
+        for (int r = head; r < min(head + K2_NSTAGE, rdata_w); r++) issue_cycle(r);
+    }
+
+    /* ---- balancer: per-cluster dynamic range, from the resident head cycles ---- */
+    mbar_wait(a_bhead, 0);
+    float low[4] = {0.f, 0.f, 0.f, 0.f}, bw[4] = {1.f, 1.f, 1.f, 1.f}, ybw[4];
+    if (alive) {
+        const int blen = min(start, P.balancer_length);
+        probe_ranges_fixed<2, 4>(P, &sm.head[warp][P.balancer_start][0][lane], (size_t)32, blen, low, bw);
+        /* fast-path preconditions; otherwise the generic kernel takes this cluster */
+        bool ok = true;
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++)
+            ok = ok && in_exp_range(bw[ch], -40, 40) && (fabsf(low[ch]) < 0x1p40f);
+        if (!ok) {
+            list_array(A.lists, 3, A.listcap)[atomicAdd(&A.lists[3], 1u)] = n;
+            alive = false;
+            kd = 0;
+            insert_len = 0; dump = 0;
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++) { low[ch] = 0.f; bw[ch] = 1.f; }
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) ybw[ch] = __frcp_rn(bw[ch]);
+
     const int scan_len = insert_len - ps;
     const int valid = min(scan_len, dump);
     const bool emit = (kd & KIND_EMIT) != 0;
     const bool ispos = (kd & KIND_POS) != 0;
+    const int rscore_end = alive ? rdata_end : 0;
 
     uint32_t *rec = nullptr;
     if (emit) {
@@ -492,34 +611,38 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
     if (kd & KIND_NEG)
         neg_inline = (P.fair_max_count == 0) || (A.fair[A.bucket[n]] <= (uint32_t)P.fair_max_count);
 
-    /* the warp walks to the last cycle any of its lanes needs; an emitting lane needs
-     * record positions up to dump-1, i.e. cycle indices up to dump-1+ps (zero padding) */
-    int cend = emit ? max(insert_len, dump + ps) : insert_len;
+    /* the warp computes on cycles [rbeg_w, rend_w): an emitting lane owns record positions up to
+     * cycle start+ps+dump-1 (zero padding past its data) */
+    int rend_w = alive ? (emit ? max(rdata_end, start + ps + dump) : rdata_end) : 0;
+    int rbeg_w = alive ? start : 0x7fff;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) cend = max(cend, __shfl_xor_sync(FULL_MASK, cend, d));
+    for (int d = 16; d > 0; d >>= 1) {
+        rend_w = max(rend_w, __shfl_xor_sync(FULL_MASK, rend_w, d));
+        rbeg_w = min(rbeg_w, __shfl_xor_sync(FULL_MASK, rbeg_w, d));
+    }
     const unsigned emitmask = __ballot_sync(FULL_MASK, emit);
-    /* lane r's record parameters, fetched by shuffle during the flush */
     const unsigned long long recaddr = (unsigned long long)(uintptr_t)rec;
-    const int recinfo = (ps & 0xffff) | (max(dump, 0) << 16);
+    const int recinfo = ((start + ps) & 0xffff) | (max(dump, 0) << 16);
 
     int ndark = 0;
     float prev_entropy = CUDART_NAN_F;
-    unsigned long long dhwin = 0;
-    const int16_t *p = cifcol + (size_t)(de - ts) * 4 * pitch;
-    const uint32_t rowbase = (uint32_t)de;
-    float *scr = A.scratch + w - (size_t)ps * spitch;       /* scr[c * spitch] = score of cycle c */
-    uint32_t (*tile)[33] = s_tile[warp];
+    double ptotal = 0.;                       /* sum of the scores from the seed start on (KIND_POS lanes) */
+    uint32_t dhwin = 0;                       /* bit k = downhill of cycle (c - k); max_mods < 32 */
+    float *scr0 = A.scratch + n - (size_t)(start + ps) * spitch;   /* scr0[r*spitch]: score of cycle r */
+    const uint32_t a_tile = smem_u32(&sm.tile[warp][0][0]);
+    const uint32_t a_mytile = a_tile + lane * ((K2_TILE_CYC + 1) * 4);
+    const uint32_t colofs = (uint32_t)lane * 2;
 
-    for (int c = 0; c < cend; c++, p += 4 * pitch) {
+    /* one cycle of this lane: r = 3'-read cycle, arow = shared address of the cycle's [4][32] rows */
+    auto cycle = [&](const int r, const uint32_t arow) {
         uint32_t word = 0;
-        if (c < insert_len) {
-            /* ---- decrosstalk (signalproc.c:85-103) ---- */
-            const int i0 = __ldg(p), i1 = __ldg(p + pitch), i2 = __ldg(p + 2 * pitch), i3 = __ldg(p + 3 * pitch);
-            /* exact int16 -> float without the conversion unit: 2^23+2^22 + i, minus the bias */
-            const float v0 = __fsub_rn(__int_as_float(0x4B400000 + i0), 12582912.f);
-            const float v1 = __fsub_rn(__int_as_float(0x4B400000 + i1), 12582912.f);
-            const float v2 = __fsub_rn(__int_as_float(0x4B400000 + i2), 12582912.f);
-            const float v3 = __fsub_rn(__int_as_float(0x4B400000 + i3), 12582912.f);
+        if (r >= start && r < rscore_end) {
+            /* ---- decrosstalk (signalproc.c:85-103); exact int16 -> float through 2^23+2^22 ---- */
+            const uint32_t ap = arow + colofs;
+            const float v0 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap)), 12582912.f);
+            const float v1 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap + 64)), 12582912.f);
+            const float v2 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap + 128)), 12582912.f);
+            const float v3 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap + 192)), 12582912.f);
             float sig[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -539,7 +662,7 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
 #pragma unroll
             for (int ch = 0; ch < 4; ch++)
                 nrm[ch] = fmaxf(div_by_rcp(__fsub_rn(sig[ch], low[ch]), bw[ch], ybw[ch]), 0.f);
-            float sum = __fadd_rn(__fadd_rn(__fadd_rn(nrm[0], nrm[1]), nrm[2]), nrm[3]);
+            const float sum = __fadd_rn(__fadd_rn(__fadd_rn(nrm[0], nrm[1]), nrm[2]), nrm[3]);
             float prob[4];
             if (__builtin_expect(in_exp_range(sum, -60, 60), 1)) {
                 const float ys = __frcp_rn(sum);
@@ -551,52 +674,77 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
                 for (int ch = 0; ch < 4; ch++) prob[ch] = __fdiv_rn(nrm[ch], sum);
             }
             lit = lit && (prob[0] == prob[0]);
-            /* ---- Shannon entropy: h -= p*logf(p) for p > 0; p <= 0 contributes p*logf(1) = +-0 ---- */
+            /* ---- Shannon entropy: h -= p*logf(p) for p > 0 (the skipped terms are 0) ---- */
             float h = 0.f;
 #pragma unroll
             for (int ch = 0; ch < 4; ch++) {
-                const int pbits = __float_as_int(prob[ch]);
-                const uint32_t ix = (pbits <= 0) ? 0x3f800000u : (uint32_t)max(pbits, 0x00800000);
-                h = __fsub_rn(h, __fmul_rn(prob[ch], logf_core(ix, sh.logtab)));
+                const float term = __fmul_rn(prob[ch], logf_core(__float_as_uint(prob[ch]), sh.logtab));
+                h = __fsub_rn(h, prob[ch] > 0.f ? term : 0.f);
             }
             const float es = __fsub_rn(1.f, div_by_rcp(h, P.maximum_entropy, rcp_maxent));
-            int ti = __float2int_rz(__fmul_rn(prob[3], (float)TSK_T_SCORE_BINS));
-            ti = max(0, min(TSK_T_SCORE_BINS, ti));
+            const uint32_t ti = min((uint32_t)__float2int_rz(__fmul_rn(prob[3], (float)TSK_T_SCORE_BINS)),
+                                    (uint32_t)TSK_T_SCORE_BINS);
             const float score = lit ? __fmul_rn(es, sh.tscore[ti]) : CUDART_NAN_F;
             const uint32_t dh = (lit && es < prev_entropy) ? 1u : 0u;
             prev_entropy = lit ? es : CUDART_NAN_F;
             ndark += lit ? 0 : 1;
             dhwin = (dhwin << 1) | dh;
 
-            if (c >= ps) {
-                if (lit) {
-                    uint32_t s = 1u + (uint32_t)__float2int_rz(__fmul_rn(score, (float)(TSK_SCORE_MAX - 1)));
-                    s = min(s, TSK_SCORE_MAX);
-                    word = (s << 1) | (uint32_t)((dhwin >> ps) & 1ull);
+            if (r >= start + ps) {
+                uint32_t s = 1u + (uint32_t)__float2int_rz(__fmul_rn(score, (float)(TSK_SCORE_MAX - 1)));
+                s = min(s, TSK_SCORE_MAX);
+                /* packet j = c - ps carries downhill[j], the UN-offset array (spotanalyzer.c:604-606) */
+                word = lit ? ((s << 1) | ((dhwin >> ps) & 1u)) : 0u;
+                if (ispos) {
+                    scr0[(size_t)r * spitch] = score;
+                    ptotal = __dadd_rn(ptotal, (double)score);      /* same order as the reference's cumsum */
                 }
-                if (ispos) scr[(size_t)c * spitch] = score;
                 if (neg_inline && lit && !isinf(score))
-                    atomicAdd(&A.neg[(size_t)(rowbase + c) * bins + score_bin(score, bins)], 1u);
+                    atomicAdd(&A.neg[(size_t)(ts + r) * bins + score_bin(score, bins)], 1u);
             }
         }
-        /* ---- stage the packed word; every 32 cycles write the emitting lanes' records with
-         *      full lines: lane l carries cycle cbase + l of record r ---- */
-        tile[lane][c & 31] = word;
-        if ((c & 31) == 31 || c == cend - 1) {
+        /* ---- stage the packed word; every 8 cycles the emitting lanes' records are written four
+         *      at a time, 8 consecutive words (one 32-byte sector) each ---- */
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_mytile + (r & (K2_TILE_CYC - 1)) * 4), "r"(word) : "memory");
+        if ((r & (K2_TILE_CYC - 1)) == K2_TILE_CYC - 1 || r == rend_w - 1) {
             __syncwarp();
-            const int cbase = c & ~31;
+            const int rbase = r & ~(K2_TILE_CYC - 1);
+            const int quarter = lane >> 3, l8 = lane & 7;
             unsigned m = emitmask;
             while (m) {
-                const int r = __ffs(m) - 1;
-                m &= m - 1;
-                const unsigned long long ra = __shfl_sync(FULL_MASK, recaddr, r);
-                const int ri = __shfl_sync(FULL_MASK, recinfo, r);
-                const int j = cbase + lane - (ri & 0xffff);
-                if (j >= 0 && j < (ri >> 16) && cbase + lane <= c)
-                    reinterpret_cast<uint32_t *>((uintptr_t)ra)[2 + j] = tile[r][lane];
+                /* next (up to) four emitting lanes */
+                int pick = -1;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int rr = m ? __ffs(m) - 1 : -1;
+                    if (m) m &= m - 1;
+                    if (k == quarter) pick = rr;
+                }
+                const int src = pick < 0 ? 0 : pick;
+                const unsigned long long ra = __shfl_sync(FULL_MASK, recaddr, src);
+                const int ri = __shfl_sync(FULL_MASK, recinfo, src);
+                const int j = rbase + l8 - (ri & 0xffff);
+                if (pick >= 0 && j >= 0 && j < (ri >> 16) && rbase + l8 <= r) {
+                    uint32_t wv;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv) : "r"(a_tile + (pick * (K2_TILE_CYC + 1) + l8) * 4));
+                    reinterpret_cast<uint32_t *>((uintptr_t)ra)[2 + j] = wv;
+                }
             }
             __syncwarp();
         }
+    };
+
+    /* ---- resident head cycles ---- */
+    for (int r = rbeg_w; r < min(rend_w, head); r++) cycle(r, a_head + r * K2_ROWB);
+
+    /* ---- streamed cycles: wait for the cycle's rows, score it, let lane 0 refill the slot ---- */
+    for (int r = max(rbeg_w, head); r < rend_w; r++) {
+        const int q = r - head;
+        const int slot = q & (K2_NSTAGE - 1);
+        if (r < rdata_w) mbar_wait(a_full + 8 * slot, (q / K2_NSTAGE) & 1);
+        cycle(r, a_stage + slot * K2_ROWB);
+        __syncwarp();
+        if (lane == 0 && r + K2_NSTAGE < rdata_w) issue_cycle(r + K2_NSTAGE);
     }
 
     if (!alive) return;
@@ -625,20 +773,29 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
      * exact IEEE value is evaluated only there.  If a second candidate lies within 1e-14 the
      * exact scan decides, so ties resolve exactly like the reference's strict '>' scan. */
     if (ispos && !aborted && scan_len > 0 && P.cctr_left + P.cctr_right < scan_len) {
-        const float *col = A.scratch + w;
+        const float *col = A.scratch + n;
         const int left = P.cctr_left, last = scan_len - P.cctr_right;
-        double total = 0.;
-        for (int i = 0; i < scan_len; i++) total = __dadd_rn(total, (double)col[(size_t)i * spitch]);
+        const double total = ptotal;
         if (total == total) {        /* a NaN anywhere makes the first candidate NaN: no sampling */
             double cum = 0., m1 = -CUDART_INF, m2 = -CUDART_INF, cum1 = 0.;
             int at = left - 1;
-            for (int i = 0; i <= last; i++) {
-                cum = __dadd_rn(cum, (double)col[(size_t)i * spitch]);
-                if (i >= left - 1) {
-                    const double v = __dsub_rn(__dmul_rn(cum, sh.rcp[i]),
-                                               __dmul_rn(__dsub_rn(total, cum), sh.rcp[scan_len - i]));
-                    if (v > m1) { m2 = m1; m1 = v; at = i; cum1 = cum; }
-                    else if (v > m2) m2 = v;
+            for (int i0 = 0; i0 <= last; i0 += 8) {
+                float v8[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++)       /* eight independent loads in flight */
+                    v8[k] = (i0 + k <= last) ? col[(size_t)(i0 + k) * spitch] : 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int i = i0 + k;
+                    if (i <= last) {
+                        cum = __dadd_rn(cum, (double)v8[k]);
+                        if (i >= left - 1) {
+                            const double v = __dsub_rn(__dmul_rn(cum, __ldg(A.rcp + i)),
+                                                       __dmul_rn(__dsub_rn(total, cum), __ldg(A.rcp + (scan_len - i))));
+                            if (v > m1) { m2 = m1; m1 = v; at = i; cum1 = cum; }
+                            else if (v > m2) m2 = v;
+                        }
+                    }
                 }
             }
             float contrast;
@@ -652,7 +809,7 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
                 atpos = contrast_exact(col, spitch, scan_len, left, P.cctr_right, total, &contrast);
             }
             if (atpos >= P.boundary_pos && contrast >= P.required_contrast)
-                sample_positive(P, col, spitch, scan_len, ps, (int)rowbase + ps, A.pos);
+                sample_positive(P, col, spitch, scan_len, ps, de + ps, A.pos);
         }
     }
 }
@@ -835,8 +992,50 @@ static ScoreArgs make_args(tsk_ctx *ctx)
     a.kind = ctx->d_kind; a.bucket = ctx->d_bucket; a.worklist = ctx->d_worklist; a.totals = ctx->d_totals;
     a.recbase = ctx->d_recbase; a.records = ctx->d_records; a.scratch = ctx->d_scratch;
     a.spitch = (size_t)ctx->cap_clusters; a.pos = ctx->d_pos; a.neg = ctx->d_neg; a.fair = ctx->d_fair;
-    a.lists = ctx->d_lists; a.listcap = ctx->cap_clusters;
+    a.lists = ctx->d_lists; a.listcap = ctx->cap_clusters; a.rcp = ctx->d_rcp;
     return a;
+}
+
+/* resident head cycles of the fast kernel: the balancer and every possible first scored cycle */
+static int fast_head_cycles(const tsk_ctx *ctx)
+{
+    const tsk_params &hp = ctx->hp;
+    int head = hp.balancer_start + hp.balancer_length;
+    for (int s = 0; s < hp.num_samples; s++)
+        if (hp.samples[s].delimiter_length > 0) {
+            const int first = hp.samples[s].delimiter_pos + hp.samples[s].delimiter_length + 1 - hp.threep_start;
+            if (first + 1 > head) head = first + 1;
+        }
+    head = (head + 3) / 4 * 4;
+    if (head > hp.threep_length) head = hp.threep_length;
+    return head;
+}
+
+/* TMA descriptor of the resident CIF tensor, i16 [threep_length][4][pitch]: boxes of
+ * {32 clusters, 4 channels, 1 cycle}; reads past nclusters are zero-filled by the engine. */
+typedef CUresult (*tsk_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+static int make_cif_tensor_map(tsk_ctx *ctx, CUtensorMap *tmap)
+{
+    static tsk_encode_tiled_fn encode = NULL;
+    if (!encode) {
+        void *fn = NULL;
+        cudaDriverEntryPointQueryResult qres;
+        TSK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) { tsk_set_error("cuTensorMapEncodeTiled unavailable"); return -1; }
+        encode = (tsk_encode_tiled_fn)fn;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)ctx->tile.nclusters, 4, (cuuint64_t)ctx->dp.threep_length};
+    const cuuint64_t strides[2] = {(cuuint64_t)ctx->tile.cif_pitch * 2, (cuuint64_t)ctx->tile.cif_pitch * 8};
+    const cuuint32_t box[3] = {32, 4, 1}, estr[3] = {1, 1, 1};
+    const CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, (void *)ctx->tile.cif, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { tsk_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
+    return 0;
 }
 
 int tsk_launch_score(tsk_ctx *ctx)
@@ -844,13 +1043,28 @@ int tsk_launch_score(tsk_ctx *ctx)
     const uint32_t N = ctx->tile.nclusters;
     if (N == 0) return 0;
     const ScoreArgs a = make_args(ctx);
-    const unsigned grid = (N + TSK_K2_THREADS - 1) / TSK_K2_THREADS;
-    if (ctx->force_generic) {
+    const int head = fast_head_cycles(ctx);
+    /* the TMA bulk copies need 16-byte aligned 256-byte rows, and the CTA windows must stay inside
+     * the row pitch; the downhill window is 32 bits */
+    const bool fast_ok = !ctx->force_generic && head <= K2_HEAD_MAX && ctx->dp.max_mods < 32 &&
+                         ctx->dp.npos == 2 && ctx->dp.nneg == 4 &&
+                         (ctx->tile.cif_pitch % 8) == 0 && ((uintptr_t)ctx->tile.cif % 16) == 0;
+    if (!fast_ok) {
+        const unsigned grid = (N + TSK_K2_THREADS - 1) / TSK_K2_THREADS;
         k_normalise_score_pack_generic<<<grid, TSK_K2_THREADS, 0, ctx->stream>>>(ctx->dp, a, 1);
         ctx->launches += 1;
     } else {
+        static bool attr_set = false;
+        if (!attr_set) {
+            TSK_CUDA(cudaFuncSetAttribute(k_normalise_score_pack, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(K2Smem)));
+            attr_set = true;
+        }
         const float rcp_maxent = 1.0f / ctx->dp.maximum_entropy;      /* IEEE RN on the host */
-        k_normalise_score_pack<<<grid, TSK_K2_THREADS, 0, ctx->stream>>>(ctx->dp, a, rcp_maxent);
+        const unsigned grid = (N + K2_CL - 1) / K2_CL;
+        CUtensorMap tmap;
+        if (make_cif_tensor_map(ctx, &tmap) != 0) return -1;
+        k_normalise_score_pack<<<grid, TSK_K2_THREADS, sizeof(K2Smem), ctx->stream>>>(ctx->dp, a, rcp_maxent, head, tmap);
         k_normalise_score_pack_generic<<<8, TSK_K2_THREADS, 0, ctx->stream>>>(ctx->dp, a, 0);
         ctx->launches += 2;
     }

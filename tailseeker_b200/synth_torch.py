@@ -44,7 +44,7 @@ def make_tile_device(cfg: ImporterConfig, nclusters: int, seed: int, device="cud
     cif = torch.zeros((L3, 4, pitch), dtype=torch.int16, device=dev)
 
     nsamp = len(cfg.samples)
-    weights = np.array([1.0 if s.fingerprint_seq else 3.0 for s in cfg.samples])
+    weights = np.array([0.25 if s.fingerprint_seq else 3.0 for s in cfg.samples])
     weights = weights / weights.sum() * (1.0 - unknown_frac)
     probs = torch.tensor(np.concatenate([weights, [unknown_frac]]), dtype=torch.float32, device=dev)
     index_codes = torch.stack([_codes(s.index, dev) for s in cfg.samples])      # [S][ilen]
