@@ -295,10 +295,8 @@ def main():
             proc.process()
             vp, vn, _ = lib_views()
             acc_pos.add_(vp); acc_neg.add_(vn)
-            for s in range(S):
-                if proc.record_count(s):
-                    lens = proc.ruler_tile(s, packed)
-                    measured += int((lens >= 0).sum())
+            lens, _ = proc.ruler_tile_all(packed)
+            measured += int((lens >= 0).sum())
         fit, _ = finish_step(True)
         return measured, fit
 
@@ -350,7 +348,7 @@ def main():
                 "slot_scan_assign": stage_ms[1] / max(1, int(stage_runs[1])),
                 "normalise_score_pack": k2_ms,
                 "fair_sampling_fixups": stage_ms[3] / max(1, int(stage_runs[3])),
-                "polya_ruler_per_sample": stage_ms[4] / max(1, int(stage_runs[4])),
+                "polya_ruler": stage_ms[4] / max(1, int(stage_runs[4])),
                 "fit_cutoffs": stage_ms[5] / max(1, int(stage_runs[5]))},
             "pipeline_algorithmic_gbs_per_gpu": ab["total"] * ntiles / (ms_step * 1e-3) / 1e9,
             "processed_fraction": ab["processed"] / N, "record_slots_per_tile": ab["records"],
@@ -388,10 +386,8 @@ def main():
                 d2h += calls.nbytes
                 vp, vn, _ = lib_views()
                 acc_pos.add_(vp); acc_neg.add_(vn)
-                for s in range(S):
-                    if proc.record_count(s):
-                        lens = proc.ruler_tile(s, packed)     # D2H 2 B / record slot
-                        d2h += lens.nbytes
+                lens, _ = proc.ruler_tile_all(packed)         # D2H 2 B / record slot
+                d2h += lens.nbytes
             fit, cnt = finish_step(True)                      # D2H of the two histograms
             cnt.cpu()
             d2h += 2 * T * bins * 8 + S * 6 * 8

@@ -222,6 +222,12 @@ int tsk_ruler_tile(tsk_ctx *ctx, int sample, const uint32_t *cutoffs, int ncutof
                    int minimum_polya_len, float downhill_ext_weight,
                    int dist_sampling_bins, float dist_sampling_gap,
                    int16_t *polya_len_out /* [nslots] host */);
+/* Same for EVERY sample of the resident tile in one launch (what measure-polya-lengths.py:53-70
+ * loops over): polya_len_out holds the slots of sample 0, then sample 1, ...;
+ * slot_offsets[num_samples + 1] receives where each sample's slots start. */
+int tsk_ruler_tile_all(tsk_ctx *ctx, const uint32_t *cutoffs, int ncutoffs,
+                       int minimum_polya_len, float downhill_ext_weight, int dist_sampling_bins,
+                       float dist_sampling_gap, int16_t *polya_len_out, uint32_t *slot_offsets);
 int tsk_ruler_hist_reset(tsk_ctx *ctx, int ncutoffs, int dist_sampling_bins);
 int tsk_ruler_get_hist(tsk_ctx *ctx, uint32_t *pos /* [ncutoffs][bins] */);
 

@@ -137,3 +137,58 @@ def write_cutoffs_file(path: str, tile_id: str, cutoffs) -> None:
             else:
                 f.write(format(v, ".6f") + "\t")
         f.write("\n")
+
+
+def run_reference_estimator(sigdists, total_cycles, conf_seeder, threads=2, workdir=None):
+    """Run the reference's scripts/calculate-optimal-parameters.py (needs /root/reference; used
+    only to GENERATE golden vectors in the build container, never on the GPU box).
+    sigdists: {(tile_id, 'pos'|'neg'): u32 array [cycles][bins]}.  Returns
+    {tile_id: list of float|None per cycle} and the bases report text."""
+    import json
+    import sys
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        raise RuntimeError("reference tree not present")
+    own = workdir is None
+    if own:
+        workdir = tempfile.mkdtemp(prefix="tskest_")
+    try:
+        inputs = []
+        tiles = sorted({t for t, _ in sigdists})
+        for (tile, kind), arr in sigdists.items():
+            d = os.path.join(workdir, "sigdists")
+            os.makedirs(d, exist_ok=True)
+            path = os.path.join(d, "%s_%s.sigdists" % (kind, tile))
+            write_sigdists(path, arr)
+            inputs.append([None, path])
+        out_values = os.path.join(workdir, "signal-cutoffs.txt")
+        out_bases = os.path.join(workdir, "signal-cutoff-bases.txt")
+        params = {
+            "input": inputs,
+            "output": [["cutoff_values", out_values], ["cutoff_bases", out_bases]],
+            "threads": threads,
+            "wildcards": [],
+            "params": [["conf", {"polyA_seeder": conf_seeder}],
+                       ["tileinfo", {t: {"id": t, "source": "run"} for t in tiles}],
+                       ["total_cycles", total_cycles]],
+        }
+        pj = os.path.join(workdir, "params.json")
+        with open(pj, "w") as f:
+            json.dump(params, f)
+        env = dict(os.environ)
+        env["SNAKEMAKE_PARAMS"] = pj
+        env["PYTHONPATH"] = os.path.join(HERE, "snakemake_stub") + ":" + ref
+        proc = subprocess.run([sys.executable, os.path.join(ref, "scripts", "calculate-optimal-parameters.py")],
+                              env=env, cwd=workdir, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        if proc.returncode != 0:
+            raise RuntimeError("reference estimator failed: " + proc.stderr.decode()[-3000:])
+        text = open(out_values).read()
+        bases = open(out_bases).read()
+        cut = {}
+        for line in text.splitlines():
+            toks = line.split("\t")
+            cut[toks[0]] = [None if t == "nan" else float(t) for t in toks[1:] if t != ""]
+        return dict(cutoffs=cut, text=text, bases=bases)
+    finally:
+        if own:
+            shutil.rmtree(workdir, ignore_errors=True)

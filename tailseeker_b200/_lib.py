@@ -17,7 +17,7 @@ SYMBOLS = [
     "tsk_last_error", "tsk_probe", "tsk_ctx_create", "tsk_ctx_destroy", "tsk_tile_upload",
     "tsk_tile_process", "tsk_tile_get_calls", "tsk_tile_get_record_count", "tsk_tile_get_records",
     "tsk_get_counters", "tsk_counters_reset", "tsk_get_hist", "tsk_get_device_ptrs",
-    "tsk_cutoff_to_packed", "tsk_ruler_records", "tsk_ruler_tile", "tsk_ruler_hist_reset",
+    "tsk_cutoff_to_packed", "tsk_ruler_records", "tsk_ruler_tile", "tsk_ruler_tile_all", "tsk_ruler_hist_reset",
     "tsk_ruler_get_hist", "tsk_fit_cutoffs", "tsk_synchronize", "tsk_tile_process_timed",
     "tsk_launch_count", "tsk_selftest_logf", "tsk_set_stream", "tsk_profile_enable", "tsk_profile_get",
     "tsk_selftest_sweeps", "tsk_debug_force_generic",
@@ -58,6 +58,7 @@ def load():
     L.tsk_cutoff_to_packed.restype = u32
     L.tsk_ruler_records.argtypes = [vp, vp, sz, i32, vp, i32, i32, f32, i32, f32, vp, i32]
     L.tsk_ruler_tile.argtypes = [vp, i32, vp, i32, i32, f32, i32, f32, vp]
+    L.tsk_ruler_tile_all.argtypes = [vp, vp, i32, i32, f32, i32, f32, vp, vp]
     L.tsk_ruler_hist_reset.argtypes = [vp, i32, i32]
     L.tsk_ruler_get_hist.argtypes = [vp, vp]
     L.tsk_fit_cutoffs.argtypes = [vp, vp, vp, i32, i32, ctypes.c_uint64, f64, f64, vp, i32, vp]

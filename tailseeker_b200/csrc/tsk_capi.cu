@@ -211,7 +211,8 @@ extern "C" int tsk_ctx_destroy(tsk_ctx *ctx)
     void *ptrs[] = {ctx->d_samples, ctx->d_tscore, ctx->d_rcp, ctx->d_bcl_own, ctx->d_cif_own, ctx->d_calls, ctx->d_kind,
                     ctx->d_bucket, ctx->d_worklist, ctx->d_blkcnt, ctx->d_totals, ctx->d_recbase,
                     ctx->d_records, ctx->d_scratch, ctx->d_pos, ctx->d_neg, ctx->d_counters, ctx->d_fair,
-                    ctx->d_lists, ctx->d_ruler_pos, ctx->d_cutoffs, ctx->d_rlen};
+                    ctx->d_lists, ctx->d_ruler_pos, ctx->d_cutoffs, ctx->d_rlen, ctx->d_rrec,
+                    ctx->d_fit_hist, ctx->d_fit_out};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)
         if (ptrs[i]) cudaFree(ptrs[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -559,17 +560,14 @@ extern "C" int tsk_ruler_records(tsk_ctx *ctx, const uint32_t *records, size_t n
     if (!ctx || (nrecords && (!records || !polya_len_out))) { tsk_set_error("null argument"); return -1; }
     TSK_CUDA(cudaSetDevice(ctx->device));
     const uint32_t *d_rec = records;
-    uint32_t *tmp = NULL;
     if (!on_device && nrecords) {
-        const size_t bytes = sizeof(uint32_t) * nrecords * (size_t)(2 + dump_len);
-        TSK_CUDA(cudaMalloc(&tmp, bytes));
-        TSK_CUDA(cudaMemcpyAsync(tmp, records, bytes, cudaMemcpyHostToDevice, ctx->stream));
-        d_rec = tmp;
+        const size_t words = nrecords * (size_t)(2 + dump_len);
+        if (ensure(&ctx->d_rrec, &ctx->rrec_cap, words) != 0) return -1;
+        TSK_CUDA(cudaMemcpyAsync(ctx->d_rrec, records, sizeof(uint32_t) * words, cudaMemcpyHostToDevice, ctx->stream));
+        d_rec = ctx->d_rrec;
     }
-    const int rc = ruler_common(ctx, d_rec, nrecords, dump_len, cutoffs, ncutoffs, minimum_polya_len,
-                                downhill_ext_weight, dist_sampling_bins, dist_sampling_gap, polya_len_out);
-    if (tmp) cudaFree(tmp);
-    return rc;
+    return ruler_common(ctx, d_rec, nrecords, dump_len, cutoffs, ncutoffs, minimum_polya_len,
+                        downhill_ext_weight, dist_sampling_bins, dist_sampling_gap, polya_len_out);
 }
 
 extern "C" int tsk_ruler_tile(tsk_ctx *ctx, int sample, const uint32_t *cutoffs, int ncutoffs,
@@ -583,6 +581,48 @@ extern "C" int tsk_ruler_tile(tsk_ctx *ctx, int sample, const uint32_t *cutoffs,
                         downhill_ext_weight, dist_sampling_bins, dist_sampling_gap, polya_len_out);
 }
 
+extern "C" int tsk_ruler_tile_all(tsk_ctx *ctx, const uint32_t *cutoffs, int ncutoffs, int minimum_polya_len,
+                                  float downhill_ext_weight, int dist_sampling_bins, float dist_sampling_gap,
+                                  int16_t *polya_len_out, uint32_t *slot_offsets)
+{
+    if (need_processed(ctx) != 0) return -1;
+    if (ncutoffs < 1 || ncutoffs > TSK_MAX_CUTOFF_CYCLES || dist_sampling_bins < 1 || !cutoffs || !slot_offsets) {
+        tsk_set_error("bad ruler argument"); return -1;
+    }
+    const int S = ctx->dp.num_samples;
+    uint32_t first[TSK_MAX_SAMPLES + 1];
+    int dump[TSK_MAX_SAMPLES];
+    first[0] = 0;
+    for (int s = 0; s < S; s++) {
+        first[s + 1] = first[s] + ctx->h_totals[s];
+        dump[s] = ctx->hp.samples[s].signal_dump_length;
+        slot_offsets[s] = first[s];
+    }
+    slot_offsets[S] = first[S];
+    const size_t n = first[S];
+    if (!ctx->d_ruler_pos || ctx->ruler_pos_words < (size_t)ncutoffs * dist_sampling_bins)
+        if (tsk_ruler_hist_reset(ctx, ncutoffs, dist_sampling_bins) != 0) return -1;
+    TSK_CUDA(cudaMemcpyAsync(ctx->d_cutoffs, cutoffs, sizeof(uint32_t) * ncutoffs, cudaMemcpyHostToDevice, ctx->stream));
+    if (ensure(&ctx->d_rlen, &ctx->rlen_cap, n ? n : 1) != 0) return -1;
+    if (n) {
+        if (!polya_len_out) { tsk_set_error("null output"); return -1; }
+        if (ctx->profile) TSK_CUDA(cudaEventRecord(ctx->pev[5], ctx->stream));
+        if (tsk_launch_ruler_segs(ctx, ctx->d_records, S, first, ctx->h_recbase, dump, ncutoffs, minimum_polya_len,
+                                  downhill_ext_weight, dist_sampling_bins, dist_sampling_gap, ctx->d_rlen) != 0)
+            return -1;
+        if (ctx->profile) TSK_CUDA(cudaEventRecord(ctx->pev[6], ctx->stream));
+        TSK_CUDA(cudaMemcpyAsync(polya_len_out, ctx->d_rlen, sizeof(int16_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    TSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n && ctx->profile) {
+        float ms = 0.f;
+        TSK_CUDA(cudaEventElapsedTime(&ms, ctx->pev[5], ctx->pev[6]));
+        ctx->stage_ms[4] += ms;
+        ctx->stage_runs[4]++;
+    }
+    return 0;
+}
+
 /* ---- cutoff estimation ----------------------------------------------------------------------- */
 extern "C" int tsk_fit_cutoffs(tsk_ctx *ctx, const uint64_t *pos, const uint64_t *neg, int cycles, int bins,
                                uint64_t min_spots, double kde_bandwidth, double search_low,
@@ -591,12 +631,12 @@ extern "C" int tsk_fit_cutoffs(tsk_ctx *ctx, const uint64_t *pos, const uint64_t
     if (!ctx || !pos || !neg || !cutoffs_out || cycles < 1 || bins < 2 || nsearch_high < 1 ||
         nsearch_high > 8 || !search_high) { tsk_set_error("bad argument"); return -1; }
     TSK_CUDA(cudaSetDevice(ctx->device));
-    uint64_t *d_pos = NULL, *d_neg = NULL;
-    double *d_out = NULL;
-    const size_t hb = sizeof(uint64_t) * (size_t)cycles * bins;
-    TSK_CUDA(cudaMalloc(&d_pos, hb));
-    TSK_CUDA(cudaMalloc(&d_neg, hb));
-    TSK_CUDA(cudaMalloc(&d_out, sizeof(double) * cycles));
+    const size_t hw = (size_t)cycles * bins;
+    const size_t hb = sizeof(uint64_t) * hw;
+    if (ensure(&ctx->d_fit_hist, &ctx->fit_cap, 2 * hw) != 0) return -1;
+    if (ensure(&ctx->d_fit_out, &ctx->fit_out_cap, (size_t)cycles) != 0) return -1;
+    uint64_t *d_pos = ctx->d_fit_hist, *d_neg = ctx->d_fit_hist + hw;
+    double *d_out = ctx->d_fit_out;
     TSK_CUDA(cudaMemcpyAsync(d_pos, pos, hb, cudaMemcpyHostToDevice, ctx->stream));
     TSK_CUDA(cudaMemcpyAsync(d_neg, neg, hb, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->profile) cudaEventRecord(ctx->pev[5], ctx->stream);
@@ -616,6 +656,5 @@ extern "C" int tsk_fit_cutoffs(tsk_ctx *ctx, const uint64_t *pos, const uint64_t
             }
         }
     }
-    cudaFree(d_pos); cudaFree(d_neg); cudaFree(d_out);
     return rc;
 }

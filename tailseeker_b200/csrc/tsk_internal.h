@@ -91,6 +91,9 @@ struct tsk_ctx {
     uint32_t *d_ruler_pos;  size_t ruler_pos_words;
     uint32_t *d_cutoffs;         /* [TSK_MAX_CUTOFF_CYCLES] */
     int16_t  *d_rlen;  size_t rlen_cap;
+    uint32_t *d_rrec;  size_t rrec_cap;       /* staging of host-provided ruler records */
+    uint64_t *d_fit_hist;  size_t fit_cap;   /* pos | neg u64 histograms of fit_cutoffs */
+    double   *d_fit_out;   size_t fit_out_cap;
 
     /* host mirrors filled by tsk_tile_process() */
     uint32_t h_totals[TSK_MAX_SAMPLES + 1];
@@ -123,6 +126,9 @@ int tsk_launch_fixups(tsk_ctx *ctx);
 int tsk_launch_ruler(tsk_ctx *ctx, const uint32_t *d_records, size_t nrecords, int dump_len,
                      int ncutoffs, int min_len, float weight, int bins, float gap,
                      int16_t *d_len_out);
+int tsk_launch_ruler_segs(tsk_ctx *ctx, const uint32_t *d_records, int nseg, const uint32_t *first,
+                          const uint64_t *base, const int *dump, int ncutoffs, int min_len, float weight,
+                          int bins, float gap, int16_t *d_len_out);
 int tsk_launch_fit(tsk_ctx *ctx, const uint64_t *d_pos, const uint64_t *d_neg, int cycles, int bins,
                    uint64_t min_spots, double bw, double low, const double *high, int nhigh,
                    double *d_out);

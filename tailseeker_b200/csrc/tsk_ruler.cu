@@ -14,8 +14,18 @@
 #define FULL_MASK 0xffffffffu
 #define RULER_THREADS 256
 
+/* Record slots come in up to TSK_MAX_SAMPLES segments (one per sample, each with its own
+ * signal_dump_length): segment g holds slots [seg.first[g], seg.first[g+1]) of the output
+ * array, stored at records + seg.base[g] with (2 + seg.dump[g]) words per slot. */
+struct RulerSegs {
+    int nseg;
+    uint32_t first[TSK_MAX_SAMPLES + 1];
+    unsigned long long base[TSK_MAX_SAMPLES];
+    int dump[TSK_MAX_SAMPLES];
+};
+
 __global__ void __launch_bounds__(RULER_THREADS)
-k_polya_ruler(const uint32_t *__restrict__ records, size_t nrecords, int dump_len,
+k_polya_ruler(const uint32_t *__restrict__ records, const __grid_constant__ RulerSegs seg,
               const uint32_t *__restrict__ g_cutoffs, int ncut, int min_len, float weight,
               int bins, float gap, int16_t *__restrict__ len_out, uint32_t *__restrict__ pos)
 {
@@ -25,11 +35,13 @@ k_polya_ruler(const uint32_t *__restrict__ records, size_t nrecords, int dump_le
 
     const int lane = threadIdx.x & 31;
     const size_t warps_total = (size_t)gridDim.x * (RULER_THREADS / 32);
-    const size_t words = 2 + (size_t)dump_len;
+    const size_t nrecords = seg.first[seg.nseg];
+    int g = 0;
 
     for (size_t r = (size_t)blockIdx.x * (RULER_THREADS / 32) + (threadIdx.x >> 5); r < nrecords;
          r += warps_total) {
-        const uint32_t *rec = records + r * words;
+        while (r >= seg.first[g + 1]) g++;           /* r only grows: segments are visited in order */
+        const uint32_t *rec = records + seg.base[g] + (r - seg.first[g]) * (size_t)(2 + seg.dump[g]);
         const uint32_t hdr = __ldg(rec + 1);
         const int first = (int16_t)(hdr & 0xffffu);
         const int valid = (int16_t)(hdr >> 16);
@@ -106,16 +118,32 @@ k_polya_ruler(const uint32_t *__restrict__ records, size_t nrecords, int dump_le
     }
 }
 
-int tsk_launch_ruler(tsk_ctx *ctx, const uint32_t *d_records, size_t nrecords, int dump_len,
-                     int ncutoffs, int min_len, float weight, int bins, float gap, int16_t *d_len_out)
+int tsk_launch_ruler_segs(tsk_ctx *ctx, const uint32_t *d_records, int nseg, const uint32_t *first,
+                          const uint64_t *base, const int *dump, int ncutoffs, int min_len, float weight,
+                          int bins, float gap, int16_t *d_len_out)
 {
+    RulerSegs seg;
+    seg.nseg = nseg;
+    for (int i = 0; i < nseg; i++) { seg.first[i] = first[i]; seg.base[i] = base[i]; seg.dump[i] = dump[i]; }
+    seg.first[nseg] = first[nseg];
+    const size_t nrecords = first[nseg];
+    if (nrecords == 0) return 0;
     size_t blocks = (nrecords + (RULER_THREADS / 32) - 1) / (RULER_THREADS / 32);
     const size_t maxblocks = 148 * 8 * 4;       /* persistent-ish: a few waves of 148 SMs x 8 CTAs */
     if (blocks > maxblocks) blocks = maxblocks;
     k_polya_ruler<<<(unsigned)blocks, RULER_THREADS, 0, ctx->stream>>>(
-        d_records, nrecords, dump_len, ctx->d_cutoffs, ncutoffs, min_len, weight, bins, gap,
-        d_len_out, ctx->d_ruler_pos);
+        d_records, seg, ctx->d_cutoffs, ncutoffs, min_len, weight, bins, gap, d_len_out, ctx->d_ruler_pos);
     ctx->launches++;
     TSK_CUDA(cudaGetLastError());
     return 0;
+}
+
+int tsk_launch_ruler(tsk_ctx *ctx, const uint32_t *d_records, size_t nrecords, int dump_len,
+                     int ncutoffs, int min_len, float weight, int bins, float gap, int16_t *d_len_out)
+{
+    const uint32_t first[2] = {0, (uint32_t)nrecords};
+    const uint64_t base[1] = {0};
+    const int dump[1] = {dump_len};
+    return tsk_launch_ruler_segs(ctx, d_records, 1, first, base, dump, ncutoffs, min_len, weight, bins, gap,
+                                 d_len_out);
 }

@@ -819,41 +819,56 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
  * ==================================================================================== */
 /* Fair sampling among the clusters of over-subscribed buckets: the reference accepts, per
  * bucket, the first fair_max_count eligible clusters in cluster order (spotanalyzer.c:476-484
- * with threads=1).  One CTA; per round every still-waiting entry bids its cluster number
- * with atomicMin, the winner of each bucket is accepted.  `fair` is reused as the bid table. */
-__global__ void __launch_bounds__(1024)
-k_fair_resolve(uint32_t *__restrict__ fair, const uint32_t *__restrict__ bucket,
-               uint32_t *__restrict__ lists, uint32_t listcap, int max_count)
+ * with threads=1).  max_count rounds; in each round every still-waiting entry bids with
+ * atomicMin and the winner of each bucket is accepted.  The bid carries the round in its high
+ * bits, counting DOWN, so a later round's bids always undercut the previous winner and the
+ * table needs no reset between rounds.  `fair` (the candidate counts, no longer needed) is the
+ * bid table. */
+#define FAIR_ROUND_SHIFT 27          /* cluster numbers < 2^27 per block, rounds <= 30 */
+
+__global__ void __launch_bounds__(256)
+k_fair_init(uint32_t *__restrict__ fair, const uint32_t *__restrict__ bucket,
+            const uint32_t *__restrict__ lists, uint32_t listcap)
+{
+    const uint32_t cnt = lists[1];
+    const uint32_t *cont = list_array(const_cast<uint32_t *>(lists), 1, listcap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x)
+        fair[bucket[cont[i]]] = 0xffffffffu;
+}
+
+__global__ void __launch_bounds__(256)
+k_fair_bid(uint32_t *__restrict__ fair, const uint32_t *__restrict__ bucket,
+           const uint32_t *__restrict__ lists, uint32_t listcap, uint32_t roundkey)
+{
+    const uint32_t cnt = lists[1];
+    const uint32_t *cont = list_array(const_cast<uint32_t *>(lists), 1, listcap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        const uint32_t e = cont[i];
+        if (!(e & 0x80000000u)) atomicMin(&fair[bucket[e]], roundkey | e);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_fair_claim(const uint32_t *__restrict__ fair, const uint32_t *__restrict__ bucket,
+             uint32_t *__restrict__ lists, uint32_t listcap, uint32_t roundkey)
 {
     const uint32_t cnt = lists[1];
     uint32_t *cont = list_array(lists, 1, listcap);
     uint32_t *acc = list_array(lists, 2, listcap);
-    if (cnt == 0) return;
-    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) fair[bucket[cont[i] & 0x7fffffffu]] = 0xffffffffu;
-    __syncthreads();
-    for (int round = 0; round < max_count; round++) {
-        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-            const uint32_t e = cont[i];
-            if (!(e & 0x80000000u)) atomicMin(&fair[bucket[e]], e);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        const uint32_t e = cont[i];
+        if (!(e & 0x80000000u) && fair[bucket[e]] == (roundkey | e)) {
+            acc[atomicAdd(&lists[2], 1u)] = e;
+            cont[i] = e | 0x80000000u;
         }
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-            const uint32_t e = cont[i];
-            if (!(e & 0x80000000u) && fair[bucket[e]] == e) {
-                acc[atomicAdd(&lists[2], 1u)] = e;
-                cont[i] = e | 0x80000000u;
-            }
-        }
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
-            fair[bucket[cont[i] & 0x7fffffffu]] = 0xffffffffu;
-        __syncthreads();
     }
 }
 
 /* Recompute the scores of the listed clusters and add `delta` (+1 / -1, as u32) to the
  * negative histogram: accepted clusters of over-subscribed buckets (+1), and inline-sampled
- * clusters that later aborted on dark cycles (-1). */
+ * clusters that later aborted on dark cycles (-1).  One WARP per listed cluster: the cycles of
+ * a cluster are independent once its signal ranges are known, so the lanes take cycles
+ * lane, lane+32, ... (the literal arithmetic of the generic path). */
 __global__ void __launch_bounds__(TSK_K2_THREADS)
 k_resample_neg(const __grid_constant__ DevParams P, const TileView tv,
                const DevSample *__restrict__ samples, const float *__restrict__ g_tscore,
@@ -864,7 +879,9 @@ k_resample_neg(const __grid_constant__ DevParams P, const TileView tv,
     load_score_shared(sh, g_tscore, samples, P.num_samples);
     const uint32_t cnt = lists[which];
     const uint32_t *arr = list_array(const_cast<uint32_t *>(lists), which, listcap);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = wid; i < cnt; i += nw) {
         const uint32_t n = arr[i] & 0x7fffffffu;
         const tsk_call call = calls[n];
         const int ts = P.threep_start, tl = P.threep_length, bins = P.bins;
@@ -874,14 +891,14 @@ k_resample_neg(const __grid_constant__ DevParams P, const TileView tv,
         int blen = de - ts;
         if (blen > P.balancer_length) blen = P.balancer_length;
         float low[4], bw[4];
-        probe_ranges(P, cifcol, pitch, blen, low, bw);
+        probe_ranges(P, cifcol, pitch, blen, low, bw);          /* every lane, same addresses */
         int insert_len = ts + tl - de;
         const int limit = sh.limit[call.sample];
         if (limit > 0 && limit < insert_len) insert_len = limit;
-        const int16_t *p = cifcol + (size_t)(de - ts) * 4 * pitch;
-        for (int c = 0; c < insert_len; c++, p += 4 * pitch) {
+        for (int c = ps + lane; c < insert_len; c += 32) {
             float es, score;
-            if (score_cycle_generic(P, sh, p, pitch, low, bw, es, score) && c >= ps && !isinf(score))
+            const int16_t *p = cifcol + (size_t)(de - ts + c) * 4 * pitch;
+            if (score_cycle_generic(P, sh, p, pitch, low, bw, es, score) && !isinf(score))
                 atomicAdd(&neg[(size_t)(de + c) * bins + score_bin(score, bins)], delta);
         }
     }
@@ -1079,12 +1096,25 @@ int tsk_launch_fixups(tsk_ctx *ctx)
     const DevParams &P = ctx->dp;
     const uint32_t listcap = ctx->cap_clusters;
     cudaStream_t st = ctx->stream;
-    k_fair_resolve<<<1, 1024, 0, st>>>(ctx->d_fair, ctx->d_bucket, ctx->d_lists, listcap, P.fair_max_count);
-    k_resample_neg<<<148, TSK_K2_THREADS, 0, st>>>(P, ctx->tile, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
-                                                  ctx->d_neg, ctx->d_lists, listcap, 2, 1u);
-    k_resample_neg<<<148, TSK_K2_THREADS, 0, st>>>(P, ctx->tile, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
-                                                  ctx->d_neg, ctx->d_lists, listcap, 0, 0xffffffffu);
-    ctx->launches += 3;
+    int rounds = P.fair_max_count;
+    if (rounds > 30 || N >= (1u << FAIR_ROUND_SHIFT)) {
+        tsk_set_error("fair-sampling-max-count > 30 or more than 2^27 clusters per block is not supported");
+        return -1;
+    }
+    if (rounds > 0) {
+        k_fair_init<<<148, 256, 0, st>>>(ctx->d_fair, ctx->d_bucket, ctx->d_lists, listcap);
+        for (int r = 0; r < rounds; r++) {
+            const uint32_t key = (uint32_t)(rounds - r) << FAIR_ROUND_SHIFT;
+            k_fair_bid<<<148, 256, 0, st>>>(ctx->d_fair, ctx->d_bucket, ctx->d_lists, listcap, key);
+            k_fair_claim<<<148, 256, 0, st>>>(ctx->d_fair, ctx->d_bucket, ctx->d_lists, listcap, key);
+        }
+        ctx->launches += 1 + 2 * rounds;
+    }
+    k_resample_neg<<<148 * 2, TSK_K2_THREADS, 0, st>>>(P, ctx->tile, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
+                                                      ctx->d_neg, ctx->d_lists, listcap, 2, 1u);
+    k_resample_neg<<<148 * 2, TSK_K2_THREADS, 0, st>>>(P, ctx->tile, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
+                                                      ctx->d_neg, ctx->d_lists, listcap, 0, 0xffffffffu);
+    ctx->launches += 2;
     TSK_CUDA(cudaGetLastError());
     return 0;
 }

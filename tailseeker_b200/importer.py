@@ -192,6 +192,19 @@ class TileProcessor:
                                            downhill_w, bins, gap, _ptr(out)))
         return out
 
+    def ruler_tile_all(self, cutoffs_packed: np.ndarray, min_polya: int = 8, downhill_w: float = 0.49,
+                       bins: int = 1000, gap: float = 0.1):
+        """All samples of the resident tile in one launch.  Returns (lengths int16 [sum of slots],
+        offsets u32 [num_samples + 1])."""
+        cut = np.ascontiguousarray(cutoffs_packed, dtype=np.uint32)
+        S = self.params.num_samples
+        total = sum(self.record_count(s) for s in range(S))
+        out = np.full(max(total, 1), -1, dtype=np.int16)
+        offs = np.zeros(S + 1, dtype=np.uint32)
+        _lib.check(self.lib.tsk_ruler_tile_all(self._ctx, _ptr(cut), cut.size, min_polya, downhill_w, bins, gap,
+                                               _ptr(out), _ptr(offs)))
+        return out[:total], offs
+
     def ruler_hist(self) -> np.ndarray:
         out = np.zeros(self._ruler_shape, dtype=np.uint32)
         _lib.check(self.lib.tsk_ruler_get_hist(self._ctx, _ptr(out)))

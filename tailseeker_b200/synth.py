@@ -51,7 +51,7 @@ def make_tile(cfg: ImporterConfig, nclusters: int, seed: int,
               dark_cluster_frac: float = 0.004, dark_cycle_frac: float = 0.0008,
               nocall_frac: float = 0.002, unknown_frac: float = 0.03,
               lowqual_frac: float = 0.05, lowdiv_frac: float = 0.01,
-              chunk: int = 1 << 16) -> Tile:
+              spikein_weight: float = 0.25, chunk: int = 1 << 16) -> Tile:
     """Deterministic in (cfg, nclusters, seed).  Memory: ~2.3 KB per cluster."""
     rng = np.random.default_rng(seed)
     T, L3 = cfg.total_cycles, cfg.threep_length
@@ -69,7 +69,7 @@ def make_tile(cfg: ImporterConfig, nclusters: int, seed: int,
 
     nsamp = len(cfg.samples)
     # spike-in standards are a small admixture: 7 x 0.25 against 4 x 3 (about 13 % of clusters)
-    weights = np.array([0.25 if s.fingerprint_seq else 3.0 for s in cfg.samples])
+    weights = np.array([spikein_weight if s.fingerprint_seq else 3.0 for s in cfg.samples])
     weights = weights / weights.sum() * (1.0 - unknown_frac)
     probs = np.concatenate([weights, [unknown_frac]])
     index_codes = np.stack([_codes(s.index) for s in cfg.samples]) if nsamp else \

@@ -204,3 +204,15 @@ def test_ruler_matches_oracle(proc, stock_cfg, oracle):
         assert (got[valid] == want).all()
         assert (got[~valid] == -1).all()
     assert (proc.ruler_hist() == want_hist).all()
+    # (c) every sample in one launch
+    proc.ruler_reset(T)
+    lens, offs = proc.ruler_tile_all(packed)
+    for s in range(proc.params.num_samples):
+        slots = proc.records(s, drop_withdrawn=False)
+        got = lens[offs[s]:offs[s + 1]]
+        assert got.size == slots.shape[0]
+        if got.size:
+            valid = (slots[:, 1] >> 16).astype(np.uint16).view(np.int16) >= 0
+            want, _ = oracle.ruler(o["records"][s], packed)
+            assert (got[valid] == want).all() and (got[~valid] == -1).all()
+    assert (proc.ruler_hist() == want_hist).all()
