@@ -59,7 +59,8 @@ def write_sigdists(path: str, counts: np.ndarray) -> None:
 
 
 def run_import(cfg, tile, workdir: Optional[str] = None, threads: int = 1,
-               keep: bool = False, gz_level: Optional[int] = 1) -> Dict:
+               keep: bool = False, gz_level: Optional[int] = 1, binary: Optional[str] = None,
+               read_buffer_size: Optional[int] = None) -> Dict:
     """Run oracle/_ref/tailseq-import on `tile` with configuration `cfg`
     (tailseeker_b200.config.ImporterConfig).  Returns dict with per-sample taginfo / seqqual
     text, sigpack arrays, pos/neg histograms, the stats CSV text and the wall time."""
@@ -75,7 +76,8 @@ def run_import(cfg, tile, workdir: Optional[str] = None, threads: int = 1,
         for sub in ("seqqual", "taginfo", "signals", "sigdists-r00", "stats"):
             os.makedirs(os.path.join(workdir, sub), exist_ok=True)
         rcfg = cfg.replace(data_dir=data, threep_colormatrix=mpath, threads=threads,
-                           read_buffer_size=max(cfg.read_buffer_size, 2147483648))
+                           read_buffer_size=(read_buffer_size if read_buffer_size is not None
+                                             else max(cfg.read_buffer_size, 2147483648)))
         ini = os.path.join(workdir, "tile.ini")
         with open(ini, "w") as f:
             f.write(rcfg.to_ini())
@@ -83,11 +85,11 @@ def run_import(cfg, tile, workdir: Optional[str] = None, threads: int = 1,
         if gz_level is not None:
             env["TSK_SHIM_GZ_LEVEL"] = str(gz_level)
         t0 = time.perf_counter()
-        proc = subprocess.run([REF_IMPORT, ini], cwd=workdir, env=env,
+        proc = subprocess.run([binary or REF_IMPORT, ini], cwd=workdir, env=env,
                               stdout=subprocess.PIPE, stderr=subprocess.PIPE)
         wall = time.perf_counter() - t0
         if proc.returncode != 0:
-            raise RuntimeError("reference tailseq-import failed (%d): %s"
+            raise RuntimeError("tailseq-import failed (%d): %s"
                                % (proc.returncode, proc.stderr.decode()[-2000:]))
         out = dict(wall_s=wall, stdout=proc.stdout.decode(), stderr=proc.stderr.decode(),
                    taginfo={}, seqqual={}, sigpack={}, workdir=workdir, ini=ini)
@@ -113,11 +115,11 @@ def run_import(cfg, tile, workdir: Optional[str] = None, threads: int = 1,
 
 def run_ruler(tile_id: str, sigpack_path: str, cutoffs_path: str, taginfo_path: str,
               sigdist_out: str, min_polya: int = 8, downhill_w: float = 0.49,
-              bins: int = 1000, gap: float = 0.1) -> Dict:
+              bins: int = 1000, gap: float = 0.1, binary: Optional[str] = None) -> Dict:
     """Run oracle/_ref/tailseq-polya-ruler with the 9 positional arguments of
     polyaruler.c:402-418 (as measure-polya-lengths.py:55-60 does)."""
     t0 = time.perf_counter()
-    proc = subprocess.run([REF_RULER, tile_id, sigpack_path, cutoffs_path, str(min_polya),
+    proc = subprocess.run([binary or REF_RULER, tile_id, sigpack_path, cutoffs_path, str(min_polya),
                            repr(downhill_w), taginfo_path, str(bins), repr(gap), sigdist_out],
                           stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     wall = time.perf_counter() - t0

@@ -85,11 +85,9 @@ static int build_device_params(const tsk_params *p, DevParams *d, DevSample *ds)
     if (p->fair_sampling_hash_space_size < 1) { tsk_set_error("bad fair-sampling-hash-space-size"); return -1; }
     if (p->fair_sampling_fingerprint_length < 0) { tsk_set_error("bad fair-sampling-fingerprint-length"); return -1; }
     if (p->max_cctr_scan_left_space < 1 || p->max_cctr_scan_right_space < 1) { tsk_set_error("bad cctr scan space"); return -1; }
-    if (p->has_control) {
-        tsk_set_error("PhiX control alignment (controlaligner.c) is not part of this library yet; "
-                      "configure no [control] section");
-        return -1;
-    }
+    /* has_control: list entry 1 is the control pseudo-sample ("XXXXXX", no files).  Control
+     * ALIGNMENT (controlaligner.c: exact substring, then Smith-Waterman against PhiX) is a later
+     * row of the scope table: barcode-unassigned clusters are all counted as Unknown. */
 
     memset(d, 0, sizeof(*d));
     d->total_cycles = p->total_cycles; d->index_start = p->index_start; d->index_length = p->index_length;
