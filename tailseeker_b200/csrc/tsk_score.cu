@@ -340,17 +340,28 @@ __device__ __forceinline__ float div_by_rcp(float a, float b, float y)
     return __fmaf_rn(r, y, q);
 }
 
+/* RN(1/x) for x in [2^-60, 2^60): the reciprocal approximation plus one Newton step, the very
+ * sequence __frcp_rn() runs on its fast path (checked against it in k_div_sweep) without its
+ * range test, which the caller has already made. */
+__device__ __forceinline__ float rcp_rn_fast(float x)
+{
+    float y0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(x));
+    const float e = -__fmaf_rn(x, y0, -1.0f);
+    return __fmaf_rn(y0, e, y0);
+}
+
 /* host-libm logf in fp64 FMAs for a NORMAL x in (0, 1] given as raw bits.  For zero, negative
  * or subnormal bit patterns the result is a finite meaningless number: callers either discard
  * it (p <= 0) or multiply it by a subnormal p, a term < 2^-119 that cannot reach the float sum
  * it feeds (h is 0 or >= 2^-24 * |log|, and 1 - h/maxent rounds to 1 for h < 2^-25). */
-__device__ __forceinline__ float logf_core(uint32_t ix, const double2 *__restrict__ tab)
+template <typename TabLoad>
+__device__ __forceinline__ float logf_core_t(uint32_t ix, TabLoad tabload)
 {
     const uint32_t tmp = ix - 0x3f330000u;
-    const int i = (tmp >> 19) & 15;
     const int k = (int32_t)tmp >> 23;
     const uint32_t iz = ix - (tmp & 0xff800000u);
-    const double2 t = tab[i];
+    const double2 t = tabload((tmp >> 15) & 0xf0u);          /* byte offset of entry (tmp >> 19) & 15 */
     const double z = (double)__uint_as_float(iz);
     /* (double)k without the conversion unit: 2^52 + 2^31 + k, minus the bias */
     const double kd = __dsub_rn(__hiloint2double(0x43300000, (int)(0x80000000u ^ (uint32_t)k)),
@@ -362,6 +373,12 @@ __device__ __forceinline__ float logf_core(uint32_t ix, const double2 *__restric
     y = __fma_rn(-0x1.00ea348b88334p-2, r2, y);
     y = __fma_rn(y, r2, __dadd_rn(y0, r));
     return (float)y;
+}
+
+__device__ __forceinline__ float logf_core(uint32_t ix, const double2 *__restrict__ tab)
+{
+    return logf_core_t(ix, [tab](uint32_t ofs) { return *reinterpret_cast<const double2 *>(
+                                                     reinterpret_cast<const char *>(tab) + ofs); });
 }
 
 /* top-npos / bottom-nneg probing with compile-time ranks (the stock configuration 2 / 4) */
@@ -467,7 +484,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-/* one TMA tensor copy: box {32 clusters, 4 channels, 1 cycle} of the CIF tensor -> shared */
+/* one TMA tensor copy: box {32 clusters, 4 channels, 4 cycles} of the CIF tensor -> shared */
 __device__ __forceinline__ void tma_cycle_g2s(uint32_t dst, const CUtensorMap *tmap, int x, int cyc, uint32_t bar)
 {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -482,7 +499,8 @@ __device__ __forceinline__ int lds_s16(uint32_t addr)
 
 #define K2_CL        TSK_K2_THREADS      /* clusters per CTA */
 #define K2_WARPS     (TSK_K2_THREADS / 32)
-#define K2_NSTAGE    8                   /* single-cycle stages per warp */
+#define K2_GROUP     4                   /* cycles per TMA copy */
+#define K2_NGROUP    3                   /* groups in each warp's ring (8-11 cycles of look-ahead) */
 #define K2_HEAD_MAX  24                  /* resident cycles [0, head): balancer + first scored cycles */
 #define K2_ROWB      (4 * 32 * 2)        /* bytes per cycle and warp: four channel rows of 32 int16 */
 #define K2_TILE_CYC  8                   /* record words staged per lane between flushes */
@@ -492,10 +510,10 @@ __device__ __forceinline__ int lds_s16(uint32_t addr)
 
 struct __align__(128) K2Smem {
     int16_t  head[K2_WARPS][K2_HEAD_MAX][4][32];
-    int16_t  stage[K2_WARPS][K2_NSTAGE][4][32];
+    int16_t  stage[K2_WARPS][K2_NGROUP * K2_GROUP][4][32];
     uint32_t tile[K2_WARPS][32][K2_TILE_CYC + 1];
     ScoreShared sh;
-    uint64_t bar_head[K2_WARPS], bar_full[K2_WARPS][K2_NSTAGE];
+    uint64_t bar_head[K2_WARPS], bar_full[K2_WARPS][K2_NGROUP];
 };
 
 /* One warp = 32 consecutive clusters, one lane per cluster, and its own little pipeline: the four
@@ -523,7 +541,7 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
 
     if (lane == 0) {
         mbar_init(a_bhead, 1);
-        for (int i = 0; i < K2_NSTAGE; i++) mbar_init(a_full + 8 * i, 1);
+        for (int i = 0; i < K2_NGROUP; i++) mbar_init(a_full + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     load_score_shared(sm.sh, A.tscore, A.samples, S);      /* ends with __syncthreads() */
@@ -560,16 +578,18 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
     for (int d = 16; d > 0; d >>= 1) rdata_w = max(rdata_w, __shfl_xor_sync(FULL_MASK, rdata_w, d));
 
     /* ---- TMA: resident head cycles, then the first ring of streamed cycles ---- */
-    auto issue_cycle = [&](int r) {          /* lane 0 only: cycle r -> ring slot (r - head) % 8 */
-        const int slot = (r - head) & (K2_NSTAGE - 1);
-        mbar_arrive_expect_tx(a_full + 8 * slot, K2_ROWB);
-        tma_cycle_g2s(a_stage + slot * K2_ROWB, &tmap, x0, r, a_full + 8 * slot);
+    auto issue_group = [&](int g) {          /* lane 0 only: cycles head+4g .. head+4g+3 -> ring slot g % 3 */
+        const int slot = g % K2_NGROUP;
+        mbar_arrive_expect_tx(a_full + 8 * slot, K2_GROUP * K2_ROWB);
+        tma_cycle_g2s(a_stage + slot * (K2_GROUP * K2_ROWB), &tmap, x0, head + g * K2_GROUP, a_full + 8 * slot);
     };
+    const int ngroups = rdata_w > head ? (rdata_w - head + K2_GROUP - 1) / K2_GROUP : 0;   /* groups with data */
     if (lane == 0) {
-        const int hrows = min(head, rdata_w);
-        mbar_arrive_expect_tx(a_bhead, (uint32_t)hrows * K2_ROWB);
-        for (int r = 0; r < hrows; r++) tma_cycle_g2s(a_head + r * K2_ROWB, &tmap, x0, r, a_bhead);
-        for (int r = head; r < min(head + K2_NSTAGE, rdata_w); r++) issue_cycle(r);
+        const int hgroups = (min(head, rdata_w) + K2_GROUP - 1) / K2_GROUP;
+        mbar_arrive_expect_tx(a_bhead, (uint32_t)hgroups * K2_GROUP * K2_ROWB);
+        for (int g = 0; g < hgroups; g++)
+            tma_cycle_g2s(a_head + g * (K2_GROUP * K2_ROWB), &tmap, x0, g * K2_GROUP, a_bhead);
+        for (int g = 0; g < min(K2_NGROUP, ngroups); g++) issue_group(g);
     }
 
     /* ---- balancer: per-cluster dynamic range, from the resident head cycles ---- */
@@ -628,7 +648,9 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
     float prev_entropy = CUDART_NAN_F;
     double ptotal = 0.;                       /* sum of the scores from the seed start on (KIND_POS lanes) */
     uint32_t dhwin = 0;                       /* bit k = downhill of cycle (c - k); max_mods < 32 */
-    float *scr0 = A.scratch + n - (size_t)(start + ps) * spitch;   /* scr0[r*spitch]: score of cycle r */
+    /* score of cycle r lives at scratch[(r - start - ps) * spitch + n]; scr walks one row per cycle */
+    float *scr = A.scratch + n + ((ptrdiff_t)rbeg_w - (start + ps)) * (ptrdiff_t)spitch;
+    const uint32_t a_logtab = smem_u32(&sm.sh.logtab[0]), a_tscore = smem_u32(&sm.sh.tscore[0]);
     const uint32_t a_tile = smem_u32(&sm.tile[warp][0][0]);
     const uint32_t a_mytile = a_tile + lane * ((K2_TILE_CYC + 1) * 4);
     const uint32_t colofs = (uint32_t)lane * 2;
@@ -665,7 +687,7 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
             const float sum = __fadd_rn(__fadd_rn(__fadd_rn(nrm[0], nrm[1]), nrm[2]), nrm[3]);
             float prob[4];
             if (__builtin_expect(in_exp_range(sum, -60, 60), 1)) {
-                const float ys = __frcp_rn(sum);
+                const float ys = rcp_rn_fast(sum);
 #pragma unroll
                 for (int ch = 0; ch < 4; ch++) prob[ch] = div_by_rcp(nrm[ch], sum, ys);
             } else {
@@ -678,13 +700,20 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
             float h = 0.f;
 #pragma unroll
             for (int ch = 0; ch < 4; ch++) {
-                const float term = __fmul_rn(prob[ch], logf_core(__float_as_uint(prob[ch]), sh.logtab));
+                const float lg = logf_core_t(__float_as_uint(prob[ch]), [a_logtab](uint32_t ofs) {
+                    double2 t;
+                    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(a_logtab + ofs));
+                    return t;
+                });
+                const float term = __fmul_rn(prob[ch], lg);
                 h = __fsub_rn(h, prob[ch] > 0.f ? term : 0.f);
             }
             const float es = __fsub_rn(1.f, div_by_rcp(h, P.maximum_entropy, rcp_maxent));
             const uint32_t ti = min((uint32_t)__float2int_rz(__fmul_rn(prob[3], (float)TSK_T_SCORE_BINS)),
                                     (uint32_t)TSK_T_SCORE_BINS);
-            const float score = lit ? __fmul_rn(es, sh.tscore[ti]) : CUDART_NAN_F;
+            float tsc;
+            asm("ld.shared.f32 %0, [%1];" : "=f"(tsc) : "r"(a_tscore + ti * 4));
+            const float score = lit ? __fmul_rn(es, tsc) : CUDART_NAN_F;
             const uint32_t dh = (lit && es < prev_entropy) ? 1u : 0u;
             prev_entropy = lit ? es : CUDART_NAN_F;
             ndark += lit ? 0 : 1;
@@ -696,7 +725,7 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
                 /* packet j = c - ps carries downhill[j], the UN-offset array (spotanalyzer.c:604-606) */
                 word = lit ? ((s << 1) | ((dhwin >> ps) & 1u)) : 0u;
                 if (ispos) {
-                    scr0[(size_t)r * spitch] = score;
+                    *scr = score;
                     ptotal = __dadd_rn(ptotal, (double)score);      /* same order as the reference's cumsum */
                 }
                 if (neg_inline && lit && !isinf(score))
@@ -732,19 +761,23 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
             }
             __syncwarp();
         }
+        scr += spitch;
     };
 
     /* ---- resident head cycles ---- */
     for (int r = rbeg_w; r < min(rend_w, head); r++) cycle(r, a_head + r * K2_ROWB);
 
-    /* ---- streamed cycles: wait for the cycle's rows, score it, let lane 0 refill the slot ---- */
-    for (int r = max(rbeg_w, head); r < rend_w; r++) {
-        const int q = r - head;
-        const int slot = q & (K2_NSTAGE - 1);
-        if (r < rdata_w) mbar_wait(a_full + 8 * slot, (q / K2_NSTAGE) & 1);
-        cycle(r, a_stage + slot * K2_ROWB);
+    /* ---- streamed cycles, four at a time: wait for the group's rows, score its cycles, let lane 0
+     *      refill the ring slot with the group three ahead ---- */
+    for (int g = 0; head + g * K2_GROUP < rend_w; g++) {
+        const int slot = g % K2_NGROUP;
+        const int r0 = head + g * K2_GROUP;
+        if (g < ngroups) mbar_wait(a_full + 8 * slot, (g / K2_NGROUP) & 1);
+#pragma unroll 1
+        for (int k = 0; k < K2_GROUP; k++)
+            if (r0 + k < rend_w) cycle(r0 + k, a_stage + (slot * K2_GROUP + k) * K2_ROWB);
         __syncwarp();
-        if (lane == 0 && r + K2_NSTAGE < rdata_w) issue_cycle(r + K2_NSTAGE);
+        if (lane == 0 && g + K2_NGROUP < ngroups) issue_group(g + K2_NGROUP);
     }
 
     if (!alive) return;
@@ -955,7 +988,9 @@ __global__ void k_div_sweep(uint64_t seed, uint64_t count, int mode, unsigned lo
             b = __uint_as_float(((124 + (bb >> 23) % 6) << 23) | (bb & 0x7fffffu));
             a = __fmul_rn(b, __uint_as_float(0x3f800000u | (ab & 0x7fffffu)) - 1.0f);
         }
-        const float q = div_by_rcp(a, b, __frcp_rn(b));
+        const float yb = rcp_rn_fast(b);
+        bad += __float_as_uint(yb) != __float_as_uint(__frcp_rn(b));
+        const float q = div_by_rcp(a, b, yb);
         const float want = __fdiv_rn(a, b);
         bad += __float_as_uint(q) != __float_as_uint(want) && !(q == 0.f && want == 0.f);
     }
@@ -1047,7 +1082,7 @@ static int make_cif_tensor_map(tsk_ctx *ctx, CUtensorMap *tmap)
     }
     const cuuint64_t dims[3] = {(cuuint64_t)ctx->tile.nclusters, 4, (cuuint64_t)ctx->dp.threep_length};
     const cuuint64_t strides[2] = {(cuuint64_t)ctx->tile.cif_pitch * 2, (cuuint64_t)ctx->tile.cif_pitch * 8};
-    const cuuint32_t box[3] = {32, 4, 1}, estr[3] = {1, 1, 1};
+    const cuuint32_t box[3] = {32, 4, K2_GROUP}, estr[3] = {1, 1, 1};
     const CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, (void *)ctx->tile.cif, dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
