@@ -169,7 +169,9 @@ int tsk_ctx_destroy(tsk_ctx *ctx);
  * pitches in ELEMENTS, >= nclusters.  on_device != 0: the pointers are device pointers that
  * the caller keeps alive until the next upload (zero copy); otherwise they are host
  * pointers (pinned or pageable) and are copied to HBM on the context's stream.
- * invmatrix = inverse colour matrix (load_color_matrix(), signalproc.c:345-375). */
+ * invmatrix = inverse colour matrix (load_color_matrix(), signalproc.c:345-375).
+ * Up to two tiles may be uploaded ahead of tsk_tile_process(), which takes them in order: the
+ * copy of tile t+1 (on its own stream) then overlaps the kernels of tile t. */
 int tsk_tile_upload(tsk_ctx *ctx, const uint8_t *bcl, size_t bcl_pitch,
                     const int16_t *cif, size_t cif_pitch,
                     const float invmatrix[16],
@@ -211,7 +213,7 @@ uint32_t tsk_cutoff_to_packed(double cutoff);
  * device pointer.  Outputs: polya_len_out[i] per slot (-1 when below minimum_polya_len or
  * withdrawn slot; host pointer), and the positive-sample histogram
  * u32[ncutoffs][dist_sampling_bins] ADDED into the context's ruler histogram
- * (zero it with tsk_ruler_hist_reset()). */
+ * (zero it with tsk_ruler_hist_reset(); a call with another (ncutoffs, bins) shape resets it). */
 int tsk_ruler_records(tsk_ctx *ctx, const uint32_t *records, size_t nrecords, int dump_len,
                       const uint32_t *cutoffs, int ncutoffs,
                       int minimum_polya_len, float downhill_ext_weight,

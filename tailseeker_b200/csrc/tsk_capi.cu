@@ -173,6 +173,9 @@ extern "C" int tsk_ctx_create(tsk_ctx **out, int device, const tsk_params *param
     TSK_CUDA(cudaSetDevice(device));
     TSK_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->own_stream = 1;
+    TSK_CUDA(cudaStreamCreateWithFlags(&ctx->cstream, cudaStreamNonBlocking));
+    TSK_CUDA(cudaEventCreateWithFlags(&ctx->ev_up[0], cudaEventDisableTiming));
+    TSK_CUDA(cudaEventCreateWithFlags(&ctx->ev_up[1], cudaEventDisableTiming));
     const int S = params->num_samples;
     const size_t histbytes = sizeof(uint32_t) * (size_t)params->total_cycles * params->dist_sampling_bins;
     TSK_CUDA(cudaMalloc(&ctx->d_samples, sizeof(DevSample) * S));
@@ -206,7 +209,8 @@ extern "C" int tsk_ctx_destroy(tsk_ctx *ctx)
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    void *ptrs[] = {ctx->d_samples, ctx->d_tscore, ctx->d_rcp, ctx->d_bcl_own, ctx->d_cif_own, ctx->d_calls, ctx->d_kind,
+    void *ptrs[] = {ctx->d_samples, ctx->d_tscore, ctx->d_rcp, ctx->d_bcl_own[0], ctx->d_cif_own[0], ctx->d_bcl_own[1],
+                    ctx->d_cif_own[1], ctx->d_calls, ctx->d_kind,
                     ctx->d_bucket, ctx->d_worklist, ctx->d_blkcnt, ctx->d_totals, ctx->d_recbase,
                     ctx->d_records, ctx->d_scratch, ctx->d_pos, ctx->d_neg, ctx->d_counters, ctx->d_fair,
                     ctx->d_lists, ctx->d_ruler_pos, ctx->d_cutoffs, ctx->d_rlen, ctx->d_rrec,
@@ -214,6 +218,8 @@ extern "C" int tsk_ctx_destroy(tsk_ctx *ctx)
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)
         if (ptrs[i]) cudaFree(ptrs[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->cstream);
+    cudaEventDestroy(ctx->ev_up[0]); cudaEventDestroy(ctx->ev_up[1]);
     if (ctx->profile) for (int i = 0; i < 7; i++) cudaEventDestroy(ctx->pev[i]);
     free(ctx);
     return 0;
@@ -243,6 +249,7 @@ static int ensure_cluster_buffers(tsk_ctx *ctx, uint32_t n)
     ctx->d_calls = NULL; ctx->d_kind = NULL; ctx->d_bucket = NULL; ctx->d_worklist = NULL;
     ctx->d_blkcnt = NULL; ctx->d_records = NULL; ctx->d_scratch = NULL; ctx->d_lists = NULL;
     ctx->cap_clusters = 0;
+    ctx->processed = 0;          /* the previous tile's result buffers are gone */
     const size_t nblk = (cap + TSK_K1_THREADS - 1) / TSK_K1_THREADS;
     const int maxinsert = ctx->dp.threep_length + 1;
     TSK_CUDA(cudaMalloc(&ctx->d_calls, sizeof(tsk_call) * (size_t)cap));
@@ -268,31 +275,59 @@ extern "C" int tsk_tile_upload(tsk_ctx *ctx, const uint8_t *bcl, size_t bcl_pitc
     if (bcl_pitch < nclusters || cif_pitch < nclusters) { tsk_set_error("pitch smaller than nclusters"); return -1; }
     if (nclusters >= 0x7fffffffu) { tsk_set_error("too many clusters in one block"); return -1; }
     TSK_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->npending >= 2) { tsk_set_error("two tiles are already uploaded; call tsk_tile_process() first"); return -1; }
     if (ensure_cluster_buffers(ctx, nclusters) != 0) return -1;
     const int T = ctx->dp.total_cycles, L3 = ctx->dp.threep_length;
-    ctx->processed = 0;
-    memcpy(ctx->dp.inv, invmatrix, sizeof(float) * 16);
-    ctx->tile.nclusters = nclusters;
-    ctx->tile.firstclusterno = firstclusterno;
+    auto &slot = ctx->pending[ctx->npending];
+    memcpy(slot.inv, invmatrix, sizeof(float) * 16);
+    slot.tv.nclusters = nclusters;
+    slot.tv.firstclusterno = firstclusterno;
     if (on_device) {
-        ctx->tile.bcl = bcl; ctx->tile.bcl_pitch = bcl_pitch;
-        ctx->tile.cif = cif; ctx->tile.cif_pitch = cif_pitch;
+        slot.tv.bcl = bcl; slot.tv.bcl_pitch = bcl_pitch;
+        slot.tv.cif = cif; slot.tv.cif_pitch = cif_pitch;
+        slot.slot = -1;
+        ctx->npending++;
         return 0;
     }
-    /* own HBM copy; rows padded to 128 B so every row starts on a full line */
+    /* own HBM copy (rows padded to 128 clusters), on the copy stream: it overlaps the processing
+     * of the previously uploaded tile */
+    const int u = ctx->up_slot;
     const size_t bpitch = ((size_t)nclusters + 127) & ~(size_t)127;
-    const size_t cpitch = ((size_t)nclusters + 127) & ~(size_t)127;   /* whole 128-cluster CTA windows */
-    if (ensure(&ctx->d_bcl_own, &ctx->bcl_cap, bpitch * T + 128) != 0) return -1;
-    if (ensure(&ctx->d_cif_own, &ctx->cif_cap, cpitch * 4 * L3 + 128) != 0) return -1;
+    const size_t cpitch = ((size_t)nclusters + 127) & ~(size_t)127;
+    if (ensure(&ctx->d_bcl_own[u], &ctx->bcl_cap[u], bpitch * T + 128) != 0) return -1;
+    if (ensure(&ctx->d_cif_own[u], &ctx->cif_cap[u], cpitch * 4 * L3 + 128) != 0) return -1;
     if (nclusters) {
-        TSK_CUDA(cudaMemcpy2DAsync(ctx->d_bcl_own, bpitch, bcl, bcl_pitch, nclusters, T,
-                                   cudaMemcpyHostToDevice, ctx->stream));
-        TSK_CUDA(cudaMemcpy2DAsync(ctx->d_cif_own, cpitch * sizeof(int16_t), cif, cif_pitch * sizeof(int16_t),
+        TSK_CUDA(cudaMemcpy2DAsync(ctx->d_bcl_own[u], bpitch, bcl, bcl_pitch, nclusters, T,
+                                   cudaMemcpyHostToDevice, ctx->cstream));
+        TSK_CUDA(cudaMemcpy2DAsync(ctx->d_cif_own[u], cpitch * sizeof(int16_t), cif, cif_pitch * sizeof(int16_t),
                                    (size_t)nclusters * sizeof(int16_t), (size_t)4 * L3,
-                                   cudaMemcpyHostToDevice, ctx->stream));
+                                   cudaMemcpyHostToDevice, ctx->cstream));
     }
-    ctx->tile.bcl = ctx->d_bcl_own; ctx->tile.bcl_pitch = bpitch;
-    ctx->tile.cif = ctx->d_cif_own; ctx->tile.cif_pitch = cpitch;
+    TSK_CUDA(cudaEventRecord(ctx->ev_up[u], ctx->cstream));
+    slot.tv.bcl = ctx->d_bcl_own[u]; slot.tv.bcl_pitch = bpitch;
+    slot.tv.cif = ctx->d_cif_own[u]; slot.tv.cif_pitch = cpitch;
+    slot.slot = u;
+    ctx->up_slot ^= 1;
+    ctx->npending++;
+    return 0;
+}
+
+/* next uploaded tile becomes the resident one */
+static int next_tile(tsk_ctx *ctx)
+{
+    if (ctx->npending == 0) {
+        if (ctx->d_calls && ctx->tile_valid) return 0;      /* re-process the resident tile */
+        tsk_set_error("no tile uploaded");
+        return -1;
+    }
+    ctx->tile = ctx->pending[0].tv;
+    memcpy(ctx->dp.inv, ctx->pending[0].inv, sizeof(float) * 16);
+    if (ctx->pending[0].slot >= 0)
+        TSK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[ctx->pending[0].slot], 0));
+    ctx->pending[0] = ctx->pending[1];
+    ctx->npending--;
+    ctx->tile_valid = 1;
+    ctx->processed = 0;
     return 0;
 }
 
@@ -311,6 +346,7 @@ extern "C" int tsk_tile_process(tsk_ctx *ctx)
 {
     if (!ctx || !ctx->d_calls) { tsk_set_error("no tile uploaded"); return -1; }
     TSK_CUDA(cudaSetDevice(ctx->device));
+    if (next_tile(ctx) != 0) return -1;
     if (tsk_launch_import(ctx, ctx->profile ? ctx->pev : NULL) != 0) return -1;
     if (fetch_totals(ctx) != 0) return -1;
     if (ctx->profile)
@@ -366,6 +402,7 @@ extern "C" int tsk_tile_process_timed(tsk_ctx *ctx, int iters, float ms_out[5])
 {
     if (!ctx || !ctx->d_calls || iters < 1) { tsk_set_error("bad argument"); return -1; }
     TSK_CUDA(cudaSetDevice(ctx->device));
+    if (next_tile(ctx) != 0) return -1;
     cudaEvent_t ev[5];
     for (int i = 0; i < 5; i++) TSK_CUDA(cudaEventCreate(&ev[i]));
     const int S = ctx->dp.num_samples;
@@ -505,7 +542,9 @@ extern "C" int tsk_ruler_hist_reset(tsk_ctx *ctx, int ncutoffs, int dist_samplin
     TSK_CUDA(cudaSetDevice(ctx->device));
     const size_t words = (size_t)ncutoffs * dist_sampling_bins;
     if (ensure(&ctx->d_ruler_pos, &ctx->ruler_pos_words, words) != 0) return -1;
-    TSK_CUDA(cudaMemsetAsync(ctx->d_ruler_pos, 0, sizeof(uint32_t) * ctx->ruler_pos_words, ctx->stream));
+    TSK_CUDA(cudaMemsetAsync(ctx->d_ruler_pos, 0, sizeof(uint32_t) * words, ctx->stream));
+    ctx->ruler_ncut = ncutoffs;
+    ctx->ruler_bins = dist_sampling_bins;
     return 0;
 }
 
@@ -513,7 +552,7 @@ extern "C" int tsk_ruler_get_hist(tsk_ctx *ctx, uint32_t *pos)
 {
     if (!ctx || !ctx->d_ruler_pos) { tsk_set_error("no ruler histogram"); return -1; }
     TSK_CUDA(cudaSetDevice(ctx->device));
-    TSK_CUDA(cudaMemcpyAsync(pos, ctx->d_ruler_pos, sizeof(uint32_t) * ctx->ruler_pos_words,
+    TSK_CUDA(cudaMemcpyAsync(pos, ctx->d_ruler_pos, sizeof(uint32_t) * (size_t)ctx->ruler_ncut * ctx->ruler_bins,
                              cudaMemcpyDeviceToHost, ctx->stream));
     TSK_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -526,7 +565,7 @@ static int ruler_common(tsk_ctx *ctx, const uint32_t *d_records, size_t nrecords
     if (ncutoffs < 1 || ncutoffs > TSK_MAX_CUTOFF_CYCLES || bins < 1 || dump_len < 0 || !cutoffs) {
         tsk_set_error("bad ruler argument"); return -1;
     }
-    if (!ctx->d_ruler_pos || ctx->ruler_pos_words < (size_t)ncutoffs * bins) {
+    if (!ctx->d_ruler_pos || ctx->ruler_ncut != ncutoffs || ctx->ruler_bins != bins) {
         if (tsk_ruler_hist_reset(ctx, ncutoffs, bins) != 0) return -1;
     }
     TSK_CUDA(cudaMemcpyAsync(ctx->d_cutoffs, cutoffs, sizeof(uint32_t) * ncutoffs, cudaMemcpyHostToDevice,
@@ -598,7 +637,7 @@ extern "C" int tsk_ruler_tile_all(tsk_ctx *ctx, const uint32_t *cutoffs, int ncu
     }
     slot_offsets[S] = first[S];
     const size_t n = first[S];
-    if (!ctx->d_ruler_pos || ctx->ruler_pos_words < (size_t)ncutoffs * dist_sampling_bins)
+    if (!ctx->d_ruler_pos || ctx->ruler_ncut != ncutoffs || ctx->ruler_bins != dist_sampling_bins)
         if (tsk_ruler_hist_reset(ctx, ncutoffs, dist_sampling_bins) != 0) return -1;
     TSK_CUDA(cudaMemcpyAsync(ctx->d_cutoffs, cutoffs, sizeof(uint32_t) * ncutoffs, cudaMemcpyHostToDevice, ctx->stream));
     if (ensure(&ctx->d_rlen, &ctx->rlen_cap, n ? n : 1) != 0) return -1;

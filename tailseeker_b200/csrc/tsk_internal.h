@@ -71,8 +71,14 @@ struct tsk_ctx {
 
     /* resident tile */
     TileView tile;
-    uint8_t *d_bcl_own;  size_t bcl_cap;
-    int16_t *d_cif_own;  size_t cif_cap;
+    /* two upload slots: tile t+1 is copied in on the copy stream while tile t is processed */
+    uint8_t *d_bcl_own[2];  size_t bcl_cap[2];
+    int16_t *d_cif_own[2];  size_t cif_cap[2];
+    cudaStream_t cstream;
+    cudaEvent_t ev_up[2];
+    int up_slot;                 /* slot of the next host upload */
+    struct { TileView tv; float inv[16]; int slot; /* -1: caller's device memory */ } pending[2];
+    int npending, tile_valid;
     uint32_t cap_clusters;       /* capacity of the per-cluster buffers below */
 
     tsk_call *d_calls;           /* [N] */
@@ -88,7 +94,8 @@ struct tsk_ctx {
     uint32_t *d_counters;        /* [num_samples][6] */
     uint32_t *d_fair;            /* [hash_size] candidate counts per bucket */
     uint32_t *d_lists;           /* undo / contended / accepted lists + their counters */
-    uint32_t *d_ruler_pos;  size_t ruler_pos_words;
+    uint32_t *d_ruler_pos;  size_t ruler_pos_words;   /* capacity */
+    int ruler_ncut, ruler_bins;                       /* current shape of the ruler histogram */
     uint32_t *d_cutoffs;         /* [TSK_MAX_CUTOFF_CYCLES] */
     int16_t  *d_rlen;  size_t rlen_cap;
     uint32_t *d_rrec;  size_t rrec_cap;       /* staging of host-provided ruler records */

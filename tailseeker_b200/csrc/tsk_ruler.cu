@@ -27,7 +27,7 @@ struct RulerSegs {
 __global__ void __launch_bounds__(RULER_THREADS)
 k_polya_ruler(const uint32_t *__restrict__ records, const __grid_constant__ RulerSegs seg,
               const uint32_t *__restrict__ g_cutoffs, int ncut, int min_len, float weight,
-              int bins, float gap, int16_t *__restrict__ len_out, uint32_t *__restrict__ pos)
+              int bins, float gap, int16_t *__restrict__ len_out, uint32_t *__restrict__ pos, int intbins)
 {
     __shared__ uint32_t s_cut[TSK_MAX_CUTOFF_CYCLES];
     for (int i = threadIdx.x; i < ncut; i += RULER_THREADS) s_cut[i] = g_cutoffs[i];
@@ -47,35 +47,47 @@ k_polya_ruler(const uint32_t *__restrict__ records, const __grid_constant__ Rule
         const int valid = (int16_t)(hdr >> 16);
         int len = 0;
 
+        /* all packets of the record in flight at once: eight independent 128-byte loads per warp
+         * (records longer than 256 cycles fall back to re-reading through L1) */
+        uint32_t w[8];
+        const bool inreg = valid <= 256;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            w[k] = (inreg && k * 32 + lane < valid) ? __ldg(rec + 2 + k * 32 + lane) : 0u;
+        auto packet = [&](int i) -> uint32_t {       /* i = base + lane, base a multiple of 32 */
+            if (!inreg) return __ldg(rec + 2 + i);
+            uint32_t v = w[0];
+#pragma unroll
+            for (int k = 1; k < 8; k++) v = ((i >> 5) == k) ? w[k] : v;
+            return v;
+        };
+
         if (valid > 0) {
-            /* ---- +-1 cumulative sum and its first strict maximum ---- */
+            /* ---- +-1 cumulative sum and its first strict maximum ----
+             * the steps are +1 / -1 / 0, so a lane's inclusive prefix sum is the difference of two
+             * population counts over ballots; the maximum of (cum, -index) keys is one REDUX. */
             int carry = 0;
             int bestkey = INT_MIN;
+            const unsigned le_mask = 0xffffffffu >> (31 - lane);
             for (int base = 0; base < valid; base += 32) {
                 const int i = base + lane;
                 const int cyc = first + i;
-                int v = 0;
+                bool up = false, down = false;
                 if (i < valid && cyc < ncut) {
                     const uint32_t cut = s_cut[cyc];
                     if (cut != 0) {
-                        const uint32_t sc = (__ldg(rec + 2 + i) >> 1) & TSK_SCORE_MAX;
-                        v = (sc >= cut) ? 1 : -1;
+                        const uint32_t sc = (packet(i) >> 1) & TSK_SCORE_MAX;
+                        up = sc >= cut;
+                        down = !up;
                     }
                 }
-                int pre = v;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int o = __shfl_up_sync(FULL_MASK, pre, d);
-                    if (lane >= d) pre += o;
-                }
-                const int cum = carry + pre;
+                const unsigned mu = __ballot_sync(FULL_MASK, up), md = __ballot_sync(FULL_MASK, down);
+                const int cum = carry + __popc(mu & le_mask) - __popc(md & le_mask);
                 /* larger cumsum wins, then the smaller cycle index */
-                const int key = ((cum + 2048) << 16) | (0xffff - i);
-                if (i < valid) bestkey = max(bestkey, key);
-                carry = __shfl_sync(FULL_MASK, cum, 31);
+                const int key = (i < valid) ? (((cum + 2048) << 16) | (0xffff - i)) : INT_MIN;
+                bestkey = max(bestkey, __reduce_max_sync(FULL_MASK, key));
+                carry += __popc(mu) - __popc(md);
             }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) bestkey = max(bestkey, __shfl_xor_sync(FULL_MASK, bestkey, d));
             const int maxcum = (bestkey >> 16) - 2048;
             const int argmax = (maxcum > 0) ? (0xffff - (bestkey & 0xffff)) : -1;
 
@@ -85,7 +97,7 @@ k_polya_ruler(const uint32_t *__restrict__ records, const __grid_constant__ Rule
                 for (int base = ((argmax + 1) >> 5) << 5; base < valid; base += 32) {
                     const int i = base + lane;
                     uint32_t x = 0;
-                    if (i < valid && i > argmax) x = __ldg(rec + 2 + i);
+                    if (i < valid && i > argmax) x = packet(i);
                     const bool lit = ((x >> 1) & TSK_SCORE_MAX) != 0;
                     const unsigned stop = __ballot_sync(FULL_MASK, lit && !(x & 1u));
                     unsigned go = __ballot_sync(FULL_MASK, lit && (x & 1u));
@@ -106,10 +118,23 @@ k_polya_ruler(const uint32_t *__restrict__ records, const __grid_constant__ Rule
         if (pass) {
             const int take = len - __float2int_rz(__fmul_rn((float)len, gap));
             for (int i = lane; i < take; i += 32) {
-                const uint32_t sc = (__ldg(rec + 2 + i) >> 1) & TSK_SCORE_MAX;
+                const uint32_t sc = (packet(i) >> 1) & TSK_SCORE_MAX;
                 if (sc > 0) {
-                    int b = __double2int_rz(__dmul_rn(__ddiv_rn(__dsub_rn((double)sc, 1.0),
+                    int b;
+                    if (intbins) {
+                        /* floor((sc-1) * bins / 16777214) in integers: with x = a*2^24 + b0 and
+                         * 2^24 = 16777214 + 2, x = a*16777214 + (2a + b0), 2a + b0 < 2*16777214.
+                         * Equals the reference's fp64 expression whenever bins shares no factor
+                         * with 2^23-1 (the host checks): the exact value is then an integer only for
+                         * sc-1 in {0, 8388607, 16777214}, which fp64 evaluates exactly, and is
+                         * otherwise >= 2^-24 away from one, far beyond the fp64 rounding error. */
+                        const unsigned long long x = (unsigned long long)(sc - 1) * (unsigned)bins;
+                        const uint32_t a = (uint32_t)(x >> 24), b0 = (uint32_t)x & 0xffffffu;
+                        b = (int)(a + ((2 * a + b0) >= 16777214u ? 1u : 0u));
+                    } else {
+                        b = __double2int_rz(__dmul_rn(__ddiv_rn(__dsub_rn((double)sc, 1.0),
                                                                (double)(TSK_SCORE_MAX - 1)), (double)bins));
+                    }
                     if (b >= bins) b = bins - 1;
                     atomicAdd(&pos[(size_t)(first + i) * bins + b], 1u);
                 }
@@ -131,8 +156,10 @@ int tsk_launch_ruler_segs(tsk_ctx *ctx, const uint32_t *d_records, int nseg, con
     size_t blocks = (nrecords + (RULER_THREADS / 32) - 1) / (RULER_THREADS / 32);
     const size_t maxblocks = 148 * 8 * 4;       /* persistent-ish: a few waves of 148 SMs x 8 CTAs */
     if (blocks > maxblocks) blocks = maxblocks;
+    /* 2^23 - 1 = 47 * 178481 */
+    const int intbins = (bins % 47 != 0) && (bins % 178481 != 0) && bins <= 65536;
     k_polya_ruler<<<(unsigned)blocks, RULER_THREADS, 0, ctx->stream>>>(
-        d_records, seg, ctx->d_cutoffs, ncutoffs, min_len, weight, bins, gap, d_len_out, ctx->d_ruler_pos);
+        d_records, seg, ctx->d_cutoffs, ncutoffs, min_len, weight, bins, gap, d_len_out, ctx->d_ruler_pos, intbins);
     ctx->launches++;
     TSK_CUDA(cudaGetLastError());
     return 0;

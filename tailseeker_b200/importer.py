@@ -65,7 +65,8 @@ class TileProcessor:
         self.lib = _lib.load()
         self._ctx = ctypes.c_void_p()
         _lib.check(self.lib.tsk_ctx_create(ctypes.byref(self._ctx), device, ctypes.byref(self.params)))
-        self.nclusters = 0
+        self.nclusters = 0          # clusters of the tile last taken by process()
+        self._pending = []          # [(nclusters, host arrays kept alive)] uploaded, not yet processed
         self._keep = None
 
     def close(self):
@@ -92,17 +93,24 @@ class TileProcessor:
             nclusters = bcl.shape[1] if nclusters is None else nclusters
             bcl_pitch = bcl.shape[1]
             cif_pitch = cif.shape[2]
-        self._keep = (bcl, cif)
         _lib.check(self.lib.tsk_tile_upload(self._ctx, _ptr(bcl), bcl_pitch, _ptr(cif), cif_pitch,
                                             _ptr(inv), nclusters, firstclusterno, int(on_device)))
-        self.nclusters = int(nclusters)
+        self._pending.append((int(nclusters), (bcl, cif)))
+
+    def _take(self):
+        if self._pending:
+            self.nclusters, self._keep = self._pending.pop(0)
 
     def process(self):
+        """Process the oldest uploaded tile (up to two may be uploaded ahead: the copy of the next
+        tile then overlaps this tile's kernels)."""
         _lib.check(self.lib.tsk_tile_process(self._ctx))
+        self._take()
 
     def process_timed(self, iters: int = 1) -> np.ndarray:
         ms = np.zeros(5, dtype=np.float32)
         _lib.check(self.lib.tsk_tile_process_timed(self._ctx, iters, _ptr(ms)))
+        self._take()
         return ms
 
     def calls(self) -> np.ndarray:

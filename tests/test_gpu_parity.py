@@ -216,3 +216,43 @@ def test_ruler_matches_oracle(proc, stock_cfg, oracle):
             want, _ = oracle.ruler(o["records"][s], packed)
             assert (got[valid] == want).all() and (got[~valid] == -1).all()
     assert (proc.ruler_hist() == want_hist).all()
+
+
+@pytest.mark.parametrize("bins", [470, 64, 1000])
+def test_ruler_histogram_bins(proc, stock_cfg, oracle, bins):
+    """Positive resampling with other bin counts: 470 = 10 * 47 shares a factor with 2^23 - 1 and
+    takes the literal fp64 binning, the others the integer form."""
+    tile, o = _run(proc, stock_cfg, oracle, 6000, 12)
+    T = stock_cfg.total_cycles
+    packed = proc.cutoffs_to_packed(np.full(T, 0.2))
+    recs = o["records"][proc.params.num_samples - 1]
+    want, want_hist = oracle.ruler(recs, packed, bins=bins, gap=0.25)
+    proc.ruler_reset(T, bins)
+    got = proc.ruler_records(recs, packed, bins=bins, gap=0.25)
+    assert (got == want).all() and int((want >= 0).sum()) > 100
+    assert (proc.ruler_hist() == want_hist).all()
+
+
+def test_two_tiles_uploaded_ahead(stock_cfg, oracle):
+    """Upload queue of depth two: tile B is copied in while tile A is processed; results of each
+    process() are those of the oldest uploaded tile; a third upload is refused."""
+    from tailseeker_b200 import _lib
+    from tailseeker_b200.synth import make_tile
+    from tailseeker_b200.importer import TileProcessor, invert_colormatrix
+    p = TileProcessor(stock_cfg)
+    try:
+        tiles = [make_tile(stock_cfg, n, seed=40 + i) for i, n in enumerate((2500, 1300, 3100))]
+        invs = [invert_colormatrix(t.matrix) for t in tiles]
+        p.upload(tiles[0].bcl, tiles[0].cif, invs[0])
+        p.upload(tiles[1].bcl, tiles[1].cif, invs[1])
+        with pytest.raises(_lib.TskError):
+            p.upload(tiles[2].bcl, tiles[2].cif, invs[2])
+        for i in range(3):
+            p.reset_counters()
+            p.process()
+            if i == 0:
+                p.upload(tiles[2].bcl, tiles[2].cif, invs[2])
+            o = oracle.process(stock_cfg, tiles[i].bcl, tiles[i].cif, invs[i])
+            compare_tile(p, stock_cfg, None, o)
+    finally:
+        p.close()
