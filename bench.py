@@ -39,7 +39,9 @@ TILES_PER_GPU = 14
 CLUSTERS_PER_TILE = 1_070_000
 METRIC = "clusters/sec for decode+normalise+poly(A) call"
 UNIT = "clusters/s"
-WORKLOAD = ("MiSeq v2 full run: %d tiles x %d clusters, 51+251 cycles, 4 exp + 7 spike-in samples "
+PHIX_FRAC = 0.6     # of the 3 % barcode-unassigned clusters: reads of the PhiX control (half with errors)
+WORKLOAD = ("MiSeq v2 full run: %d tiles x %d clusters, 51+251 cycles, 4 exp + 7 spike-in samples, "
+            "[control] PhiX as generate-signalproc-conf.py always emits it "
             "(BASELINE.json configs[1]) per GPU" % (TILES_PER_GPU, CLUSTERS_PER_TILE))
 
 
@@ -147,7 +149,7 @@ def run_reference_arm(args):
     from oracle import refrun
     from tailseeker_b200.config import stock_config
     from tailseeker_b200.synth import make_tile
-    cfg = stock_config("miseq")
+    cfg = stock_config("miseq", phix_match_name="PhiX")
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -158,7 +160,7 @@ def run_reference_arm(args):
         return 0
     cores = os.cpu_count() or 1
     nsample = args.ref_clusters
-    tile = make_tile(cfg, nsample, seed=1234)
+    tile = make_tile(cfg, nsample, seed=1234, phix_frac=PHIX_FRAC)
     cut = default_cutoffs(cfg.total_cycles)
     times = []
     for it in range(args.warmup + args.steps):
@@ -245,7 +247,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = stock_config("miseq")
+    cfg = stock_config("miseq", phix_match_name="PhiX")
     T, L3, bins = cfg.total_cycles, cfg.threep_length, cfg.dist_sampling_bins
     ntiles, N = args.tiles, args.clusters_per_tile
 
@@ -257,7 +259,7 @@ def main():
     # ---- synthetic tile set, generated in HBM (one lane's worth per rank) -------------------
     tiles = []
     for t in range(ntiles):
-        bcl, cif, mtext, pitch = make_tile_device(cfg, N, seed=1000 * (rank + 1) + t, device=dev)
+        bcl, cif, mtext, pitch = make_tile_device(cfg, N, seed=1000 * (rank + 1) + t, device=dev, phix_frac=PHIX_FRAC)
         mtx = np.array([np.float32(x) for x in mtext.split()], dtype=np.float32)
         tiles.append((bcl, cif, invert_colormatrix(mtx), pitch, mtext))
     torch.cuda.synchronize()

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TSK_ABI_VERSION          1
+#define TSK_ABI_VERSION          2
 
 #define TSK_NUM_CHANNELS         4      /* tailseq-import.h:40 */
 #define TSK_MAX_SAMPLES          64
@@ -40,6 +40,7 @@ extern "C" {
 #define TSK_T_SCORE_BINS         200    /* T_INTENSITY_SCORE_BINS, tailseq-import.h:206 */
 #define TSK_SCORE_MAX            ((1u << 24) - 1u)   /* signal-packs.h:36-37 */
 #define TSK_MAX_CUTOFF_CYCLES    1024   /* MAX_NUM_CYCLES, polyaruler.c:39 */
+#define TSK_MAX_CONTROL_READ     64     /* longest phix-match-length */
 
 /* PAFLAG_* bits, src/sigproc-flags.h:30-43 (same values, same meaning). */
 #define TSK_PAFLAG_POLYA_DETECTED              0x0001
@@ -90,8 +91,14 @@ typedef struct tsk_params {
     int32_t keep_no_delimiter;
     int32_t keep_low_quality_balancer;
 
-    /* [control]: 1 when the PhiX pseudo-sample (list entry 1) exists */
+    /* [control]: 1 when the PhiX pseudo-sample (list entry 1) exists.  Barcode-unassigned
+     * clusters are then classified against the PhiX174 genome (controlaligner.c:107-145):
+     * control_read_length bases from cycle 0 by exact substring, else the same number of
+     * bases from control_first_cycle by local alignment (match 1, mismatch 2, gap 4+1,
+     * score >= (int)(control_read_length * 0.65), tailseq-import.h:151-156). */
     int32_t has_control;
+    int32_t control_first_cycle;         /* phix-match-start - 1 (parseconfig.c:195) */
+    int32_t control_read_length;         /* phix-match-length, 8..64 */
 
     /* [balancer] */
     int32_t balancer_start, balancer_length;   /* end = start + length */

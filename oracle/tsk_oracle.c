@@ -70,6 +70,90 @@ static int pick_sample(const tsk_params *p, const char *indexread, int *mismatch
     return best;
 }
 
+/* ----------------------------------------------------------------------------------- */
+/* try_alignment_to_control(), controlaligner.c:107-145.                                 */
+/*  1. fast path (:117-119): the first read_length characters of the WHOLE read (cycle 0  */
+/*     onwards, not first_cycle -- SURVEY quirk 6) occur verbatim in either PhiX strand;   */
+/*  2. otherwise Smith-Waterman of read[first_cycle .. +read_length) against               */
+/*     forward + 20 x N + reverse (load_control_sequence, :74-104): match +1, mismatch -2, */
+/*     any N 0 (:54-66), a gap of length l costs 4 + (l - 1) (ssw.c:226-233,              */
+/*     tailseq-import.h:152-155); aligned when the best local score reaches                */
+/*     (int)(read_length * 0.65) (:162-163, :135).                                         */
+/* ssw.c's striped byte kernel returns the exact optimum here (scores <= read_length,      */
+/* far from the 8-bit saturation point), so a plain Gotoh recurrence restates it.          */
+/* ----------------------------------------------------------------------------------- */
+#include "../tailseeker_b200/csrc/phix174.h"
+
+#define CONTROL_SPACING 20
+#define CONTROL_TARGET_LEN (2 * TSK_PHIX174_LENGTH + CONTROL_SPACING)
+
+static char phix_fwd[TSK_PHIX174_LENGTH + 1], phix_rev[TSK_PHIX174_LENGTH + 1];
+static int8_t phix_target[CONTROL_TARGET_LEN];
+
+static void control_prepare(void)
+{
+    static const char letters[4] = {'A', 'C', 'G', 'T'};
+    if (phix_fwd[0] != '\0') return;
+    for (int i = 0; i < TSK_PHIX174_LENGTH; i++) {
+        int b = (TSK_PHIX174_2BIT[i / 16] >> (2 * (i % 16))) & 3;
+        phix_fwd[i] = letters[b];
+        phix_rev[TSK_PHIX174_LENGTH - 1 - i] = letters[3 - b];
+    }
+    for (int i = 0; i < TSK_PHIX174_LENGTH; i++) {
+        phix_target[i] = (int8_t)((TSK_PHIX174_2BIT[i / 16] >> (2 * (i % 16))) & 3);
+        phix_target[2 * TSK_PHIX174_LENGTH + CONTROL_SPACING - 1 - i] = (int8_t)(3 - phix_target[i]);
+    }
+    for (int i = 0; i < CONTROL_SPACING; i++) phix_target[TSK_PHIX174_LENGTH + i] = 4;
+}
+
+static int contains(const char *hay, int haylen, const char *needle, int n)
+{
+    for (int i = 0; i + n <= haylen; i++)
+        if (memcmp(hay + i, needle, (size_t)n) == 0) return 1;
+    return 0;
+}
+
+int tsk_oracle_control_score(const char *read, int n)
+{
+    int h[TSK_MAX_CONTROL_READ + 1], e[TSK_MAX_CONTROL_READ + 1], best = 0;
+    int8_t r[TSK_MAX_CONTROL_READ];
+    control_prepare();
+    for (int i = 0; i < n; i++)
+        r[i] = read[i] == 'A' ? 0 : read[i] == 'C' ? 1 : read[i] == 'G' ? 2 : read[i] == 'T' ? 3 : 4;
+    for (int i = 0; i <= n; i++) h[i] = e[i] = 0;
+    for (int j = 0; j < CONTROL_TARGET_LEN; j++) {
+        int diag = 0, f = 0, t = phix_target[j];
+        for (int i = 1; i <= n; i++) {
+            int sub = (t == 4 || r[i - 1] == 4) ? 0 : (t == r[i - 1] ? 1 : -2);
+            int v = diag + sub;                    /* H(i-1, j-1) + s */
+            int ee = e[i] - 1 > h[i] - 4 ? e[i] - 1 : h[i] - 4;      /* gap along the target */
+            int ff = f - 1 > h[i - 1] - 4 ? f - 1 : h[i - 1] - 4;    /* gap along the read   */
+            if (ee < 0) ee = 0;
+            if (ff < 0) ff = 0;
+            if (v < ee) v = ee;
+            if (v < ff) v = ff;
+            if (v < 0) v = 0;
+            diag = h[i];
+            h[i] = v; e[i] = ee; f = ff;
+            if (v > best) best = v;
+        }
+    }
+    return best;
+}
+
+int tsk_oracle_control_try(const char *seq, int first_cycle, int n)
+{
+    control_prepare();
+    if (contains(phix_fwd, TSK_PHIX174_LENGTH, seq, n) || contains(phix_rev, TSK_PHIX174_LENGTH, seq, n))
+        return 1;
+    return tsk_oracle_control_score(seq + first_cycle, n) >= (int)(n * 0.65);
+}
+
+static int control_aligned(const tsk_params *p, const char *seq)
+{
+    return tsk_oracle_control_try(seq, p->control_first_cycle, p->control_read_length);
+}
+
 /* IUPAC sets, spotanalyzer.c:35-62 (note: a read 'N' matches nothing, not even N/X). */
 static const char *iupac_set(char code)
 {
@@ -371,8 +455,8 @@ int tsk_oracle_process(const tsk_params *p,
 
         /* process_spots(), spotanalyzer.c:648-679 */
         sidx = pick_sample(p, seq + p->index_start, &mismatches);
-        if (sidx < 0)
-            sidx = 0;   /* Unknown; control alignment (controlaligner.c) is a later row */
+        if (sidx < 0)            /* :650-666: Unknown (entry 0) or the control pseudo-sample (entry 1) */
+            sidx = (p->has_control && control_aligned(p, seq)) ? 1 : 0;
         s = &p->samples[sidx];
         if (mismatches <= 0) counters[sidx].clusters_mm0++;
         else {

@@ -49,6 +49,15 @@ int tsk_oracle_ruler(const uint32_t *records, size_t nrecords, int dump_len,
                      int bins, float gap,
                      int16_t *polya_len_out, uint32_t *pos);
 
+/* Best local alignment score of read[0..n) (characters ACGTN) against PhiX forward + 20 N +
+ * reverse, the quantity ssw_align() reports as score1 in try_alignment_to_control()
+ * (controlaligner.c:127-135). */
+int tsk_oracle_control_score(const char *read, int n);
+
+/* try_alignment_to_control() (controlaligner.c:107-145) on a whole read: exact substring of
+ * seq[0..n) in either strand, else the score of seq[first_cycle..+n) reaches (int)(n * 0.65). */
+int tsk_oracle_control_try(const char *seq, int first_cycle, int n);
+
 /* host libm logf, exported so tests can pin the device logf against it */
 float tsk_oracle_logf(float x);
 

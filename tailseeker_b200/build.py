@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtailseeker_b200.so")
-SOURCES = ["tsk_kernels.cu", "tsk_score.cu", "tsk_capi.cu", "tsk_ruler.cu", "tsk_fit.cu"]
+SOURCES = ["tsk_kernels.cu", "tsk_score.cu", "tsk_capi.cu", "tsk_ruler.cu", "tsk_fit.cu", "tsk_control.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false", "--shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
 
@@ -38,7 +38,8 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("TSK_NVCC_EXTRA", "").split()      # experiments only (e.g. -DNAME=1)
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or proc.returncode != 0:

@@ -22,7 +22,7 @@ from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
-TSK_ABI_VERSION = 1
+TSK_ABI_VERSION = 2
 TSK_MAX_SAMPLES = 64
 TSK_MAX_SEQ = 32
 TSK_T_SCORE_BINS = 200
@@ -74,6 +74,8 @@ class CParams(ctypes.Structure):
         ("keep_no_delimiter", ctypes.c_int32),
         ("keep_low_quality_balancer", ctypes.c_int32),
         ("has_control", ctypes.c_int32),
+        ("control_first_cycle", ctypes.c_int32),
+        ("control_read_length", ctypes.c_int32),
         ("balancer_start", ctypes.c_int32),
         ("balancer_length", ctypes.c_int32),
         ("balancer_min_quality", ctypes.c_int32),
@@ -406,6 +408,8 @@ class ImporterConfig:
         p.keep_no_delimiter = self.keep_no_delimiter
         p.keep_low_quality_balancer = self.keep_low_quality_balancer
         p.has_control = 1 if self.phix_match_name else 0
+        p.control_first_cycle = self.phix_match_start - 1
+        p.control_read_length = self.phix_match_length
         p.balancer_start = self.balancer_start - 1
         p.balancer_length = self.balancer_length
         p.balancer_min_quality = self.balancer_minimum_quality

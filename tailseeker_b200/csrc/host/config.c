@@ -303,6 +303,8 @@ int tsk_build_params(const struct host_config *c, tsk_params *p)
     p->keep_no_delimiter = c->keep_no_delimiter;
     p->keep_low_quality_balancer = c->keep_low_quality_balancer;
     p->has_control = c->control_name[0] != '\0';
+    p->control_first_cycle = c->control_first_cycle;
+    p->control_read_length = c->control_read_length;
     p->balancer_start = c->balancer_start; p->balancer_length = c->balancer_length;
     p->balancer_min_quality = c->balancer_min_quality;
     p->balancer_min_bases_passes = (int)(c->balancer_length * c->balancer_min_fraction_passes);

@@ -123,9 +123,6 @@ int main(int argc, char *argv[])
         fprintf(stderr, "[alternative_calls] (third-party base-caller override, altcalls.c) is not supported.\n");
         return -1;
     }
-    if (cfg->control_name[0] != '\0')
-        fprintf(stderr, "Note: control (%s) alignment is not performed; control reads are counted as Unknown.\n",
-                cfg->control_name);
     if (tsk_load_color_matrix(inv, cfg->threep_colormatrix_filename) < 0) return -1;
     params = malloc(sizeof(*params));
     if (!params || tsk_build_params(cfg, params) < 0) return -1;

@@ -85,9 +85,18 @@ static int build_device_params(const tsk_params *p, DevParams *d, DevSample *ds)
     if (p->fair_sampling_hash_space_size < 1) { tsk_set_error("bad fair-sampling-hash-space-size"); return -1; }
     if (p->fair_sampling_fingerprint_length < 0) { tsk_set_error("bad fair-sampling-fingerprint-length"); return -1; }
     if (p->max_cctr_scan_left_space < 1 || p->max_cctr_scan_right_space < 1) { tsk_set_error("bad cctr scan space"); return -1; }
-    /* has_control: list entry 1 is the control pseudo-sample ("XXXXXX", no files).  Control
-     * ALIGNMENT (controlaligner.c: exact substring, then Smith-Waterman against PhiX) is a later
-     * row of the scope table: barcode-unassigned clusters are all counted as Unknown. */
+    /* has_control: list entry 1 is the control pseudo-sample ("XXXXXX", no files); the
+     * barcode-unassigned clusters are classified by tsk_control.cu (controlaligner.c:107-145).
+     * The reference reads control_read_length characters from cycle 0 and from first_cycle. */
+    if (p->has_control) {
+        if (p->num_samples < 2) { tsk_set_error("has_control needs the control pseudo-sample as list entry 1"); return -1; }
+        if (p->control_read_length < 8 || p->control_read_length > TSK_MAX_CONTROL_READ) {
+            tsk_set_error("phix-match-length must be 8..%d", TSK_MAX_CONTROL_READ); return -1;
+        }
+        if (p->control_first_cycle < 0 || p->control_first_cycle + p->control_read_length > p->total_cycles) {
+            tsk_set_error("control window outside the read"); return -1;
+        }
+    }
 
     memset(d, 0, sizeof(*d));
     d->total_cycles = p->total_cycles; d->index_start = p->index_start; d->index_length = p->index_length;
@@ -200,6 +209,12 @@ extern "C" int tsk_ctx_create(tsk_ctx **out, int device, const tsk_params *param
     TSK_CUDA(cudaMalloc(&ctx->d_totals, sizeof(uint32_t) * (TSK_MAX_SAMPLES + 1)));
     TSK_CUDA(cudaMalloc(&ctx->d_recbase, sizeof(uint64_t) * (TSK_MAX_SAMPLES + 1)));
     TSK_CUDA(cudaMalloc(&ctx->d_cutoffs, sizeof(uint32_t) * TSK_MAX_CUTOFF_CYCLES));
+    if (params->has_control) {
+        if (tsk_control_setup(ctx) != 0) return -1;
+        TSK_CUDA(cudaStreamCreateWithFlags(&ctx->xstream, cudaStreamNonBlocking));
+        TSK_CUDA(cudaEventCreateWithFlags(&ctx->ev_ctl[0], cudaEventDisableTiming));
+        TSK_CUDA(cudaEventCreateWithFlags(&ctx->ev_ctl[1], cudaEventDisableTiming));
+    }
     *out = ctx;
     return 0;
 }
@@ -214,11 +229,12 @@ extern "C" int tsk_ctx_destroy(tsk_ctx *ctx)
                     ctx->d_bucket, ctx->d_worklist, ctx->d_blkcnt, ctx->d_totals, ctx->d_recbase,
                     ctx->d_records, ctx->d_scratch, ctx->d_pos, ctx->d_neg, ctx->d_counters, ctx->d_fair,
                     ctx->d_lists, ctx->d_ruler_pos, ctx->d_cutoffs, ctx->d_rlen, ctx->d_rrec,
-                    ctx->d_fit_hist, ctx->d_fit_out};
+                    ctx->d_fit_hist, ctx->d_fit_out, ctx->d_ctl_queue, ctx->d_ctl_index};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)
         if (ptrs[i]) cudaFree(ptrs[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->cstream);
+    if (ctx->xstream) { cudaStreamDestroy(ctx->xstream); cudaEventDestroy(ctx->ev_ctl[0]); cudaEventDestroy(ctx->ev_ctl[1]); }
     cudaEventDestroy(ctx->ev_up[0]); cudaEventDestroy(ctx->ev_up[1]);
     if (ctx->profile) for (int i = 0; i < 7; i++) cudaEventDestroy(ctx->pev[i]);
     free(ctx);
@@ -244,8 +260,9 @@ static int ensure_cluster_buffers(tsk_ctx *ctx, uint32_t n)
     if (cap < 4096) cap = 4096;
     const int S = ctx->dp.num_samples;
     void *old[] = {ctx->d_calls, ctx->d_kind, ctx->d_bucket, ctx->d_worklist, ctx->d_blkcnt,
-                   ctx->d_records, ctx->d_scratch, ctx->d_lists};
+                   ctx->d_records, ctx->d_scratch, ctx->d_lists, ctx->d_ctl_queue};
     for (size_t i = 0; i < sizeof(old) / sizeof(old[0]); i++) if (old[i]) cudaFree(old[i]);
+    ctx->d_ctl_queue = NULL;
     ctx->d_calls = NULL; ctx->d_kind = NULL; ctx->d_bucket = NULL; ctx->d_worklist = NULL;
     ctx->d_blkcnt = NULL; ctx->d_records = NULL; ctx->d_scratch = NULL; ctx->d_lists = NULL;
     ctx->cap_clusters = 0;
@@ -262,6 +279,7 @@ static int ensure_cluster_buffers(tsk_ctx *ctx, uint32_t n)
     ctx->scratch_cap = (size_t)cap * (size_t)maxinsert;
     TSK_CUDA(cudaMalloc(&ctx->d_scratch, sizeof(float) * ctx->scratch_cap));
     TSK_CUDA(cudaMalloc(&ctx->d_lists, sizeof(uint32_t) * (16 + 4 * (size_t)cap)));
+    if (ctx->hp.has_control) TSK_CUDA(cudaMalloc(&ctx->d_ctl_queue, sizeof(uint32_t) * (4 + (size_t)cap)));
     ctx->cap_clusters = cap;
     return 0;
 }

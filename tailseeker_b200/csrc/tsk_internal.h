@@ -94,6 +94,12 @@ struct tsk_ctx {
     uint32_t *d_counters;        /* [num_samples][6] */
     uint32_t *d_fair;            /* [hash_size] candidate counts per bucket */
     uint32_t *d_lists;           /* undo / contended / accepted lists + their counters */
+    /* control classification (tsk_control.cu); allocated only when a control is configured */
+    uint32_t *d_ctl_queue;       /* [4 + N]: [0] = queued clusters, [1] = next to classify, entries from [4] */
+    uint8_t  *d_ctl_index;       /* PhiX target bases | exact-substring hash | q-gram indexes */
+    size_t ctl_off_hash, ctl_off_qoff, ctl_off_qpos;
+    cudaStream_t xstream;        /* side stream of the classifier */
+    cudaEvent_t ev_ctl[2];       /* K1 done -> classifier may start; classifier done */
     uint32_t *d_ruler_pos;  size_t ruler_pos_words;   /* capacity */
     int ruler_ncut, ruler_bins;                       /* current shape of the ruler histogram */
     uint32_t *d_cutoffs;         /* [TSK_MAX_CUTOFF_CYCLES] */
@@ -130,6 +136,8 @@ void tsk_set_error(const char *fmt, ...);
 int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev /* optional [5] */);
 int tsk_launch_score(tsk_ctx *ctx);
 int tsk_launch_fixups(tsk_ctx *ctx);
+int tsk_control_setup(tsk_ctx *ctx);      /* builds the PhiX index (tsk_control.cu) */
+int tsk_launch_control(tsk_ctx *ctx);
 int tsk_launch_ruler(tsk_ctx *ctx, const uint32_t *d_records, size_t nrecords, int dump_len,
                      int ncutoffs, int min_len, float weight, int bins, float gap,
                      int16_t *d_len_out);

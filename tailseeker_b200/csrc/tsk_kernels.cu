@@ -36,7 +36,8 @@ k_decode_demux_seed(const __grid_constant__ DevParams P, const TileView tv,
                     const DevSample *__restrict__ g_samples,
                     tsk_call *__restrict__ calls, uint8_t *__restrict__ kind,
                     uint32_t *__restrict__ bucket, uint32_t *__restrict__ blkcnt,
-                    uint32_t *__restrict__ counters, uint32_t *__restrict__ fair)
+                    uint32_t *__restrict__ counters, uint32_t *__restrict__ fair,
+                    uint32_t *__restrict__ ctl_queue /* [0] = length, entries from [4]; NULL = no control */)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = P.num_samples;
@@ -61,6 +62,7 @@ k_decode_demux_seed(const __grid_constant__ DevParams P, const TileView tv,
     int sample = 0, flags = 0, de = -1, status = -1, mods = -1;
     int written = 0;
     uint32_t kd = 0, bk = 0;
+    bool to_control = false;     /* unassigned and a control is configured: k_control_classify decides */
 
     if (active) {
         const int ts = P.threep_start, tl = P.threep_length;
@@ -94,7 +96,9 @@ k_decode_demux_seed(const __grid_constant__ DevParams P, const TileView tv,
         else { mismatches = bestmm; sample = best; }
         const DevSample &sm = s_samples[sample];
 
-        if (mismatches <= 0) atomicAdd(&s_cnt[sample * TSK_NCOUNT + 0], 1u);
+        to_control = mismatches < 0 && ctl_queue != nullptr;
+        if (to_control) { /* counted as Unknown or control once classified (spotanalyzer.c:652-670) */ }
+        else if (mismatches <= 0) atomicAdd(&s_cnt[sample * TSK_NCOUNT + 0], 1u);
         else {
             flags |= TSK_PAFLAG_BARCODE_HAS_MISMATCHES;
             atomicAdd(&s_cnt[sample * TSK_NCOUNT + (mismatches == 1 ? 1 : 2)], 1u);
@@ -232,6 +236,17 @@ k_decode_demux_seed(const __grid_constant__ DevParams P, const TileView tv,
         }
     }
 
+    /* ---- queue for the control classifier (order is irrelevant there) ---- */
+    if (ctl_queue != nullptr) {
+        const unsigned cb = __ballot_sync(FULL_MASK, to_control);
+        if (cb) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&ctl_queue[0], (uint32_t)__popc(cb));
+            base = __shfl_sync(FULL_MASK, base, 0);
+            if (to_control) ctl_queue[4 + base + __popc(cb & ((1u << lane) - 1u))] = n;
+        }
+    }
+
     /* ---- order-preserving ranks inside the CTA: record slots per sample, work items ---- */
     const int ekey = (kd & KIND_EMIT) ? sample : -1;
     const unsigned lt = (1u << lane) - 1u;
@@ -339,6 +354,8 @@ int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev)
     TSK_CUDA(cudaMemsetAsync(ctx->d_neg, 0, histbytes, st));
     TSK_CUDA(cudaMemsetAsync(ctx->d_fair, 0, sizeof(uint32_t) * (size_t)P.fair_hash_size, st));
     TSK_CUDA(cudaMemsetAsync(ctx->d_lists, 0, sizeof(uint32_t) * 16, st));
+    const bool control = ctx->hp.has_control != 0;
+    if (control) TSK_CUDA(cudaMemsetAsync(ctx->d_ctl_queue, 0, sizeof(uint32_t) * 4, st));
     if (ev) TSK_CUDA(cudaEventRecord(ev[0], st));
 
     if (N > 0) {
@@ -346,10 +363,19 @@ int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev)
                              sizeof(uint32_t) * (S * TSK_NCOUNT + (TSK_K1_THREADS / 32) * (S + 1));
         k_decode_demux_seed<<<nblk, TSK_K1_THREADS, smem1, st>>>(
             P, tv, ctx->d_samples, ctx->d_calls, ctx->d_kind, ctx->d_bucket, ctx->d_blkcnt,
-            ctx->d_counters, ctx->d_fair);
+            ctx->d_counters, ctx->d_fair, control ? ctx->d_ctl_queue : nullptr);
         ctx->launches++;
     }
     if (ev) TSK_CUDA(cudaEventRecord(ev[1], st));
+    if (N > 0 && control) {
+        /* The classifier only touches calls[].sample of unassigned clusters and the two
+         * pseudo-sample counters, which nothing below reads: it runs on a side stream next to
+         * the scan and normalise/score/pack kernels and is joined before the fix-ups. */
+        TSK_CUDA(cudaEventRecord(ctx->ev_ctl[0], st));
+        TSK_CUDA(cudaStreamWaitEvent(ctx->xstream, ctx->ev_ctl[0], 0));
+        if (tsk_launch_control(ctx) != 0) return -1;
+        TSK_CUDA(cudaEventRecord(ctx->ev_ctl[1], ctx->xstream));
+    }
     if (N > 0) {
         k_scan_blocks<<<S + 1, 256, 0, st>>>(ctx->d_blkcnt, ctx->d_totals, nblk, S + 1);
         k_record_bases<<<1, 32, 0, st>>>(ctx->d_totals, ctx->d_samples, ctx->d_recbase, S);
@@ -362,6 +388,7 @@ int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev)
     }
     if (ev) TSK_CUDA(cudaEventRecord(ev[2], st));
     if (tsk_launch_score(ctx) != 0) return -1;
+    if (N > 0 && control) TSK_CUDA(cudaStreamWaitEvent(st, ctx->ev_ctl[1], 0));
     if (ev) TSK_CUDA(cudaEventRecord(ev[3], st));
     if (tsk_launch_fixups(ctx) != 0) return -1;
     if (ev) TSK_CUDA(cudaEventRecord(ev[4], st));

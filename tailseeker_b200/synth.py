@@ -51,8 +51,13 @@ def make_tile(cfg: ImporterConfig, nclusters: int, seed: int,
               dark_cluster_frac: float = 0.004, dark_cycle_frac: float = 0.0008,
               nocall_frac: float = 0.002, unknown_frac: float = 0.03,
               lowqual_frac: float = 0.05, lowdiv_frac: float = 0.01,
-              spikein_weight: float = 0.25, chunk: int = 1 << 16) -> Tile:
-    """Deterministic in (cfg, nclusters, seed).  Memory: ~2.3 KB per cluster."""
+              spikein_weight: float = 0.25, phix_frac: float = 0.0,
+              chunk: int = 1 << 16) -> Tile:
+    """Deterministic in (cfg, nclusters, seed).  Memory: ~2.3 KB per cluster.
+
+    phix_frac: fraction of the unknown-barcode clusters whose 5' read is drawn from the PhiX174
+    control genome (see overlay_phix_reads); 0 leaves the random stream of earlier fixtures
+    untouched."""
     rng = np.random.default_rng(seed)
     T, L3 = cfg.total_cycles, cfg.threep_length
     ts = cfg.threep_start - 1
@@ -195,7 +200,52 @@ def make_tile(cfg: ImporterConfig, nclusters: int, seed: int,
         cif[:, :, c0:c0 + n] = np.clip(np.rint(raw), -32768, 32767).astype(np.int16)
         del pure, raw, onehot
 
+    if phix_frac > 0:
+        overlay_phix_reads(bcl, np.where(truth < 0)[0], phix_frac, seed)
     return Tile(bcl=bcl, cif=cif, matrix_text=matrix_text, nclusters=N, truth_sample=truth)
+
+
+def phix_genome() -> np.ndarray:
+    """Forward strand of the PhiX174 control as base codes 0-3, unpacked from
+    csrc/phix174.h (the table the library itself is built from)."""
+    import re
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "phix174.h")
+    text = open(path).read()
+    length = int(re.search(r"TSK_PHIX174_LENGTH (\d+)", text).group(1))
+    words = np.array([int(w, 16) for w in re.findall(r"0x([0-9a-f]{8})u", text)], dtype=np.uint64)
+    codes = (words[:, None] >> (2 * np.arange(16, dtype=np.uint64))[None, :]) & np.uint64(3)
+    return codes.reshape(-1)[:length].astype(np.uint8)
+
+
+def overlay_phix_reads(bcl: np.ndarray, candidates: np.ndarray, frac: float, seed: int,
+                       span: int = 51) -> np.ndarray:
+    """Rewrite the base bits of cycles [0, span) of a random `frac` of `candidates` with reads
+    from either PhiX strand.  Half are verbatim (the exact-substring path of
+    controlaligner.c:117-119); the rest carry 1-8 substitutions and, for a quarter, one 1-3 nt
+    insertion or deletion, so that local-alignment scores land on both sides of the
+    acceptance threshold (:135).  No-call bytes stay no-calls.  Returns the chosen clusters."""
+    rng = np.random.default_rng([seed, 0x50486958])
+    fwd = phix_genome()
+    rev = (3 - fwd)[::-1]
+    span = min(span, bcl.shape[0])
+    chosen = candidates[rng.random(candidates.size) < frac]
+    for n in chosen:
+        strand = fwd if rng.random() < 0.5 else rev
+        start = int(rng.integers(0, strand.size - span - 8))
+        read = strand[start:start + span + 8].copy()
+        if rng.random() >= 0.5:
+            if rng.random() < 0.25:
+                at, ln = int(rng.integers(8, 40)), int(rng.integers(1, 4))
+                if rng.random() < 0.5:
+                    read = np.concatenate([read[:at], rng.integers(0, 4, ln).astype(np.uint8), read[at:]])
+                else:
+                    read = np.concatenate([read[:at], read[at + ln:]])
+            nsub = int(rng.integers(1, 9))
+            where = rng.integers(0, 46, size=nsub)
+            read[where] = (read[where] + rng.integers(1, 4, size=nsub)) & 3
+        col = bcl[:span, n]
+        bcl[:span, n] = np.where(col == 0, 0, (col & 0xfc) | read[:span]).astype(np.uint8)
+    return chosen
 
 
 # --------------------------------------------------------------------------------------

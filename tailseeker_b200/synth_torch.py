@@ -23,8 +23,12 @@ def make_tile_device(cfg: ImporterConfig, nclusters: int, seed: int, device="cud
                      pitch_align: int = 128, dark_cluster_frac: float = 0.004,
                      dark_cycle_frac: float = 0.0008, nocall_frac: float = 0.002,
                      unknown_frac: float = 0.03, lowqual_frac: float = 0.05,
-                     lowdiv_frac: float = 0.01, chunk: int = 1 << 18):
-    """Returns (bcl u8[T][pitch], cif i16[L3][4][pitch], matrix_text, pitch)."""
+                     lowdiv_frac: float = 0.01, phix_frac: float = 0.0, chunk: int = 1 << 18):
+    """Returns (bcl u8[T][pitch], cif i16[L3][4][pitch], matrix_text, pitch).
+
+    phix_frac: fraction of the unknown-barcode clusters whose 5' read comes from the PhiX174
+    control genome (half verbatim, half with substitutions and an occasional indel), like
+    synth.overlay_phix_reads()."""
     dev = torch.device(device)
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
@@ -60,6 +64,11 @@ def make_tile_device(cfg: ImporterConfig, nclusters: int, seed: int, device="cud
     motif = _codes("ACGGCATCAGGACTGACCGATGCAAGCTGACGATCGACTGCAGTCAGCTAGC", dev)
     truns = torch.tensor([0, 0, 5, 12, 30, 60, 100, 150, 200], dtype=torch.int32, device=dev)
     pos3 = torch.arange(L3, dtype=torch.int32, device=dev)[:, None]
+    if phix_frac > 0:
+        from .synth import phix_genome
+        fwd = torch.tensor(phix_genome(), dtype=torch.uint8, device=dev)
+        strands = torch.stack([fwd, (3 - fwd).flip(0)])                              # [2][5386]
+        span = min(51, T)
 
     def rnd(*shape):
         return torch.rand(shape, generator=g, device=dev)
@@ -134,6 +143,25 @@ def make_tile_device(cfg: ImporterConfig, nclusters: int, seed: int, device="cud
         nlow = int(lowq.sum())
         if nlow:
             qual[:25, lowq] = rint(2, 24, 25, nlow).to(torch.uint8)
+        if phix_frac > 0:
+            sel = ar[~known & (rnd(n) < phix_frac)]
+            m = sel.numel()
+            if m:
+                strand = rint(0, 2, m)
+                start = rint(0, strands.shape[1] - span - 8, m)
+                col = torch.arange(span, device=dev)[None, :]                            # [1][span]
+                # one deletion (shift > 0) or insertion-like slip (shift < 0) for 1/8 of the reads
+                shift = torch.where(rnd(m) < 0.125, rint(-3, 4, m), torch.zeros(m, dtype=torch.long, device=dev))
+                at = rint(8, 40, m)
+                src = start[:, None] + col + (col >= at[:, None]) * shift[:, None]
+                read = strands[strand[:, None], src.clamp(0, strands.shape[1] - 1)]     # [m][span]
+                noisy = rnd(m) < 0.5
+                nsub = rint(1, 9, m)
+                hit = noisy[:, None] & (rnd(m, span) < (nsub[:, None].float() / 46.0)) & (col < 46)
+                read = torch.where(hit, (read + rint(1, 4, m, span).to(torch.uint8)) & 3, read)
+                read = torch.where(noisy[:, None] | (shift[:, None] == 0), read,
+                                   strands[strand[:, None], start[:, None] + col])
+                bases[:span, sel] = read.T.contiguous()
         byte = (qual << 2) | bases
         byte[rnd(T, n) < nocall_frac] = 0
         bcl[:, c0:c0 + n] = byte

@@ -79,9 +79,34 @@ def estimator_fixture(name):
     print(name, est["bases"])
 
 
+def control_fixture(name, first=5, length=40, tile_n=2000, tile_seed=303):
+    """Per-read scores / decisions of the reference control aligner (controlaligner.c + ssw.c via
+    oracle/_ref/libtskref_control.so) and the demultiplexing statistics of the reference importer
+    run with a [control] section on a tile regenerated from (tile_n, tile_seed)."""
+    import ctypes
+    sys.path.insert(0, os.path.dirname(HERE))
+    from test_control import control_reads, REFLIB
+    ref = ctypes.CDLL(REFLIB)
+    assert ref.tskref_control_setup(first, length) == int(length * 0.65)
+    reads = control_reads(4242, 3000)
+    score = np.array([ref.tskref_control_score(bytes(r)) for r in reads], dtype=np.int32)
+    decision = np.array([ref.tskref_control_try(bytes(r) + b"\0") for r in reads], dtype=np.int8)
+    cfg = stock_config("miseq", phix_match_name="PhiX")
+    tile = make_tile(cfg, tile_n, seed=tile_seed, unknown_frac=0.2, phix_frac=0.6)
+    r = refrun.run_import(cfg, tile)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), reads=reads, score=score, decision=decision,
+                        first=first, length=length, tile_n=tile_n, tile_seed=tile_seed,
+                        stats_csv=r["stats_csv"])
+    print(name, "reads", len(reads), "aligned", int(decision.sum()), r["stats_csv"].splitlines()[:3])
+
+
 if __name__ == "__main__":
     assert refrun.available(), "build oracle/_ref first (make -C oracle ref)"
+    if sys.argv[1:] == ["control"]:
+        control_fixture("control_reads")
+        sys.exit(0)
     importer_fixture("importer_miseq", stock_config("miseq"), 640, 101, dark_cluster_frac=0.02, lowdiv_frac=0.08)
     importer_fixture("importer_hiseq_keep", stock_config("hiseq", keep_no_delimiter=1, keep_low_quality_balancer=1),
                      384, 202, spikein_weight=1.0)
     estimator_fixture("estimator_two_tiles")
+    control_fixture("control_reads")

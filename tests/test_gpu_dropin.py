@@ -34,7 +34,8 @@ def test_programs_match_reference(tmp_path, control, bufsize):
     assert os.access(OUR_IMPORT, os.X_OK), "host programs not built (__graft_entry__.build())"
     cfg = stock_config("miseq", phix_match_name=control)
     n = 3000 if bufsize is None else 3500          # 4 MiB buffer -> several read blocks
-    tile = make_tile(cfg, n, seed=55, lowdiv_frac=0.05, dark_cluster_frac=0.01, spikein_weight=1.0)
+    tile = make_tile(cfg, n, seed=55, lowdiv_frac=0.05, dark_cluster_frac=0.01, spikein_weight=1.0,
+                     unknown_frac=0.15 if control else 0.03, phix_frac=0.6 if control else 0.0)
     wref, wour = str(tmp_path / "ref"), str(tmp_path / "our")
     os.makedirs(wref); os.makedirs(wour)
     ref = refrun.run_import(cfg, tile, workdir=wref, read_buffer_size=bufsize)

@@ -256,3 +256,56 @@ def test_two_tiles_uploaded_ahead(stock_cfg, oracle):
             compare_tile(p, stock_cfg, None, o)
     finally:
         p.close()
+
+
+# ---- PhiX control classification (controlaligner.c:107-145) ------------------------------
+
+def _control_cfg(**kw):
+    from tailseeker_b200.config import stock_config
+    return stock_config("miseq", phix_match_name="PhiX", **kw)
+
+
+@pytest.mark.parametrize("kw,n", [(dict(), 20000),
+                                  (dict(phix_match_start=4, phix_match_length=36), 6000),
+                                  (dict(phix_match_start=1, phix_match_length=48), 6000),
+                                  # 64 > 20 / 0.35: alignments may cross the spacer, whole-target scan
+                                  (dict(phix_match_start=2, phix_match_length=64), 1500)])
+def test_control_classification(oracle, kw, n):
+    from tailseeker_b200.importer import TileProcessor
+    cfg = _control_cfg(**kw)
+    p = TileProcessor(cfg)
+    try:
+        _, o = _run(p, cfg, oracle, n, 21, unknown_frac=0.2, phix_frac=0.6)
+        calls = compare_tile(p, cfg, None, o)
+        assert (calls["sample"] == 1).sum() > n // 50 and (calls["sample"] == 0).sum() > n // 50
+    finally:
+        p.close()
+
+
+def test_control_golden_reads():
+    """The reads scored by the reference aligner itself (tests/golden/control_reads.npz), laid
+    out as a tile whose index reads are all no-calls, hence all barcode-unassigned."""
+    import os
+    from tailseeker_b200.importer import TileProcessor
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "control_reads.npz"))
+    cfg = _control_cfg(phix_match_start=int(g["first"]) + 1, phix_match_length=int(g["length"]))
+    reads = g["reads"]
+    n, span = reads.shape
+    code = np.full(256, 255, np.uint8)
+    code[np.frombuffer(b"ACGT", np.uint8)] = np.arange(4)
+    bcl = np.zeros((cfg.total_cycles, n), np.uint8)
+    span = min(span, cfg.index_start - 1)          # keep the index read all no-calls
+    assert span >= int(g["first"]) + int(g["length"])
+    c = code[reads[:, :span]].T
+    bcl[:span] = np.where(c == 255, 0, (30 << 2) | c)
+    cif = np.zeros((cfg.threep_length, 4, n), np.int16)
+    p = TileProcessor(cfg)
+    try:
+        p.upload(bcl, cif, np.eye(4, dtype=np.float32))
+        p.process()
+        calls = p.calls()
+        assert (calls["sample"] == g["decision"]).all()
+        cnt = p.counters()
+        assert cnt[1, 0] == int(g["decision"].sum()) and cnt[0, 0] == n - int(g["decision"].sum())
+    finally:
+        p.close()
