@@ -121,6 +121,7 @@ static int build_device_params(const tsk_params *p, DevParams *d, DevSample *ds)
     d->dark_threshold = p->dark_cycles_threshold; d->max_dark_cycles = p->max_dark_cycles;
     d->maximum_entropy = p->maximum_entropy;
     d->num_samples = p->num_samples;
+    d->has_control = p->has_control != 0;
     d->index_words = (p->index_length + 9) / 10;
     if (d->index_words > 4) { tsk_set_error("index too long"); return -1; }
 
@@ -211,6 +212,7 @@ extern "C" int tsk_ctx_create(tsk_ctx **out, int device, const tsk_params *param
     TSK_CUDA(cudaMalloc(&ctx->d_cutoffs, sizeof(uint32_t) * TSK_MAX_CUTOFF_CYCLES));
     if (params->has_control) {
         if (tsk_control_setup(ctx) != 0) return -1;
+        TSK_CUDA(cudaMalloc(&ctx->d_ctl_queue, sizeof(uint32_t) * 4));
         TSK_CUDA(cudaStreamCreateWithFlags(&ctx->xstream, cudaStreamNonBlocking));
         TSK_CUDA(cudaEventCreateWithFlags(&ctx->ev_ctl[0], cudaEventDisableTiming));
         TSK_CUDA(cudaEventCreateWithFlags(&ctx->ev_ctl[1], cudaEventDisableTiming));
@@ -260,9 +262,8 @@ static int ensure_cluster_buffers(tsk_ctx *ctx, uint32_t n)
     if (cap < 4096) cap = 4096;
     const int S = ctx->dp.num_samples;
     void *old[] = {ctx->d_calls, ctx->d_kind, ctx->d_bucket, ctx->d_worklist, ctx->d_blkcnt,
-                   ctx->d_records, ctx->d_scratch, ctx->d_lists, ctx->d_ctl_queue};
+                   ctx->d_records, ctx->d_scratch, ctx->d_lists};
     for (size_t i = 0; i < sizeof(old) / sizeof(old[0]); i++) if (old[i]) cudaFree(old[i]);
-    ctx->d_ctl_queue = NULL;
     ctx->d_calls = NULL; ctx->d_kind = NULL; ctx->d_bucket = NULL; ctx->d_worklist = NULL;
     ctx->d_blkcnt = NULL; ctx->d_records = NULL; ctx->d_scratch = NULL; ctx->d_lists = NULL;
     ctx->cap_clusters = 0;
@@ -279,7 +280,6 @@ static int ensure_cluster_buffers(tsk_ctx *ctx, uint32_t n)
     ctx->scratch_cap = (size_t)cap * (size_t)maxinsert;
     TSK_CUDA(cudaMalloc(&ctx->d_scratch, sizeof(float) * ctx->scratch_cap));
     TSK_CUDA(cudaMalloc(&ctx->d_lists, sizeof(uint32_t) * (16 + 4 * (size_t)cap)));
-    if (ctx->hp.has_control) TSK_CUDA(cudaMalloc(&ctx->d_ctl_queue, sizeof(uint32_t) * (4 + (size_t)cap)));
     ctx->cap_clusters = cap;
     return 0;
 }

@@ -47,6 +47,7 @@
 #define CTL_BINW      16
 #define CTL_NBIN      704                                 /* >= (CTL_TLEN + 64) / 16 + 2, multiple of 64 */
 #define CTL_HASH      32768
+#define CTL_CHUNK     128                                 /* clusters per work unit */
 #define CTL_MAXWILD   3                                   /* Ns expanded per q-gram */
 
 struct ControlPlan {
@@ -115,7 +116,8 @@ __device__ static bool window_reaches(const uint8_t *__restrict__ target, int t0
 __global__ void __launch_bounds__(CTL_THREADS)
 k_control_classify(const TileView tv, const __grid_constant__ ControlPlan plan,
                    const __grid_constant__ ControlIndex ix,
-                   uint32_t *__restrict__ queue, tsk_call *__restrict__ calls, uint32_t *__restrict__ counters)
+                   const uint8_t *__restrict__ kind, uint32_t *__restrict__ queue, tsk_call *__restrict__ calls,
+                   uint32_t *__restrict__ counters)
 {
     __shared__ uint32_t s_bins[CTL_WARPS][CTL_NBIN / 2];   /* two 16-bit counts per word */
     __shared__ uint8_t s_read[CTL_WARPS][256];
@@ -128,16 +130,33 @@ k_control_classify(const TileView tv, const __grid_constant__ ControlPlan plan,
     if (threadIdx.x < 2) s_tot[threadIdx.x] = 0;
     __syncthreads();
 
-    const uint32_t total = queue[0];
-    const uint32_t *list = queue + 4;
+    /* K1 marked the clusters to classify in kind[].  Reads differ a lot in cost (none / one /
+     * many windows), so warps pull chunks of CTL_CHUNK clusters from a counter. */
+    const uint32_t nchunks = (tv.nclusters + CTL_CHUNK - 1) / CTL_CHUNK;
     uint32_t n_unknown = 0, n_control = 0;
+    uint32_t chunk = 0, lanemask = 0;      /* lanemask: this lane's 4 clusters of the chunk still to do */
+    unsigned lanes = 0;                    /* lanes with work left in the chunk */
     for (;;) {
-        /* reads differ a lot in cost (none / a few / many windows): warps pull the next one */
-        uint32_t item = 0;
-        if (lane == 0) item = atomicAdd(&queue[1], 1u);
-        item = __shfl_sync(FULL_MASK, item, 0);
-        if (item >= total) break;
-        const uint32_t n = list[item];
+        if (lanes == 0) {
+            if (lane == 0) chunk = atomicAdd(&queue[1], 1u);
+            chunk = __shfl_sync(FULL_MASK, chunk, 0);
+            if (chunk >= nchunks) break;
+            const uint32_t c0 = chunk * CTL_CHUNK + lane * 4;
+            const uint32_t kd4 = __ldg(reinterpret_cast<const uint32_t *>(kind + c0));   /* capacity is padded */
+            lanemask = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (((kd4 >> (8 * j)) & KIND_CONTROL) && c0 + j < tv.nclusters) lanemask |= 1u << j;
+            lanes = __ballot_sync(FULL_MASK, lanemask != 0);
+            continue;
+        }
+        const int src = __ffs(lanes) - 1;
+        uint32_t sm = __shfl_sync(FULL_MASK, lanemask, src);
+        const int bit = __ffs(sm) - 1;
+        sm &= sm - 1;
+        if (lane == src) lanemask = sm;
+        if (sm == 0) lanes &= lanes - 1;
+        const uint32_t n = chunk * CTL_CHUNK + src * 4 + bit;
         for (int c = lane; c < ncyc; c += 32) {
             const uint32_t b = __ldg(tv.bcl + (size_t)c * tv.bcl_pitch + n);
             rd[c] = b == 0 ? 4 : (uint8_t)(b & 3);
@@ -357,7 +376,7 @@ int tsk_control_setup(tsk_ctx *ctx)
     return 0;
 }
 
-/* Classifies the clusters K1 queued in ctx->d_ctl_queue, on the side stream ctx->xstream
+/* Classifies the clusters K1 marked KIND_CONTROL, on the side stream ctx->xstream
  * (tsk_launch_import orders it after K1 and joins it). */
 int tsk_launch_control(tsk_ctx *ctx)
 {
@@ -371,7 +390,7 @@ int tsk_launch_control(tsk_ctx *ctx)
     /* the queue length lives on the device: a fixed grid of warps pulls reads from it */
     const unsigned want = (ctx->tile.nclusters + CTL_WARPS - 1) / CTL_WARPS;
     const unsigned blocks = want < 148u * 8u ? (want ? want : 1u) : 148u * 8u;
-    k_control_classify<<<blocks, CTL_THREADS, 0, ctx->xstream>>>(ctx->tile, pl, ix, ctx->d_ctl_queue,
+    k_control_classify<<<blocks, CTL_THREADS, 0, ctx->xstream>>>(ctx->tile, pl, ix, ctx->d_kind, ctx->d_ctl_queue,
                                                                ctx->d_calls, ctx->d_counters);
     ctx->launches++;
     TSK_CUDA(cudaGetLastError());

@@ -17,6 +17,7 @@
 #define KIND_EMIT      0x02      /* seed poly(A) >= signal-analysis-trigger: owns a record slot */
 #define KIND_POS       0x04      /* seed poly(A) >= seed-trigger: contrast test / positive sampling */
 #define KIND_NEG       0x08      /* negative-sampling candidate (before fair sampling) */
+#define KIND_CONTROL   0x10      /* barcode-unassigned with a control configured: to be classified */
 
 /* Device-side sample descriptor (128 bytes), built by the host from tsk_sample. */
 struct DevSample {
@@ -49,6 +50,7 @@ struct DevParams {
     float   maximum_entropy;
     int32_t num_samples;
     int32_t index_words;         /* ceil(index_length / 10) */
+    int32_t has_control;
     float   inv[16];             /* inverse colour matrix of the resident tile */
 };
 
@@ -95,7 +97,7 @@ struct tsk_ctx {
     uint32_t *d_fair;            /* [hash_size] candidate counts per bucket */
     uint32_t *d_lists;           /* undo / contended / accepted lists + their counters */
     /* control classification (tsk_control.cu); allocated only when a control is configured */
-    uint32_t *d_ctl_queue;       /* [4 + N]: [0] = queued clusters, [1] = next to classify, entries from [4] */
+    uint32_t *d_ctl_queue;       /* [4]: [1] = next chunk of clusters to look at */
     uint8_t  *d_ctl_index;       /* PhiX target bases | exact-substring hash | q-gram indexes */
     size_t ctl_off_hash, ctl_off_qoff, ctl_off_qpos;
     cudaStream_t xstream;        /* side stream of the classifier */

@@ -36,8 +36,7 @@ k_decode_demux_seed(const __grid_constant__ DevParams P, const TileView tv,
                     const DevSample *__restrict__ g_samples,
                     tsk_call *__restrict__ calls, uint8_t *__restrict__ kind,
                     uint32_t *__restrict__ bucket, uint32_t *__restrict__ blkcnt,
-                    uint32_t *__restrict__ counters, uint32_t *__restrict__ fair,
-                    uint32_t *__restrict__ ctl_queue /* [0] = length, entries from [4]; NULL = no control */)
+                    uint32_t *__restrict__ counters, uint32_t *__restrict__ fair)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = P.num_samples;
@@ -96,7 +95,7 @@ k_decode_demux_seed(const __grid_constant__ DevParams P, const TileView tv,
         else { mismatches = bestmm; sample = best; }
         const DevSample &sm = s_samples[sample];
 
-        to_control = mismatches < 0 && ctl_queue != nullptr;
+        to_control = mismatches < 0 && P.has_control;
         if (to_control) { /* counted as Unknown or control once classified (spotanalyzer.c:652-670) */ }
         else if (mismatches <= 0) atomicAdd(&s_cnt[sample * TSK_NCOUNT + 0], 1u);
         else {
@@ -236,16 +235,7 @@ k_decode_demux_seed(const __grid_constant__ DevParams P, const TileView tv,
         }
     }
 
-    /* ---- queue for the control classifier (order is irrelevant there) ---- */
-    if (ctl_queue != nullptr) {
-        const unsigned cb = __ballot_sync(FULL_MASK, to_control);
-        if (cb) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&ctl_queue[0], (uint32_t)__popc(cb));
-            base = __shfl_sync(FULL_MASK, base, 0);
-            if (to_control) ctl_queue[4 + base + __popc(cb & ((1u << lane) - 1u))] = n;
-        }
-    }
+    if (to_control) kd |= KIND_CONTROL;     /* k_control_classify picks these up from kind[] */
 
     /* ---- order-preserving ranks inside the CTA: record slots per sample, work items ---- */
     const int ekey = (kd & KIND_EMIT) ? sample : -1;
@@ -363,7 +353,7 @@ int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev)
                              sizeof(uint32_t) * (S * TSK_NCOUNT + (TSK_K1_THREADS / 32) * (S + 1));
         k_decode_demux_seed<<<nblk, TSK_K1_THREADS, smem1, st>>>(
             P, tv, ctx->d_samples, ctx->d_calls, ctx->d_kind, ctx->d_bucket, ctx->d_blkcnt,
-            ctx->d_counters, ctx->d_fair, control ? ctx->d_ctl_queue : nullptr);
+            ctx->d_counters, ctx->d_fair);
         ctx->launches++;
     }
     if (ev) TSK_CUDA(cudaEventRecord(ev[1], st));
