@@ -287,20 +287,23 @@ def main():
         hn = acc_neg.cpu().numpy().astype(np.uint64)
         return proc.fit_cutoffs(hp, hn), cnt
 
+    views = lib_views()          # the library's histograms / counters live at fixed device addresses
+
     def device_step():
+        """One pass over the rank's tiles, queued back to back on the stream: nothing about a
+        tile is read on the host until the end of the step (histogram sums for the fit and the
+        number of measured tails)."""
         acc_pos.zero_(); acc_neg.zero_()
         proc.reset_counters()
-        measured = 0
+        proc.ruler_reset(T)
         for (bcl, cif, inv, pitch, _) in tiles:
             proc.upload(bcl.data_ptr(), cif.data_ptr(), inv, nclusters=N, on_device=True,
                         bcl_pitch=pitch, cif_pitch=pitch)
-            proc.process()
-            vp, vn, _ = lib_views()
-            acc_pos.add_(vp); acc_neg.add_(vn)
-            lens, _ = proc.ruler_tile_all(packed)
-            measured += int((lens >= 0).sum())
+            proc.process_async()
+            acc_pos.add_(views[0]); acc_neg.add_(views[1])
+            proc.ruler_tile_all_async(packed)
         fit, _ = finish_step(True)
-        return measured, fit
+        return proc.ruler_called(), fit
 
     # ---- warm-up, then K timed steps (device-resident inputs) --------------------------------
     proc.ruler_reset(T)

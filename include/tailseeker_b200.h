@@ -189,6 +189,10 @@ int tsk_tile_upload(tsk_ctx *ctx, const uint8_t *bcl, size_t bcl_pitch,
  * pos/neg histograms and a zeroed fair-sampling table; counters accumulate across calls
  * (they live in SampleInfo in the reference) until tsk_counters_reset(). */
 int tsk_tile_process(tsk_ctx *ctx);
+/* The same work, only enqueued on the context's stream: returns without waiting for the device,
+ * so that a caller can queue tile after tile (tsk_tile_upload / _process_async /
+ * tsk_ruler_tile_all_async) and keep the GPU busy back to back.  Any getter below waits. */
+int tsk_tile_process_async(tsk_ctx *ctx);
 
 /* Results of the last tsk_tile_process().  All copies are synchronous w.r.t. the call. */
 int tsk_tile_get_calls(tsk_ctx *ctx, tsk_call *calls /* [nclusters] */);
@@ -237,6 +241,18 @@ int tsk_ruler_tile(tsk_ctx *ctx, int sample, const uint32_t *cutoffs, int ncutof
 int tsk_ruler_tile_all(tsk_ctx *ctx, const uint32_t *cutoffs, int ncutoffs,
                        int minimum_polya_len, float downhill_ext_weight, int dist_sampling_bins,
                        float dist_sampling_gap, int16_t *polya_len_out, uint32_t *slot_offsets);
+/* tsk_ruler_tile_all() in two halves.  The first only enqueues the measurement of every record
+ * slot of the resident tile (the per-sample slot counts are read on the device, so it may
+ * directly follow tsk_tile_process_async()); lengths stay in device memory and the
+ * histogram / called counter accumulate.  The second waits and copies the lengths out. */
+int tsk_ruler_tile_all_async(tsk_ctx *ctx, const uint32_t *cutoffs, int ncutoffs,
+                             int minimum_polya_len, float downhill_ext_weight, int dist_sampling_bins,
+                             float dist_sampling_gap);
+int tsk_ruler_get_lengths(tsk_ctx *ctx, int16_t *polya_len_out, uint32_t *slot_offsets);
+/* Number of records whose measured length reached minimum_polya_len (the lines
+ * process_polya_ruling() prints with a length, polyaruler.c:289-299) since the last
+ * tsk_ruler_hist_reset(). */
+int tsk_ruler_get_called(tsk_ctx *ctx, uint64_t *ncalled);
 int tsk_ruler_hist_reset(tsk_ctx *ctx, int ncutoffs, int dist_sampling_bins);
 int tsk_ruler_get_hist(tsk_ctx *ctx, uint32_t *pos /* [ncutoffs][bins] */);
 

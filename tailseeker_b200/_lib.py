@@ -20,7 +20,8 @@ SYMBOLS = [
     "tsk_cutoff_to_packed", "tsk_ruler_records", "tsk_ruler_tile", "tsk_ruler_tile_all", "tsk_ruler_hist_reset",
     "tsk_ruler_get_hist", "tsk_fit_cutoffs", "tsk_synchronize", "tsk_tile_process_timed",
     "tsk_launch_count", "tsk_selftest_logf", "tsk_set_stream", "tsk_profile_enable", "tsk_profile_get",
-    "tsk_selftest_sweeps", "tsk_debug_force_generic",
+    "tsk_selftest_sweeps", "tsk_debug_force_generic", "tsk_tile_process_async",
+    "tsk_ruler_tile_all_async", "tsk_ruler_get_lengths", "tsk_ruler_get_called",
 ]
 
 _lib = None
@@ -46,6 +47,7 @@ def load():
     L.tsk_ctx_destroy.argtypes = [vp]
     L.tsk_tile_upload.argtypes = [vp, vp, sz, vp, sz, vp, u32, u32, i32]
     L.tsk_tile_process.argtypes = [vp]
+    L.tsk_tile_process_async.argtypes = [vp]
     L.tsk_tile_get_calls.argtypes = [vp, vp]
     L.tsk_tile_get_record_count.argtypes = [vp, i32, ctypes.POINTER(u32)]
     L.tsk_tile_get_records.argtypes = [vp, i32, vp, sz]
@@ -60,6 +62,9 @@ def load():
     L.tsk_ruler_tile.argtypes = [vp, i32, vp, i32, i32, f32, i32, f32, vp]
     L.tsk_ruler_tile_all.argtypes = [vp, vp, i32, i32, f32, i32, f32, vp, vp]
     L.tsk_ruler_hist_reset.argtypes = [vp, i32, i32]
+    L.tsk_ruler_tile_all_async.argtypes = [vp, vp, i32, i32, f32, i32, f32]
+    L.tsk_ruler_get_lengths.argtypes = [vp, vp, vp]
+    L.tsk_ruler_get_called.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
     L.tsk_ruler_get_hist.argtypes = [vp, vp]
     L.tsk_fit_cutoffs.argtypes = [vp, vp, vp, i32, i32, ctypes.c_uint64, f64, f64, vp, i32, vp]
     L.tsk_synchronize.argtypes = [vp]

@@ -164,6 +164,47 @@ static int build_device_params(const tsk_params *p, DevParams *d, DevSample *ds)
     return 0;
 }
 
+/* ---- per-stage timing without host waits ------------------------------------------------- */
+static void prof_destroy(tsk_ctx *ctx)
+{
+    for (int i = 0; i < TSK_PROF_RING; i++)
+        for (int k = 0; k < 5; k++) cudaEventDestroy(ctx->prof[i].ev[k]);
+}
+
+/* adds the oldest pending event set to the stage totals (waits for it if it has not finished) */
+static int prof_harvest_one(tsk_ctx *ctx)
+{
+    tsk_ctx::ProfSlot &p = ctx->prof[ctx->prof_head];
+    TSK_CUDA(cudaEventSynchronize(p.ev[p.nev - 1]));
+    for (int i = 0; i + 1 < p.nev; i++) {
+        float ms = 0.f;
+        TSK_CUDA(cudaEventElapsedTime(&ms, p.ev[i], p.ev[i + 1]));
+        ctx->stage_ms[p.first_stage + i] += ms;
+        ctx->stage_runs[p.first_stage + i]++;
+    }
+    ctx->prof_head = (ctx->prof_head + 1) % TSK_PROF_RING;
+    ctx->prof_count--;
+    return 0;
+}
+
+static int prof_harvest_all(tsk_ctx *ctx)
+{
+    while (ctx->prof_count > 0)
+        if (prof_harvest_one(ctx) != 0) return -1;
+    return 0;
+}
+
+/* next free event set (NULL when timing is off); the caller records ev[0..nev-1] in order */
+static cudaEvent_t *prof_take(tsk_ctx *ctx, int nev, int first_stage)
+{
+    if (!ctx->profile) return NULL;
+    if (ctx->prof_count == TSK_PROF_RING && prof_harvest_one(ctx) != 0) return NULL;
+    tsk_ctx::ProfSlot &p = ctx->prof[(ctx->prof_head + ctx->prof_count) % TSK_PROF_RING];
+    p.nev = nev; p.first_stage = first_stage;
+    ctx->prof_count++;
+    return p.ev;
+}
+
 /* ---- context --------------------------------------------------------------------------- */
 extern "C" int tsk_ctx_create(tsk_ctx **out, int device, const tsk_params *params)
 {
@@ -210,6 +251,8 @@ extern "C" int tsk_ctx_create(tsk_ctx **out, int device, const tsk_params *param
     TSK_CUDA(cudaMalloc(&ctx->d_totals, sizeof(uint32_t) * (TSK_MAX_SAMPLES + 1)));
     TSK_CUDA(cudaMalloc(&ctx->d_recbase, sizeof(uint64_t) * (TSK_MAX_SAMPLES + 1)));
     TSK_CUDA(cudaMalloc(&ctx->d_cutoffs, sizeof(uint32_t) * TSK_MAX_CUTOFF_CYCLES));
+    TSK_CUDA(cudaMalloc(&ctx->d_ruler_called, sizeof(unsigned long long)));
+    TSK_CUDA(cudaMemset(ctx->d_ruler_called, 0, sizeof(unsigned long long)));
     if (params->has_control) {
         if (tsk_control_setup(ctx) != 0) return -1;
         TSK_CUDA(cudaMalloc(&ctx->d_ctl_queue, sizeof(uint32_t) * 4));
@@ -231,14 +274,14 @@ extern "C" int tsk_ctx_destroy(tsk_ctx *ctx)
                     ctx->d_bucket, ctx->d_worklist, ctx->d_blkcnt, ctx->d_totals, ctx->d_recbase,
                     ctx->d_records, ctx->d_scratch, ctx->d_pos, ctx->d_neg, ctx->d_counters, ctx->d_fair,
                     ctx->d_lists, ctx->d_ruler_pos, ctx->d_cutoffs, ctx->d_rlen, ctx->d_rrec,
-                    ctx->d_fit_hist, ctx->d_fit_out, ctx->d_ctl_queue, ctx->d_ctl_index};
+                    ctx->d_fit_hist, ctx->d_fit_out, ctx->d_ctl_queue, ctx->d_ctl_index, ctx->d_ruler_called};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)
         if (ptrs[i]) cudaFree(ptrs[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->cstream);
     if (ctx->xstream) { cudaStreamDestroy(ctx->xstream); cudaEventDestroy(ctx->ev_ctl[0]); cudaEventDestroy(ctx->ev_ctl[1]); }
     cudaEventDestroy(ctx->ev_up[0]); cudaEventDestroy(ctx->ev_up[1]);
-    if (ctx->profile) for (int i = 0; i < 7; i++) cudaEventDestroy(ctx->pev[i]);
+    if (ctx->profile) prof_destroy(ctx);
     free(ctx);
     return 0;
 }
@@ -360,20 +403,21 @@ static int fetch_totals(tsk_ctx *ctx)
     return 0;
 }
 
-extern "C" int tsk_tile_process(tsk_ctx *ctx)
+extern "C" int tsk_tile_process_async(tsk_ctx *ctx)
 {
     if (!ctx || !ctx->d_calls) { tsk_set_error("no tile uploaded"); return -1; }
     TSK_CUDA(cudaSetDevice(ctx->device));
     if (next_tile(ctx) != 0) return -1;
-    if (tsk_launch_import(ctx, ctx->profile ? ctx->pev : NULL) != 0) return -1;
+    if (tsk_launch_import(ctx, prof_take(ctx, 5, 0)) != 0) return -1;
+    ctx->processed = 2;          /* enqueued; the host mirrors of the slot counts are not fetched yet */
+    ctx->rlen_resident = 0;
+    return 0;
+}
+
+extern "C" int tsk_tile_process(tsk_ctx *ctx)
+{
+    if (tsk_tile_process_async(ctx) != 0) return -1;
     if (fetch_totals(ctx) != 0) return -1;
-    if (ctx->profile)
-        for (int i = 0; i < 4; i++) {
-            float ms = 0.f;
-            TSK_CUDA(cudaEventElapsedTime(&ms, ctx->pev[i], ctx->pev[i + 1]));
-            ctx->stage_ms[i] += ms;
-            ctx->stage_runs[i]++;
-        }
     ctx->processed = 1;
     return 0;
 }
@@ -400,11 +444,13 @@ extern "C" int tsk_profile_enable(tsk_ctx *ctx, int on)
 {
     if (!ctx) { tsk_set_error("null ctx"); return -1; }
     TSK_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->profile && prof_harvest_all(ctx) != 0) return -1;
     if (on && !ctx->profile)
-        for (int i = 0; i < 7; i++) TSK_CUDA(cudaEventCreate(&ctx->pev[i]));
-    if (!on && ctx->profile)
-        for (int i = 0; i < 7; i++) cudaEventDestroy(ctx->pev[i]);
+        for (int i = 0; i < TSK_PROF_RING; i++)
+            for (int k = 0; k < 5; k++) TSK_CUDA(cudaEventCreate(&ctx->prof[i].ev[k]));
+    if (!on && ctx->profile) prof_destroy(ctx);
     ctx->profile = on ? 1 : 0;
+    ctx->prof_head = ctx->prof_count = 0;
     for (int i = 0; i < 6; i++) { ctx->stage_ms[i] = 0.; ctx->stage_runs[i] = 0; }
     return 0;
 }
@@ -412,6 +458,8 @@ extern "C" int tsk_profile_enable(tsk_ctx *ctx, int on)
 extern "C" int tsk_profile_get(tsk_ctx *ctx, double stage_ms[6], uint64_t stage_runs[6])
 {
     if (!ctx) { tsk_set_error("null ctx"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->profile && prof_harvest_all(ctx) != 0) return -1;      /* waits for the timed work */
     for (int i = 0; i < 6; i++) { stage_ms[i] = ctx->stage_ms[i]; stage_runs[i] = ctx->stage_runs[i]; }
     return 0;
 }
@@ -456,7 +504,12 @@ extern "C" int tsk_tile_process_timed(tsk_ctx *ctx, int iters, float ms_out[5])
 static int need_processed(tsk_ctx *ctx)
 {
     if (!ctx || !ctx->processed) { tsk_set_error("tsk_tile_process() has not run on this tile"); return -1; }
-    return cudaSetDevice(ctx->device) == cudaSuccess ? 0 : -1;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return -1;
+    if (ctx->processed == 2) {   /* enqueued by tsk_tile_process_async(): wait and fetch the slot counts */
+        if (fetch_totals(ctx) != 0) return -1;
+        ctx->processed = 1;
+    }
+    return 0;
 }
 
 extern "C" int tsk_tile_get_calls(tsk_ctx *ctx, tsk_call *calls)
@@ -561,6 +614,7 @@ extern "C" int tsk_ruler_hist_reset(tsk_ctx *ctx, int ncutoffs, int dist_samplin
     const size_t words = (size_t)ncutoffs * dist_sampling_bins;
     if (ensure(&ctx->d_ruler_pos, &ctx->ruler_pos_words, words) != 0) return -1;
     TSK_CUDA(cudaMemsetAsync(ctx->d_ruler_pos, 0, sizeof(uint32_t) * words, ctx->stream));
+    TSK_CUDA(cudaMemsetAsync(ctx->d_ruler_called, 0, sizeof(unsigned long long), ctx->stream));
     ctx->ruler_ncut = ncutoffs;
     ctx->ruler_bins = dist_sampling_bins;
     return 0;
@@ -576,34 +630,42 @@ extern "C" int tsk_ruler_get_hist(tsk_ctx *ctx, uint32_t *pos)
     return 0;
 }
 
+/* histogram shape and cutoffs on the device; the cutoffs are re-sent only when they change */
+static int ruler_prepare(tsk_ctx *ctx, const uint32_t *cutoffs, int ncutoffs, int bins)
+{
+    if (ncutoffs < 1 || ncutoffs > TSK_MAX_CUTOFF_CYCLES || bins < 1 || !cutoffs) {
+        tsk_set_error("bad ruler argument"); return -1;
+    }
+    if (!ctx->d_ruler_pos || ctx->ruler_ncut != ncutoffs || ctx->ruler_bins != bins)
+        if (tsk_ruler_hist_reset(ctx, ncutoffs, bins) != 0) return -1;
+    if (ctx->h_ncut != ncutoffs || memcmp(ctx->h_cutoffs, cutoffs, sizeof(uint32_t) * ncutoffs) != 0) {
+        /* h_cutoffs outlives the call, so the copy may complete later */
+        memcpy(ctx->h_cutoffs, cutoffs, sizeof(uint32_t) * ncutoffs);
+        ctx->h_ncut = ncutoffs;
+        TSK_CUDA(cudaMemcpyAsync(ctx->d_cutoffs, ctx->h_cutoffs, sizeof(uint32_t) * ncutoffs, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    }
+    return 0;
+}
+
 static int ruler_common(tsk_ctx *ctx, const uint32_t *d_records, size_t nrecords, int dump_len,
                         const uint32_t *cutoffs, int ncutoffs, int min_len, float weight, int bins,
                         float gap, int16_t *polya_len_out)
 {
-    if (ncutoffs < 1 || ncutoffs > TSK_MAX_CUTOFF_CYCLES || bins < 1 || dump_len < 0 || !cutoffs) {
-        tsk_set_error("bad ruler argument"); return -1;
-    }
-    if (!ctx->d_ruler_pos || ctx->ruler_ncut != ncutoffs || ctx->ruler_bins != bins) {
-        if (tsk_ruler_hist_reset(ctx, ncutoffs, bins) != 0) return -1;
-    }
-    TSK_CUDA(cudaMemcpyAsync(ctx->d_cutoffs, cutoffs, sizeof(uint32_t) * ncutoffs, cudaMemcpyHostToDevice,
-                             ctx->stream));
+    if (dump_len < 0) { tsk_set_error("bad ruler argument"); return -1; }
+    if (ruler_prepare(ctx, cutoffs, ncutoffs, bins) != 0) return -1;
     if (ensure(&ctx->d_rlen, &ctx->rlen_cap, nrecords ? nrecords : 1) != 0) return -1;
+    ctx->rlen_resident = 0;
     if (nrecords) {
-        if (ctx->profile) TSK_CUDA(cudaEventRecord(ctx->pev[5], ctx->stream));
+        cudaEvent_t *ev = prof_take(ctx, 2, 4);
+        if (ev) TSK_CUDA(cudaEventRecord(ev[0], ctx->stream));
         if (tsk_launch_ruler(ctx, d_records, nrecords, dump_len, ncutoffs, min_len, weight, bins, gap,
                              ctx->d_rlen) != 0) return -1;
-        if (ctx->profile) TSK_CUDA(cudaEventRecord(ctx->pev[6], ctx->stream));
+        if (ev) TSK_CUDA(cudaEventRecord(ev[1], ctx->stream));
         TSK_CUDA(cudaMemcpyAsync(polya_len_out, ctx->d_rlen, sizeof(int16_t) * nrecords,
                                  cudaMemcpyDeviceToHost, ctx->stream));
     }
     TSK_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (nrecords && ctx->profile) {
-        float ms = 0.f;
-        TSK_CUDA(cudaEventElapsedTime(&ms, ctx->pev[5], ctx->pev[6]));
-        ctx->stage_ms[4] += ms;
-        ctx->stage_runs[4]++;
-    }
     return 0;
 }
 
@@ -636,45 +698,57 @@ extern "C" int tsk_ruler_tile(tsk_ctx *ctx, int sample, const uint32_t *cutoffs,
                         downhill_ext_weight, dist_sampling_bins, dist_sampling_gap, polya_len_out);
 }
 
+extern "C" int tsk_ruler_tile_all_async(tsk_ctx *ctx, const uint32_t *cutoffs, int ncutoffs, int minimum_polya_len,
+                                        float downhill_ext_weight, int dist_sampling_bins, float dist_sampling_gap)
+{
+    if (!ctx || !ctx->processed) { tsk_set_error("tsk_tile_process() has not run on this tile"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    if (ruler_prepare(ctx, cutoffs, ncutoffs, dist_sampling_bins) != 0) return -1;
+    /* a tile has at most one record slot per cluster */
+    if (ensure(&ctx->d_rlen, &ctx->rlen_cap, (size_t)ctx->cap_clusters) != 0) return -1;
+    cudaEvent_t *ev = prof_take(ctx, 2, 4);
+    if (ev) TSK_CUDA(cudaEventRecord(ev[0], ctx->stream));
+    if (tsk_launch_ruler_resident(ctx, ncutoffs, minimum_polya_len, downhill_ext_weight, dist_sampling_bins,
+                                  dist_sampling_gap, ctx->d_rlen) != 0) return -1;
+    if (ev) TSK_CUDA(cudaEventRecord(ev[1], ctx->stream));
+    ctx->rlen_resident = 1;
+    return 0;
+}
+
+extern "C" int tsk_ruler_get_lengths(tsk_ctx *ctx, int16_t *polya_len_out, uint32_t *slot_offsets)
+{
+    if (need_processed(ctx) != 0) return -1;
+    if (!ctx->rlen_resident) { tsk_set_error("tsk_ruler_tile_all_async() has not run on this tile"); return -1; }
+    if (!slot_offsets) { tsk_set_error("null argument"); return -1; }
+    const int S = ctx->dp.num_samples;
+    uint32_t at = 0;
+    for (int s = 0; s < S; s++) { slot_offsets[s] = at; at += ctx->h_totals[s]; }
+    slot_offsets[S] = at;
+    if (at) {
+        if (!polya_len_out) { tsk_set_error("null output"); return -1; }
+        TSK_CUDA(cudaMemcpyAsync(polya_len_out, ctx->d_rlen, sizeof(int16_t) * at, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    TSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 extern "C" int tsk_ruler_tile_all(tsk_ctx *ctx, const uint32_t *cutoffs, int ncutoffs, int minimum_polya_len,
                                   float downhill_ext_weight, int dist_sampling_bins, float dist_sampling_gap,
                                   int16_t *polya_len_out, uint32_t *slot_offsets)
 {
-    if (need_processed(ctx) != 0) return -1;
-    if (ncutoffs < 1 || ncutoffs > TSK_MAX_CUTOFF_CYCLES || dist_sampling_bins < 1 || !cutoffs || !slot_offsets) {
-        tsk_set_error("bad ruler argument"); return -1;
-    }
-    const int S = ctx->dp.num_samples;
-    uint32_t first[TSK_MAX_SAMPLES + 1];
-    int dump[TSK_MAX_SAMPLES];
-    first[0] = 0;
-    for (int s = 0; s < S; s++) {
-        first[s + 1] = first[s] + ctx->h_totals[s];
-        dump[s] = ctx->hp.samples[s].signal_dump_length;
-        slot_offsets[s] = first[s];
-    }
-    slot_offsets[S] = first[S];
-    const size_t n = first[S];
-    if (!ctx->d_ruler_pos || ctx->ruler_ncut != ncutoffs || ctx->ruler_bins != dist_sampling_bins)
-        if (tsk_ruler_hist_reset(ctx, ncutoffs, dist_sampling_bins) != 0) return -1;
-    TSK_CUDA(cudaMemcpyAsync(ctx->d_cutoffs, cutoffs, sizeof(uint32_t) * ncutoffs, cudaMemcpyHostToDevice, ctx->stream));
-    if (ensure(&ctx->d_rlen, &ctx->rlen_cap, n ? n : 1) != 0) return -1;
-    if (n) {
-        if (!polya_len_out) { tsk_set_error("null output"); return -1; }
-        if (ctx->profile) TSK_CUDA(cudaEventRecord(ctx->pev[5], ctx->stream));
-        if (tsk_launch_ruler_segs(ctx, ctx->d_records, S, first, ctx->h_recbase, dump, ncutoffs, minimum_polya_len,
-                                  downhill_ext_weight, dist_sampling_bins, dist_sampling_gap, ctx->d_rlen) != 0)
-            return -1;
-        if (ctx->profile) TSK_CUDA(cudaEventRecord(ctx->pev[6], ctx->stream));
-        TSK_CUDA(cudaMemcpyAsync(polya_len_out, ctx->d_rlen, sizeof(int16_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    }
+    if (tsk_ruler_tile_all_async(ctx, cutoffs, ncutoffs, minimum_polya_len, downhill_ext_weight, dist_sampling_bins,
+                                 dist_sampling_gap) != 0) return -1;
+    return tsk_ruler_get_lengths(ctx, polya_len_out, slot_offsets);
+}
+
+extern "C" int tsk_ruler_get_called(tsk_ctx *ctx, uint64_t *ncalled)
+{
+    if (!ctx || !ncalled) { tsk_set_error("null argument"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    unsigned long long v = 0;
+    TSK_CUDA(cudaMemcpyAsync(&v, ctx->d_ruler_called, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
     TSK_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (n && ctx->profile) {
-        float ms = 0.f;
-        TSK_CUDA(cudaEventElapsedTime(&ms, ctx->pev[5], ctx->pev[6]));
-        ctx->stage_ms[4] += ms;
-        ctx->stage_runs[4]++;
-    }
+    *ncalled = v;
     return 0;
 }
 
@@ -694,22 +768,16 @@ extern "C" int tsk_fit_cutoffs(tsk_ctx *ctx, const uint64_t *pos, const uint64_t
     double *d_out = ctx->d_fit_out;
     TSK_CUDA(cudaMemcpyAsync(d_pos, pos, hb, cudaMemcpyHostToDevice, ctx->stream));
     TSK_CUDA(cudaMemcpyAsync(d_neg, neg, hb, cudaMemcpyHostToDevice, ctx->stream));
-    if (ctx->profile) cudaEventRecord(ctx->pev[5], ctx->stream);
+    cudaEvent_t *pev = prof_take(ctx, 2, 5);
+    if (pev) cudaEventRecord(pev[0], ctx->stream);
     int rc = tsk_launch_fit(ctx, d_pos, d_neg, cycles, bins, min_spots, kde_bandwidth, search_low,
                             search_high, nsearch_high, d_out);
-    if (ctx->profile) cudaEventRecord(ctx->pev[6], ctx->stream);
+    if (pev) cudaEventRecord(pev[1], ctx->stream);
     if (rc == 0) {
         cudaError_t e = cudaMemcpyAsync(cutoffs_out, d_out, sizeof(double) * cycles, cudaMemcpyDeviceToHost,
                                         ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { tsk_set_error("fit copy back: %s", cudaGetErrorString(e)); rc = -1; }
-        else if (ctx->profile) {
-            float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, ctx->pev[5], ctx->pev[6]) == cudaSuccess) {
-                ctx->stage_ms[5] += ms;
-                ctx->stage_runs[5]++;
-            }
-        }
     }
     return rc;
 }

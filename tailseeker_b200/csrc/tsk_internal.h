@@ -11,6 +11,7 @@
 #define TSK_MAX_MODS     64      /* upper bound on max_terminal_modifications */
 #define TSK_MAX_RANK     8       /* upper bound on balancer num-positive/negative samples */
 #define TSK_NCOUNT       6       /* counters per sample */
+#define TSK_PROF_RING    64      /* event sets in flight with tsk_profile_enable() */
 
 /* cluster kinds produced by decode_demux_seed (bit field, one byte per cluster) */
 #define KIND_PROCESS   0x01      /* reaches process_polya_signal() and passes the balancer check */
@@ -103,6 +104,9 @@ struct tsk_ctx {
     cudaStream_t xstream;        /* side stream of the classifier */
     cudaEvent_t ev_ctl[2];       /* K1 done -> classifier may start; classifier done */
     uint32_t *d_ruler_pos;  size_t ruler_pos_words;   /* capacity */
+    unsigned long long *d_ruler_called;               /* records measured since the last ruler reset */
+    uint32_t h_cutoffs[TSK_MAX_CUTOFF_CYCLES];  int h_ncut;   /* what d_cutoffs currently holds */
+    int rlen_resident;           /* d_rlen holds the lengths of every slot of the resident tile */
     int ruler_ncut, ruler_bins;                       /* current shape of the ruler histogram */
     uint32_t *d_cutoffs;         /* [TSK_MAX_CUTOFF_CYCLES] */
     int16_t  *d_rlen;  size_t rlen_cap;
@@ -118,7 +122,10 @@ struct tsk_ctx {
 
     /* optional per-stage device timing (tsk_profile_enable) */
     int profile, own_stream, force_generic;
-    cudaEvent_t pev[7];
+    /* a ring of event sets, harvested when their work has finished, so that timing does not
+     * force the host to wait for the device between tiles */
+    struct ProfSlot { cudaEvent_t ev[5]; int nev, first_stage; } prof[TSK_PROF_RING];
+    int prof_head, prof_count;   /* oldest pending slot, number pending */
     double stage_ms[6];          /* decode, scan, normalise/score/pack, fix-ups, ruler, fit */
     uint64_t stage_runs[6];
 };
@@ -143,6 +150,8 @@ int tsk_launch_control(tsk_ctx *ctx);
 int tsk_launch_ruler(tsk_ctx *ctx, const uint32_t *d_records, size_t nrecords, int dump_len,
                      int ncutoffs, int min_len, float weight, int bins, float gap,
                      int16_t *d_len_out);
+int tsk_launch_ruler_resident(tsk_ctx *ctx, int ncutoffs, int min_len, float weight, int bins, float gap,
+                              int16_t *d_len_out);
 int tsk_launch_ruler_segs(tsk_ctx *ctx, const uint32_t *d_records, int nseg, const uint32_t *first,
                           const uint64_t *base, const int *dump, int ncutoffs, int min_len, float weight,
                           int bins, float gap, int16_t *d_len_out);

@@ -24,89 +24,166 @@ struct RulerSegs {
     int dump[TSK_MAX_SAMPLES];
 };
 
-__global__ void __launch_bounds__(RULER_THREADS)
-k_polya_ruler(const uint32_t *__restrict__ records, const __grid_constant__ RulerSegs seg,
-              const uint32_t *__restrict__ g_cutoffs, int ncut, int min_len, float weight,
-              int bins, float gap, int16_t *__restrict__ len_out, uint32_t *__restrict__ pos, int intbins)
+/* floor((sc - 1) * bins / 16777214) of add_polya_score_sample() (polyaruler.c:163-168). */
+__device__ __forceinline__ int score_bin(uint32_t sc, int bins, int intbins)
 {
-    __shared__ uint32_t s_cut[TSK_MAX_CUTOFF_CYCLES];
-    for (int i = threadIdx.x; i < ncut; i += RULER_THREADS) s_cut[i] = g_cutoffs[i];
+    int b;
+    if (intbins) {
+        /* in integers: with x = a*2^24 + b0 and 2^24 = 16777214 + 2, x = a*16777214 + (2a + b0),
+         * 2a + b0 < 2*16777214.  Equals the reference's fp64 expression whenever bins shares no
+         * factor with 2^23-1 (the host checks): the exact value is then an integer only for
+         * sc-1 in {0, 8388607, 16777214}, which fp64 evaluates exactly, and is otherwise
+         * >= 2^-24 away from one, far beyond the fp64 rounding error. */
+        const unsigned long long x = (unsigned long long)(sc - 1) * (unsigned)bins;
+        const uint32_t a = (uint32_t)(x >> 24), b0 = (uint32_t)x & 0xffffffu;
+        b = (int)(a + ((2 * a + b0) >= 16777214u ? 1u : 0u));
+    } else {
+        b = __double2int_rz(__dmul_rn(__ddiv_rn(__dsub_rn((double)sc, 1.0), (double)(TSK_SCORE_MAX - 1)),
+                                      (double)bins));
+    }
+    return b >= bins ? bins - 1 : b;
+}
+
+/* Records longer than 256 cycles: the same steps with the packets re-read through L1. */
+__device__ __noinline__ int ruler_long_record(const uint32_t *__restrict__ rec, int first, int valid,
+                                              const uint32_t *s_cut, float weight, int lane)
+{
+    int carry = 0, bestkey = INT_MIN;
+    const unsigned le_mask = 0xffffffffu >> (31 - lane);
+    for (int base = 0; base < valid; base += 32) {
+        const int i = base + lane;
+        const uint32_t cut = (i < valid && first + i < TSK_MAX_CUTOFF_CYCLES) ? s_cut[first + i] : 0u;
+        const uint32_t sc = i < valid ? (__ldg(rec + 2 + i) >> 1) & TSK_SCORE_MAX : 0u;
+        const unsigned mu = __ballot_sync(FULL_MASK, cut != 0 && sc >= cut), md = __ballot_sync(FULL_MASK, sc < cut);
+        const int cum = carry + __popc(mu & le_mask) - __popc(md & le_mask);
+        const int key = (i < valid) ? (((cum + 2048) << 16) | (0xffff - i)) : INT_MIN;
+        bestkey = max(bestkey, __reduce_max_sync(FULL_MASK, key));
+        carry += __popc(mu) - __popc(md);
+    }
+    const int maxcum = (bestkey >> 16) - 2048;
+    const int argmax = (maxcum > 0) ? (0xffff - (bestkey & 0xffff)) : -1;
+    int ext = -1;
+    if (argmax >= 0) {
+        for (int base = ((argmax + 1) >> 5) << 5; base < valid; base += 32) {
+            const int i = base + lane;
+            uint32_t x = 0;
+            if (i < valid && i > argmax) x = __ldg(rec + 2 + i);
+            const bool lit = ((x >> 1) & TSK_SCORE_MAX) != 0;
+            const unsigned stop = __ballot_sync(FULL_MASK, lit && !(x & 1u));
+            unsigned go = __ballot_sync(FULL_MASK, lit && (x & 1u));
+            if (stop) go &= (1u << (__ffs(stop) - 1)) - 1u;
+            if (go) ext = base + 31 - __clz(go);
+            if (stop) break;
+        }
+    }
+    int len = argmax + 1;
+    if (ext >= 0) len += (int)roundf(__fmul_rn((float)(ext - argmax), weight));
+    return len;
+}
+
+#define RULER_CUT_PAD 320       /* zero cutoffs past the table: first + i needs no range check */
+
+__global__ void __launch_bounds__(RULER_THREADS)
+k_polya_ruler(const uint32_t *__restrict__ records, const __grid_constant__ RulerSegs hseg,
+              const uint32_t *__restrict__ d_totals, const uint64_t *__restrict__ d_recbase,
+              const DevSample *__restrict__ d_samples,
+              const uint32_t *__restrict__ g_cutoffs, int ncut, int min_len, float weight,
+              int bins, float gap, int16_t *__restrict__ len_out, uint32_t *__restrict__ pos, int intbins,
+              unsigned long long *__restrict__ called)
+{
+    __shared__ uint32_t s_cut[TSK_MAX_CUTOFF_CYCLES + RULER_CUT_PAD];
+    __shared__ RulerSegs seg;
+    __shared__ unsigned s_called;
+    for (int i = threadIdx.x; i < TSK_MAX_CUTOFF_CYCLES + RULER_CUT_PAD; i += RULER_THREADS)
+        s_cut[i] = i < ncut ? g_cutoffs[i] : 0u;
+    if (threadIdx.x == 0) {
+        s_called = 0;
+        if (d_totals != nullptr) {
+            /* streamed mode: the slot counts of the resident tile are still on the device
+             * (hseg.nseg = number of samples) */
+            uint32_t at = 0;
+            seg.nseg = hseg.nseg;
+            for (int s = 0; s < hseg.nseg; s++) {
+                seg.first[s] = at;
+                seg.base[s] = d_recbase[s];
+                seg.dump[s] = d_samples[s].dump_len;
+                at += d_totals[s];
+            }
+            seg.first[hseg.nseg] = at;
+        } else {
+            seg.nseg = hseg.nseg;
+            for (int s = 0; s < hseg.nseg; s++) { seg.first[s] = hseg.first[s]; seg.base[s] = hseg.base[s]; seg.dump[s] = hseg.dump[s]; }
+            seg.first[hseg.nseg] = hseg.first[hseg.nseg];
+        }
+    }
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
     const size_t warps_total = (size_t)gridDim.x * (RULER_THREADS / 32);
     const size_t nrecords = seg.first[seg.nseg];
+    const unsigned le_mask = 0xffffffffu >> (31 - lane);
+    /* larger cumulative sum wins, then the smaller cycle index */
+    const int keybase = (2048 << 16) | (0xffff - lane);
     int g = 0;
+    unsigned ncalled = 0;
 
     for (size_t r = (size_t)blockIdx.x * (RULER_THREADS / 32) + (threadIdx.x >> 5); r < nrecords;
          r += warps_total) {
         while (r >= seg.first[g + 1]) g++;           /* r only grows: segments are visited in order */
         const uint32_t *rec = records + seg.base[g] + (r - seg.first[g]) * (size_t)(2 + seg.dump[g]);
         const uint32_t hdr = __ldg(rec + 1);
-        const int first = (int16_t)(hdr & 0xffffu);
+        int first = (int16_t)(hdr & 0xffffu);
         const int valid = (int16_t)(hdr >> 16);
+        if (first < 0) first = 0;
+        if (first > TSK_MAX_CUTOFF_CYCLES) first = TSK_MAX_CUTOFF_CYCLES;
         int len = 0;
 
-        /* all packets of the record in flight at once: eight independent 128-byte loads per warp
-         * (records longer than 256 cycles fall back to re-reading through L1) */
+        /* all packets of the record in flight at once: eight independent 128-byte loads */
         uint32_t w[8];
-        const bool inreg = valid <= 256;
 #pragma unroll
-        for (int k = 0; k < 8; k++)
-            w[k] = (inreg && k * 32 + lane < valid) ? __ldg(rec + 2 + k * 32 + lane) : 0u;
-        auto packet = [&](int i) -> uint32_t {       /* i = base + lane, base a multiple of 32 */
-            if (!inreg) return __ldg(rec + 2 + i);
-            uint32_t v = w[0];
-#pragma unroll
-            for (int k = 1; k < 8; k++) v = ((i >> 5) == k) ? w[k] : v;
-            return v;
-        };
+        for (int k = 0; k < 8; k++) w[k] = (k * 32 + lane < valid) ? __ldg(rec + 2 + k * 32 + lane) : 0u;
 
-        if (valid > 0) {
+        if (valid > 256) {
+            len = ruler_long_record(rec, first, valid, s_cut, weight, lane);
+        } else if (valid > 0) {
             /* ---- +-1 cumulative sum and its first strict maximum ----
              * the steps are +1 / -1 / 0, so a lane's inclusive prefix sum is the difference of two
              * population counts over ballots; the maximum of (cum, -index) keys is one REDUX. */
-            int carry = 0;
-            int bestkey = INT_MIN;
-            const unsigned le_mask = 0xffffffffu >> (31 - lane);
-            for (int base = 0; base < valid; base += 32) {
-                const int i = base + lane;
-                const int cyc = first + i;
-                bool up = false, down = false;
-                if (i < valid && cyc < ncut) {
-                    const uint32_t cut = s_cut[cyc];
-                    if (cut != 0) {
-                        const uint32_t sc = (packet(i) >> 1) & TSK_SCORE_MAX;
-                        up = sc >= cut;
-                        down = !up;
-                    }
+            int carry = 0, bestkey = INT_MIN;
+            const uint32_t *cutp = s_cut + first + lane;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (k * 32 < valid) {
+                    const bool in = k * 32 + lane < valid;
+                    const uint32_t cut = in ? cutp[k * 32] : 0u;          /* 0: this cycle does not count */
+                    const uint32_t sc = (w[k] >> 1) & TSK_SCORE_MAX;
+                    const unsigned mu = __ballot_sync(FULL_MASK, cut != 0 && sc >= cut);
+                    const unsigned md = __ballot_sync(FULL_MASK, sc < cut);
+                    const int cum = carry + __popc(mu & le_mask) - __popc(md & le_mask);
+                    bestkey = max(bestkey, in ? (cum << 16) + (keybase - 32 * k) : INT_MIN);
+                    carry += __popc(mu) - __popc(md);
                 }
-                const unsigned mu = __ballot_sync(FULL_MASK, up), md = __ballot_sync(FULL_MASK, down);
-                const int cum = carry + __popc(mu & le_mask) - __popc(md & le_mask);
-                /* larger cumsum wins, then the smaller cycle index */
-                const int key = (i < valid) ? (((cum + 2048) << 16) | (0xffff - i)) : INT_MIN;
-                bestkey = max(bestkey, __reduce_max_sync(FULL_MASK, key));
-                carry += __popc(mu) - __popc(md);
             }
+            bestkey = __reduce_max_sync(FULL_MASK, bestkey);
             const int maxcum = (bestkey >> 16) - 2048;
             const int argmax = (maxcum > 0) ? (0xffff - (bestkey & 0xffff)) : -1;
 
-            /* ---- downhill extension ---- */
+            /* ---- downhill extension: lit downhill packets right after the maximum, up to the
+             *      first lit packet that is not downhill ---- */
             int ext = -1;
             if (argmax >= 0) {
-                for (int base = ((argmax + 1) >> 5) << 5; base < valid; base += 32) {
-                    const int i = base + lane;
-                    uint32_t x = 0;
-                    if (i < valid && i > argmax) x = packet(i);
-                    const bool lit = ((x >> 1) & TSK_SCORE_MAX) != 0;
-                    const unsigned stop = __ballot_sync(FULL_MASK, lit && !(x & 1u));
-                    unsigned go = __ballot_sync(FULL_MASK, lit && (x & 1u));
-                    if (stop) {
-                        go &= (1u << (__ffs(stop) - 1)) - 1u;
-                        if (go) ext = base + 31 - __clz(go);
-                        break;
+                bool open = true;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (open && k * 32 + 31 > argmax && k * 32 < valid) {
+                        const int i = k * 32 + lane;
+                        const uint32_t x = (i > argmax) ? w[k] : 0u;          /* w[] is 0 past valid */
+                        const bool lit = ((x >> 1) & TSK_SCORE_MAX) != 0;
+                        const unsigned stop = __ballot_sync(FULL_MASK, lit && !(x & 1u));
+                        unsigned go = __ballot_sync(FULL_MASK, lit && (x & 1u));
+                        if (stop) { go &= (1u << (__ffs(stop) - 1)) - 1u; open = false; }
+                        if (go) ext = k * 32 + 31 - __clz(go);
                     }
-                    if (go) ext = base + 31 - __clz(go);
                 }
             }
             len = argmax + 1;
@@ -114,33 +191,31 @@ k_polya_ruler(const uint32_t *__restrict__ records, const __grid_constant__ Rule
         }
 
         const bool pass = len >= min_len;
-        if (lane == 0) len_out[r] = pass ? (int16_t)len : (int16_t)-1;
+        if (lane == 0) { len_out[r] = pass ? (int16_t)len : (int16_t)-1; ncalled += pass; }
         if (pass) {
-            const int take = len - __float2int_rz(__fmul_rn((float)len, gap));
-            for (int i = lane; i < take; i += 32) {
-                const uint32_t sc = (packet(i) >> 1) & TSK_SCORE_MAX;
-                if (sc > 0) {
-                    int b;
-                    if (intbins) {
-                        /* floor((sc-1) * bins / 16777214) in integers: with x = a*2^24 + b0 and
-                         * 2^24 = 16777214 + 2, x = a*16777214 + (2a + b0), 2a + b0 < 2*16777214.
-                         * Equals the reference's fp64 expression whenever bins shares no factor
-                         * with 2^23-1 (the host checks): the exact value is then an integer only for
-                         * sc-1 in {0, 8388607, 16777214}, which fp64 evaluates exactly, and is
-                         * otherwise >= 2^-24 away from one, far beyond the fp64 rounding error. */
-                        const unsigned long long x = (unsigned long long)(sc - 1) * (unsigned)bins;
-                        const uint32_t a = (uint32_t)(x >> 24), b0 = (uint32_t)x & 0xffffffu;
-                        b = (int)(a + ((2 * a + b0) >= 16777214u ? 1u : 0u));
-                    } else {
-                        b = __double2int_rz(__dmul_rn(__ddiv_rn(__dsub_rn((double)sc, 1.0),
-                                                               (double)(TSK_SCORE_MAX - 1)), (double)bins));
+            /* positive score samples of the called tail, polyaruler.c:154-172,296-298 */
+            const int take = min(len - __float2int_rz(__fmul_rn((float)len, gap)), ncut - first);
+            uint32_t *row = pos + (size_t)(first + lane) * bins;
+            if (valid <= 256) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    if (k * 32 < take) {
+                        const uint32_t sc = (w[k] >> 1) & TSK_SCORE_MAX;
+                        if (k * 32 + lane < take && sc > 0)
+                            atomicAdd(row + (size_t)(k * 32) * bins + score_bin(sc, bins, intbins), 1u);
                     }
-                    if (b >= bins) b = bins - 1;
-                    atomicAdd(&pos[(size_t)(first + i) * bins + b], 1u);
+                }
+            } else {
+                for (int i = lane; i < take; i += 32) {
+                    const uint32_t sc = (__ldg(rec + 2 + i) >> 1) & TSK_SCORE_MAX;
+                    if (sc > 0) atomicAdd(pos + (size_t)(first + i) * bins + score_bin(sc, bins, intbins), 1u);
                 }
             }
         }
     }
+    if (lane == 0 && ncalled) atomicAdd(&s_called, ncalled);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_called) atomicAdd(called, (unsigned long long)s_called);
 }
 
 int tsk_launch_ruler_segs(tsk_ctx *ctx, const uint32_t *d_records, int nseg, const uint32_t *first,
@@ -159,7 +234,28 @@ int tsk_launch_ruler_segs(tsk_ctx *ctx, const uint32_t *d_records, int nseg, con
     /* 2^23 - 1 = 47 * 178481 */
     const int intbins = (bins % 47 != 0) && (bins % 178481 != 0) && bins <= 65536;
     k_polya_ruler<<<(unsigned)blocks, RULER_THREADS, 0, ctx->stream>>>(
-        d_records, seg, ctx->d_cutoffs, ncutoffs, min_len, weight, bins, gap, d_len_out, ctx->d_ruler_pos, intbins);
+        d_records, seg, nullptr, nullptr, nullptr, ctx->d_cutoffs, ncutoffs, min_len, weight, bins, gap, d_len_out,
+        ctx->d_ruler_pos, intbins, ctx->d_ruler_called);
+    ctx->launches++;
+    TSK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+/* Every record slot of the resident tile, with the per-sample slot counts read on the device
+ * (nothing about the tile needs to be known on the host yet). */
+int tsk_launch_ruler_resident(tsk_ctx *ctx, int ncutoffs, int min_len, float weight, int bins, float gap,
+                              int16_t *d_len_out)
+{
+    RulerSegs seg;
+    seg.nseg = ctx->dp.num_samples;
+    size_t blocks = ((size_t)ctx->tile.nclusters + (RULER_THREADS / 32) - 1) / (RULER_THREADS / 32);
+    const size_t maxblocks = 148 * 8 * 4;
+    if (blocks > maxblocks) blocks = maxblocks;
+    if (blocks == 0) return 0;
+    const int intbins = (bins % 47 != 0) && (bins % 178481 != 0) && bins <= 65536;
+    k_polya_ruler<<<(unsigned)blocks, RULER_THREADS, 0, ctx->stream>>>(
+        ctx->d_records, seg, ctx->d_totals, ctx->d_recbase, ctx->d_samples, ctx->d_cutoffs, ncutoffs, min_len,
+        weight, bins, gap, d_len_out, ctx->d_ruler_pos, intbins, ctx->d_ruler_called);
     ctx->launches++;
     TSK_CUDA(cudaGetLastError());
     return 0;

@@ -107,6 +107,12 @@ class TileProcessor:
         _lib.check(self.lib.tsk_tile_process(self._ctx))
         self._take()
 
+    def process_async(self):
+        """process() without waiting for the device: queue tile after tile (upload / process_async
+        / ruler_tile_all_async) and read results later; every getter waits for the device."""
+        _lib.check(self.lib.tsk_tile_process_async(self._ctx))
+        self._take()
+
     def process_timed(self, iters: int = 1) -> np.ndarray:
         ms = np.zeros(5, dtype=np.float32)
         _lib.check(self.lib.tsk_tile_process_timed(self._ctx, iters, _ptr(ms)))
@@ -212,6 +218,30 @@ class TileProcessor:
         _lib.check(self.lib.tsk_ruler_tile_all(self._ctx, _ptr(cut), cut.size, min_polya, downhill_w, bins, gap,
                                                _ptr(out), _ptr(offs)))
         return out[:total], offs
+
+    def ruler_tile_all_async(self, cutoffs_packed: np.ndarray, min_polya: int = 8, downhill_w: float = 0.49,
+                             bins: int = 1000, gap: float = 0.1) -> None:
+        """Enqueue the measurement of every record slot of the resident tile; lengths stay on the
+        device (ruler_lengths()), histogram and called counter accumulate."""
+        cut = np.ascontiguousarray(cutoffs_packed, dtype=np.uint32)
+        _lib.check(self.lib.tsk_ruler_tile_all_async(self._ctx, _ptr(cut), cut.size, min_polya, downhill_w,
+                                                     bins, gap))
+
+    def ruler_lengths(self):
+        """(lengths int16 [sum of slots], offsets u32 [num_samples + 1]) of the last
+        ruler_tile_all_async(); waits for the device."""
+        S = self.params.num_samples
+        total = sum(self.record_count(s) for s in range(S))
+        out = np.full(max(total, 1), -1, dtype=np.int16)
+        offs = np.zeros(S + 1, dtype=np.uint32)
+        _lib.check(self.lib.tsk_ruler_get_lengths(self._ctx, _ptr(out), _ptr(offs)))
+        return out[:total], offs
+
+    def ruler_called(self) -> int:
+        """Records measured with a length >= min_polya since the last ruler_reset()."""
+        v = ctypes.c_uint64(0)
+        _lib.check(self.lib.tsk_ruler_get_called(self._ctx, ctypes.byref(v)))
+        return int(v.value)
 
     def ruler_hist(self) -> np.ndarray:
         out = np.zeros(self._ruler_shape, dtype=np.uint32)

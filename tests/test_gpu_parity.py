@@ -309,3 +309,77 @@ def test_control_golden_reads():
         assert cnt[1, 0] == int(g["decision"].sum()) and cnt[0, 0] == n - int(g["decision"].sum())
     finally:
         p.close()
+
+
+@pytest.mark.parametrize("dump_len", [300, 231, 64, 7])
+def test_ruler_synthetic_records(proc, oracle, dump_len):
+    """Hand-made records: every valid length 0..dump_len (ragged ends, block boundaries at
+    multiples of 32, records longer than 256 cycles), runs of +1 / -1 steps of random length,
+    downhill tails, zero-score packets."""
+    rng = np.random.default_rng(dump_len)
+    n, ncut = 4000, 400
+    cut = np.clip(0.3 + 0.05 * rng.standard_normal(ncut), 0.05, 0.9)
+    cut[rng.random(ncut) < 0.03] = np.nan
+    packed = proc.cutoffs_to_packed(cut)
+    first = rng.integers(0, 60, n)
+    valid = rng.integers(0, dump_len + 1, n)
+    valid[:dump_len + 1] = np.arange(dump_len + 1)
+    recs = np.zeros((n, 2 + dump_len), np.uint32)
+    recs[:, 0] = np.arange(n)
+    recs[:, 1] = (first & 0xffff) | (valid << 16)
+    for r in range(n):
+        tail = int(rng.integers(0, valid[r] + 1))
+        hi = rng.random(valid[r]) < np.where(np.arange(valid[r]) < tail, 0.9, 0.15)
+        score = np.where(hi, rng.uniform(0.4, 1.0, valid[r]), rng.uniform(0.0, 0.25, valid[r]))
+        score[rng.random(valid[r]) < 0.05] = 0.0
+        word = (np.round(score * 16777215).astype(np.uint32) << 1) | (rng.random(valid[r]) < 0.6)
+        recs[r, 2:2 + valid[r]] = word
+    want, want_hist = oracle.ruler(recs, packed)
+    proc.ruler_reset(ncut)
+    got = proc.ruler_records(recs, packed)
+    assert (got == want).all() and (dump_len < 8 or int((want >= 0).sum()) > 500)
+    assert (proc.ruler_hist() == want_hist).all()
+
+
+def test_streamed_mode(stock_cfg, oracle):
+    """tsk_tile_process_async / tsk_ruler_tile_all_async: two tiles queued back to back without
+    reading anything in between; results of the second tile, the accumulated ruler histogram
+    and the called counter equal the blocking calls'."""
+    from tailseeker_b200.synth import make_tile
+    from tailseeker_b200.importer import TileProcessor, invert_colormatrix
+    cfg = stock_cfg
+    T = cfg.total_cycles
+    tiles = [make_tile(cfg, n, seed=sd) for n, sd in ((9000, 31), (7000, 32))]
+    packed = None
+    p = TileProcessor(cfg)
+    try:
+        packed = p.cutoffs_to_packed(np.full(T, 0.25))
+        # blocking reference run
+        want_called, want_hist = 0, None
+        p.ruler_reset(T)
+        for t in tiles:
+            p.upload(t.bcl, t.cif, invert_colormatrix(t.matrix))
+            p.process()
+            lens, offs = p.ruler_tile_all(packed)
+            want_called += int((lens >= 0).sum())
+        want_hist = p.ruler_hist()
+        want_lens, want_calls, want_counters = lens, p.calls(), p.counters()
+        assert p.ruler_called() == want_called
+        # streamed run
+        p.reset_counters()
+        p.ruler_reset(T)
+        for t in tiles:
+            p.upload(t.bcl, t.cif, invert_colormatrix(t.matrix))
+            p.process_async()
+            p.ruler_tile_all_async(packed)
+        assert p.ruler_called() == want_called
+        assert (p.ruler_hist() == want_hist).all()
+        lens, offs2 = p.ruler_lengths()
+        assert (offs2 == offs).all() and (lens == want_lens).all()
+        assert (p.calls() == want_calls).all()
+        assert (p.counters() == want_counters).all()
+        o = oracle.process(cfg, tiles[1].bcl, tiles[1].cif, oracle.invert_matrix(tiles[1].matrix))
+        for s in range(p.params.num_samples):
+            assert (p.records(s) == o["records"][s]).all()
+    finally:
+        p.close()
