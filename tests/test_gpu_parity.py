@@ -218,10 +218,11 @@ def test_ruler_matches_oracle(proc, stock_cfg, oracle):
     assert (proc.ruler_hist() == want_hist).all()
 
 
-@pytest.mark.parametrize("bins", [470, 64, 1000])
+@pytest.mark.parametrize("bins", [470, 64, 1000, 30000])
 def test_ruler_histogram_bins(proc, stock_cfg, oracle, bins):
     """Positive resampling with other bin counts: 470 = 10 * 47 shares a factor with 2^23 - 1 and
-    takes the literal fp64 binning, the others the integer form."""
+    takes the literal fp64 binning, the others the integer form; 30000 bins do not fit the
+    histogram kernel's private shared-memory rows and go straight to the global histogram."""
     tile, o = _run(proc, stock_cfg, oracle, 6000, 12)
     T = stock_cfg.total_cycles
     packed = proc.cutoffs_to_packed(np.full(T, 0.2))
