@@ -436,7 +436,7 @@ extern "C" int tsk_set_stream(tsk_ctx *ctx, void *cuda_stream)
 extern "C" int tsk_debug_force_generic(tsk_ctx *ctx, int on)
 {
     if (!ctx) { tsk_set_error("null ctx"); return -1; }
-    ctx->force_generic = on ? 1 : 0;
+    ctx->force_generic = on;     /* 0: default, 1: literal kernel for every cluster, 2: row form of the fast kernel */
     return 0;
 }
 

@@ -847,6 +847,403 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
     }
 }
 
+/* ---- compact form: the same per-cycle arithmetic over WORK ITEMS instead of cluster rows.
+ * A warp takes 32 consecutive entries of the work list (the clusters that reach
+ * process_polya_signal(), in ascending order), so no lane idles on a dropped cluster (unknown
+ * barcode / PhiX, failed fingerprint or balancer QC, no delimiter: 13 % of the synthetic tile,
+ * far more with a large PhiX spike-in).  The TMA box is K2C_W clusters wide starting at the item's
+ * first cluster (rounded down to 8) and each lane reads its own column of it; clusters further
+ * than K2C_W from there (an item spanning > 89 clusters, i.e. under ~40 % kept) go to the literal kernel.  Nothing is
+ * resident: the balancer cycles and then the scored cycles stream through the same ring of three
+ * 4-cycle groups (the few cycles both passes need are fetched twice, from L2). ---- */
+#define K2C_W     96                     /* clusters per TMA box */
+#define K2C_CHB   (K2C_W * 2)            /* bytes per channel row */
+#define K2C_ROWB  (4 * K2C_CHB)          /* bytes per cycle and warp */
+
+struct __align__(128) K2SmemC {
+    int16_t  stage[K2_WARPS][K2_NGROUP * K2_GROUP][4][K2C_W];
+    uint32_t tile[K2_WARPS][32][K2_TILE_CYC + 1];
+    ScoreShared sh;
+    uint64_t bar_full[K2_WARPS][K2_NGROUP];
+};
+
+__global__ void __launch_bounds__(TSK_K2_THREADS, K2_MIN_CTAS)
+k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreArgs A, const float rcp_maxent,
+                               const __grid_constant__ CUtensorMap tmap)
+{
+    extern __shared__ __align__(128) unsigned char k2_smem_raw[];
+    K2SmemC &sm = *reinterpret_cast<K2SmemC *>(k2_smem_raw);
+    const ScoreShared &sh = sm.sh;
+    const int S = P.num_samples;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const TileView &tv = A.tv;
+    const int ts = P.threep_start, tl = P.threep_length, bins = P.bins;
+    const size_t spitch = A.spitch;
+    const uint32_t a_stage = smem_u32(&sm.stage[warp][0][0][0]);
+    const uint32_t a_full = smem_u32(&sm.bar_full[warp][0]);
+
+    if (lane == 0) {
+        for (int i = 0; i < K2_NGROUP; i++) mbar_init(a_full + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    load_score_shared(sm.sh, A.tscore, A.samples, S);      /* ends with __syncthreads() */
+
+    /* ---- work item: 32 consecutive entries of the work list (clusters that reach
+     *      process_polya_signal(), ascending); lane -> cluster, window = [x0, x0 + K2C_W) ---- */
+    const uint32_t nwork = A.totals[S];
+    const uint32_t w0 = (blockIdx.x * K2_WARPS + warp) * 32;
+    if (w0 >= nwork) return;
+    uint32_t kd = 0;
+    tsk_call call;
+    int de = ts, ps = 0, sample = 0;
+    bool alive = w0 + lane < nwork;
+    uint32_t n = alive ? A.worklist[w0 + lane] : 0u;          /* my cluster */
+    /* window start: a tiled TMA copy must begin on a 16-byte boundary of the plane (8 clusters);
+     * a box starting elsewhere faults with "illegal instruction" */
+    const int x0 = (int)(__shfl_sync(FULL_MASK, n, 0) & ~7u);
+    if (alive && n - (uint32_t)x0 >= K2C_W) {
+        /* the window does not reach this far (long run of dropped clusters): literal kernel */
+        list_array(A.lists, 3, A.listcap)[atomicAdd(&A.lists[3], 1u)] = n;
+        alive = false;
+    }
+    if (!alive) n = (uint32_t)x0;
+    if (alive) {
+        kd = A.kind[n];
+        const uint4 craw = *reinterpret_cast<const uint4 *>(&A.calls[n]);
+        call = *reinterpret_cast<const tsk_call *>(&craw);
+        de = call.delimiter_end; ps = call.terminal_mods; sample = call.sample;
+    }
+    const int start = de - ts;                                /* first scored cycle (3'-read index) */
+
+    int insert_len = 0, dump = 0;
+    if (alive) {
+        insert_len = ts + tl - de;
+        const int limit = sh.limit[sample];
+        dump = sh.dump[sample];
+        if (limit > 0 && limit < insert_len) insert_len = limit;
+    }
+    const int rdata_end = start + insert_len;                 /* this lane scores cycles [start, rdata_end) */
+    int rdata_w = alive ? rdata_end : 0;                      /* the warp needs data of cycles [0, rdata_w) */
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) rdata_w = max(rdata_w, __shfl_xor_sync(FULL_MASK, rdata_w, d));
+
+    /* ---- streaming: cycles [c0, c1) in groups of four through the warp's ring; data exist for
+     *      cycles < cdata (later ones only pad records).  G counts groups over both passes so that
+     *      ring slots and barrier phases carry on. ---- */
+    const uint32_t colofs = (n - (uint32_t)x0) * 2;
+    int G = 0;
+    auto issue_group = [&](int gabs, int cyc) {       /* lane 0 only */
+        const int slot = gabs % K2_NGROUP;
+        mbar_arrive_expect_tx(a_full + 8 * slot, K2_GROUP * K2C_ROWB);
+        tma_cycle_g2s(a_stage + slot * (K2_GROUP * K2C_ROWB), &tmap, x0, cyc, a_full + 8 * slot);
+    };
+    auto stream = [&](const int c0, const int c1, const int cdata, auto &&fn) {
+        const int ng = c1 > c0 ? (c1 - c0 + K2_GROUP - 1) / K2_GROUP : 0;
+        const int ngd = cdata > c0 ? min(ng, (cdata - c0 + K2_GROUP - 1) / K2_GROUP) : 0;
+        if (lane == 0)
+            for (int g = 0; g < min(K2_NGROUP, ngd); g++) issue_group(G + g, c0 + g * K2_GROUP);
+        for (int g = 0; g < ng; g++) {
+            const int slot = (G + g) % K2_NGROUP;
+            if (g < ngd) mbar_wait(a_full + 8 * slot, ((G + g) / K2_NGROUP) & 1);
+#pragma unroll 1
+            for (int k = 0; k < K2_GROUP; k++)
+                if (c0 + g * K2_GROUP + k < c1) fn(c0 + g * K2_GROUP + k, a_stage + (slot * K2_GROUP + k) * K2C_ROWB);
+            __syncwarp();
+            if (lane == 0 && g + K2_NGROUP < ngd) issue_group(G + g + K2_NGROUP, c0 + (g + K2_NGROUP) * K2_GROUP);
+        }
+        G += ngd;
+    };
+
+    /* ---- balancer: per-cluster dynamic range (top 2 / bottom 4 per channel over the balancer
+     *      cycles, signalproc.c:106-243), streamed once ---- */
+    float low[4] = {0.f, 0.f, 0.f, 0.f}, bw[4] = {1.f, 1.f, 1.f, 1.f}, ybw[4];
+    {
+        float top[4][2], bot[4][4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++) {
+            top[ch][0] = top[ch][1] = -CUDART_INF_F;
+            bot[ch][0] = bot[ch][1] = bot[ch][2] = bot[ch][3] = CUDART_INF_F;
+        }
+        const int blen = alive ? min(start, P.balancer_length) : 0;
+        int blen_w = blen;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) blen_w = max(blen_w, __shfl_xor_sync(FULL_MASK, blen_w, d));
+        stream(P.balancer_start, P.balancer_start + blen_w, P.balancer_start + blen_w, [&](const int r, const uint32_t arow) {
+            if (r - P.balancer_start < blen) {
+                const uint32_t ap = arow + colofs;
+                const float v0 = (float)lds_s16(ap), v1 = (float)lds_s16(ap + K2C_CHB), v2 = (float)lds_s16(ap + 2 * K2C_CHB),
+                            v3 = (float)lds_s16(ap + 3 * K2C_CHB);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    float a = __fmul_rn(P.inv[4 * j + 0], v0);
+                    a = __fadd_rn(a, __fmul_rn(P.inv[4 * j + 1], v1));
+                    a = __fadd_rn(a, __fmul_rn(P.inv[4 * j + 2], v2));
+                    const float sg = __fadd_rn(a, __fmul_rn(P.inv[4 * j + 3], v3));
+                    float carry = sg;
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const bool sw = carry > top[j][q];
+                        const float t = top[j][q];
+                        top[j][q] = sw ? carry : t;
+                        carry = sw ? t : carry;
+                    }
+                    carry = sg;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const bool sw = carry < bot[j][q];
+                        const float t = bot[j][q];
+                        bot[j][q] = sw ? carry : t;
+                        carry = sw ? t : carry;
+                    }
+                }
+            }
+        });
+        if (alive) {
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++) {
+                float acc = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; q++) acc = __fadd_rn(acc, bot[ch][q]);
+                low[ch] = __fdiv_rn(acc, 4.f);
+                acc = __fadd_rn(__fadd_rn(0.f, top[ch][0]), top[ch][1]);
+                bw[ch] = __fsub_rn(__fdiv_rn(acc, 2.f), low[ch]);
+            }
+            /* fast-path preconditions; otherwise the generic kernel takes this cluster */
+            bool ok = true;
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++)
+                ok = ok && in_exp_range(bw[ch], -40, 40) && (fabsf(low[ch]) < 0x1p40f);
+            if (!ok) {
+                list_array(A.lists, 3, A.listcap)[atomicAdd(&A.lists[3], 1u)] = n;
+                alive = false;
+                kd = 0;
+                insert_len = 0; dump = 0;
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) { low[ch] = 0.f; bw[ch] = 1.f; }
+            }
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) ybw[ch] = __frcp_rn(bw[ch]);
+
+    const int scan_len = insert_len - ps;
+    const int valid = min(scan_len, dump);
+    const bool emit = (kd & KIND_EMIT) != 0;
+    const bool ispos = (kd & KIND_POS) != 0;
+    const int rscore_end = alive ? rdata_end : 0;
+
+    uint32_t *rec = nullptr;
+    if (emit) {
+        rec = A.records + A.recbase[sample] + (size_t)call.record_slot * (size_t)(2 + dump);
+        rec[0] = tv.firstclusterno + n;
+        rec[1] = (uint32_t)(uint16_t)(int16_t)(de + ps) | ((uint32_t)(uint16_t)(int16_t)valid << 16);
+    }
+    bool neg_inline = false;
+    if (kd & KIND_NEG)
+        neg_inline = (P.fair_max_count == 0) || (A.fair[A.bucket[n]] <= (uint32_t)P.fair_max_count);
+
+    /* the warp computes on cycles [rbeg_w, rend_w): an emitting lane owns record positions up to
+     * cycle start+ps+dump-1 (zero padding past its data) */
+    int rend_w = alive ? (emit ? max(rdata_end, start + ps + dump) : rdata_end) : 0;
+    int rbeg_w = alive ? start : 0x7fff;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        rend_w = max(rend_w, __shfl_xor_sync(FULL_MASK, rend_w, d));
+        rbeg_w = min(rbeg_w, __shfl_xor_sync(FULL_MASK, rbeg_w, d));
+    }
+    const unsigned emitmask = __ballot_sync(FULL_MASK, emit);
+    const unsigned long long recaddr = (unsigned long long)(uintptr_t)rec;
+    const int recinfo = ((start + ps) & 0xffff) | (max(dump, 0) << 16);
+
+    int ndark = 0;
+    float prev_entropy = CUDART_NAN_F;
+    double ptotal = 0.;                       /* sum of the scores from the seed start on (KIND_POS lanes) */
+    uint32_t dhwin = 0;                       /* bit k = downhill of cycle (c - k); max_mods < 32 */
+    /* score of cycle r lives at scratch[(r - start - ps) * spitch + n]; scr walks one row per cycle */
+    float *scr = A.scratch + n + ((ptrdiff_t)rbeg_w - (start + ps)) * (ptrdiff_t)spitch;
+    const uint32_t a_logtab = smem_u32(&sm.sh.logtab[0]), a_tscore = smem_u32(&sm.sh.tscore[0]);
+    const uint32_t a_tile = smem_u32(&sm.tile[warp][0][0]);
+    const uint32_t a_mytile = a_tile + lane * ((K2_TILE_CYC + 1) * 4);
+
+    /* one cycle of this lane: r = 3'-read cycle, arow = shared address of the cycle's [4][32] rows */
+    auto cycle = [&](const int r, const uint32_t arow) {
+        uint32_t word = 0;
+        if (r >= start && r < rscore_end) {
+            /* ---- decrosstalk (signalproc.c:85-103); exact int16 -> float through 2^23+2^22 ---- */
+            const uint32_t ap = arow + colofs;
+            const float v0 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap)), 12582912.f);
+            const float v1 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap + K2C_CHB)), 12582912.f);
+            const float v2 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap + 2 * K2C_CHB)), 12582912.f);
+            const float v3 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap + 3 * K2C_CHB)), 12582912.f);
+            float sig[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float a = __fmul_rn(P.inv[4 * j + 0], v0);
+                a = __fadd_rn(a, __fmul_rn(P.inv[4 * j + 1], v1));
+                a = __fadd_rn(a, __fmul_rn(P.inv[4 * j + 2], v2));
+                sig[j] = __fadd_rn(a, __fmul_rn(P.inv[4 * j + 3], v3));
+            }
+            /* ---- dark test: sum of the positive channels (x + 0 == x, so max(.,0) is exact) ---- */
+            float tot = fmaxf(sig[0], 0.f);
+            tot = __fadd_rn(tot, fmaxf(sig[1], 0.f));
+            tot = __fadd_rn(tot, fmaxf(sig[2], 0.f));
+            tot = __fadd_rn(tot, fmaxf(sig[3], 0.f));
+            bool lit = !(tot < P.dark_threshold);
+            /* ---- normalise into the cluster's dynamic range (signalproc.c:246-266) ---- */
+            float nrm[4];
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++)
+                nrm[ch] = fmaxf(div_by_rcp(__fsub_rn(sig[ch], low[ch]), bw[ch], ybw[ch]), 0.f);
+            const float sum = __fadd_rn(__fadd_rn(__fadd_rn(nrm[0], nrm[1]), nrm[2]), nrm[3]);
+            float prob[4];
+            if (__builtin_expect(in_exp_range(sum, -60, 60), 1)) {
+                const float ys = rcp_rn_fast(sum);
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) prob[ch] = div_by_rcp(nrm[ch], sum, ys);
+            } else {
+                /* sum == 0 (0/0 -> NaN -> dark) or a pathological magnitude: IEEE division */
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) prob[ch] = __fdiv_rn(nrm[ch], sum);
+            }
+            lit = lit && (prob[0] == prob[0]);
+            /* ---- Shannon entropy: h -= p*logf(p) for p > 0 (the skipped terms are 0) ---- */
+            float h = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++) {
+                const float lg = logf_core_t(__float_as_uint(prob[ch]), [a_logtab](uint32_t ofs) {
+                    double2 t;
+                    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(a_logtab + ofs));
+                    return t;
+                });
+                const float term = __fmul_rn(prob[ch], lg);
+                h = __fsub_rn(h, prob[ch] > 0.f ? term : 0.f);
+            }
+            const float es = __fsub_rn(1.f, div_by_rcp(h, P.maximum_entropy, rcp_maxent));
+            const uint32_t ti = min((uint32_t)__float2int_rz(__fmul_rn(prob[3], (float)TSK_T_SCORE_BINS)),
+                                    (uint32_t)TSK_T_SCORE_BINS);
+            float tsc;
+            asm("ld.shared.f32 %0, [%1];" : "=f"(tsc) : "r"(a_tscore + ti * 4));
+            const float score = lit ? __fmul_rn(es, tsc) : CUDART_NAN_F;
+            const uint32_t dh = (lit && es < prev_entropy) ? 1u : 0u;
+            prev_entropy = lit ? es : CUDART_NAN_F;
+            ndark += lit ? 0 : 1;
+            dhwin = (dhwin << 1) | dh;
+
+            if (r >= start + ps) {
+                uint32_t s = 1u + (uint32_t)__float2int_rz(__fmul_rn(score, (float)(TSK_SCORE_MAX - 1)));
+                s = min(s, TSK_SCORE_MAX);
+                /* packet j = c - ps carries downhill[j], the UN-offset array (spotanalyzer.c:604-606) */
+                word = lit ? ((s << 1) | ((dhwin >> ps) & 1u)) : 0u;
+                if (ispos) {
+                    *scr = score;
+                    ptotal = __dadd_rn(ptotal, (double)score);      /* same order as the reference's cumsum */
+                }
+                if (neg_inline && lit && !isinf(score))
+                    atomicAdd(&A.neg[(size_t)(ts + r) * bins + score_bin(score, bins)], 1u);
+            }
+        }
+        /* ---- stage the packed word; every 8 cycles the emitting lanes' records are written four
+         *      at a time, 8 consecutive words (one 32-byte sector) each ---- */
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_mytile + (r & (K2_TILE_CYC - 1)) * 4), "r"(word) : "memory");
+        if ((r & (K2_TILE_CYC - 1)) == K2_TILE_CYC - 1 || r == rend_w - 1) {
+            __syncwarp();
+            const int rbase = r & ~(K2_TILE_CYC - 1);
+            const int quarter = lane >> 3, l8 = lane & 7;
+            unsigned m = emitmask;
+            while (m) {
+                /* next (up to) four emitting lanes */
+                int pick = -1;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int rr = m ? __ffs(m) - 1 : -1;
+                    if (m) m &= m - 1;
+                    if (k == quarter) pick = rr;
+                }
+                const int src = pick < 0 ? 0 : pick;
+                const unsigned long long ra = __shfl_sync(FULL_MASK, recaddr, src);
+                const int ri = __shfl_sync(FULL_MASK, recinfo, src);
+                const int j = rbase + l8 - (ri & 0xffff);
+                if (pick >= 0 && j >= 0 && j < (ri >> 16) && rbase + l8 <= r) {
+                    uint32_t wv;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv) : "r"(a_tile + (pick * (K2_TILE_CYC + 1) + l8) * 4));
+                    reinterpret_cast<uint32_t *>((uintptr_t)ra)[2 + j] = wv;
+                }
+            }
+            __syncwarp();
+        }
+        scr += spitch;
+    };
+
+    /* ---- scored cycles ---- */
+    stream(rbeg_w, rend_w, rdata_w, cycle);
+
+    if (!alive) return;
+    bool aborted = false;
+    if (ndark > 0) {
+        call.flags |= TSK_PAFLAG_DARKCYCLE_EXISTS;
+        if (ndark >= P.max_dark_cycles) {
+            call.flags |= TSK_PAFLAG_DARKCYCLE_OVER_THRESHOLD;
+            call.polya_len = -1;
+            call.emitted = 0;
+            aborted = true;
+            if (rec != nullptr) rec[1] |= 0xffff0000u;     /* withdraw the slot: valid = -1 */
+        }
+        *reinterpret_cast<uint4 *>(&A.calls[n]) = *reinterpret_cast<const uint4 *>(&call);
+    }
+    if (kd & KIND_NEG) {
+        if (aborted && neg_inline)
+            list_array(A.lists, 0, A.listcap)[atomicAdd(&A.lists[0], 1u)] = n;
+        else if (!aborted && !neg_inline)
+            list_array(A.lists, 1, A.listcap)[atomicAdd(&A.lists[1], 1u)] = n;
+    }
+
+    /* ---- contrast test (find_max_cumulative_contrast) and positive sampling ----
+     * f(i) = cum_i/i - (total-cum_i)/(len-i).  The divisions are replaced by table reciprocals
+     * to locate the maximum (error < 1.2e-15 per value, all terms <= 1 in magnitude); the
+     * exact IEEE value is evaluated only there.  If a second candidate lies within 1e-14 the
+     * exact scan decides, so ties resolve exactly like the reference's strict '>' scan. */
+    if (ispos && !aborted && scan_len > 0 && P.cctr_left + P.cctr_right < scan_len) {
+        const float *col = A.scratch + n;
+        const int left = P.cctr_left, last = scan_len - P.cctr_right;
+        const double total = ptotal;
+        if (total == total) {        /* a NaN anywhere makes the first candidate NaN: no sampling */
+            double cum = 0., m1 = -CUDART_INF, m2 = -CUDART_INF, cum1 = 0.;
+            int at = left - 1;
+            for (int i0 = 0; i0 <= last; i0 += 8) {
+                float v8[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++)       /* eight independent loads in flight */
+                    v8[k] = (i0 + k <= last) ? col[(size_t)(i0 + k) * spitch] : 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int i = i0 + k;
+                    if (i <= last) {
+                        cum = __dadd_rn(cum, (double)v8[k]);
+                        if (i >= left - 1) {
+                            const double v = __dsub_rn(__dmul_rn(cum, __ldg(A.rcp + i)),
+                                                       __dmul_rn(__dsub_rn(total, cum), __ldg(A.rcp + (scan_len - i))));
+                            if (v > m1) { m2 = m1; m1 = v; at = i; cum1 = cum; }
+                            else if (v > m2) m2 = v;
+                        }
+                    }
+                }
+            }
+            float contrast;
+            int atpos;
+            if (m1 - m2 > 1e-14 && at > 0) {
+                const double v = __dsub_rn(__ddiv_rn(cum1, (double)at),
+                                           __ddiv_rn(__dsub_rn(total, cum1), (double)(scan_len - at)));
+                contrast = (float)v;
+                atpos = at + 1;
+            } else {
+                atpos = contrast_exact(col, spitch, scan_len, left, P.cctr_right, total, &contrast);
+            }
+            if (atpos >= P.boundary_pos && contrast >= P.required_contrast)
+                sample_positive(P, col, spitch, scan_len, ps, de + ps, A.pos);
+        }
+    }
+}
+
 /* ======================================================================================
  * fair-sampling fix-ups
  * ==================================================================================== */
@@ -1070,7 +1467,7 @@ typedef CUresult (*tsk_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuui
                                         CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                         CUtensorMapFloatOOBfill);
 
-static int make_cif_tensor_map(tsk_ctx *ctx, CUtensorMap *tmap)
+static int make_cif_tensor_map(tsk_ctx *ctx, CUtensorMap *tmap, unsigned boxw)
 {
     static tsk_encode_tiled_fn encode = NULL;
     if (!encode) {
@@ -1082,7 +1479,7 @@ static int make_cif_tensor_map(tsk_ctx *ctx, CUtensorMap *tmap)
     }
     const cuuint64_t dims[3] = {(cuuint64_t)ctx->tile.nclusters, 4, (cuuint64_t)ctx->dp.threep_length};
     const cuuint64_t strides[2] = {(cuuint64_t)ctx->tile.cif_pitch * 2, (cuuint64_t)ctx->tile.cif_pitch * 8};
-    const cuuint32_t box[3] = {32, 4, K2_GROUP}, estr[3] = {1, 1, 1};
+    const cuuint32_t box[3] = {boxw, 4, K2_GROUP}, estr[3] = {1, 1, 1};
     const CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, (void *)ctx->tile.cif, dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1098,7 +1495,7 @@ int tsk_launch_score(tsk_ctx *ctx)
     const int head = fast_head_cycles(ctx);
     /* the TMA bulk copies need 16-byte aligned 256-byte rows, and the CTA windows must stay inside
      * the row pitch; the downhill window is 32 bits */
-    const bool fast_ok = !ctx->force_generic && head <= K2_HEAD_MAX && ctx->dp.max_mods < 32 &&
+    const bool fast_ok = ctx->force_generic != 1 && head <= K2_HEAD_MAX && ctx->dp.max_mods < 32 &&
                          ctx->dp.npos == 2 && ctx->dp.nneg == 4 &&
                          (ctx->tile.cif_pitch % 8) == 0 && ((uintptr_t)ctx->tile.cif % 16) == 0;
     if (!fast_ok) {
@@ -1110,13 +1507,21 @@ int tsk_launch_score(tsk_ctx *ctx)
         if (!attr_set) {
             TSK_CUDA(cudaFuncSetAttribute(k_normalise_score_pack, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(K2Smem)));
+            TSK_CUDA(cudaFuncSetAttribute(k_normalise_score_pack_compact, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(K2SmemC)));
             attr_set = true;
         }
         const float rcp_maxent = 1.0f / ctx->dp.maximum_entropy;      /* IEEE RN on the host */
+        /* at most N work items, whose number is only known on the device: surplus warps return */
         const unsigned grid = (N + K2_CL - 1) / K2_CL;
         CUtensorMap tmap;
-        if (make_cif_tensor_map(ctx, &tmap) != 0) return -1;
-        k_normalise_score_pack<<<grid, TSK_K2_THREADS, sizeof(K2Smem), ctx->stream>>>(ctx->dp, a, rcp_maxent, head, tmap);
+        if (ctx->force_generic == 2) {       /* row form (tests): warp = 32 consecutive clusters */
+            if (make_cif_tensor_map(ctx, &tmap, 32) != 0) return -1;
+            k_normalise_score_pack<<<grid, TSK_K2_THREADS, sizeof(K2Smem), ctx->stream>>>(ctx->dp, a, rcp_maxent, head, tmap);
+        } else {
+            if (make_cif_tensor_map(ctx, &tmap, K2C_W) != 0) return -1;
+            k_normalise_score_pack_compact<<<grid, TSK_K2_THREADS, sizeof(K2SmemC), ctx->stream>>>(ctx->dp, a, rcp_maxent, tmap);
+        }
         k_normalise_score_pack_generic<<<8, TSK_K2_THREADS, 0, ctx->stream>>>(ctx->dp, a, 0);
         ctx->launches += 2;
     }

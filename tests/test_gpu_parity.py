@@ -74,6 +74,27 @@ def test_generic_kernel_matches_oracle(stock_cfg, oracle):
         p.close()
 
 
+def test_row_form_of_fast_kernel(stock_cfg, oracle):
+    """The fast kernel's row form (warp = 32 consecutive clusters, resident balancer cycles); the
+    default is the compact form over the work list."""
+    from tailseeker_b200.importer import TileProcessor
+    p = TileProcessor(stock_cfg)
+    try:
+        p.force_generic(2)
+        _, o = _run(p, stock_cfg, oracle, 9000, 22, dark_cluster_frac=0.03, lowdiv_frac=0.05)
+        compare_tile(p, stock_cfg, None, o)
+    finally:
+        p.close()
+
+
+@pytest.mark.parametrize("unknown_frac", [0.5, 0.9])
+def test_sparse_work_list(proc, stock_cfg, oracle, unknown_frac):
+    """Mostly dropped clusters: work items span more clusters than the TMA window and hand their
+    far lanes to the literal kernel."""
+    _, o = _run(proc, stock_cfg, oracle, 15000, 23, unknown_frac=unknown_frac)
+    compare_tile(proc, stock_cfg, None, o)
+
+
 def test_degenerate_bandwidth_handover(stock_cfg, oracle):
     """Clusters whose balancer cycles are constant (zero signal bandwidth -> division by zero,
     NaN/inf normalised signals) leave the fast kernel for the generic one; results still
