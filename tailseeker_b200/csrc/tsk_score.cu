@@ -175,10 +175,15 @@ __device__ __forceinline__ void sample_positive(const DevParams &P, const float 
                                                 uint32_t *__restrict__ pos)
 {
     const int take = -ps + min(scan_len, P.boundary_pos - P.sampling_gap);
-    for (int i = 0; i < take; i++) {
-        const float sc = col[(size_t)i * spitch];
-        if (!isnan(sc) && !isinf(sc))
-            atomicAdd(&pos[(size_t)(firstrow + i) * P.bins + score_bin(sc, P.bins)], 1u);
+    for (int i0 = 0; i0 < take; i0 += 16) {
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++)          /* sixteen independent loads in flight */
+            v[k] = (i0 + k < take) ? col[(size_t)(i0 + k) * spitch] : CUDART_NAN_F;
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            if (!isnan(v[k]) && !isinf(v[k]))
+                atomicAdd(&pos[(size_t)(firstrow + i0 + k) * P.bins + score_bin(v[k], P.bins)], 1u);
     }
 }
 
@@ -812,13 +817,13 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
         if (total == total) {        /* a NaN anywhere makes the first candidate NaN: no sampling */
             double cum = 0., m1 = -CUDART_INF, m2 = -CUDART_INF, cum1 = 0.;
             int at = left - 1;
-            for (int i0 = 0; i0 <= last; i0 += 8) {
-                float v8[8];
+            for (int i0 = 0; i0 <= last; i0 += 16) {
+                float v8[16];
 #pragma unroll
-                for (int k = 0; k < 8; k++)       /* eight independent loads in flight */
+                for (int k = 0; k < 16; k++)      /* sixteen independent loads in flight */
                     v8[k] = (i0 + k <= last) ? col[(size_t)(i0 + k) * spitch] : 0.f;
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
+                for (int k = 0; k < 16; k++) {
                     const int i = i0 + k;
                     if (i <= last) {
                         cum = __dadd_rn(cum, (double)v8[k]);
@@ -1209,13 +1214,13 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
         if (total == total) {        /* a NaN anywhere makes the first candidate NaN: no sampling */
             double cum = 0., m1 = -CUDART_INF, m2 = -CUDART_INF, cum1 = 0.;
             int at = left - 1;
-            for (int i0 = 0; i0 <= last; i0 += 8) {
-                float v8[8];
+            for (int i0 = 0; i0 <= last; i0 += 16) {
+                float v8[16];
 #pragma unroll
-                for (int k = 0; k < 8; k++)       /* eight independent loads in flight */
+                for (int k = 0; k < 16; k++)      /* sixteen independent loads in flight */
                     v8[k] = (i0 + k <= last) ? col[(size_t)(i0 + k) * spitch] : 0.f;
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
+                for (int k = 0; k < 16; k++) {
                     const int i = i0 + k;
                     if (i <= last) {
                         cum = __dadd_rn(cum, (double)v8[k]);
