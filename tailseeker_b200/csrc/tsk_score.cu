@@ -1555,9 +1555,9 @@ int tsk_launch_fixups(tsk_ctx *ctx)
         }
         ctx->launches += 1 + 2 * rounds;
     }
-    k_resample_neg<<<148 * 2, TSK_K2_THREADS, 0, st>>>(P, ctx->tile, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
+    k_resample_neg<<<148 * 12, TSK_K2_THREADS, 0, st>>>(P, ctx->tile, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
                                                       ctx->d_neg, ctx->d_lists, listcap, 2, 1u);
-    k_resample_neg<<<148 * 2, TSK_K2_THREADS, 0, st>>>(P, ctx->tile, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
+    k_resample_neg<<<148 * 12, TSK_K2_THREADS, 0, st>>>(P, ctx->tile, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
                                                       ctx->d_neg, ctx->d_lists, listcap, 0, 0xffffffffu);
     ctx->launches += 2;
     TSK_CUDA(cudaGetLastError());
