@@ -416,8 +416,8 @@ def main():
         if world > 1:
             dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
         e2e = {"value": clusters_step / float(tdt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(ntiles * N * (T + 8 * L3)),
-               "d2h_bytes_per_step": int(d2h_bytes), "steps": esteps,
+               "h2d_bytes_per_step": int(ntiles * N * (T + 8 * L3)) * world,      # whole job, like value
+               "d2h_bytes_per_step": int(d2h_bytes) * world, "steps": esteps,
                "note": "H2D of tile t+1 (copy stream) overlaps the kernels of tile t; results read back per tile; 2 distinct pinned host tiles cycled"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) --------------------------------------------

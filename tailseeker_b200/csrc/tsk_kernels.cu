@@ -277,29 +277,56 @@ k_decode_demux_seed(const __grid_constant__ DevParams P, const TileView tv,
 
 /* Exclusive scan of the per-CTA counts, one CTA per column (sample 0..S-1 = record slots,
  * column S = work items). */
-__global__ void __launch_bounds__(256)
+#define SCAN_THREADS 1024
+#define SCAN_CHUNK   16          /* entries per thread and pass, all loads in flight at once */
+__global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_blocks(uint32_t *__restrict__ blkcnt, uint32_t *__restrict__ totals, int nblk, int ncol)
 {
-    __shared__ uint32_t s_part[256];
-    const int col = blockIdx.x, tid = threadIdx.x;
-    const int per = (nblk + 255) / 256;
-    const int b0 = min(nblk, tid * per), b1 = min(nblk, b0 + per);
-    uint32_t sum = 0;
-    for (int b = b0; b < b1; b++) sum += blkcnt[(size_t)b * ncol + col];
-    s_part[tid] = sum;
+    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+    __shared__ uint32_t s_carry;
+    const int col = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
     __syncthreads();
-    if (tid == 0) {
-        uint32_t run = 0;
-        for (int i = 0; i < 256; i++) { uint32_t v = s_part[i]; s_part[i] = run; run += v; }
-        totals[col] = run;
+    /* the column is walked in passes of SCAN_THREADS * SCAN_CHUNK entries (one pass for a tile of up
+     * to 2 M clusters); thread t owns SCAN_CHUNK consecutive entries of the pass */
+    for (int base = 0; base < nblk; base += SCAN_THREADS * SCAN_CHUNK) {
+        const int b0 = base + tid * SCAN_CHUNK;
+        uint32_t v[SCAN_CHUNK], sum = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_CHUNK; k++) {
+            v[k] = (b0 + k < nblk) ? blkcnt[(size_t)(b0 + k) * ncol + col] : 0u;
+            sum += v[k];
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = s_warp[lane];
+            uint32_t wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += o;
+            }
+            s_warp[lane] = wi - w;                       /* exclusive prefix of the warp sums */
+        }
+        __syncthreads();
+        uint32_t run = s_carry + s_warp[warp] + (incl - sum);
+#pragma unroll
+        for (int k = 0; k < SCAN_CHUNK; k++) {
+            if (b0 + k < nblk) blkcnt[(size_t)(b0 + k) * ncol + col] = run;
+            run += v[k];
+        }
+        __syncthreads();
+        if (tid == SCAN_THREADS - 1) s_carry = run;      /* the last thread ends on the pass total */
+        __syncthreads();
     }
-    __syncthreads();
-    uint32_t run = s_part[tid];
-    for (int b = b0; b < b1; b++) {
-        uint32_t v = blkcnt[(size_t)b * ncol + col];
-        blkcnt[(size_t)b * ncol + col] = run;
-        run += v;
-    }
+    if (tid == 0) totals[col] = s_carry;
 }
 
 __global__ void k_record_bases(const uint32_t *__restrict__ totals, const DevSample *__restrict__ samples,
@@ -367,7 +394,7 @@ int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev)
         TSK_CUDA(cudaEventRecord(ctx->ev_ctl[1], ctx->xstream));
     }
     if (N > 0) {
-        k_scan_blocks<<<S + 1, 256, 0, st>>>(ctx->d_blkcnt, ctx->d_totals, nblk, S + 1);
+        k_scan_blocks<<<S + 1, SCAN_THREADS, 0, st>>>(ctx->d_blkcnt, ctx->d_totals, nblk, S + 1);
         k_record_bases<<<1, 32, 0, st>>>(ctx->d_totals, ctx->d_samples, ctx->d_recbase, S);
         k_assign<<<(N + 255) / 256, 256, 0, st>>>(tv, ctx->d_calls, ctx->d_kind, ctx->d_blkcnt,
                                                   ctx->d_worklist, S);
