@@ -345,7 +345,7 @@ def main():
     peak, peak_src = measured_peaks()
     k2_ms = stage_ms[2] / max(1, int(stage_runs[2]))
     k2_gbs = ab["k2"] / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else 0.0
-    roof = {"bound": "hbm", "kernel": "k_normalise_score_pack", "achieved": k2_gbs, "peak": peak,
+    roof = {"bound": "hbm", "kernel": "k_normalise_score_pack_compact", "achieved": k2_gbs, "peak": peak,
             "unit": "GB/s", "frac": k2_gbs / peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": ab["k2"], "ms_per_launch": k2_ms,
             "stages_ms_per_tile": {

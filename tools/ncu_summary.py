@@ -8,10 +8,27 @@ def raw(rep):
     rows = list(csv.reader(out.splitlines()))
     return rows[0], rows[1], rows[2:]
 
-def source(rep):
+def source(rep, kernel=None):
+    """Source page of ONE kernel of the report (the first, or the first whose name contains `kernel`)."""
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(out.splitlines()))
-    return rows[1], rows[2:]
+    blocks, cur = [], None
+    for r in csv.reader(out.splitlines()):
+        if r and r[0] == "Kernel Name":
+            cur = {"name": r[1], "hdr": None, "rows": []}
+            blocks.append(cur)
+            continue
+        if cur is None:
+            cur = {"name": "?", "hdr": None, "rows": []}
+            blocks.append(cur)
+        if cur["hdr"] is None:
+            if "Source" in r:
+                cur["hdr"] = r
+            continue
+        if len(r) == len(cur["hdr"]):
+            cur["rows"].append(r)
+    pick = next((b for b in blocks if kernel and kernel in b["name"]), blocks[0])
+    print("== source page of", pick["name"].split("(")[0])
+    return pick["hdr"], pick["rows"]
 
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
@@ -34,7 +51,7 @@ def main():
         for i, h in enumerate(hdr):
             if h in KEYS:
                 print("  %-80s %s %s" % (h, r[i], units[i]))
-    shdr, data = source(rep)
+    shdr, data = source(rep, sys.argv[3] if len(sys.argv) > 3 else None)
     ix = {h: i for i, h in enumerate(shdr)}
     inst = [int(r[ix["Instructions Executed"]]) for r in data]
     samp = [int(r[ix["# Samples"]]) for r in data]
