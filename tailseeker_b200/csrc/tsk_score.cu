@@ -646,6 +646,23 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
         rbeg_w = min(rbeg_w, __shfl_xor_sync(FULL_MASK, rbeg_w, d));
     }
     const unsigned emitmask = __ballot_sync(FULL_MASK, emit);
+    /* record flushes write four emitting lanes' words per round, one per quarter-warp: the lane
+     * this quarter serves in round `it` sits in bits [6 it, 6 it + 6) of flushpick (63 = none) */
+    const int nflush = (__popc(emitmask) + 3) >> 2;
+    unsigned long long flushpick = ~0ull;
+    {
+        unsigned m = emitmask;
+        for (int it = 0; it < nflush; it++) {
+            int pick = 63;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int rr = m ? __ffs(m) - 1 : 63;
+                if (m) m &= m - 1;
+                if (k == (lane >> 3)) pick = rr;
+            }
+            flushpick = (flushpick & ~(63ull << (6 * it))) | ((unsigned long long)pick << (6 * it));
+        }
+    }
     const unsigned long long recaddr = (unsigned long long)(uintptr_t)rec;
     const int recinfo = ((start + ps) & 0xffff) | (max(dump, 0) << 16);
 
@@ -743,17 +760,11 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
         if ((r & (K2_TILE_CYC - 1)) == K2_TILE_CYC - 1 || r == rend_w - 1) {
             __syncwarp();
             const int rbase = r & ~(K2_TILE_CYC - 1);
-            const int quarter = lane >> 3, l8 = lane & 7;
-            unsigned m = emitmask;
-            while (m) {
-                /* next (up to) four emitting lanes */
-                int pick = -1;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int rr = m ? __ffs(m) - 1 : -1;
-                    if (m) m &= m - 1;
-                    if (k == quarter) pick = rr;
-                }
+            const int l8 = lane & 7;
+            for (int it = 0; it < nflush; it++) {
+                /* next (up to) four emitting lanes: this quarter-warp's is in flushpick */
+                const int p6 = (int)(flushpick >> (6 * it)) & 63;
+                const int pick = p6 == 63 ? -1 : p6;
                 const int src = pick < 0 ? 0 : pick;
                 const unsigned long long ra = __shfl_sync(FULL_MASK, recaddr, src);
                 const int ri = __shfl_sync(FULL_MASK, recinfo, src);
@@ -1057,6 +1068,23 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
         rbeg_w = min(rbeg_w, __shfl_xor_sync(FULL_MASK, rbeg_w, d));
     }
     const unsigned emitmask = __ballot_sync(FULL_MASK, emit);
+    /* record flushes write four emitting lanes' words per round, one per quarter-warp: the lane
+     * this quarter serves in round `it` sits in bits [6 it, 6 it + 6) of flushpick (63 = none) */
+    const int nflush = (__popc(emitmask) + 3) >> 2;
+    unsigned long long flushpick = ~0ull;
+    {
+        unsigned m = emitmask;
+        for (int it = 0; it < nflush; it++) {
+            int pick = 63;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int rr = m ? __ffs(m) - 1 : 63;
+                if (m) m &= m - 1;
+                if (k == (lane >> 3)) pick = rr;
+            }
+            flushpick = (flushpick & ~(63ull << (6 * it))) | ((unsigned long long)pick << (6 * it));
+        }
+    }
     const unsigned long long recaddr = (unsigned long long)(uintptr_t)rec;
     const int recinfo = ((start + ps) & 0xffff) | (max(dump, 0) << 16);
 
@@ -1153,17 +1181,11 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
         if ((r & (K2_TILE_CYC - 1)) == K2_TILE_CYC - 1 || r == rend_w - 1) {
             __syncwarp();
             const int rbase = r & ~(K2_TILE_CYC - 1);
-            const int quarter = lane >> 3, l8 = lane & 7;
-            unsigned m = emitmask;
-            while (m) {
-                /* next (up to) four emitting lanes */
-                int pick = -1;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int rr = m ? __ffs(m) - 1 : -1;
-                    if (m) m &= m - 1;
-                    if (k == quarter) pick = rr;
-                }
+            const int l8 = lane & 7;
+            for (int it = 0; it < nflush; it++) {
+                /* next (up to) four emitting lanes: this quarter-warp's is in flushpick */
+                const int p6 = (int)(flushpick >> (6 * it)) & 63;
+                const int pick = p6 == 63 ? -1 : p6;
                 const int src = pick < 0 ? 0 : pick;
                 const unsigned long long ra = __shfl_sync(FULL_MASK, recaddr, src);
                 const int ri = __shfl_sync(FULL_MASK, recinfo, src);
