@@ -7,6 +7,7 @@
 #include "../../include/tailseeker_b200.h"
 
 #define TSK_K1_THREADS   128     /* clusters per decode_demux_seed CTA */
+#define TSK_K1_SLAB      32      /* cycles per TMA copy of its base-call slab */
 #define TSK_K2_THREADS   128
 #define TSK_MAX_MODS     64      /* upper bound on max_terminal_modifications */
 #define TSK_MAX_RANK     8       /* upper bound on balancer num-positive/negative samples */

@@ -4,6 +4,8 @@
  *
  * One thread per cluster.  Inputs stay in the files' cycle-major layouts, so consecutive
  * lanes read consecutive bytes (BCL) or int16 (CIF planes): every request is coalesced.
+ * K1 stages its CTA's [cycles][128 clusters] slab of base calls in shared memory with TMA
+ * tensor copies first: the per-cluster scans then read shared memory, not a global byte per step.
  * All per-cluster state lives in registers; nothing here is a dense contraction, so no
  * tensor cores.  Compiled with -fmad=false: the reference is built without FMA
  * contraction and parity of the packed scores needs separately rounded IEEE operations.
@@ -14,6 +16,7 @@
 #include <math_constants.h>
 #include "tsk_internal.h"
 #include "tsk_device.cuh"
+#include "tsk_tma.cuh"
 
 #define FULL_MASK 0xffffffffu
 
@@ -36,15 +39,28 @@ k_decode_demux_seed(const __grid_constant__ DevParams P, const TileView tv,
                     const DevSample *__restrict__ g_samples,
                     tsk_call *__restrict__ calls, uint8_t *__restrict__ kind,
                     uint32_t *__restrict__ bucket, uint32_t *__restrict__ blkcnt,
-                    uint32_t *__restrict__ counters, uint32_t *__restrict__ fair)
+                    uint32_t *__restrict__ counters, uint32_t *__restrict__ fair,
+                    const __grid_constant__ CUtensorMap bclmap, const int slab_rows)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int S = P.num_samples;
-    DevSample *s_samples = reinterpret_cast<DevSample *>(smem_raw);
-    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(smem_raw + sizeof(DevSample) * S); /* [S][6] */
+    /* [slab_rows][128] base-call bytes of this CTA's clusters | mbarrier | samples | counters */
+    const uint8_t *s_bcl = smem_raw;
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)slab_rows * TSK_K1_THREADS);
+    DevSample *s_samples = reinterpret_cast<DevSample *>(s_bar + 2);
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_samples + S);                   /* [S][6] */
     uint32_t *s_wcnt = s_cnt + S * TSK_NCOUNT;       /* [warps][S+1] */
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = TSK_K1_THREADS / 32;
+
+    if (tid == 0) {
+        const uint32_t bar = smem_u32(s_bar);
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_arrive_expect_tx(bar, (uint32_t)slab_rows * TSK_K1_THREADS);
+        for (int r = 0; r < slab_rows; r += TSK_K1_SLAB)
+            tma_2d_g2s(smem_u32(s_bcl) + r * TSK_K1_THREADS, &bclmap, (int)(blockIdx.x * TSK_K1_THREADS), r, bar);
+    }
 
     for (int i = tid; i < (int)(sizeof(DevSample) / 4) * S; i += TSK_K1_THREADS)
         reinterpret_cast<uint32_t *>(s_samples)[i] = reinterpret_cast<const uint32_t *>(g_samples)[i];
@@ -54,9 +70,9 @@ k_decode_demux_seed(const __grid_constant__ DevParams P, const TileView tv,
 
     const uint32_t n = blockIdx.x * TSK_K1_THREADS + tid;
     const bool active = n < tv.nclusters;
-    const size_t pitch = tv.bcl_pitch;
-    const uint8_t *col = tv.bcl + n;
-    auto rd = [&](int c) -> uint32_t { return (uint32_t)__ldg(col + (size_t)c * pitch); };
+    mbar_wait(smem_u32(s_bar), 0);              /* init is visible: the __syncthreads() above */
+    const uint8_t *col = s_bcl + tid;
+    auto rd = [&](int c) -> uint32_t { return (uint32_t)col[c * TSK_K1_THREADS]; };
 
     int sample = 0, flags = 0, de = -1, status = -1, mods = -1;
     int written = 0;
@@ -376,11 +392,34 @@ int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev)
     if (ev) TSK_CUDA(cudaEventRecord(ev[0], st));
 
     if (N > 0) {
-        const size_t smem1 = sizeof(DevSample) * S +
+        /* base calls u8 [T][pitch] as a 2-D tensor: boxes of {128 clusters, TSK_K1_SLAB cycles};
+         * rows past T and clusters past N are zero-filled (= no-calls, never looked at) */
+        const int slab_rows = (P.total_cycles + TSK_K1_SLAB - 1) / TSK_K1_SLAB * TSK_K1_SLAB;
+        tsk_encode_tiled_fn encode = tsk_tensor_map_encoder();
+        if (!encode) return -1;
+        if ((uintptr_t)tv.bcl % 16 != 0 || tv.bcl_pitch % 16 != 0) {
+            tsk_set_error("base-call rows must be 16-byte aligned"); return -1;
+        }
+        CUtensorMap bclmap;
+        {
+            const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)P.total_cycles};
+            const cuuint64_t strides[1] = {(cuuint64_t)tv.bcl_pitch};
+            const cuuint32_t box[2] = {TSK_K1_THREADS, TSK_K1_SLAB}, estr[2] = {1, 1};
+            const CUresult r = encode(&bclmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)tv.bcl, dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { tsk_set_error("cuTensorMapEncodeTiled (base calls) failed (%d)", (int)r); return -1; }
+        }
+        const size_t smem1 = (size_t)slab_rows * TSK_K1_THREADS + 16 + sizeof(DevSample) * S +
                              sizeof(uint32_t) * (S * TSK_NCOUNT + (TSK_K1_THREADS / 32) * (S + 1));
+        static size_t configured = 0;
+        if (smem1 > configured) {
+            TSK_CUDA(cudaFuncSetAttribute(k_decode_demux_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+            configured = smem1;
+        }
         k_decode_demux_seed<<<nblk, TSK_K1_THREADS, smem1, st>>>(
             P, tv, ctx->d_samples, ctx->d_calls, ctx->d_kind, ctx->d_bucket, ctx->d_blkcnt,
-            ctx->d_counters, ctx->d_fair);
+            ctx->d_counters, ctx->d_fair, bclmap, slab_rows);
         ctx->launches++;
     }
     if (ev) TSK_CUDA(cudaEventRecord(ev[1], st));

@@ -18,10 +18,10 @@
  *       its preconditions do not hold (degenerate signal bandwidths), and is what the fast
  *       path is tested against.
  */
-#include <cuda.h>
 #include <math_constants.h>
 #include "tsk_internal.h"
 #include "tsk_device.cuh"
+#include "tsk_tma.cuh"
 
 #define FULL_MASK 0xffffffffu
 #define CONTRAST_MAXLEN 288          /* reciprocal table length (scan_len <= threep_length + 1) */
@@ -451,50 +451,6 @@ __device__ __forceinline__ bool in_exp_range(float v, int lo_exp, int hi_exp)
     return e >= 127 + lo_exp && e < 127 + hi_exp;
 }
 
-/* ---- TMA engine plumbing: bulk asynchronous copies global -> shared, completion on an mbarrier.
- *      All helpers take 32-bit shared-window addresses computed once per thread. ---- */
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_drop(uint32_t bar)
-{   /* arrive for the current phase and leave the barrier for all later phases */
-    asm volatile("mbarrier.arrive_drop.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    /* try_wait suspends the thread in hardware up to the hint (ns) instead of spinning */
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-/* one TMA tensor copy: box {32 clusters, 4 channels, 4 cycles} of the CIF tensor -> shared */
-__device__ __forceinline__ void tma_cycle_g2s(uint32_t dst, const CUtensorMap *tmap, int x, int cyc, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(dst), "l"(tmap), "r"(x), "r"(0), "r"(cyc), "r"(bar) : "memory");
-}
 __device__ __forceinline__ int lds_s16(uint32_t addr)
 {
     int v;
@@ -1489,21 +1445,10 @@ static int fast_head_cycles(const tsk_ctx *ctx)
 
 /* TMA descriptor of the resident CIF tensor, i16 [threep_length][4][pitch]: boxes of
  * {32 clusters, 4 channels, 1 cycle}; reads past nclusters are zero-filled by the engine. */
-typedef CUresult (*tsk_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                        CUtensorMapFloatOOBfill);
-
 static int make_cif_tensor_map(tsk_ctx *ctx, CUtensorMap *tmap, unsigned boxw)
 {
-    static tsk_encode_tiled_fn encode = NULL;
-    if (!encode) {
-        void *fn = NULL;
-        cudaDriverEntryPointQueryResult qres;
-        TSK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (qres != cudaDriverEntryPointSuccess || !fn) { tsk_set_error("cuTensorMapEncodeTiled unavailable"); return -1; }
-        encode = (tsk_encode_tiled_fn)fn;
-    }
+    tsk_encode_tiled_fn encode = tsk_tensor_map_encoder();
+    if (!encode) return -1;
     const cuuint64_t dims[3] = {(cuuint64_t)ctx->tile.nclusters, 4, (cuuint64_t)ctx->dp.threep_length};
     const cuuint64_t strides[2] = {(cuuint64_t)ctx->tile.cif_pitch * 2, (cuuint64_t)ctx->tile.cif_pitch * 8};
     const cuuint32_t box[3] = {boxw, 4, K2_GROUP}, estr[3] = {1, 1, 1};
