@@ -181,7 +181,21 @@ k_decode_demux_seed(const __grid_constant__ DevParams P, const TileView tv,
                     {
                         int Srun = 0, minS = 0x3fffffff, argj = -1;
                         const int captop = M + mlen - 1;    /* j below this may be a j_min(i) */
-                        for (int j = L - 1; j >= 0; j--) {
+                        int j = L - 1;
+                        if (P.w_small) {
+                            /* the long stretch above the captured region only carries the running
+                             * sum and its minimum: weights from a byte-permute of five packed int8
+                             * (selector nibbles 8+code replicate the sign) instead of a table load */
+#pragma unroll 4
+                            for (; j >= captop; j--) {
+                                const uint32_t code = tsk_base_code(rd(de + j));
+                                if (Srun <= minS) { minS = Srun; argj = j; }
+                                int wv;     /* prmt, default mode: nibble 8+k = sign of byte k replicated */
+                                asm("prmt.b32 %0, %1, %2, %3;" : "=r"(wv) : "r"(P.wpk_lo), "r"(P.wpk_hi), "r"(code * 0x1111u + 0x8880u));
+                                Srun += wv;
+                            }
+                        }
+                        for (; j >= 0; j--) {
                             const uint32_t code = tsk_base_code(rd(de + j));
                             if (Srun <= minS) { minS = Srun; argj = j; }
                             if (j < captop) {
