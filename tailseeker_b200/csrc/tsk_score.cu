@@ -360,6 +360,16 @@ __device__ __forceinline__ float rcp_rn_fast(float x)
  * or subnormal bit patterns the result is a finite meaningless number: callers either discard
  * it (p <= 0) or multiply it by a subnormal p, a term < 2^-119 that cannot reach the float sum
  * it feeds (h is 0 or >= 2^-24 * |log|, and 1 - h/maxent rounds to 1 for h < 2^-25). */
+/* The polynomial's fp64 constants live in constant memory: DFMA / DADD take a constant-bank
+ * operand directly, whereas 64-bit literals are rebuilt with two moves each on every use. */
+__device__ __constant__ double c_logf_k[5] = {
+    0x1.62e42fefa39efp-1,        /* ln 2 */
+    0x1.5575b0be00b6ap-2,        /* A[1] */
+    -0x1.ffffef20a4123p-2,       /* A[2] */
+    -0x1.00ea348b88334p-2,       /* A[0] */
+    4503601774854144.0,          /* 2^52 + 2^31 */
+};
+
 template <typename TabLoad>
 __device__ __forceinline__ float logf_core_t(uint32_t ix, TabLoad tabload)
 {
@@ -369,13 +379,12 @@ __device__ __forceinline__ float logf_core_t(uint32_t ix, TabLoad tabload)
     const double2 t = tabload((tmp >> 15) & 0xf0u);          /* byte offset of entry (tmp >> 19) & 15 */
     const double z = (double)__uint_as_float(iz);
     /* (double)k without the conversion unit: 2^52 + 2^31 + k, minus the bias */
-    const double kd = __dsub_rn(__hiloint2double(0x43300000, (int)(0x80000000u ^ (uint32_t)k)),
-                                4503601774854144.0);
+    const double kd = __dsub_rn(__hiloint2double(0x43300000, (int)(0x80000000u ^ (uint32_t)k)), c_logf_k[4]);
     const double r = __fma_rn(z, t.x, -1.0);
-    const double y0 = __fma_rn(kd, 0x1.62e42fefa39efp-1, t.y);
+    const double y0 = __fma_rn(kd, c_logf_k[0], t.y);
     const double r2 = __dmul_rn(r, r);
-    double y = __fma_rn(0x1.5575b0be00b6ap-2, r, -0x1.ffffef20a4123p-2);
-    y = __fma_rn(-0x1.00ea348b88334p-2, r2, y);
+    double y = __fma_rn(c_logf_k[1], r, c_logf_k[2]);
+    y = __fma_rn(c_logf_k[3], r2, y);
     y = __fma_rn(y, r2, __dadd_rn(y0, r));
     return (float)y;
 }

@@ -175,6 +175,20 @@ def test_nondefault_parameters(oracle):
         p.close()
 
 
+def test_wide_seed_weights(oracle):
+    """find_polya weights that do not fit the packed int8 form of the seed scan."""
+    from tailseeker_b200.config import stock_config
+    from tailseeker_b200.importer import TileProcessor
+    cfg = stock_config("miseq", polyA_weights=dict(T=200, A=-900, C=-900, G=-900, N=-100),
+                       nonA_weights=dict(T=-100, A=0, C=-400, G=-400, N=0))
+    p = TileProcessor(cfg)
+    try:
+        _, o = _run(p, cfg, oracle, 5000, 7)
+        compare_tile(p, cfg, None, o)
+    finally:
+        p.close()
+
+
 def test_firstclusterno_and_pitch(stock_cfg, oracle):
     """Second read block of a tile (global cluster numbers) and padded row pitches."""
     from tailseeker_b200.synth import make_tile
