@@ -470,7 +470,7 @@ __device__ __forceinline__ int lds_s16(uint32_t addr)
 #define K2_CL        TSK_K2_THREADS      /* clusters per CTA */
 #define K2_WARPS     (TSK_K2_THREADS / 32)
 #define K2_GROUP     4                   /* cycles per TMA copy */
-#define K2_NGROUP    3                   /* groups in each warp's ring (8-11 cycles of look-ahead) */
+#define K2_NGROUP    2                   /* groups in each warp's ring (4-7 cycles of look-ahead; 3 groups were 2 % slower) */
 #define K2_HEAD_MAX  24                  /* resident cycles [0, head): balancer + first scored cycles */
 #define K2_ROWB      (4 * 32 * 2)        /* bytes per cycle and warp: four channel rows of 32 int16 */
 #define K2_TILE_CYC  8                   /* record words staged per lane between flushes */
@@ -835,7 +835,7 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
  * far more with a large PhiX spike-in).  The TMA box is K2C_W clusters wide starting at the item's
  * first cluster (rounded down to 8) and each lane reads its own column of it; clusters further
  * than K2C_W from there (an item spanning > 89 clusters, i.e. under ~40 % kept) go to the literal kernel.  Nothing is
- * resident: the balancer cycles and then the scored cycles stream through the same ring of three
+ * resident: the balancer cycles and then the scored cycles stream through the same ring of two
  * 4-cycle groups (the few cycles both passes need are fetched twice, from L2). ---- */
 #define K2C_W     96                     /* clusters per TMA box */
 #define K2C_CHB   (K2C_W * 2)            /* bytes per channel row */
