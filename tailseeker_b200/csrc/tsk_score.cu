@@ -859,7 +859,9 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TileView &tv = A.tv;
     const int ts = P.threep_start, tl = P.threep_length, bins = P.bins;
-    const size_t spitch = A.spitch;
+    /* contrast scratch, dense per work item: row i of item w at scratch[(w * (tl + 1) + i) * 32 + lane],
+     * so every row is one full 128-byte line */
+    const size_t spitch = 32;
     const uint32_t a_stage = smem_u32(&sm.stage[warp][0][0][0]);
     const uint32_t a_full = smem_u32(&sm.bar_full[warp][0]);
 
@@ -1057,8 +1059,9 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
     float prev_entropy = CUDART_NAN_F;
     double ptotal = 0.;                       /* sum of the scores from the seed start on (KIND_POS lanes) */
     uint32_t dhwin = 0;                       /* bit k = downhill of cycle (c - k); max_mods < 32 */
-    /* score of cycle r lives at scratch[(r - start - ps) * spitch + n]; scr walks one row per cycle */
-    float *scr = A.scratch + n + ((ptrdiff_t)rbeg_w - (start + ps)) * (ptrdiff_t)spitch;
+    /* score of cycle r lives in row (r - start - ps) of the item's scratch block; scr walks one row per cycle */
+    float *const scol = A.scratch + (size_t)(w0 >> 5) * (size_t)(tl + 1) * 32 + lane;
+    float *scr = scol + ((ptrdiff_t)rbeg_w - (start + ps)) * (ptrdiff_t)spitch;
     const uint32_t a_logtab = smem_u32(&sm.sh.logtab[0]), a_tscore = smem_u32(&sm.sh.tscore[0]);
     const uint32_t a_tile = smem_u32(&sm.tile[warp][0][0]);
     const uint32_t a_mytile = a_tile + lane * ((K2_TILE_CYC + 1) * 4);
@@ -1195,7 +1198,7 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
      * exact IEEE value is evaluated only there.  If a second candidate lies within 1e-14 the
      * exact scan decides, so ties resolve exactly like the reference's strict '>' scan. */
     if (ispos && !aborted && scan_len > 0 && P.cctr_left + P.cctr_right < scan_len) {
-        const float *col = A.scratch + n;
+        const float *col = scol;
         const int left = P.cctr_left, last = scan_len - P.cctr_right;
         const double total = ptotal;
         if (total == total) {        /* a NaN anywhere makes the first candidate NaN: no sampling */
