@@ -489,8 +489,7 @@ struct __align__(128) K2Smem {
 /* One warp = 32 consecutive clusters, one lane per cluster, and its own little pipeline: the four
  * channel planes of every 3'-read cycle (4 x 64 bytes) are brought into shared memory by the TMA
  * engine (bulk asynchronous copies completing on an mbarrier) -- cycles [0, head) once, then a
- * ring of eight single-cycle stages that lane 0 refills right after the warp has consumed a
- * cycle.  The arithmetic therefore never waits on a global load, no warp waits for another, and
+ * ring of 4-cycle groups that lane 0 refills right after the warp has consumed a group.  The arithmetic therefore never waits on a global load, no warp waits for another, and
  * every DRAM request is a full, aligned 64-byte segment of a cycle-major plane. */
 __global__ void __launch_bounds__(TSK_K2_THREADS, K2_MIN_CTAS)
 k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, const float rcp_maxent,
