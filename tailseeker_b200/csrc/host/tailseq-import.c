@@ -6,8 +6,24 @@
  */
 #include <stdlib.h>
 #include <string.h>
-#include <cuda_runtime_api.h>
+#include <pthread.h>
+#include <time.h>
 #include "tsk_host.h"
+
+/* TSK_HOST_TIMING=1: wall time of each phase on stderr */
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+static int timing_on = -1;
+static double t_last;
+static void phase(const char *what)
+{
+    if (timing_on < 0) { timing_on = getenv("TSK_HOST_TIMING") != NULL; t_last = now_s(); }
+    if (timing_on) { const double t = now_s(); fprintf(stderr, "[timing] %-28s %.3f s\n", what, t - t_last); t_last = t; }
+}
 
 static void usage(const char *prog)
 {
@@ -16,8 +32,34 @@ static void usage(const char *prog)
            "\n\nUsage: %s {config.ini}\n\n", prog);
 }
 
-static int process(struct host_config *cfg, tsk_ctx *ctx, const float *invmatrix)
+/* The CUDA context (0.7 s to create) comes up on its own thread while the main thread opens the
+ * output files and reads the first block of CIF / BCL data. */
+struct ctx_boot {
+    pthread_t thread;
+    const tsk_params *params;
+    int device, rc, started;
+    tsk_ctx *ctx;
+    char error[512];
+};
+
+static void *boot_context(void *arg)
 {
+    struct ctx_boot *b = arg;
+    b->rc = tsk_ctx_create(&b->ctx, b->device, b->params);
+    if (b->rc != 0) snprintf(b->error, sizeof(b->error), "%s", tsk_last_error());
+    return NULL;
+}
+
+static tsk_ctx *await_context(struct ctx_boot *b)
+{
+    if (b->started) { pthread_join(b->thread, NULL); b->started = 0; }
+    if (b->rc != 0) { fprintf(stderr, "%s\n", b->error); return NULL; }
+    return b->ctx;
+}
+
+static int process(struct host_config *cfg, struct ctx_boot *boot, const float *invmatrix)
+{
+    tsk_ctx *ctx = NULL;
     char msgprefix[BUFSIZ];
     struct tile_files *tf = NULL;
     uint8_t *bcl = NULL;
@@ -42,9 +84,9 @@ static int process(struct host_config *cfg, tsk_ctx *ctx, const float *invmatrix
     printf("%sProcessing %u clusters.\n", msgprefix, nclusters);
     if (tsk_write_signal_headers(cfg, nclusters) < 0) goto done;
 
-    /* pinned host buffers: the upload is an asynchronous DMA from these */
-    if (cudaMallocHost((void **)&bcl, (size_t)T * blocksize) != cudaSuccess ||
-        cudaMallocHost((void **)&cif, sizeof(int16_t) * 4 * (size_t)L3 * blocksize) != cudaSuccess) {
+    /* plain page-aligned buffers: pinning 2.5 GB for a single pass costs more than the staged copy */
+    if (posix_memalign((void **)&bcl, 4096, (size_t)T * blocksize + 4096) != 0 ||
+        posix_memalign((void **)&cif, 4096, sizeof(int16_t) * 4 * (size_t)L3 * blocksize + 4096) != 0) {
         fprintf(stderr, "Cannot allocate the read buffers.\n");
         goto done;
     }
@@ -55,12 +97,16 @@ static int process(struct host_config *cfg, tsk_ctx *ctx, const float *invmatrix
     neg = malloc(sizeof(uint32_t) * (size_t)T * cfg->bins);
     counters = calloc(S, sizeof(*counters));
     if (!calls || !records || !nslots || !pos || !neg || !counters) { perror("process"); goto done; }
+    phase("open files + buffers");
 
     for (blockno = 0; togo > 0; blockno++) {
         const uint32_t count = togo >= blocksize ? blocksize : togo;
         snprintf(msgprefix, BUFSIZ, "[%s%d#%d/%d] ", cfg->laneid, cfg->tile, blockno + 1, totalblocks);
         printf("%sLoading CIF and BCL files\n", msgprefix);
         if (tsk_read_block(tf, count, bcl, cif) < 0) goto done;
+        phase("read CIF/BCL");
+        if (!ctx && !(ctx = await_context(boot))) goto done;
+        phase("wait for the CUDA context");
 
         printf("%sAnalyzing and writing out\n", msgprefix);
         if (tsk_tile_upload(ctx, bcl, count, cif, count, invmatrix, count, nclusters - togo, 0) != 0 ||
@@ -68,6 +114,7 @@ static int process(struct host_config *cfg, tsk_ctx *ctx, const float *invmatrix
             fprintf(stderr, "%s\n", tsk_last_error());
             goto done;
         }
+        phase("upload + kernels + calls");
         for (struct host_sample *s = cfg->samples; s; s = s->next) {
             const int i = s->numindex;
             free(records[i]); records[i] = NULL; nslots[i] = 0;
@@ -80,7 +127,9 @@ static int process(struct host_config *cfg, tsk_ctx *ctx, const float *invmatrix
                 goto done;
             }
         }
+        phase("fetch records");
         if (tsk_write_block_outputs(cfg, calls, count, nclusters - togo, bcl, records, nslots) < 0) goto done;
+        phase("format + compress + write");
         /* like the reference, the pos/neg distributions are rewritten after every block
          * (tailseq-import.c:358-370,559): a multi-block tile keeps its last block's */
         if (cfg->signal_dists_output) {
@@ -91,17 +140,19 @@ static int process(struct host_config *cfg, tsk_ctx *ctx, const float *invmatrix
         togo -= count;
     }
     printf("%sClearing\n", msgprefix);
+    if (!ctx && !(ctx = await_context(boot))) goto done;      /* a tile without clusters */
     if (cfg->stats_output) {
         if (tsk_get_counters(ctx, counters) != 0) { fprintf(stderr, "%s\n", tsk_last_error()); goto done; }
         if (tsk_write_stats(cfg->stats_output, cfg, counters) < 0) goto done;
     }
+    phase("sigdists + stats");
     printf("[%s%d] Finished.\n", cfg->laneid, cfg->tile);
     rc = 0;
 done:
     if (records) for (int i = 0; i < S; i++) free(records[i]);
     free(records); free(nslots); free(calls); free(pos); free(neg); free(counters);
-    if (bcl) cudaFreeHost(bcl);
-    if (cif) cudaFreeHost(cif);
+    free(bcl);
+    free(cif);
     tsk_close_tile(tf);
     tsk_close_writers(cfg);
     return rc;
@@ -112,11 +163,13 @@ int main(int argc, char *argv[])
     struct host_config *cfg;
     tsk_params *params;
     tsk_ctx *ctx = NULL;
+    struct ctx_boot boot;
     float inv[16];
     int r, device = 0;
     const char *dev = getenv("TAILSEEKER_DEVICE");
 
     if (argc < 2) { usage(argv[0]); return 0; }
+    phase("start");
     cfg = tsk_parse_config(argv[1]);
     if (cfg == NULL) return -1;
     if (cfg->altcalls_given) {
@@ -127,12 +180,14 @@ int main(int argc, char *argv[])
     params = malloc(sizeof(*params));
     if (!params || tsk_build_params(cfg, params) < 0) return -1;
     if (dev) device = atoi(dev);
-    if (tsk_ctx_create(&ctx, device, params) != 0) {
-        fprintf(stderr, "%s\n", tsk_last_error());
-        return -1;
-    }
-    r = process(cfg, ctx, inv);
-    tsk_ctx_destroy(ctx);
+    memset(&boot, 0, sizeof(boot));
+    boot.params = params; boot.device = device;
+    if (pthread_create(&boot.thread, NULL, boot_context, &boot) == 0) boot.started = 1;
+    else boot_context(&boot);
+    r = process(cfg, &boot, inv);
+    phase("close files");
+    ctx = await_context(&boot);
+    if (ctx) tsk_ctx_destroy(ctx);
     free(params);
     tsk_free_config(cfg);
     return r;

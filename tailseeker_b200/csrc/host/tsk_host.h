@@ -30,7 +30,7 @@ struct host_sample {
     int umi_count;
     int limit_threep_processing, signal_dump_length;
     int numindex;
-    gzFile stream_seqqual, stream_taginfo, stream_signal;
+    FILE *stream_seqqual, *stream_taginfo, *stream_signal;   /* series of gzip members (writers.c) */
     struct host_sample *next;
 };
 

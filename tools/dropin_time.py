@@ -1,0 +1,18 @@
+#!/usr/bin/env python
+"""Wall time of the drop-in tailseq-import against the reference binary on one synthetic tile
+(GPU box; files on /dev/shm)."""
+import os, sys, time
+os.environ["TSK_HOST_TIMING"] = "1"
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import refrun
+from tailseeker_b200.config import stock_config
+from tailseeker_b200.synth import make_tile
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
+cfg = stock_config("miseq", phix_match_name="PhiX")
+tile = make_tile(cfg, n, seed=5, phix_frac=0.6)
+ours = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tailseeker_b200", "bin", "tailseq-import")
+for name, binary, threads in (("reference x16", None, 16), ("drop-in", ours, 16), ("drop-in", ours, 1)):
+    r = refrun.run_import(cfg, tile, threads=threads, binary=binary)
+    print("%-14s threads=%-2d %7.2f s  %9.0f clusters/s" % (name, threads, r["wall_s"], n / r["wall_s"]))
+    print("\n".join(l for l in r["stderr"].splitlines() if l.startswith("[timing]")))
