@@ -4,6 +4,7 @@
  * argv[9]; exit codes 1 (usage / cutoffs), 2 (ruling), 3 (taginfo) as in polyaruler.c:402-444.
  * measure_polya_length() and the resampling run on the GPU through tsk_ruler_records().
  */
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 #include "tsk_host.h"
@@ -120,6 +121,25 @@ static int rewrite_taginfo(const char *taginfo_file, const int16_t *meas, const 
     return 0;
 }
 
+/* Creating the CUDA context costs far more than measuring one sample's records (0.7 s against
+ * milliseconds): it is created on its own thread while the signal pack is read and inflated, and
+ * torn down on one while the taginfo stream is rewritten. */
+struct ctx_boot { pthread_t thread; const tsk_params *params; int device, rc; tsk_ctx *ctx; char error[512]; };
+
+static void *boot_context(void *arg)
+{
+    struct ctx_boot *b = arg;
+    b->rc = tsk_ctx_create(&b->ctx, b->device, b->params);
+    if (b->rc != 0) snprintf(b->error, sizeof(b->error), "%s", tsk_last_error());
+    return NULL;
+}
+
+static void *drop_context(void *arg)
+{
+    tsk_ctx_destroy((tsk_ctx *)arg);
+    return NULL;
+}
+
 int main(int argc, char *argv[])
 {
     static uint32_t cutoffs[TSK_MAX_CUTOFF_CYCLES];
@@ -142,8 +162,6 @@ int main(int argc, char *argv[])
     const char *sigdist_file = argv[9];
 
     if (load_cutoffs(cutoffs_file, tile_id, cutoffs, &ncycles) < 0) return 1;
-    recs = read_sigpack(signals_file, &total_clusters, &max_cycles, &nrecords);
-    if (!recs) return 2;
 
     /* the ruler needs no importer parameters: a minimal context */
     p = calloc(1, sizeof(*p));
@@ -154,7 +172,17 @@ int main(int argc, char *argv[])
     p->max_cctr_scan_left_space = p->max_cctr_scan_right_space = 1;
     p->num_samples = 1; p->samples[0].delimiter_pos = -1;
     if (dev) device = atoi(dev);
-    if (tsk_ctx_create(&ctx, device, p) != 0) { fprintf(stderr, "%s\n", tsk_last_error()); return 2; }
+    struct ctx_boot boot;
+    int threaded;
+    memset(&boot, 0, sizeof(boot));
+    boot.params = p; boot.device = device;
+    threaded = pthread_create(&boot.thread, NULL, boot_context, &boot) == 0;
+    if (!threaded) boot_context(&boot);
+    recs = read_sigpack(signals_file, &total_clusters, &max_cycles, &nrecords);
+    if (threaded) pthread_join(boot.thread, NULL);
+    if (!recs) return 2;
+    if (boot.rc != 0) { fprintf(stderr, "%s\n", boot.error); return 2; }
+    ctx = boot.ctx;
 
     lens = malloc(sizeof(int16_t) * (nrecords ? nrecords : 1));
     meas = malloc(sizeof(int16_t) * (total_clusters ? total_clusters : 1));
@@ -183,7 +211,14 @@ int main(int argc, char *argv[])
         }
         gzclose(f);
     }
-    tsk_ctx_destroy(ctx);
-    if (rewrite_taginfo(taginfo_file, meas, tile_id) < 0) return 3;
+    {
+        pthread_t th;
+        const int bg = pthread_create(&th, NULL, drop_context, ctx) == 0;
+        if (!bg) tsk_ctx_destroy(ctx);
+        const int rc = rewrite_taginfo(taginfo_file, meas, tile_id);
+        fflush(stdout);
+        if (bg) pthread_join(th, NULL);
+        if (rc < 0) return 3;
+    }
     return 0;
 }

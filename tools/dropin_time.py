@@ -16,3 +16,19 @@ for name, binary, threads in (("reference x16", None, 16), ("drop-in", ours, 16)
     r = refrun.run_import(cfg, tile, threads=threads, binary=binary)
     print("%-14s threads=%-2d %7.2f s  %9.0f clusters/s" % (name, threads, r["wall_s"], n / r["wall_s"]))
     print("\n".join(l for l in r["stderr"].splitlines() if l.startswith("[timing]")))
+
+# ---- the ruler programs on the largest sample of that tile
+import numpy as np
+work = "/dev/shm/tsk_dropin_ruler"
+os.makedirs(work, exist_ok=True)
+r = refrun.run_import(cfg, tile, workdir=work, threads=16, binary=ours)
+tid = cfg.tile_id
+cpath = os.path.join(work, "cutoffs.txt")
+refrun.write_cutoffs_file(cpath, tid, [0.25] * cfg.total_cycles)
+best = max(cfg.samples, key=lambda s: r["sigpack"][s.name][2].shape[0])
+args = (tid, os.path.join(work, "signals", "%s_%s.sigpack" % (best.name, tid)), cpath,
+        os.path.join(work, "taginfo", "%s_%s.txt.gz" % (best.name, tid)))
+our_ruler = os.path.join(os.path.dirname(ours), "tailseq-polya-ruler")
+for name, binary in (("reference ruler", None), ("drop-in ruler", our_ruler), ("drop-in ruler", our_ruler)):
+    rr = refrun.run_ruler(*args, os.path.join(work, "rp.gz"), binary=binary)
+    print("%-16s %6.2f s  (%d records of %s)" % (name, rr["wall_s"], r["sigpack"][best.name][2].shape[0], best.name))
