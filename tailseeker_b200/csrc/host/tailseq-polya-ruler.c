@@ -78,7 +78,7 @@ static uint32_t *read_sigpack(const char *filename, uint32_t *total_clusters, ui
 }
 
 /* output_corrected_polya_measurements(), polyaruler.c:316-388 */
-static int rewrite_taginfo(const char *taginfo_file, const int16_t *meas, const char *tile_id)
+static int rewrite_taginfo(const char *taginfo_file, const int16_t *meas, const char *tile_id, FILE *out)
 {
     gzFile fp = gzopen(taginfo_file, "rt");
     if (!fp) return -1;
@@ -103,7 +103,7 @@ static int rewrite_taginfo(const char *taginfo_file, const int16_t *meas, const 
             tok[strlen(tok)] = '\t';
             term = strlen(tok);
             if (term > 0) tok[term - 1] = '\n';
-            fputs(tile_id, stdout); fputc('\t', stdout); fputs(line, stdout);
+            fputs(tile_id, out); fputc('\t', out); fputs(line, out);
             continue;
         }
         for (i = 0; (tok = strsep(&bptr, "\t\n\r")) != NULL; i++)
@@ -114,80 +114,79 @@ static int rewrite_taginfo(const char *taginfo_file, const int16_t *meas, const 
             default: break;
             }
         flags |= TSK_PAFLAG_MEASURED_FROM_FLUORESCENCE;
-        printf("%s\t%d\t%d\t%d\t%s\t%s\n", tile_id, clusterno, flags, meas[clusterno],
+        fprintf(out, "%s\t%d\t%d\t%d\t%s\t%s\n", tile_id, clusterno, flags, meas[clusterno],
                mods ? mods : "(null)", umi ? umi : "(null)");
     }
     gzclose(fp);
     return 0;
 }
 
-/* Creating the CUDA context costs far more than measuring one sample's records (0.7 s against
- * milliseconds): it is created on its own thread while the signal pack is read and inflated, and
- * torn down on one while the taginfo stream is rewritten. */
-struct ctx_boot { pthread_t thread; const tsk_params *params; int device, rc; tsk_ctx *ctx; char error[512]; };
+/* Creating the CUDA context costs far more than measuring one sample's records (0.7 s or more
+ * against milliseconds): it is created on its own thread while the first signal pack is read and
+ * inflated, and ONE context serves every job of a batch (`--batch`, below). */
+struct ctx_boot { pthread_t thread; tsk_params params; int device, rc, threaded, ncycles, bins; tsk_ctx *ctx; char error[512]; };
 
 static void *boot_context(void *arg)
 {
     struct ctx_boot *b = arg;
-    b->rc = tsk_ctx_create(&b->ctx, b->device, b->params);
+    b->rc = tsk_ctx_create(&b->ctx, b->device, &b->params);
     if (b->rc != 0) snprintf(b->error, sizeof(b->error), "%s", tsk_last_error());
     return NULL;
 }
 
-static void *drop_context(void *arg)
+/* (re)start a context for histograms of ncycles x bins; the ruler needs no importer parameters */
+static void start_context(struct ctx_boot *b, int ncycles, int bins)
 {
-    tsk_ctx_destroy((tsk_ctx *)arg);
-    return NULL;
-}
-
-int main(int argc, char *argv[])
-{
-    static uint32_t cutoffs[TSK_MAX_CUTOFF_CYCLES];
-    uint32_t total_clusters = 0, max_cycles = 0, *recs, *hist;
-    int ncycles = 0, device = 0;
-    size_t nrecords = 0;
-    int16_t *lens, *meas;
-    tsk_ctx *ctx = NULL;
-    tsk_params *p;
-    const char *dev = getenv("TAILSEEKER_DEVICE");
-
-    if (argc < 10) {
-        fprintf(stderr, "Usage: %s {tile id} {signals} {cutoffs} {min polya} {downhill ext weight} {taginfo} "
-                        "{sampling bin count} {positive sampling gap} {positive sampling output}\n", argv[0]);
-        return 1;
-    }
-    const char *tile_id = argv[1], *signals_file = argv[2], *cutoffs_file = argv[3], *taginfo_file = argv[6];
-    const int min_len = atoi(argv[4]), bins = atoi(argv[7]);
-    const float weight = atof(argv[5]), gap = atof(argv[8]);
-    const char *sigdist_file = argv[9];
-
-    if (load_cutoffs(cutoffs_file, tile_id, cutoffs, &ncycles) < 0) return 1;
-
-    /* the ruler needs no importer parameters: a minimal context */
-    p = calloc(1, sizeof(*p));
+    tsk_params *p = &b->params;
+    if (b->ctx) { tsk_ctx_destroy(b->ctx); b->ctx = NULL; }
+    memset(p, 0, sizeof(*p));
     p->abi_version = TSK_ABI_VERSION;
     p->total_cycles = ncycles > 0 ? ncycles : 1; p->threep_start = 0; p->threep_length = p->total_cycles;
     p->index_length = 0; p->balancer_num_positive_samples = 2; p->balancer_num_negative_samples = 4;
     p->dist_sampling_bins = bins > 0 ? bins : 1; p->fair_sampling_hash_space_size = 1;
     p->max_cctr_scan_left_space = p->max_cctr_scan_right_space = 1;
     p->num_samples = 1; p->samples[0].delimiter_pos = -1;
-    if (dev) device = atoi(dev);
-    struct ctx_boot boot;
-    int threaded;
-    memset(&boot, 0, sizeof(boot));
-    boot.params = p; boot.device = device;
-    threaded = pthread_create(&boot.thread, NULL, boot_context, &boot) == 0;
-    if (!threaded) boot_context(&boot);
+    b->ncycles = ncycles; b->bins = bins; b->rc = 0;
+    b->threaded = pthread_create(&b->thread, NULL, boot_context, b) == 0;
+    if (!b->threaded) boot_context(b);
+}
+
+static tsk_ctx *await_context(struct ctx_boot *b)
+{
+    if (b->threaded) { pthread_join(b->thread, NULL); b->threaded = 0; }
+    if (b->rc != 0) { fprintf(stderr, "%s\n", b->error); return NULL; }
+    return b->ctx;
+}
+
+/* One job = the nine positional arguments of polyaruler.c:402-418; corrected taginfo to `out`.
+ * Returns the reference's exit code (0, 1 cutoffs, 2 ruling, 3 taginfo). */
+static int run_job(struct ctx_boot *boot, char *const a[9], FILE *out)
+{
+    static uint32_t cutoffs[TSK_MAX_CUTOFF_CYCLES];
+    uint32_t total_clusters = 0, max_cycles = 0, *recs = NULL, *hist = NULL;
+    int ncycles = 0, rc = 2;
+    size_t nrecords = 0;
+    int16_t *lens = NULL, *meas = NULL;
+    const char *tile_id = a[0], *signals_file = a[1], *cutoffs_file = a[2], *taginfo_file = a[5];
+    const int min_len = atoi(a[3]), bins = atoi(a[6]);
+    const float weight = atof(a[4]), gap = atof(a[7]);
+    const char *sigdist_file = a[8];
+    tsk_ctx *ctx;
+
+    if (load_cutoffs(cutoffs_file, tile_id, cutoffs, &ncycles) < 0) return 1;
+    if (!boot->ctx && !boot->threaded) start_context(boot, ncycles, bins);
     recs = read_sigpack(signals_file, &total_clusters, &max_cycles, &nrecords);
-    if (threaded) pthread_join(boot.thread, NULL);
-    if (!recs) return 2;
-    if (boot.rc != 0) { fprintf(stderr, "%s\n", boot.error); return 2; }
-    ctx = boot.ctx;
+    ctx = await_context(boot);
+    if (ctx && (boot->ncycles != ncycles || boot->bins != bins)) {      /* another histogram shape */
+        start_context(boot, ncycles, bins);
+        ctx = await_context(boot);
+    }
+    if (!recs || !ctx) goto done;
 
     lens = malloc(sizeof(int16_t) * (nrecords ? nrecords : 1));
     meas = malloc(sizeof(int16_t) * (total_clusters ? total_clusters : 1));
     hist = calloc((size_t)(ncycles > 0 ? ncycles : 1) * (bins > 0 ? bins : 1), sizeof(uint32_t));
-    if (!lens || !meas || !hist) { perror("process_polya_ruling"); return 2; }
+    if (!lens || !meas || !hist) { perror("process_polya_ruling"); goto done; }
     memset(meas, 0xff, sizeof(int16_t) * (total_clusters ? total_clusters : 1));
     if (ncycles > 0 && bins > 0) {
         if (tsk_ruler_hist_reset(ctx, ncycles, bins) != 0 ||
@@ -195,7 +194,7 @@ int main(int argc, char *argv[])
                               lens, 0) != 0 ||
             tsk_ruler_get_hist(ctx, hist) != 0) {
             fprintf(stderr, "%s\n", tsk_last_error());
-            return 2;
+            goto done;
         }
         for (size_t r = 0; r < nrecords; r++)
             if (lens[r] >= 0) meas[recs[r * (2 + (size_t)max_cycles)]] = lens[r];
@@ -203,22 +202,57 @@ int main(int argc, char *argv[])
     {
         const uint32_t h[3] = {4, (uint32_t)ncycles, (uint32_t)bins};
         gzFile f = gzopen(sigdist_file, "wb");
-        if (!f) { fprintf(stderr, "Cannot open %s to write.\n", sigdist_file); return 2; }
+        if (!f) { fprintf(stderr, "Cannot open %s to write.\n", sigdist_file); goto done; }
         if (gzwrite(f, h, sizeof(h)) <= 0 ||
             (ncycles > 0 && bins > 0 && gzwrite(f, hist, (unsigned)(sizeof(uint32_t) * (size_t)ncycles * bins)) <= 0)) {
             gzclose(f);
-            return 2;
+            goto done;
         }
         gzclose(f);
     }
-    {
-        pthread_t th;
-        const int bg = pthread_create(&th, NULL, drop_context, ctx) == 0;
-        if (!bg) tsk_ctx_destroy(ctx);
-        const int rc = rewrite_taginfo(taginfo_file, meas, tile_id);
+    rc = rewrite_taginfo(taginfo_file, meas, tile_id, out) < 0 ? 3 : 0;
+done:
+    free(recs); free(lens); free(meas); free(hist);
+    return rc;
+}
+
+int main(int argc, char *argv[])
+{
+    struct ctx_boot *boot = calloc(1, sizeof(*boot));
+    const char *dev = getenv("TAILSEEKER_DEVICE");
+    int rc = 0;
+    if (!boot) return 2;
+    if (dev) boot->device = atoi(dev);
+
+    if (argc == 3 && strcmp(argv[1], "--batch") == 0) {
+        /* not in the reference: one job per line of argv[2] -- the nine arguments and the file the
+         * corrected taginfo goes to, tab separated -- all on one CUDA context */
+        char line[8192];
+        FILE *jobs = fopen(argv[2], "r");
+        if (!jobs) { fprintf(stderr, "Cannot open %s.\n", argv[2]); return 1; }
+        while (rc == 0 && fgets(line, sizeof(line), jobs)) {
+            char *a[10], *bptr = line, *tok;
+            int n = 0;
+            while (n < 10 && (tok = strsep(&bptr, "\t\r\n")) != NULL) if (*tok) a[n++] = tok;
+            if (n == 0) continue;
+            if (n != 10) { fprintf(stderr, "A batch line needs 10 fields.\n"); rc = 1; break; }
+            FILE *out = fopen(a[9], "w");
+            if (!out) { fprintf(stderr, "Cannot open %s to write.\n", a[9]); rc = 3; break; }
+            rc = run_job(boot, a, out);
+            if (fclose(out) != 0 && rc == 0) rc = 3;
+        }
+        fclose(jobs);
+    } else if (argc >= 10) {
+        rc = run_job(boot, argv + 1, stdout);
         fflush(stdout);
-        if (bg) pthread_join(th, NULL);
-        if (rc < 0) return 3;
+    } else {
+        fprintf(stderr, "Usage: %s {tile id} {signals} {cutoffs} {min polya} {downhill ext weight} {taginfo} "
+                        "{sampling bin count} {positive sampling gap} {positive sampling output}\n"
+                        "       %s --batch {job list}\n", argv[0], argv[0]);
+        return 1;
     }
-    return 0;
+    if (boot->threaded) pthread_join(boot->thread, NULL);
+    if (boot->ctx) tsk_ctx_destroy(boot->ctx);
+    free(boot);
+    return rc;
 }

@@ -62,6 +62,22 @@ def test_programs_match_reference(tmp_path, control, bufsize):
         assert a["taginfo"] == b["taginfo"], s.name
         assert (a["pos"] == b["pos"]).all(), s.name
 
+    # --batch: every sample of the tile on one CUDA context (not in the reference)
+    import subprocess
+    jobs, want = [], {}
+    for s in cfg.samples:
+        args = (tid, os.path.join(wref, "signals", "%s_%s.sigpack" % (s.name, tid)), cpath, "8", "0.49",
+                os.path.join(wref, "taginfo", "%s_%s.txt.gz" % (s.name, tid)), "1000", "0.1",
+                str(tmp_path / ("bpos_%s.gz" % s.name)), str(tmp_path / ("btag_%s.txt" % s.name)))
+        jobs.append("\t".join(args))
+        want[s.name] = refrun.run_ruler(*args[:3], args[5], str(tmp_path / "rc.gz"))
+    (tmp_path / "jobs.tsv").write_text("\n".join(jobs) + "\n")
+    r = subprocess.run([OUR_RULER, "--batch", str(tmp_path / "jobs.tsv")], capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    for s in cfg.samples:
+        assert (tmp_path / ("btag_%s.txt" % s.name)).read_bytes() == want[s.name]["taginfo"], s.name
+        assert (refrun.read_sigdists(str(tmp_path / ("bpos_%s.gz" % s.name))) == want[s.name]["pos"]).all(), s.name
+
 
 def test_ruler_exit_codes(tmp_path):
     import subprocess

@@ -32,3 +32,21 @@ our_ruler = os.path.join(os.path.dirname(ours), "tailseq-polya-ruler")
 for name, binary in (("reference ruler", None), ("drop-in ruler", our_ruler), ("drop-in ruler", our_ruler)):
     rr = refrun.run_ruler(*args, os.path.join(work, "rp.gz"), binary=binary)
     print("%-16s %6.2f s  (%d records of %s)" % (name, rr["wall_s"], r["sigpack"][best.name][2].shape[0], best.name))
+
+# ---- --batch: all samples of the tile on one context
+import subprocess
+jobs = []
+for s in cfg.samples:
+    jobs.append("\t".join([tid, os.path.join(work, "signals", "%s_%s.sigpack" % (s.name, tid)), cpath, "8", "0.49",
+                           os.path.join(work, "taginfo", "%s_%s.txt.gz" % (s.name, tid)), "1000", "0.1",
+                           os.path.join(work, "bpos_%s.gz" % s.name), os.path.join(work, "btag_%s.txt" % s.name)]))
+open(os.path.join(work, "jobs.tsv"), "w").write("\n".join(jobs) + "\n")
+t0 = time.perf_counter()
+subprocess.run([our_ruler, "--batch", os.path.join(work, "jobs.tsv")], check=True)
+tb = time.perf_counter() - t0
+t0 = time.perf_counter()
+for s in cfg.samples:
+    refrun.run_ruler(tid, os.path.join(work, "signals", "%s_%s.sigpack" % (s.name, tid)), cpath,
+                     os.path.join(work, "taginfo", "%s_%s.txt.gz" % (s.name, tid)), os.path.join(work, "rp.gz"))
+tr = time.perf_counter() - t0
+print("all %d samples: reference ruler (one process each) %.2f s, drop-in --batch %.2f s" % (len(cfg.samples), tr, tb))
