@@ -174,8 +174,10 @@ int tsk_ctx_destroy(tsk_ctx *ctx);
  * AoS transpose of cifreader.c:163-164: data stay in the files' native layouts,
  *   bcl[total_cycles][bcl_pitch] u8,   cif[threep_length][4][cif_pitch] i16  (A,C,G,T planes)
  * pitches in ELEMENTS, >= nclusters.  on_device != 0: the pointers are device pointers that
- * the caller keeps alive until the next upload (zero copy); otherwise they are host
- * pointers (pinned or pageable) and are copied to HBM on the context's stream.
+ * the caller keeps alive until the next upload (zero copy) -- bcl must then be 16-byte aligned
+ * with bcl_pitch a multiple of 16 (the rows are fetched by TMA tensor copies; refused otherwise),
+ * and cif 16-byte aligned with cif_pitch a multiple of 8 for the fast scoring kernel; otherwise
+ * they are host pointers (pinned or pageable) and are copied to HBM on the context's stream.
  * invmatrix = inverse colour matrix (load_color_matrix(), signalproc.c:345-375).
  * Up to two tiles may be uploaded ahead of tsk_tile_process(), which takes them in order: the
  * copy of tile t+1 (on its own stream) then overlaps the kernels of tile t. */

@@ -351,6 +351,10 @@ extern "C" int tsk_tile_upload(tsk_ctx *ctx, const uint8_t *bcl, size_t bcl_pitc
     slot.tv.nclusters = nclusters;
     slot.tv.firstclusterno = firstclusterno;
     if (on_device) {
+        if (nclusters && (((uintptr_t)bcl % 16) != 0 || (bcl_pitch % 16) != 0)) {
+            tsk_set_error("device base calls must be 16-byte aligned with a pitch that is a multiple of 16");
+            return -1;
+        }
         slot.tv.bcl = bcl; slot.tv.bcl_pitch = bcl_pitch;
         slot.tv.cif = cif; slot.tv.cif_pitch = cif_pitch;
         slot.slot = -1;

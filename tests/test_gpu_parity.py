@@ -419,3 +419,22 @@ def test_streamed_mode(stock_cfg, oracle):
             assert (p.records(s) == o["records"][s]).all()
     finally:
         p.close()
+
+
+def test_device_pointer_requirements(stock_cfg):
+    """Zero-copy uploads: base-call rows must be 16-byte aligned (TMA); a misaligned pitch is refused
+    at upload time with a message, nothing is launched."""
+    import torch
+    from tailseeker_b200 import _lib
+    from tailseeker_b200.importer import TileProcessor
+    T, L3 = stock_cfg.total_cycles, stock_cfg.threep_length
+    n, pitch = 1000, 1004
+    bcl = torch.zeros((T, pitch), dtype=torch.uint8, device="cuda")
+    cif = torch.zeros((L3, 4, pitch), dtype=torch.int16, device="cuda")
+    p = TileProcessor(stock_cfg)
+    try:
+        with pytest.raises(_lib.TskError, match="16-byte"):
+            p.upload(bcl.data_ptr(), cif.data_ptr(), np.eye(4, dtype=np.float32), nclusters=n, on_device=True,
+                     bcl_pitch=pitch, cif_pitch=pitch)
+    finally:
+        p.close()
