@@ -357,8 +357,12 @@ def main():
                 "fit_cutoffs": stage_ms[5] / max(1, int(stage_runs[5]))},
             "pipeline_algorithmic_gbs_per_gpu": ab["total"] * ntiles / (ms_step * 1e-3) / 1e9,
             "processed_fraction": ab["processed"] / N, "record_slots_per_tile": ab["records"],
-            "note": "K1 %.0f GB/s algorithmic" % (
-                ab["k1"] / (1e-3 * stage_ms[0] / max(1, int(stage_runs[0]))) / 1e9 if stage_ms[0] > 0 else 0)}
+            "other_kernels": {}}
+    for name, key, st in (("k_decode_demux_seed", "k1", 0), ("k_polya_ruler", "ruler", 4)):
+        ms = stage_ms[st] / max(1, int(stage_runs[st]))
+        gbs = ab[key] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        roof["other_kernels"][name] = {"achieved": gbs, "frac": gbs / peak, "ms_per_launch": ms,
+                                       "algorithmic_bytes_per_launch": ab[key]}
     tfile = os.path.join(ROOT, "profiles", "k2_traffic.json")
     if os.path.exists(tfile):
         try:

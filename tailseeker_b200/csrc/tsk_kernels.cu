@@ -176,25 +176,58 @@ k_decode_demux_seed(const __grid_constant__ DevParams P, const TileView tv,
                     const int L = ts + tl - de;
                     const int M = min(P.max_mods, L);
                     const int mlen = max(P.min_polya_len, 1);
-                    int candS[TSK_MAX_MODS], candJ[TSK_MAX_MODS], sfull[TSK_MAX_MODS];
-                    uint8_t codes[TSK_MAX_MODS];
-                    {
-                        int Srun = 0, minS = 0x3fffffff, argj = -1;
-                        const int captop = M + mlen - 1;    /* j below this may be a j_min(i) */
-                        int j = L - 1;
-                        if (P.w_small) {
-                            /* the long stretch above the captured region only carries the running
-                             * sum and its minimum: weights from a byte-permute of five packed int8
-                             * (selector nibbles 8+code replicate the sign) instead of a table load */
+                    int bi = -1, bj = -1, bscore = -1;
+                    int Srun = 0, minS = 0x3fffffff, argj = -1;
+                    const int captop = M + mlen - 1;        /* j below this may be a j_min(i) */
+                    int j = L - 1;
+                    if (P.w_small) {
+                        /* the long stretch above the captured region only carries the running
+                         * sum and its minimum: weights from a byte-permute of five packed int8
+                         * (selector nibbles 8+code replicate the sign) instead of a table load */
 #pragma unroll 4
-                            for (; j >= captop; j--) {
-                                const uint32_t code = tsk_base_code(rd(de + j));
-                                if (Srun <= minS) { minS = Srun; argj = j; }
-                                int wv;     /* prmt, default mode: nibble 8+k = sign of byte k replicated */
-                                asm("prmt.b32 %0, %1, %2, %3;" : "=r"(wv) : "r"(P.wpk_lo), "r"(P.wpk_hi), "r"(code * 0x1111u + 0x8880u));
-                                Srun += wv;
+                        for (; j >= captop; j--) {
+                            const uint32_t code = tsk_base_code(rd(de + j));
+                            if (Srun <= minS) { minS = Srun; argj = j; }
+                            int wv;     /* prmt, default mode: nibble 8+k = sign of byte k replicated */
+                            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(wv) : "r"(P.wpk_lo), "r"(P.wpk_hi), "r"(code * 0x1111u + 0x8880u));
+                            Srun += wv;
+                        }
+                    }
+                    if (mlen - 1 <= 8) {
+                        /* Candidate start i = j is complete at step j: S(i) has just been formed, and
+                         * (min, arg min) of S(j'+1) over j' >= i + mlen - 1 was taken mlen - 1 steps
+                         * earlier -- kept in an eight-deep shift register instead of arrays in local
+                         * memory.  With Vsuf(i) = sum of the non-A weights of positions i..M-1,
+                         * V(i) = V(M) - Vsuf(i), so the start is chosen on g(i) = S(i) - min - Vsuf(i);
+                         * descending i with >= ends on the smallest maximiser, like the ascending
+                         * strict > of the reference. */
+                        const int DL = mlen - 1;
+                        int dS[8], dJ[8], bestg = INT_MIN, Vsuf = 0;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) { dS[k] = 0; dJ[k] = -1; }
+                        for (; j >= 0; j--) {
+                            const uint32_t code = tsk_base_code(rd(de + j));
+                            if (Srun <= minS) { minS = Srun; argj = j; }
+                            int cS = minS, cJ = argj;
+#pragma unroll
+                            for (int k = 0; k < 8; k++)
+                                if (k == DL - 1) { cS = dS[k]; cJ = dJ[k]; }
+#pragma unroll
+                            for (int k = 7; k > 0; k--) { dS[k] = dS[k - 1]; dJ[k] = dJ[k - 1]; }
+                            dS[0] = minS; dJ[0] = argj;
+                            Srun += P.w_polyA[code];
+                            if (j < M) {
+                                Vsuf += P.w_nonA[code];
+                                if (j + DL <= L - 1) {
+                                    const int g = Srun - cS - Vsuf;
+                                    if (g >= bestg) { bestg = g; bi = j; bj = cJ; }
+                                }
                             }
                         }
+                        if (bi >= 0) bscore = Vsuf + bestg;       /* Vsuf is V(M) now */
+                    } else {
+                        int candS[TSK_MAX_MODS], candJ[TSK_MAX_MODS], sfull[TSK_MAX_MODS];
+                        uint8_t codes[TSK_MAX_MODS];
                         for (; j >= 0; j--) {
                             const uint32_t code = tsk_base_code(rd(de + j));
                             if (Srun <= minS) { minS = Srun; argj = j; }
@@ -205,14 +238,14 @@ k_decode_demux_seed(const __grid_constant__ DevParams P, const TileView tv,
                             Srun += P.w_polyA[code];
                             if (j < M) { sfull[j] = Srun; codes[j] = (uint8_t)code; }
                         }
-                    }
-                    int bi = -1, bj = -1, bscore = -1, V = 0;
-                    for (int i = 0; i < M; i++) {
-                        if (i + mlen - 1 <= L - 1) {
-                            const int sc = V + sfull[i] - candS[i];
-                            if (sc > bscore) { bscore = sc; bi = i; bj = candJ[i]; }
+                        int V = 0;
+                        for (int i = 0; i < M; i++) {
+                            if (i + mlen - 1 <= L - 1) {
+                                const int sc = V + sfull[i] - candS[i];
+                                if (sc > bscore) { bscore = sc; bi = i; bj = candJ[i]; }
+                            }
+                            V += P.w_nonA[codes[i]];
                         }
-                        V += P.w_nonA[codes[i]];
                     }
                     int ps = 0, plen = 0;
                     if (bi >= 0 && bscore >= 1 && (bj - bi + 1) >= P.min_polya_len) {

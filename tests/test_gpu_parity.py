@@ -189,6 +189,21 @@ def test_wide_seed_weights(oracle):
         p.close()
 
 
+@pytest.mark.parametrize("minlen,maxmods", [(1, 5), (9, 30), (12, 30), (5, 0)])
+def test_seed_finder_shapes(oracle, minlen, maxmods):
+    """find_polya with other minimum lengths / modification limits: the shift-register form of
+    the seed scan (minimum length <= 9) and its array form (longer)."""
+    from tailseeker_b200.config import stock_config
+    from tailseeker_b200.importer import TileProcessor
+    cfg = stock_config("miseq", minimum_polya_length=minlen, maximum_modifications=maxmods)
+    p = TileProcessor(cfg)
+    try:
+        _, o = _run(p, cfg, oracle, 6000, 40 + minlen)
+        compare_tile(p, cfg, None, o)
+    finally:
+        p.close()
+
+
 def test_firstclusterno_and_pitch(stock_cfg, oracle):
     """Second read block of a tile (global cluster numbers) and padded row pitches."""
     from tailseeker_b200.synth import make_tile
