@@ -1288,11 +1288,53 @@ k_fair_claim(const uint32_t *__restrict__ fair, const uint32_t *__restrict__ buc
     }
 }
 
+/* probe_ranges() by a whole warp (balancer of at most 32 cycles): lane c de-crosstalks balancer
+ * cycle c, the npos largest / nneg smallest values per channel are taken with warp-wide max / min
+ * reductions on order-preserving integer keys (one instance removed per round, so duplicates count
+ * like in the insertion form) and summed in the same order, largest / smallest first.  Unfilled
+ * ranks keep -inf / +inf exactly like the arrays of the sequential form.  Every lane returns the
+ * result. */
+__device__ __forceinline__ int float_key(float x)
+{
+    const int b = __float_as_int(x);
+    return b ^ ((b >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k ^ ((k >> 31) & 0x7fffffff)); }
+
+__device__ __forceinline__ void probe_ranges_warp(const DevParams &P, const int16_t *__restrict__ cifcol, size_t pitch,
+                                                  int blen, float low[4], float bw[4], int lane)
+{
+    float sig[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool mine = lane < blen;
+    if (mine) decrosstalk(sig, cifcol + (size_t)(P.balancer_start + lane) * 4 * pitch, pitch, P.inv);
+    const int kneg = float_key(-CUDART_INF_F), kpos = float_key(CUDART_INF_F);
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) {
+        int kmax = mine ? float_key(sig[ch]) : kneg, kmin = mine ? float_key(sig[ch]) : kpos;
+        float acc = 0.f;
+        for (int r = 0; r < P.nneg; r++) {
+            const int m = __reduce_min_sync(FULL_MASK, kmin);
+            const unsigned who = __ballot_sync(FULL_MASK, kmin == m && m != kpos);
+            if (who && lane == __ffs(who) - 1) kmin = kpos;
+            acc = __fadd_rn(acc, key_float(m));
+        }
+        low[ch] = __fdiv_rn(acc, (float)P.nneg);
+        acc = 0.f;
+        for (int r = 0; r < P.npos; r++) {
+            const int m = __reduce_max_sync(FULL_MASK, kmax);
+            const unsigned who = __ballot_sync(FULL_MASK, kmax == m && m != kneg);
+            if (who && lane == __ffs(who) - 1) kmax = kneg;
+            acc = __fadd_rn(acc, key_float(m));
+        }
+        bw[ch] = __fsub_rn(__fdiv_rn(acc, (float)P.npos), low[ch]);
+    }
+}
+
 /* Recompute the scores of the listed clusters and add `delta` (+1 / -1, as u32) to the
  * negative histogram: accepted clusters of over-subscribed buckets (+1), and inline-sampled
- * clusters that later aborted on dark cycles (-1).  One WARP per listed cluster: the cycles of
- * a cluster are independent once its signal ranges are known, so the lanes take cycles
- * lane, lane+32, ... (the literal arithmetic of the generic path). */
+ * clusters that later aborted on dark cycles (-1).  One CTA per listed cluster: the cycles of
+ * a cluster are independent once its signal ranges are known, so the threads take cycles
+ * tid, tid+128, ... (the literal arithmetic of the generic path). */
 __global__ void __launch_bounds__(TSK_K2_THREADS)
 k_resample_neg(const __grid_constant__ DevParams P, const TileView tv,
                const DevSample *__restrict__ samples, const float *__restrict__ g_tscore,
@@ -1304,8 +1346,8 @@ k_resample_neg(const __grid_constant__ DevParams P, const TileView tv,
     const uint32_t cnt = lists[which];
     const uint32_t *arr = list_array(const_cast<uint32_t *>(lists), which, listcap);
     const int lane = threadIdx.x & 31;
-    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t i = wid; i < cnt; i += nw) {
+    /* one CTA per listed cluster: the lists are short, a cluster's latency is what counts */
+    for (uint32_t i = blockIdx.x; i < cnt; i += gridDim.x) {
         const uint32_t n = arr[i] & 0x7fffffffu;
         const tsk_call call = calls[n];
         const int ts = P.threep_start, tl = P.threep_length, bins = P.bins;
@@ -1315,11 +1357,12 @@ k_resample_neg(const __grid_constant__ DevParams P, const TileView tv,
         int blen = de - ts;
         if (blen > P.balancer_length) blen = P.balancer_length;
         float low[4], bw[4];
-        probe_ranges(P, cifcol, pitch, blen, low, bw);          /* every lane, same addresses */
+        if (blen <= 32) probe_ranges_warp(P, cifcol, pitch, blen, low, bw, lane);
+        else probe_ranges(P, cifcol, pitch, blen, low, bw);        /* every lane, same addresses */
         int insert_len = ts + tl - de;
         const int limit = sh.limit[call.sample];
         if (limit > 0 && limit < insert_len) insert_len = limit;
-        for (int c = ps + lane; c < insert_len; c += 32) {
+        for (int c = ps + (int)threadIdx.x; c < insert_len; c += TSK_K2_THREADS) {
             float es, score;
             const int16_t *p = cifcol + (size_t)(de - ts + c) * 4 * pitch;
             if (score_cycle_generic(P, sh, p, pitch, low, bw, es, score) && !isinf(score))
@@ -1533,9 +1576,9 @@ int tsk_launch_fixups(tsk_ctx *ctx)
         }
         ctx->launches += 1 + 2 * rounds;
     }
-    k_resample_neg<<<148 * 12, TSK_K2_THREADS, 0, st>>>(P, ctx->tile, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
+    k_resample_neg<<<148 * 16, TSK_K2_THREADS, 0, st>>>(P, ctx->tile, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
                                                       ctx->d_neg, ctx->d_lists, listcap, 2, 1u);
-    k_resample_neg<<<148 * 12, TSK_K2_THREADS, 0, st>>>(P, ctx->tile, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
+    k_resample_neg<<<148 * 16, TSK_K2_THREADS, 0, st>>>(P, ctx->tile, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
                                                       ctx->d_neg, ctx->d_lists, listcap, 0, 0xffffffffu);
     ctx->launches += 2;
     TSK_CUDA(cudaGetLastError());
