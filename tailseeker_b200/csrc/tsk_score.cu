@@ -833,10 +833,10 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
  * barcode / PhiX, failed fingerprint or balancer QC, no delimiter: 13 % of the synthetic tile,
  * far more with a large PhiX spike-in).  The TMA box is K2C_W clusters wide starting at the item's
  * first cluster (rounded down to 8) and each lane reads its own column of it; clusters further
- * than K2C_W from there (an item spanning > 89 clusters, i.e. under ~40 % kept) go to the literal kernel.  Nothing is
+ * than K2C_W from there (an item spanning > 121 clusters, i.e. under ~30 % kept) go to the literal kernel.  Nothing is
  * resident: the balancer cycles and then the scored cycles stream through the same ring of two
  * 4-cycle groups (the few cycles both passes need are fetched twice, from L2). ---- */
-#define K2C_W     96                     /* clusters per TMA box */
+#define K2C_W     128                    /* clusters per TMA box */
 #define K2C_CHB   (K2C_W * 2)            /* bytes per channel row */
 #define K2C_ROWB  (4 * K2C_CHB)          /* bytes per cycle and warp */
 
@@ -1548,7 +1548,8 @@ int tsk_launch_score(tsk_ctx *ctx)
             if (make_cif_tensor_map(ctx, &tmap, K2C_W) != 0) return -1;
             k_normalise_score_pack_compact<<<grid, TSK_K2_THREADS, sizeof(K2SmemC), ctx->stream>>>(ctx->dp, a, rcp_maxent, tmap);
         }
-        k_normalise_score_pack_generic<<<8, TSK_K2_THREADS, 0, ctx->stream>>>(ctx->dp, a, 0);
+        /* handed-over clusters: usually none, many on tiles that are mostly dropped clusters */
+        k_normalise_score_pack_generic<<<148 * 2, TSK_K2_THREADS, 0, ctx->stream>>>(ctx->dp, a, 0);
         ctx->launches += 2;
     }
     TSK_CUDA(cudaGetLastError());
