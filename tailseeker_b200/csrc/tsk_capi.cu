@@ -279,7 +279,7 @@ extern "C" int tsk_ctx_destroy(tsk_ctx *ctx)
     void *ptrs[] = {ctx->d_samples, ctx->d_tscore, ctx->d_rcp, ctx->d_bcl_own[0], ctx->d_cif_own[0], ctx->d_bcl_own[1],
                     ctx->d_cif_own[1], ctx->d_calls, ctx->d_kind,
                     ctx->d_bucket, ctx->d_worklist, ctx->d_blkcnt, ctx->d_totals, ctx->d_recbase,
-                    ctx->d_records, ctx->d_scratch, ctx->d_pos, ctx->d_neg, ctx->d_counters, ctx->d_fair,
+                    ctx->d_records, ctx->d_scratch, ctx->d_pos, ctx->d_neg, ctx->d_counters, ctx->d_fair, ctx->d_fairslots,
                     ctx->d_lists, ctx->d_ruler_pos, ctx->d_cutoffs, ctx->d_rlen, ctx->d_rrec,
                     ctx->d_fit_hist, ctx->d_fit_out, ctx->d_ctl_queue, ctx->d_ctl_index, ctx->d_ruler_called};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)

@@ -99,6 +99,7 @@ struct tsk_ctx {
     uint32_t *d_pos, *d_neg;     /* [T][bins] */
     uint32_t *d_counters;        /* [num_samples][6] */
     uint32_t *d_fair;            /* [hash_size] candidate counts per bucket */
+    uint32_t *d_fairslots;  size_t fairslots_cap;   /* [hash_size][fair_max_count] smallest contended clusters per bucket */
     uint32_t *d_lists;           /* undo / contended / accepted lists + their counters */
     /* control classification (tsk_control.cu); allocated only when a control is configured */
     uint32_t *d_ctl_queue;       /* [4]: [1] = next chunk of clusters to look at */

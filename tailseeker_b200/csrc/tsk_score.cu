@@ -1243,48 +1243,53 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
  * ==================================================================================== */
 /* Fair sampling among the clusters of over-subscribed buckets: the reference accepts, per
  * bucket, the first fair_max_count eligible clusters in cluster order (spotanalyzer.c:476-484
- * with threads=1).  max_count rounds; in each round every still-waiting entry bids with
- * atomicMin and the winner of each bucket is accepted.  The bid carries the round in its high
- * bits, counting DOWN, so a later round's bids always undercut the previous winner and the
- * table needs no reset between rounds.  `fair` (the candidate counts, no longer needed) is the
- * bid table. */
-#define FAIR_ROUND_SHIFT 27          /* cluster numbers < 2^27 per block, rounds <= 30 */
-
+ * with threads=1), i.e. the fair_max_count smallest cluster numbers of the bucket's entries in
+ * the contended list.  Each contended bucket owns fair_max_count slots; every entry walks down
+ * its bucket's slots with atomicMin, leaving the smaller value in the slot and carrying the larger
+ * one on -- an insertion sort whose steps are atomic exchanges of a sorted pair, so in any
+ * interleaving slot s ends up with the (s+1)-th smallest number.  An entry is accepted when it
+ * finds its own number in one of the slots. */
 __global__ void __launch_bounds__(256)
-k_fair_init(uint32_t *__restrict__ fair, const uint32_t *__restrict__ bucket,
+k_fair_init(uint32_t *__restrict__ slots, int K, const uint32_t *__restrict__ bucket,
             const uint32_t *__restrict__ lists, uint32_t listcap)
 {
     const uint32_t cnt = lists[1];
     const uint32_t *cont = list_array(const_cast<uint32_t *>(lists), 1, listcap);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x)
-        fair[bucket[cont[i]]] = 0xffffffffu;
-}
-
-__global__ void __launch_bounds__(256)
-k_fair_bid(uint32_t *__restrict__ fair, const uint32_t *__restrict__ bucket,
-           const uint32_t *__restrict__ lists, uint32_t listcap, uint32_t roundkey)
-{
-    const uint32_t cnt = lists[1];
-    const uint32_t *cont = list_array(const_cast<uint32_t *>(lists), 1, listcap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-        const uint32_t e = cont[i];
-        if (!(e & 0x80000000u)) atomicMin(&fair[bucket[e]], roundkey | e);
+        uint32_t *sl = slots + (size_t)bucket[cont[i]] * K;
+        for (int s = 0; s < K; s++) sl[s] = 0xffffffffu;
     }
 }
 
 __global__ void __launch_bounds__(256)
-k_fair_claim(const uint32_t *__restrict__ fair, const uint32_t *__restrict__ bucket,
-             uint32_t *__restrict__ lists, uint32_t listcap, uint32_t roundkey)
+k_fair_insert(uint32_t *__restrict__ slots, int K, const uint32_t *__restrict__ bucket,
+              const uint32_t *__restrict__ lists, uint32_t listcap)
 {
     const uint32_t cnt = lists[1];
-    uint32_t *cont = list_array(lists, 1, listcap);
+    const uint32_t *cont = list_array(const_cast<uint32_t *>(lists), 1, listcap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        uint32_t v = cont[i];
+        uint32_t *sl = slots + (size_t)bucket[v] * K;
+        for (int s = 0; s < K && v != 0xffffffffu; s++) {
+            const uint32_t old = atomicMin(&sl[s], v);
+            v = max(old, v);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_fair_claim(const uint32_t *__restrict__ slots, int K, const uint32_t *__restrict__ bucket,
+             uint32_t *__restrict__ lists, uint32_t listcap)
+{
+    const uint32_t cnt = lists[1];
+    const uint32_t *cont = list_array(lists, 1, listcap);
     uint32_t *acc = list_array(lists, 2, listcap);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
         const uint32_t e = cont[i];
-        if (!(e & 0x80000000u) && fair[bucket[e]] == (roundkey | e)) {
-            acc[atomicAdd(&lists[2], 1u)] = e;
-            cont[i] = e | 0x80000000u;
-        }
+        const uint32_t *sl = slots + (size_t)bucket[e] * K;
+        bool mine = false;
+        for (int s = 0; s < K; s++) mine |= sl[s] == e;
+        if (mine) acc[atomicAdd(&lists[2], 1u)] = e;
     }
 }
 
@@ -1563,19 +1568,19 @@ int tsk_launch_fixups(tsk_ctx *ctx)
     const DevParams &P = ctx->dp;
     const uint32_t listcap = ctx->cap_clusters;
     cudaStream_t st = ctx->stream;
-    int rounds = P.fair_max_count;
-    if (rounds > 30 || N >= (1u << FAIR_ROUND_SHIFT)) {
-        tsk_set_error("fair-sampling-max-count > 30 or more than 2^27 clusters per block is not supported");
-        return -1;
-    }
-    if (rounds > 0) {
-        k_fair_init<<<148, 256, 0, st>>>(ctx->d_fair, ctx->d_bucket, ctx->d_lists, listcap);
-        for (int r = 0; r < rounds; r++) {
-            const uint32_t key = (uint32_t)(rounds - r) << FAIR_ROUND_SHIFT;
-            k_fair_bid<<<148, 256, 0, st>>>(ctx->d_fair, ctx->d_bucket, ctx->d_lists, listcap, key);
-            k_fair_claim<<<148, 256, 0, st>>>(ctx->d_fair, ctx->d_bucket, ctx->d_lists, listcap, key);
+    const int K = P.fair_max_count;
+    if (K > 0) {
+        const size_t need = (size_t)K * (size_t)P.fair_hash_size;
+        if (ctx->fairslots_cap < need) {
+            if (ctx->d_fairslots) cudaFree(ctx->d_fairslots);
+            ctx->d_fairslots = NULL; ctx->fairslots_cap = 0;
+            TSK_CUDA(cudaMalloc(&ctx->d_fairslots, sizeof(uint32_t) * need));
+            ctx->fairslots_cap = need;
         }
-        ctx->launches += 1 + 2 * rounds;
+        k_fair_init<<<148, 256, 0, st>>>(ctx->d_fairslots, K, ctx->d_bucket, ctx->d_lists, listcap);
+        k_fair_insert<<<148, 256, 0, st>>>(ctx->d_fairslots, K, ctx->d_bucket, ctx->d_lists, listcap);
+        k_fair_claim<<<148, 256, 0, st>>>(ctx->d_fairslots, K, ctx->d_bucket, ctx->d_lists, listcap);
+        ctx->launches += 3;
     }
     k_resample_neg<<<148 * 16, TSK_K2_THREADS, 0, st>>>(P, ctx->tile, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
                                                       ctx->d_neg, ctx->d_lists, listcap, 2, 1u);
