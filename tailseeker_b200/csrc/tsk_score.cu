@@ -919,7 +919,7 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
         mbar_arrive_expect_tx(a_full + 8 * slot, K2_GROUP * K2C_ROWB);
         tma_cycle_g2s(a_stage + slot * (K2_GROUP * K2C_ROWB), &tmap, x0, cyc, a_full + 8 * slot);
     };
-    auto stream = [&](const int c0, const int c1, const int cdata, auto &&fn) {
+    auto stream = [&](const int c0, const int c1, const int cdata, auto &&fn, auto &&after_group) {
         const int ng = c1 > c0 ? (c1 - c0 + K2_GROUP - 1) / K2_GROUP : 0;
         const int ngd = cdata > c0 ? min(ng, (cdata - c0 + K2_GROUP - 1) / K2_GROUP) : 0;
         if (lane == 0)
@@ -932,6 +932,7 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
                 if (c0 + g * K2_GROUP + k < c1) fn(c0 + g * K2_GROUP + k, a_stage + (slot * K2_GROUP + k) * K2C_ROWB);
             __syncwarp();
             if (lane == 0 && g + K2_NGROUP < ngd) issue_group(G + g + K2_NGROUP, c0 + (g + K2_NGROUP) * K2_GROUP);
+            after_group(g, ng, min(c0 + g * K2_GROUP + K2_GROUP, c1) - 1);
         }
         G += ngd;
     };
@@ -979,7 +980,7 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
                     }
                 }
             }
-        });
+        }, [](int, int, int) {});
         if (alive) {
 #pragma unroll
             for (int ch = 0; ch < 4; ch++) {
@@ -1144,32 +1145,33 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
         }
         /* ---- stage the packed word; every 8 cycles the emitting lanes' records are written four
          *      at a time, 8 consecutive words (one 32-byte sector) each ---- */
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_mytile + (r & (K2_TILE_CYC - 1)) * 4), "r"(word) : "memory");
-        if ((r & (K2_TILE_CYC - 1)) == K2_TILE_CYC - 1 || r == rend_w - 1) {
-            __syncwarp();
-            const int rbase = r & ~(K2_TILE_CYC - 1);
-            const int l8 = lane & 7;
-            for (int it = 0; it < nflush; it++) {
-                /* next (up to) four emitting lanes: this quarter-warp's is in flushpick */
-                const int p6 = (int)(flushpick >> (6 * it)) & 63;
-                const int pick = p6 == 63 ? -1 : p6;
-                const int src = pick < 0 ? 0 : pick;
-                const unsigned long long ra = __shfl_sync(FULL_MASK, recaddr, src);
-                const int ri = __shfl_sync(FULL_MASK, recinfo, src);
-                const int j = rbase + l8 - (ri & 0xffff);
-                if (pick >= 0 && j >= 0 && j < (ri >> 16) && rbase + l8 <= r) {
-                    uint32_t wv;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv) : "r"(a_tile + (pick * (K2_TILE_CYC + 1) + l8) * 4));
-                    reinterpret_cast<uint32_t *>((uintptr_t)ra)[2 + j] = wv;
-                }
-            }
-            __syncwarp();
-        }
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_mytile + ((r - rbeg_w) & (K2_TILE_CYC - 1)) * 4), "r"(word) : "memory");
         scr += spitch;
+    };
+    /* after every second group (8 cycles) and after the last one: r = last cycle staged */
+    auto flush = [&](const int g, const int ng, const int r) {
+        if (!(g & 1) && g != ng - 1) return;
+        const int rbase = r - ((r - rbeg_w) & (K2_TILE_CYC - 1));     /* cycle in tile column 0 */
+        const int l8 = lane & 7;
+        for (int it = 0; it < nflush; it++) {
+            /* next (up to) four emitting lanes: this quarter-warp's is in flushpick */
+            const int p6 = (int)(flushpick >> (6 * it)) & 63;
+            const int pick = p6 == 63 ? -1 : p6;
+            const int src = pick < 0 ? 0 : pick;
+            const unsigned long long ra = __shfl_sync(FULL_MASK, recaddr, src);
+            const int ri = __shfl_sync(FULL_MASK, recinfo, src);
+            const int j = rbase + l8 - (ri & 0xffff);
+            if (pick >= 0 && j >= 0 && j < (ri >> 16) && rbase + l8 <= r) {
+                uint32_t wv;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv) : "r"(a_tile + (pick * (K2_TILE_CYC + 1) + l8) * 4));
+                reinterpret_cast<uint32_t *>((uintptr_t)ra)[2 + j] = wv;
+            }
+        }
+        __syncwarp();
     };
 
     /* ---- scored cycles ---- */
-    stream(rbeg_w, rend_w, rdata_w, cycle);
+    stream(rbeg_w, rend_w, rdata_w, cycle, flush);
 
     if (!alive) return;
     bool aborted = false;
