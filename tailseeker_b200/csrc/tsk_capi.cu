@@ -258,6 +258,11 @@ extern "C" int tsk_ctx_create(tsk_ctx **out, int device, const tsk_params *param
     TSK_CUDA(cudaMalloc(&ctx->d_totals, sizeof(uint32_t) * (TSK_MAX_SAMPLES + 1)));
     TSK_CUDA(cudaMalloc(&ctx->d_recbase, sizeof(uint64_t) * (TSK_MAX_SAMPLES + 1)));
     TSK_CUDA(cudaMalloc(&ctx->d_cutoffs, sizeof(uint32_t) * TSK_MAX_CUTOFF_CYCLES));
+    TSK_CUDA(cudaStreamCreateWithFlags(&ctx->rstream, cudaStreamNonBlocking));
+    TSK_CUDA(cudaEventCreateWithFlags(&ctx->ev_rul[0], cudaEventDisableTiming));
+    TSK_CUDA(cudaEventCreateWithFlags(&ctx->ev_rul[1], cudaEventDisableTiming));
+    TSK_CUDA(cudaMalloc(&ctx->d_rtotals, sizeof(uint32_t) * (TSK_MAX_SAMPLES + 1)));
+    TSK_CUDA(cudaMalloc(&ctx->d_rrecbase, sizeof(uint64_t) * (TSK_MAX_SAMPLES + 1)));
     TSK_CUDA(cudaMalloc(&ctx->d_ruler_called, sizeof(unsigned long long)));
     TSK_CUDA(cudaMemset(ctx->d_ruler_called, 0, sizeof(unsigned long long)));
     if (params->has_control) {
@@ -276,7 +281,12 @@ extern "C" int tsk_ctx_destroy(tsk_ctx *ctx)
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    void *ptrs[] = {ctx->d_samples, ctx->d_tscore, ctx->d_rcp, ctx->d_bcl_own[0], ctx->d_cif_own[0], ctx->d_bcl_own[1],
+    if (ctx->rstream) {
+        cudaStreamSynchronize(ctx->rstream);
+        cudaStreamDestroy(ctx->rstream);
+        cudaEventDestroy(ctx->ev_rul[0]); cudaEventDestroy(ctx->ev_rul[1]);
+    }
+    void *ptrs[] = {ctx->d_rtotals, ctx->d_rrecbase, ctx->d_samples, ctx->d_tscore, ctx->d_rcp, ctx->d_bcl_own[0], ctx->d_cif_own[0], ctx->d_bcl_own[1],
                     ctx->d_cif_own[1], ctx->d_calls, ctx->d_kind,
                     ctx->d_bucket, ctx->d_worklist, ctx->d_blkcnt, ctx->d_totals, ctx->d_recbase,
                     ctx->d_records, ctx->d_scratch, ctx->d_pos, ctx->d_neg, ctx->d_counters, ctx->d_fair, ctx->d_fairslots,
@@ -403,6 +413,15 @@ static int next_tile(tsk_ctx *ctx)
     return 0;
 }
 
+int tsk_ruler_join(tsk_ctx *ctx)
+{
+    if (ctx->ruler_inflight) {
+        TSK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_rul[1], 0));
+        ctx->ruler_inflight = 0;
+    }
+    return 0;
+}
+
 static int fetch_totals(tsk_ctx *ctx)
 {
     const int S = ctx->dp.num_samples;
@@ -437,6 +456,7 @@ extern "C" int tsk_set_stream(tsk_ctx *ctx, void *cuda_stream)
 {
     if (!ctx) { tsk_set_error("null ctx"); return -1; }
     TSK_CUDA(cudaSetDevice(ctx->device));
+    if (tsk_ruler_join(ctx) != 0) return -1;
     TSK_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)cuda_stream;
@@ -590,7 +610,7 @@ extern "C" int tsk_get_device_ptrs(tsk_ctx *ctx, void **pos_hist, void **neg_his
     if (pos_hist) *pos_hist = ctx->d_pos;
     if (neg_hist) *neg_hist = ctx->d_neg;
     if (counters) *counters = ctx->d_counters;
-    if (ruler_pos_hist) *ruler_pos_hist = ctx->d_ruler_pos;
+    if (ruler_pos_hist) { if (tsk_ruler_join(ctx) != 0) return -1; *ruler_pos_hist = ctx->d_ruler_pos; }
     return 0;
 }
 
@@ -598,6 +618,7 @@ extern "C" int tsk_synchronize(tsk_ctx *ctx)
 {
     if (!ctx) { tsk_set_error("null ctx"); return -1; }
     TSK_CUDA(cudaSetDevice(ctx->device));
+    if (tsk_ruler_join(ctx) != 0) return -1;
     TSK_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -622,6 +643,7 @@ extern "C" int tsk_ruler_hist_reset(tsk_ctx *ctx, int ncutoffs, int dist_samplin
         tsk_set_error("bad argument"); return -1;
     }
     TSK_CUDA(cudaSetDevice(ctx->device));
+    if (tsk_ruler_join(ctx) != 0) return -1;
     const size_t words = (size_t)ncutoffs * dist_sampling_bins;
     if (ensure(&ctx->d_ruler_pos, &ctx->ruler_pos_words, words) != 0) return -1;
     TSK_CUDA(cudaMemsetAsync(ctx->d_ruler_pos, 0, sizeof(uint32_t) * words, ctx->stream));
@@ -635,6 +657,7 @@ extern "C" int tsk_ruler_get_hist(tsk_ctx *ctx, uint32_t *pos)
 {
     if (!ctx || !ctx->d_ruler_pos) { tsk_set_error("no ruler histogram"); return -1; }
     TSK_CUDA(cudaSetDevice(ctx->device));
+    if (tsk_ruler_join(ctx) != 0) return -1;
     TSK_CUDA(cudaMemcpyAsync(pos, ctx->d_ruler_pos, sizeof(uint32_t) * (size_t)ctx->ruler_ncut * ctx->ruler_bins,
                              cudaMemcpyDeviceToHost, ctx->stream));
     TSK_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -647,6 +670,7 @@ static int ruler_prepare(tsk_ctx *ctx, const uint32_t *cutoffs, int ncutoffs, in
     if (ncutoffs < 1 || ncutoffs > TSK_MAX_CUTOFF_CYCLES || bins < 1 || !cutoffs) {
         tsk_set_error("bad ruler argument"); return -1;
     }
+    if (tsk_ruler_join(ctx) != 0) return -1;      /* cutoffs / histogram shape may change below */
     if (!ctx->d_ruler_pos || ctx->ruler_ncut != ncutoffs || ctx->ruler_bins != bins)
         if (tsk_ruler_hist_reset(ctx, ncutoffs, bins) != 0) return -1;
     if (ctx->h_ncut != ncutoffs || memcmp(ctx->h_cutoffs, cutoffs, sizeof(uint32_t) * ncutoffs) != 0) {
@@ -717,11 +741,21 @@ extern "C" int tsk_ruler_tile_all_async(tsk_ctx *ctx, const uint32_t *cutoffs, i
     if (ruler_prepare(ctx, cutoffs, ncutoffs, dist_sampling_bins) != 0) return -1;
     /* a tile has at most one record slot per cluster */
     if (ensure(&ctx->d_rlen, &ctx->rlen_cap, (size_t)ctx->cap_clusters) != 0) return -1;
+    /* the ruler runs on its own stream from here on: the next tile's decode and scan kernels
+     * (main stream) do not wait for it; tsk_launch_import joins before the record slots are reused */
+    TSK_CUDA(cudaMemcpyAsync(ctx->d_rtotals, ctx->d_totals, sizeof(uint32_t) * (TSK_MAX_SAMPLES + 1),
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+    TSK_CUDA(cudaMemcpyAsync(ctx->d_rrecbase, ctx->d_recbase, sizeof(uint64_t) * (TSK_MAX_SAMPLES + 1),
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+    TSK_CUDA(cudaEventRecord(ctx->ev_rul[0], ctx->stream));
+    TSK_CUDA(cudaStreamWaitEvent(ctx->rstream, ctx->ev_rul[0], 0));
     cudaEvent_t *ev = prof_take(ctx, 2, 4);
-    if (ev) TSK_CUDA(cudaEventRecord(ev[0], ctx->stream));
-    if (tsk_launch_ruler_resident(ctx, ncutoffs, minimum_polya_len, downhill_ext_weight, dist_sampling_bins,
+    if (ev) TSK_CUDA(cudaEventRecord(ev[0], ctx->rstream));
+    if (tsk_launch_ruler_resident(ctx, ctx->rstream, ncutoffs, minimum_polya_len, downhill_ext_weight, dist_sampling_bins,
                                   dist_sampling_gap, ctx->d_rlen) != 0) return -1;
-    if (ev) TSK_CUDA(cudaEventRecord(ev[1], ctx->stream));
+    if (ev) TSK_CUDA(cudaEventRecord(ev[1], ctx->rstream));
+    TSK_CUDA(cudaEventRecord(ctx->ev_rul[1], ctx->rstream));
+    ctx->ruler_inflight = 1;
     ctx->rlen_resident = 1;
     return 0;
 }
@@ -730,6 +764,7 @@ extern "C" int tsk_ruler_get_lengths(tsk_ctx *ctx, int16_t *polya_len_out, uint3
 {
     if (need_processed(ctx) != 0) return -1;
     if (!ctx->rlen_resident) { tsk_set_error("tsk_ruler_tile_all_async() has not run on this tile"); return -1; }
+    if (tsk_ruler_join(ctx) != 0) return -1;
     if (!slot_offsets) { tsk_set_error("null argument"); return -1; }
     const int S = ctx->dp.num_samples;
     uint32_t at = 0;
@@ -756,6 +791,7 @@ extern "C" int tsk_ruler_get_called(tsk_ctx *ctx, uint64_t *ncalled)
 {
     if (!ctx || !ncalled) { tsk_set_error("null argument"); return -1; }
     TSK_CUDA(cudaSetDevice(ctx->device));
+    if (tsk_ruler_join(ctx) != 0) return -1;
     unsigned long long v = 0;
     TSK_CUDA(cudaMemcpyAsync(&v, ctx->d_ruler_called, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
     TSK_CUDA(cudaStreamSynchronize(ctx->stream));

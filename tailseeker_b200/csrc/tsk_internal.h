@@ -111,6 +111,14 @@ struct tsk_ctx {
     unsigned long long *d_ruler_called;               /* records measured since the last ruler reset */
     uint32_t h_cutoffs[TSK_MAX_CUTOFF_CYCLES];  int h_ncut;   /* what d_cutoffs currently holds */
     int rlen_resident;           /* d_rlen holds the lengths of every slot of the resident tile */
+    /* tsk_ruler_tile_all_async() runs on its own stream, next to the decode / scan kernels of the
+     * following tile; it reads a snapshot of the slot counts and is joined before that tile's
+     * scoring kernel overwrites the record slots */
+    cudaStream_t rstream;
+    cudaEvent_t ev_rul[2];       /* tile ready for the ruler; ruler done */
+    int ruler_inflight;
+    uint32_t *d_rtotals;         /* [TSK_MAX_SAMPLES + 1] snapshot of d_totals */
+    uint64_t *d_rrecbase;        /* [TSK_MAX_SAMPLES + 1] snapshot of d_recbase */
     int ruler_ncut, ruler_bins;                       /* current shape of the ruler histogram */
     uint32_t *d_cutoffs;         /* [TSK_MAX_CUTOFF_CYCLES] */
     int16_t  *d_rlen;  size_t rlen_cap;
@@ -154,8 +162,9 @@ int tsk_launch_control(tsk_ctx *ctx);
 int tsk_launch_ruler(tsk_ctx *ctx, const uint32_t *d_records, size_t nrecords, int dump_len,
                      int ncutoffs, int min_len, float weight, int bins, float gap,
                      int16_t *d_len_out);
-int tsk_launch_ruler_resident(tsk_ctx *ctx, int ncutoffs, int min_len, float weight, int bins, float gap,
-                              int16_t *d_len_out);
+int tsk_launch_ruler_resident(tsk_ctx *ctx, cudaStream_t st, int ncutoffs, int min_len, float weight, int bins,
+                              float gap, int16_t *d_len_out);
+int tsk_ruler_join(tsk_ctx *ctx);         /* main stream waits for a ruler still running on rstream */
 int tsk_launch_ruler_segs(tsk_ctx *ctx, const uint32_t *d_records, int nseg, const uint32_t *first,
                           const uint64_t *base, const int *dump, int ncutoffs, int min_len, float weight,
                           int bins, float gap, int16_t *d_len_out);

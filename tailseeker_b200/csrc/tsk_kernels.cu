@@ -490,6 +490,7 @@ int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev)
         TSK_CUDA(cudaMemsetAsync(ctx->d_recbase, 0, sizeof(uint64_t) * (S + 1), st));
     }
     if (ev) TSK_CUDA(cudaEventRecord(ev[2], st));
+    if (tsk_ruler_join(ctx) != 0) return -1;     /* the previous tile's ruler still reads the record slots */
     if (tsk_launch_score(ctx) != 0) return -1;
     if (N > 0 && control) TSK_CUDA(cudaStreamWaitEvent(st, ctx->ev_ctl[1], 0));
     if (ev) TSK_CUDA(cudaEventRecord(ev[3], st));

@@ -243,8 +243,8 @@ int tsk_launch_ruler_segs(tsk_ctx *ctx, const uint32_t *d_records, int nseg, con
 
 /* Every record slot of the resident tile, with the per-sample slot counts read on the device
  * (nothing about the tile needs to be known on the host yet). */
-int tsk_launch_ruler_resident(tsk_ctx *ctx, int ncutoffs, int min_len, float weight, int bins, float gap,
-                              int16_t *d_len_out)
+int tsk_launch_ruler_resident(tsk_ctx *ctx, cudaStream_t st, int ncutoffs, int min_len, float weight, int bins,
+                              float gap, int16_t *d_len_out)
 {
     RulerSegs seg;
     seg.nseg = ctx->dp.num_samples;
@@ -253,8 +253,8 @@ int tsk_launch_ruler_resident(tsk_ctx *ctx, int ncutoffs, int min_len, float wei
     if (blocks > maxblocks) blocks = maxblocks;
     if (blocks == 0) return 0;
     const int intbins = (bins % 47 != 0) && (bins % 178481 != 0) && bins <= 65536;
-    k_polya_ruler<<<(unsigned)blocks, RULER_THREADS, 0, ctx->stream>>>(
-        ctx->d_records, seg, ctx->d_totals, ctx->d_recbase, ctx->d_samples, ctx->d_cutoffs, ncutoffs, min_len,
+    k_polya_ruler<<<(unsigned)blocks, RULER_THREADS, 0, st>>>(
+        ctx->d_records, seg, ctx->d_rtotals, ctx->d_rrecbase, ctx->d_samples, ctx->d_cutoffs, ncutoffs, min_len,
         weight, bins, gap, d_len_out, ctx->d_ruler_pos, intbins, ctx->d_ruler_called);
     ctx->launches++;
     TSK_CUDA(cudaGetLastError());
