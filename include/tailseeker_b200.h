@@ -269,6 +269,63 @@ int tsk_fit_cutoffs(tsk_ctx *ctx, const uint64_t *pos, const uint64_t *neg,
                     double search_low, const double *search_high, int nsearch_high,
                     double *cutoffs_out);
 
+/* ---- duplicate collapsing: tailseq-dedup-perfect ------------------------------------- */
+/* Replaces the per-UMI-group loop of src/deduplicator/tailseq-dedup-perfect.c (main()
+ * :368-400, tqueue_append() :168-214, process_tag_duplicates() :277-345, tag priority
+ * :87-105) and, with sort_by_umi, the `sort -t "\t" -k6,6 -k1,1 -k2,2n` that feeds it
+ * (tailseeker/main.py:272-278).  One record = one taginfo line as parse_line() (:216-274)
+ * reads it: flags, poly(A) length, UMI.  Tile name, cluster number and modification text stay
+ * with the caller (they are only printed).
+ *
+ * UMI key: 3 bits per base, first base in the most significant bits of key[0], 21 bases per
+ * word (bit 63 unused), end-of-string 0, A 1, C 2, G 3, N 4, T 5, so comparing (key[0], key[1])
+ * as integers is strcmp() on the strings (what `sort` does in the C locale).  <= 42 bases.
+ * Returns -1 for a longer UMI or another character. */
+#define TSK_DEDUP_MAX_UMI 42
+int tsk_dedup_pack_umi(const char *umi, size_t length, uint64_t key[2]);
+
+typedef struct tsk_dedup tsk_dedup;
+/* Device buffers for up to `capacity` records (< 2^32). */
+int tsk_dedup_create(tsk_dedup **out, int device, uint64_t capacity);
+void tsk_dedup_destroy(tsk_dedup *d);
+/* Host or device pointers, n <= capacity. */
+int tsk_dedup_upload(tsk_dedup *d, uint64_t n, const uint64_t *umi_hi, const uint64_t *umi_lo,
+                     const int32_t *flags, const int32_t *polya);
+/* sort_by_umi == 0: the records are taken in the given order and a group is a run of equal
+ * UMIs, exactly like the reference program reading its (pre-sorted) stdin.
+ * sort_by_umi != 0: records are first ordered by UMI key, ties in the given order (a stable
+ * sort: when the input is the tiles' taginfo files concatenated in (tile, cluster) order this
+ * is the reference's `sort -k6,6 -k1,1 -k2,2n`).  "Position" below means position in that order. */
+int tsk_dedup_run(tsk_dedup *d, int sort_by_umi, uint64_t *n_groups);
+/* Per position p (arrays of n, any may be NULL):
+ *   order[p]       index of the record in the uploaded arrays (p itself without sorting)
+ *   group[p]       number of its UMI group, 0-based in order of appearance (`next_group`, :71)
+ *   trace_value[p] last column of its line in the duplicate trace: -3 dropped for a
+ *                  lower tag priority (:184,208), -2 kept but not the representative (:335),
+ *                  else the poly(A) length reported for the group (:291,335)
+ *   trace_slot[p]  0-based line number of that line in the trace output */
+int tsk_dedup_get_records(tsk_dedup *d, uint32_t *order, uint32_t *group, int32_t *trace_value,
+                          uint32_t *trace_slot);
+/* Per group g (arrays of n_groups, any may be NULL):
+ *   rep[g]    position of the representative: the first highest-priority record nearest to
+ *             the mean poly(A) length of the highest-priority records (:298-315)
+ *   polya[g]  (int)roundf(mean), -1 if the representative's own length is negative (:323);
+ *             the record's own length when kept[g] == 1 (its line is printed as is, :286-287)
+ *   ndup[g]   records in the group (`num_duplicates`)
+ *   kept[g]   records of the highest priority (the queue length at :282) */
+int tsk_dedup_get_groups(tsk_dedup *d, uint32_t *rep, int32_t *polya, uint32_t *ndup, uint32_t *kept);
+/* Positions (ascending) of the records the reference loses: its queue has 2048 slots for the whole
+ * run, grows by half when a record arrives at a full queue, and tqueue_expand() (:142-166) does
+ * not carry the arriving record over, which continues as tile "", cluster 0, flags 0, length 0,
+ * no modifications.  Lengths, representatives and trace values above already account for it; the
+ * caller prints such a record with those empty fields.  At most 56 per run; none unless more than
+ * 2047 records of one UMI share a priority.  positions may be NULL to ask for the count. */
+int tsk_dedup_get_lost(tsk_dedup *d, uint32_t *positions, uint32_t capacity, uint32_t *count);
+/* Device time of the last tsk_dedup_run (CUDA events on its stream): sort, grouping + collapse. */
+int tsk_dedup_elapsed_ms(tsk_dedup *d, float *sort_ms, float *collapse_ms);
+/* Number of kernel launches issued by tsk_dedup_run so far. */
+uint64_t tsk_dedup_launch_count(tsk_dedup *d);
+
 /* ---- stream control (for callers that overlap copies and kernels) -------------------- */
 int tsk_synchronize(tsk_ctx *ctx);
 /* Timed re-run of the kernels of tsk_tile_process() on the resident tile: CUDA events on the

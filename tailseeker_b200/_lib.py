@@ -22,6 +22,8 @@ SYMBOLS = [
     "tsk_launch_count", "tsk_selftest_logf", "tsk_set_stream", "tsk_profile_enable", "tsk_profile_get",
     "tsk_selftest_sweeps", "tsk_debug_force_generic", "tsk_tile_process_async",
     "tsk_ruler_tile_all_async", "tsk_ruler_get_lengths", "tsk_ruler_get_called",
+    "tsk_dedup_pack_umi", "tsk_dedup_create", "tsk_dedup_destroy", "tsk_dedup_upload", "tsk_dedup_run",
+    "tsk_dedup_get_records", "tsk_dedup_get_groups", "tsk_dedup_get_lost", "tsk_dedup_elapsed_ms", "tsk_dedup_launch_count",
 ]
 
 _lib = None
@@ -66,6 +68,19 @@ def load():
     L.tsk_ruler_get_lengths.argtypes = [vp, vp, vp]
     L.tsk_ruler_get_called.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
     L.tsk_ruler_get_hist.argtypes = [vp, vp]
+    u64 = ctypes.c_uint64
+    L.tsk_dedup_pack_umi.argtypes = [ctypes.c_char_p, sz, ctypes.POINTER(u64)]
+    L.tsk_dedup_create.argtypes = [ctypes.POINTER(vp), i32, u64]
+    L.tsk_dedup_destroy.argtypes = [vp]
+    L.tsk_dedup_destroy.restype = None
+    L.tsk_dedup_upload.argtypes = [vp, u64, vp, vp, vp, vp]
+    L.tsk_dedup_run.argtypes = [vp, i32, ctypes.POINTER(u64)]
+    L.tsk_dedup_get_records.argtypes = [vp, vp, vp, vp, vp]
+    L.tsk_dedup_get_groups.argtypes = [vp, vp, vp, vp, vp]
+    L.tsk_dedup_get_lost.argtypes = [vp, vp, u32, ctypes.POINTER(u32)]
+    L.tsk_dedup_elapsed_ms.argtypes = [vp, ctypes.POINTER(f32), ctypes.POINTER(f32)]
+    L.tsk_dedup_launch_count.argtypes = [vp]
+    L.tsk_dedup_launch_count.restype = u64
     L.tsk_fit_cutoffs.argtypes = [vp, vp, vp, i32, i32, ctypes.c_uint64, f64, f64, vp, i32, vp]
     L.tsk_synchronize.argtypes = [vp]
     L.tsk_tile_process_timed.argtypes = [vp, i32, vp]

@@ -102,5 +102,10 @@ int tsk_write_block_outputs(struct host_config *cfg, const tsk_call *calls, uint
 int tsk_write_sigdists(const char *filename_format, const char *type, const uint32_t *counts,
                        int total_cycles, int bins);
 int tsk_write_stats(const char *output, const struct host_config *cfg, const tsk_counters *counters);
+/* one gzip member holding src[0..n) (*out is malloc'ed; level from TSK_GZ_LEVEL), and a few worker
+ * threads over an array of independent tasks */
+struct tsk_task { int (*fn)(void *); void *arg; };
+int tsk_gz_member(const void *src, size_t n, unsigned char **out, size_t *outn);
+int tsk_run_tasks(struct tsk_task *tasks, int ntasks, int nthreads);
 
 #endif

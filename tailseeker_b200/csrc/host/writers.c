@@ -402,3 +402,14 @@ int tsk_write_stats(const char *output, const struct host_config *cfg, const tsk
     fclose(fp);
     return 0;
 }
+
+/* ---- shared with the other host programs ------------------------------------------------ */
+int tsk_gz_member(const void *src, size_t n, unsigned char **out, size_t *outn)
+{
+    return gz_member(src, n, out, outn);
+}
+
+int tsk_run_tasks(struct tsk_task *tasks, int ntasks, int nthreads)
+{
+    return run_tasks((struct task *)tasks, ntasks, nthreads);      /* same layout */
+}

@@ -100,8 +100,29 @@ def control_fixture(name, first=5, length=40, tile_n=2000, tile_seed=303):
     print(name, "reads", len(reads), "aligned", int(decision.sum()), r["stats_csv"].splitlines()[:3])
 
 
+def dedup_fixture(name):
+    """Inputs for tailseq-dedup-perfect and the reference binary's stdout / duplicate trace."""
+    import tempfile
+    from oracle import dedup_oracle
+    assert dedup_oracle.ref_available(), "build oracle/_ref first (make -C oracle ref)"
+    cases = {"mixed": dict(n=2500, seed=11, n_umis=700, big_groups=(300, 70, 40)),
+             "sparse": dict(n=1500, seed=12),
+             "one_group": dict(n=600, seed=13, n_umis=1)}
+    out = {}
+    for key, kw in cases.items():
+        data = dedup_oracle.synth_taginfo(**kw)
+        with tempfile.TemporaryDirectory() as d:
+            so, tr = dedup_oracle.run_reference(data, d)
+        out[key + "_in"], out[key + "_out"], out[key + "_trace"] = _bytes(data), _bytes(so), _bytes(tr)
+        print(name, key, len(data), len(so), len(tr))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+
+
 if __name__ == "__main__":
     assert refrun.available(), "build oracle/_ref first (make -C oracle ref)"
+    if sys.argv[1:] == ["dedup"]:
+        dedup_fixture("dedup_perfect")
+        sys.exit(0)
     if sys.argv[1:] == ["control"]:
         control_fixture("control_reads")
         sys.exit(0)
@@ -110,3 +131,4 @@ if __name__ == "__main__":
                      384, 202, spikein_weight=1.0)
     estimator_fixture("estimator_two_tiles")
     control_fixture("control_reads")
+    dedup_fixture("dedup_perfect")
