@@ -225,8 +225,16 @@ def main():
     ap.add_argument("--clusters-per-tile", type=int, default=CLUSTERS_PER_TILE)
     ap.add_argument("--ref-clusters", type=int, default=100_000,
                     help="clusters in the bounded CPU sample (reference arm / cpu_baseline)")
+    ap.add_argument("--workload", default="import", choices=["import", "dedup"],
+                    help="import (default): the north-star path; dedup: the duplicate-collapsing row (tools/dedup_bench.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    if "--workload" in sys.argv and "dedup" in sys.argv:
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+        import dedup_bench
+        known = ap.parse_known_args()[0]
+        return dedup_bench.main(["--steps", str(known.steps), "--warmup", str(known.warmup)] +
+                                (["--no-cpu-baseline"] if known.no_cpu_baseline else []))
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -27,8 +27,8 @@
  * empty strings (see dd_lost_records()).  Reproduced: the few records that arrive at a queue of
  * exactly one of the possible sizes are listed by the kernel, the host walks them in order.
  *
- * Groups of one record (nearly all) are finished by one lane; groups of 2..32 by one warp with
- * ballots; larger groups by one CTA in two passes of block scans.
+ * Groups of up to 32 records are finished by one lane (the classes above are 32-bit masks and the
+ * counts population counts); larger groups by one CTA in two passes of block scans.
  *
  * Sort: least-significant-digit radix sort, 8 bits a pass, stable (per-warp match_any ranks inside
  * a 256-record tile, tiles of a block in order, block bases from a digit-major histogram scan).
@@ -43,6 +43,8 @@
 #define FULL 0xffffffffu
 #define DD_THREADS 256
 #define DD_WARPS 8
+#define DD_BIG_THREADS 1024                 /* CTA of the large-group kernel */
+#define DD_BIG_WARPS 32
 #define DD_SCAN_ITEMS 8                      /* records per thread in the group-number scan */
 #define DD_SCAN_TILE (DD_THREADS * DD_SCAN_ITEMS)
 #define DD_MAX_EPOCHS 2048
@@ -63,7 +65,7 @@ struct tsk_dedup {
     uint32_t *biglist;                       /* [0] count, then group numbers */
     uint32_t *cands; uint32_t cand_cap;      /* [0] count, then (position, size index) pairs */
     uint32_t *lost; uint32_t nlost;          /* host: positions whose record the reference loses */
-    uint32_t *hist, *partials;
+    uint32_t *hist, *rowtot, *partials;
     uint64_t *varbits;                       /* [2] */
     uint32_t nblk;
     int cur;                                 /* which of the ping-pong buffers holds the sorted keys */
@@ -140,6 +142,27 @@ k_dedup_sort_hist(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ 
     hist[threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
 }
 
+/* digit-major histogram [256][nblk]: block d scans row d in place (exclusive) and leaves the row
+ * total; the scatter kernel adds the exclusive prefix of the 256 totals itself */
+__global__ void __launch_bounds__(DD_THREADS) k_dedup_hist_rowscan(uint32_t *hist, uint32_t nblk, uint32_t *rowtot)
+{
+    __shared__ uint32_t ws[DD_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t *row = hist + (size_t)blockIdx.x * nblk;
+    const uint32_t per = (nblk + DD_THREADS - 1) / DD_THREADS;
+    const uint32_t beg = min(nblk, tid * per), end = min(nblk, beg + per);
+    uint32_t s = 0;
+    for (uint32_t i = beg; i < end; i++) s += row[i];
+    uint32_t inc = s;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += v; }
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    uint32_t run = inc - s;
+    for (int w = 0; w < warp; w++) run += ws[w];
+    for (uint32_t i = beg; i < end; i++) { const uint32_t v = row[i]; row[i] = run; run += v; }
+    if (tid == DD_THREADS - 1) rowtot[blockIdx.x] = run;
+}
+
 /* exclusive scan of `count` u32 in place, one block */
 __global__ void __launch_bounds__(1024) k_dedup_scan_single(uint32_t *data, uint32_t count)
 {
@@ -166,12 +189,23 @@ __global__ void __launch_bounds__(1024) k_dedup_scan_single(uint32_t *data, uint
 __global__ void __launch_bounds__(DD_THREADS)
 k_dedup_sort_scatter(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, const uint32_t *__restrict__ ord,
                      uint64_t *__restrict__ hi2, uint64_t *__restrict__ lo2, uint32_t *__restrict__ ord2,
-                     uint32_t n, int shift, uint32_t chunk, const uint32_t *__restrict__ hist, uint32_t nblk)
+                     uint32_t n, int shift, uint32_t chunk, const uint32_t *__restrict__ hist, uint32_t nblk,
+                     const uint32_t *__restrict__ rowtot)
 {
     __shared__ uint32_t base[256];
     __shared__ uint32_t wcnt[DD_WARPS][256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    base[tid] = hist[tid * nblk + blockIdx.x];
+    {   /* first slot of digit `tid` in this block = records of smaller digits + this digit's in earlier blocks */
+        const uint32_t t = rowtot[tid];
+        uint32_t inc = t;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += v; }
+        if (lane == 31) wcnt[0][warp] = inc;
+        __syncthreads();
+        uint32_t pre = inc - t;
+        for (int w = 0; w < warp; w++) pre += wcnt[0][w];
+        base[tid] = pre + hist[tid * nblk + blockIdx.x];
+        __syncthreads();
+    }
     const uint32_t beg = blockIdx.x * chunk;
     const uint32_t end = (n - beg < chunk) ? n : beg + chunk;
     for (uint32_t t0 = beg; t0 < end; t0 += DD_THREADS) {
@@ -209,18 +243,21 @@ __device__ __forceinline__ bool dd_head(const uint64_t *hi, const uint64_t *lo, 
     return p == 0 || hi[p] != hi[p - 1] || lo[p] != lo[p - 1];
 }
 
+/* a block takes DD_SCAN_TILE positions, a warp 8 rows of 32 consecutive ones (coalesced); a row's
+ * heads are one ballot */
 __global__ void __launch_bounds__(DD_THREADS)
 k_dedup_heads_count(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, uint32_t n, uint32_t *partials)
 {
     __shared__ uint32_t ws[DD_WARPS];
-    const uint32_t t0 = blockIdx.x * DD_SCAN_TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t w0 = blockIdx.x * DD_SCAN_TILE + warp * (32 * DD_SCAN_ITEMS);
     uint32_t c = 0;
+#pragma unroll
     for (int k = 0; k < DD_SCAN_ITEMS; k++) {
-        const uint32_t p = t0 + k * DD_THREADS + threadIdx.x;
-        if (p < n) c += dd_head(hi, lo, p);
+        const uint32_t p = w0 + k * 32 + lane;
+        c += __popc(__ballot_sync(FULL, p < n && dd_head(hi, lo, p)));
     }
-    c = __reduce_add_sync(FULL, c);
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+    if (lane == 0) ws[warp] = c;
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t s = 0;
@@ -239,34 +276,33 @@ k_dedup_heads_apply(const uint64_t *__restrict__ hi, const uint64_t *__restrict_
                     int32_t *__restrict__ prio, int32_t *__restrict__ pa)
 {
     __shared__ uint32_t ws[DD_WARPS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    /* thread owns DD_SCAN_ITEMS consecutive positions */
-    const uint32_t p0 = blockIdx.x * DD_SCAN_TILE + tid * DD_SCAN_ITEMS;
-    bool hd[DD_SCAN_ITEMS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t w0 = blockIdx.x * DD_SCAN_TILE + warp * (32 * DD_SCAN_ITEMS);
+    unsigned heads[DD_SCAN_ITEMS];
     uint32_t c = 0;
 #pragma unroll
     for (int k = 0; k < DD_SCAN_ITEMS; k++) {
-        const uint32_t p = p0 + k;
-        hd[k] = p < n && dd_head(hi, lo, p);
-        c += hd[k];
+        const uint32_t p = w0 + k * 32 + lane;
+        heads[k] = __ballot_sync(FULL, p < n && dd_head(hi, lo, p));
+        c += __popc(heads[k]);
     }
-    uint32_t inc = c;
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += v; }
-    if (lane == 31) ws[warp] = inc;
+    if (lane == 0) ws[warp] = c;
     __syncthreads();
-    uint32_t run = partials[blockIdx.x] + inc - c;            /* partials are already scanned (exclusive) */
+    uint32_t run = partials[blockIdx.x];                      /* already scanned (exclusive) */
     for (int w = 0; w < warp; w++) run += ws[w];
+    const unsigned le = 0xffffffffu >> (31 - lane);
 #pragma unroll
     for (int k = 0; k < DD_SCAN_ITEMS; k++) {
-        const uint32_t p = p0 + k;
-        if (p >= n) break;
-        run += hd[k];
-        const uint32_t g = run - 1;
-        gid[p] = g;
-        if (hd[k]) gstart[g] = p;
-        const uint32_t r = ord ? ord[p] : p;
-        prio[p] = dd_priority(flags[r]);
-        pa[p] = polya[r];
+        const uint32_t p = w0 + k * 32 + lane;
+        if (p < n) {
+            const uint32_t g = run + __popc(heads[k] & le) - 1;
+            gid[p] = g;
+            if ((heads[k] >> lane) & 1u) gstart[g] = p;
+            const uint32_t r = ord ? ord[p] : p;
+            prio[p] = dd_priority(flags[r]);
+            pa[p] = polya[r];
+        }
+        run += __popc(heads[k]);
     }
 }
 
@@ -297,85 +333,77 @@ __device__ __forceinline__ int dd_final_length(int rep_polya, float mean, uint32
     return rep_polya >= 0 ? (int)roundf(mean) : -1;           /* :323 */
 }
 
-/* one group of 2..32 records on one warp */
-__device__ __forceinline__ void dd_warp_group(const DdArgs &A, uint32_t g, uint32_t s, uint32_t m, int lane)
+/* one group of 2..32 records on one lane: the four record classes as bit masks */
+__device__ __forceinline__ void dd_lane_group(const DdArgs &A, uint32_t g, uint32_t s, uint32_t m)
 {
-    const bool act = (uint32_t)lane < m;
-    const int pr = act ? A.prio[s + lane] : -1;
-    const int pa = act ? A.pa[s + lane] : 0;
-    int rmax = pr;
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, rmax, o); if (lane >= o) rmax = max(rmax, v); }
-    int rex = __shfl_up_sync(FULL, rmax, 1);
-    if (lane == 0) rex = -1;
-    const int gmax = __shfl_sync(FULL, rmax, m - 1);
-    const bool imm = act && pr < rex, brk = act && pr > rex, kept = act && pr == gmax;
-    const bool q = act && !imm && !kept;
-    const unsigned Bimm = __ballot_sync(FULL, imm), Bbrk = __ballot_sync(FULL, brk);
-    const unsigned Bq = __ballot_sync(FULL, q), Bk = __ballot_sync(FULL, kept);
-    const unsigned lt = (1u << lane) - 1, le = lt | (1u << lane);
+    unsigned Bimm = 0, Bbrk = 0, Bk = 0;
+    int rmax = -1, sum = 0;
+    for (uint32_t j = 0; j < m; j++) {
+        const int pr = A.prio[s + j];
+        const unsigned bit = 1u << j;
+        if (pr > rmax) { rmax = pr; Bbrk |= bit; Bk = bit; sum = A.pa[s + j]; }
+        else if (pr == rmax) { Bk |= bit; sum += A.pa[s + j]; }
+        else Bimm |= bit;
+    }
+    const unsigned all = 0xffffffffu >> (32 - m);
+    const unsigned Bq = all & ~Bimm & ~Bk;
     const uint32_t nkept = __popc(Bk);
-    const int sum = __reduce_add_sync(FULL, kept ? pa : 0);
     const float mean = __fdiv_rn((float)sum, (float)nkept);                     /* :303 */
-    const float dist = fabsf(__fsub_rn((float)pa, mean));                       /* :307,310 */
-    const unsigned dbits = kept ? __float_as_uint(dist) : 0xffffffffu;
-    const unsigned dmin = __reduce_min_sync(FULL, dbits);
-    const int rep = __ffs(__ballot_sync(FULL, kept && dbits == dmin)) - 1;      /* first strict minimum */
-    const int final_len = dd_final_length(__shfl_sync(FULL, pa, rep), mean, nkept);
-    if (act) {
+    int rep = __ffs(Bk) - 1, rep_pa = 0;
+    {
+        float best = 0.f;
+        bool first = true;
+        for (unsigned rest = Bk; rest; rest &= rest - 1) {
+            const int j = __ffs(rest) - 1;
+            const int pa = A.pa[s + j];
+            const float dist = fabsf(__fsub_rn((float)pa, mean));               /* :307,310 */
+            if (first || dist < best) { best = dist; rep = j; rep_pa = pa; first = false; }
+        }
+    }
+    const int final_len = dd_final_length(rep_pa, mean, nkept);
+    for (uint32_t j = 0; j < m; j++) {
+        const unsigned bit = 1u << j, lt = bit - 1, le = lt | bit;
         uint32_t pos;
         int val = -3;
-        if (imm) {
+        if (Bimm & bit) {
             const int b = 31 - __clz(Bbrk & le);
             pos = __popc(Bimm & lt) + __popc(Bq & ((1u << b) - 1));
-        } else if (q) {
+        } else if (Bq & bit) {
             const int k = __ffs(Bbrk & ~le) - 1;
             pos = __popc(Bimm & ((1u << k) - 1)) + __popc(Bq & lt);
         } else {
             pos = (m - nkept) + __popc(Bk & lt);
-            val = lane == rep ? final_len : -2;
+            val = (int)j == rep ? final_len : -2;
         }
-        A.tval[s + lane] = val;
-        A.tslot[s + lane] = s + pos;
+        A.tval[s + j] = val;
+        A.tslot[s + j] = s + pos;
     }
-    if (lane == 0) {
-        A.rep[g] = s + rep; A.gpolya[g] = final_len; A.ndup[g] = m; A.nkept[g] = nkept;
-    }
+    A.rep[g] = s + rep; A.gpolya[g] = final_len; A.ndup[g] = m; A.nkept[g] = nkept;
 }
 
-/* a warp takes 32 consecutive groups: single records by their lane, 2..32 by the warp, more -> list */
+/* a lane takes a group: single records directly, 2..32 with bit masks, more -> list */
 __global__ void __launch_bounds__(DD_THREADS) k_dedup_collapse(const DdArgs A)
 {
-    const int lane = threadIdx.x & 31;
     const uint32_t ngroups = *A.last_gid + 1;
-    const uint32_t nwarps = (ngroups + 31) / 32;
-    for (uint32_t w = blockIdx.x * DD_WARPS + (threadIdx.x >> 5); w < nwarps; w += gridDim.x * DD_WARPS) {
-        const uint32_t g = w * 32 + lane;
-        uint32_t s = 0, m = 0;
-        if (g < ngroups) { s = A.gstart[g]; m = A.gstart[g + 1] - s; }
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += gridDim.x * blockDim.x) {
+        const uint32_t s = A.gstart[g], m = A.gstart[g + 1] - s;
         if (m == 1) {
             const int pa = A.pa[s];
             A.tval[s] = pa; A.tslot[s] = s;
             A.rep[g] = s; A.gpolya[g] = pa; A.ndup[g] = 1; A.nkept[g] = 1;
-        }
-        unsigned multi = __ballot_sync(FULL, m > 1);
-        while (multi) {
-            const int src = __ffs(multi) - 1;
-            multi &= multi - 1;
-            const uint32_t mm = __shfl_sync(FULL, m, src), ss = __shfl_sync(FULL, s, src);
-            if (mm <= 32) dd_warp_group(A, w * 32 + src, ss, mm, lane);
-            else if (lane == 0) A.biglist[1 + atomicAdd(&A.biglist[0], 1u)] = w * 32 + src;
-        }
+        } else if (m <= 32) dd_lane_group(A, g, s, m);
+        else A.biglist[1 + atomicAdd(&A.biglist[0], 1u)] = g;
     }
 }
 
 struct DdBlock {
-    int wmax[DD_WARPS];
-    unsigned long long wsum[DD_WARPS];
+    int wmax[DD_BIG_WARPS];
+    unsigned long long wsum[DD_BIG_WARPS];
     int cmax;
     unsigned long long carry;
     uint32_t epoch_ci[DD_MAX_EPOCHS + 2], epoch_cq[DD_MAX_EPOCHS + 2], epoch_ce[DD_MAX_EPOCHS + 2];
-    int rmax[DD_WARPS]; unsigned long long rcnt[DD_WARPS]; long long rsum[DD_WARPS];
-    unsigned long long rkey[DD_WARPS];
+    int rmax[DD_BIG_WARPS]; unsigned long long rcnt[DD_BIG_WARPS]; long long rsum[DD_BIG_WARPS];
+    unsigned long long rkey[DD_BIG_WARPS];
 };
 
 /* exclusive running maximum over the block's threads on top of `carry` */
@@ -394,7 +422,7 @@ __device__ __forceinline__ int dd_block_exmax(int v, int carry, int *wmax, int t
     return max(ex, pre);
 }
 
-/* exclusive sum of four 16-bit counters packed in 64 bits (a tile has 256 records) */
+/* exclusive sum of four 16-bit counters packed in 64 bits (a tile has 1024 records) */
 __device__ __forceinline__ unsigned long long dd_block_exsum(unsigned long long v, unsigned long long *wsum, int tid,
                                                              unsigned long long *total)
 {
@@ -404,14 +432,14 @@ __device__ __forceinline__ unsigned long long dd_block_exsum(unsigned long long 
     if (lane == 31) wsum[warp] = inc;
     __syncthreads();
     unsigned long long pre = 0, tot = 0;
-    for (int w = 0; w < DD_WARPS; w++) { if (w < warp) pre += wsum[w]; tot += wsum[w]; }
+    for (int w = 0; w < DD_BIG_WARPS; w++) { if (w < warp) pre += wsum[w]; tot += wsum[w]; }
     __syncthreads();
     *total = tot;
     return pre + inc - v;
 }
 
 /* groups of more than 32 records: one CTA each, two passes over the group */
-__global__ void __launch_bounds__(DD_THREADS) k_dedup_collapse_big(const DdArgs A, const DdSizes Z)
+__global__ void __launch_bounds__(DD_BIG_THREADS) k_dedup_collapse_big(const DdArgs A, const DdSizes Z)
 {
     __shared__ DdBlock sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -425,7 +453,7 @@ __global__ void __launch_bounds__(DD_THREADS) k_dedup_collapse_big(const DdArgs 
         int cmax = -1;
         uint32_t c_imm = 0, c_brk = 0;
         int tmax = -1; uint32_t tcnt = 0; int tsum = 0;
-        for (uint32_t t0 = 0; t0 < m; t0 += DD_THREADS) {
+        for (uint32_t t0 = 0; t0 < m; t0 += DD_BIG_THREADS) {
             const uint32_t j = t0 + tid;
             const bool act = j < m;
             const int pr = act ? A.prio[s + j] : -1;
@@ -445,7 +473,7 @@ __global__ void __launch_bounds__(DD_THREADS) k_dedup_collapse_big(const DdArgs 
             wm = __reduce_max_sync(FULL, wm);
             if (lane == 0) sm.wmax[warp] = wm;
             __syncthreads();
-            for (int w = 0; w < DD_WARPS; w++) cmax = max(cmax, sm.wmax[w]);
+            for (int w = 0; w < DD_BIG_WARPS; w++) cmax = max(cmax, sm.wmax[w]);
             __syncthreads();
         }
         const int gmax = cmax;
@@ -455,7 +483,7 @@ __global__ void __launch_bounds__(DD_THREADS) k_dedup_collapse_big(const DdArgs 
         if (lane == 0) { sm.rcnt[warp] = wc; sm.rsum[warp] = wsu; }
         __syncthreads();
         uint32_t nkept = 0; int sum = 0;
-        for (int w = 0; w < DD_WARPS; w++) { nkept += (uint32_t)sm.rcnt[w]; sum += (int)sm.rsum[w]; }
+        for (int w = 0; w < DD_BIG_WARPS; w++) { nkept += (uint32_t)sm.rcnt[w]; sum += (int)sm.rsum[w]; }
         __syncthreads();
         const float mean = __fdiv_rn((float)sum, (float)nkept);
 
@@ -463,7 +491,7 @@ __global__ void __launch_bounds__(DD_THREADS) k_dedup_collapse_big(const DdArgs 
         cmax = -1; c_imm = 0; c_brk = 0;
         uint32_t c_q = 0, c_k = 0;
         unsigned long long best = ~0ull;
-        for (uint32_t t0 = 0; t0 < m; t0 += DD_THREADS) {
+        for (uint32_t t0 = 0; t0 < m; t0 += DD_BIG_THREADS) {
             const uint32_t j = t0 + tid;
             const bool act = j < m;
             const int pr = act ? A.prio[s + j] : -1;
@@ -508,14 +536,14 @@ __global__ void __launch_bounds__(DD_THREADS) k_dedup_collapse_big(const DdArgs 
             wm = __reduce_max_sync(FULL, wm);
             if (lane == 0) sm.wmax[warp] = wm;
             __syncthreads();
-            for (int w = 0; w < DD_WARPS; w++) cmax = max(cmax, sm.wmax[w]);
+            for (int w = 0; w < DD_BIG_WARPS; w++) cmax = max(cmax, sm.wmax[w]);
             __syncthreads();
         }
         for (int o = 16; o; o >>= 1) { const unsigned long long t = __shfl_xor_sync(FULL, best, o); best = t < best ? t : best; }
         if (lane == 0) sm.rkey[warp] = best;
         __syncthreads();
         if (tid == 0) {
-            for (int w = 1; w < DD_WARPS; w++) best = sm.rkey[w] < best ? sm.rkey[w] : best;
+            for (int w = 1; w < DD_BIG_WARPS; w++) best = sm.rkey[w] < best ? sm.rkey[w] : best;
             const uint32_t rep = (uint32_t)(best & 0xffffffffu);
             const int final_len = dd_final_length(A.pa[s + rep], mean, nkept);
             A.tval[s + rep] = final_len;                      /* after the barrier: overwrites the -2 */
@@ -529,7 +557,7 @@ __global__ void __launch_bounds__(DD_THREADS) k_dedup_collapse_big(const DdArgs 
 static void dd_free(tsk_dedup *d)
 {
     void *bufs[] = {d->kin_hi, d->kin_lo, d->khi[0], d->khi[1], d->klo[0], d->klo[1], d->ord[0], d->ord[1], d->flags, d->polya, d->prio, d->pa,
-                    d->gid, d->gstart, d->tval, d->tslot, d->rep, d->ndup, d->nkept, d->gpolya, d->biglist, d->cands, d->hist,
+                    d->gid, d->gstart, d->tval, d->tslot, d->rep, d->ndup, d->nkept, d->gpolya, d->biglist, d->cands, d->hist, d->rowtot,
                     d->partials, d->varbits};
     for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++) if (bufs[i]) cudaFree(bufs[i]);
     for (int i = 0; i < 3; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
@@ -564,6 +592,7 @@ static int dd_alloc(tsk_dedup *d)
     TSK_CUDA(cudaMalloc(&d->cands, 4 * (1 + 2 * (size_t)d->cand_cap)));
     d->nblk = 148 * 8;
     TSK_CUDA(cudaMalloc(&d->hist, 4 * 256 * (size_t)d->nblk));
+    TSK_CUDA(cudaMalloc(&d->rowtot, 4 * 256));
     TSK_CUDA(cudaMalloc(&d->partials, 4 * (c / DD_SCAN_TILE + 2)));
     TSK_CUDA(cudaMalloc(&d->varbits, 16));
     TSK_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
@@ -624,9 +653,9 @@ static int dd_sort(tsk_dedup *d)
         const uint64_t v = shift < 64 ? var[1] >> shift : var[0] >> (shift - 64);
         if ((v & 0xff) == 0) continue;
         k_dedup_sort_hist<<<nblk, DD_THREADS, 0, d->stream>>>(shi, slo, n, shift, chunk, d->hist, nblk);
-        k_dedup_scan_single<<<1, 1024, 0, d->stream>>>(d->hist, 256 * nblk);
+        k_dedup_hist_rowscan<<<256, DD_THREADS, 0, d->stream>>>(d->hist, nblk, d->rowtot);
         k_dedup_sort_scatter<<<nblk, DD_THREADS, 0, d->stream>>>(shi, slo, sord, d->khi[dst], d->klo[dst], d->ord[dst],
-                                                                 n, shift, chunk, d->hist, nblk);
+                                                                 n, shift, chunk, d->hist, nblk, d->rowtot);
         d->launches += 3;
         shi = d->khi[dst]; slo = d->klo[dst]; sord = d->ord[dst];
         d->cur = dst; dst ^= 1; passes++;
@@ -688,7 +717,7 @@ static int dd_lost_records(tsk_dedup *d, DdArgs a, const DdSizes &z, uint32_t nc
             tsk_set_error("lost-record fix-up failed"); rc = -1;
         } else {
             a.cands = NULL;
-            k_dedup_collapse_big<<<ng < 296 ? ng : 296, DD_THREADS, 0, d->stream>>>(a, z);
+            k_dedup_collapse_big<<<ng < 148 ? ng : 148, DD_BIG_THREADS, 0, d->stream>>>(a, z);
             d->launches++;
             if (cudaStreamSynchronize(d->stream) != cudaSuccess) { tsk_set_error("lost-record fix-up kernel failed"); rc = -1; }
         }
@@ -724,10 +753,10 @@ extern "C" int tsk_dedup_run(tsk_dedup *d, int sort_by_umi, uint64_t *n_groups)
     z.n = 0;
     for (uint64_t sz = 2048; sz <= 0xffffffffull && z.n < DD_MAX_SIZES; sz = (uint64_t)(long long)((float)(long long)sz * 1.5f))
         z.s[z.n++] = (uint32_t)sz;
-    uint32_t grid = ((n + 31) / 32 + DD_WARPS - 1) / DD_WARPS;      /* at most n groups */
+    uint32_t grid = (n + DD_THREADS - 1) / DD_THREADS;              /* at most n groups */
     if (grid > 148 * 8) grid = 148 * 8;
     k_dedup_collapse<<<grid, DD_THREADS, 0, d->stream>>>(a);
-    k_dedup_collapse_big<<<148 * 2, DD_THREADS, 0, d->stream>>>(a, z);
+    k_dedup_collapse_big<<<148, DD_BIG_THREADS, 0, d->stream>>>(a, z);
     d->launches += 6;
     TSK_CUDA(cudaGetLastError());
     uint32_t last = 0, ncand = 0;
