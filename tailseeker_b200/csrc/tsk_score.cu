@@ -859,7 +859,7 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
     const TileView &tv = A.tv;
     const int ts = P.threep_start, tl = P.threep_length, bins = P.bins;
     /* contrast scratch, dense per work item: row i of item w at scratch[(w * (tl + 1) + i) * 32 + lane],
-     * so every row is one full 128-byte line */
+     * so every row starts a 128-byte line */
     const size_t spitch = 32;
     const uint32_t a_stage = smem_u32(&sm.stage[warp][0][0][0]);
     const uint32_t a_full = smem_u32(&sm.bar_full[warp][0]);
@@ -1060,7 +1060,11 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
     double ptotal = 0.;                       /* sum of the scores from the seed start on (KIND_POS lanes) */
     uint32_t dhwin = 0;                       /* bit k = downhill of cycle (c - k); max_mods < 32 */
     /* score of cycle r lives in row (r - start - ps) of the item's scratch block; scr walks one row per cycle */
-    float *const scol = A.scratch + (size_t)(w0 >> 5) * (size_t)(tl + 1) * 32 + lane;
+    /* columns are handed to the KIND_POS lanes only, packed to the left: a row is then a run of
+     * completely written sectors (a sector with unwritten bytes is first filled from DRAM when it
+     * leaves L2: 0.44 GB of reads per tile) and the other lanes' slots cost no traffic at all */
+    float *const scol = A.scratch + (size_t)(w0 >> 5) * (size_t)(tl + 1) * 32 +
+                        __popc(__ballot_sync(FULL_MASK, ispos) & ((1u << lane) - 1));
     float *scr = scol + ((ptrdiff_t)rbeg_w - (start + ps)) * (ptrdiff_t)spitch;
     const uint32_t a_logtab = smem_u32(&sm.sh.logtab[0]), a_tscore = smem_u32(&sm.sh.tscore[0]);
     const uint32_t a_tile = smem_u32(&sm.tile[warp][0][0]);
