@@ -186,53 +186,98 @@ __global__ void __launch_bounds__(1024) k_dedup_scan_single(uint32_t *data, uint
     for (uint32_t i = beg; i < end; i++) { const uint32_t v = data[i]; data[i] = run; run += v; }
 }
 
+/* One pass of the sort.  A block walks its chunk in tiles of DD_SORT_ROWS x 256 records.  Rank of a
+ * record among the tile's records of the same digit (stable: rows in order, warps in order, lanes
+ * in order) from __match_any_sync per warp-row and a running per-digit count; the tile is then put
+ * in digit order in shared memory and written out from there, so that the records of one digit
+ * leave as one run of consecutive addresses (a scattered 8-byte store takes a whole sector slot in
+ * L2: three of those per record made the first version L2-write-bound at 0.30 ms a pass). */
+#define DD_SORT_ROWS 4
+#define DD_SORT_TILE (DD_SORT_ROWS * DD_THREADS)
 __global__ void __launch_bounds__(DD_THREADS)
 k_dedup_sort_scatter(const uint64_t *__restrict__ hi, const uint64_t *__restrict__ lo, const uint32_t *__restrict__ ord,
                      uint64_t *__restrict__ hi2, uint64_t *__restrict__ lo2, uint32_t *__restrict__ ord2,
                      uint32_t n, int shift, uint32_t chunk, const uint32_t *__restrict__ hist, uint32_t nblk,
                      const uint32_t *__restrict__ rowtot)
 {
-    __shared__ uint32_t base[256];
+    __shared__ uint32_t base[256];               /* next global slot of every digit for this block */
+    __shared__ uint32_t tcnt[256];               /* records of the digit in the tile so far */
+    __shared__ uint32_t dstart[256];             /* first staged slot of the digit */
+    __shared__ uint32_t wsum[DD_WARPS];
     __shared__ uint32_t wcnt[DD_WARPS][256];
+    __shared__ uint64_t s_hi[DD_SORT_TILE], s_lo[DD_SORT_TILE];
+    __shared__ uint32_t s_ord[DD_SORT_TILE];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {   /* first slot of digit `tid` in this block = records of smaller digits + this digit's in earlier blocks */
         const uint32_t t = rowtot[tid];
         uint32_t inc = t;
         for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += v; }
-        if (lane == 31) wcnt[0][warp] = inc;
+        if (lane == 31) wsum[warp] = inc;
         __syncthreads();
         uint32_t pre = inc - t;
-        for (int w = 0; w < warp; w++) pre += wcnt[0][w];
+        for (int w = 0; w < warp; w++) pre += wsum[w];
         base[tid] = pre + hist[tid * nblk + blockIdx.x];
         __syncthreads();
     }
     const uint32_t beg = blockIdx.x * chunk;
     const uint32_t end = (n - beg < chunk) ? n : beg + chunk;
-    for (uint32_t t0 = beg; t0 < end; t0 += DD_THREADS) {
+    for (uint32_t t0 = beg; t0 < end; t0 += DD_SORT_TILE) {
+        uint64_t h[DD_SORT_ROWS], l[DD_SORT_ROWS];
+        uint32_t o[DD_SORT_ROWS], rk[DD_SORT_ROWS];
+        unsigned d[DD_SORT_ROWS];
 #pragma unroll
-        for (int w = 0; w < DD_WARPS; w++) wcnt[w][tid] = 0;
-        __syncthreads();
-        const uint32_t i = t0 + tid;
-        const bool act = i < end;
-        uint64_t h = 0, l = 0;
-        uint32_t o = 0;
-        unsigned d = 256;
-        if (act) { h = hi[i]; l = lo[i]; o = ord ? ord[i] : i; d = dd_digit(h, l, shift); }
-        const unsigned peers = __match_any_sync(FULL, d);
-        const unsigned rank = __popc(peers & ((1u << lane) - 1));
-        if (act && rank == 0) wcnt[warp][d] = __popc(peers);
-        __syncthreads();
-        {
-            uint32_t acc = base[tid];
+        for (int k = 0; k < DD_SORT_ROWS; k++) {
+            const uint32_t i = t0 + k * DD_THREADS + tid;
+            d[k] = 256; h[k] = 0; l[k] = 0; o[k] = 0;
+            if (i < end) { h[k] = hi[i]; l[k] = lo[i]; o[k] = ord ? ord[i] : i; d[k] = dd_digit(h[k], l[k], shift); }
+        }
+        tcnt[tid] = 0;
 #pragma unroll
-            for (int w = 0; w < DD_WARPS; w++) { const uint32_t c = wcnt[w][tid]; wcnt[w][tid] = acc; acc += c; }
-            base[tid] = acc;
+        for (int k = 0; k < DD_SORT_ROWS; k++) {
+#pragma unroll
+            for (int w = 0; w < DD_WARPS; w++) wcnt[w][tid] = 0;
+            __syncthreads();
+            const unsigned peers = __match_any_sync(FULL, d[k]);
+            const unsigned rank = __popc(peers & ((1u << lane) - 1));
+            if (d[k] < 256 && rank == 0) wcnt[warp][d[k]] = __popc(peers);
+            __syncthreads();
+            {
+                uint32_t acc = tcnt[tid];
+#pragma unroll
+                for (int w = 0; w < DD_WARPS; w++) { const uint32_t c = wcnt[w][tid]; wcnt[w][tid] = acc; acc += c; }
+                tcnt[tid] = acc;
+            }
+            __syncthreads();
+            rk[k] = d[k] < 256 ? wcnt[warp][d[k]] + rank : 0;
+            __syncthreads();
+        }
+        {   /* staged slot of the first record of every digit: exclusive scan of the tile's counts */
+            const uint32_t t = tcnt[tid];
+            uint32_t inc = t;
+            for (int q = 1; q < 32; q <<= 1) { const uint32_t v = __shfl_up_sync(FULL, inc, q); if (lane >= q) inc += v; }
+            if (lane == 31) wsum[warp] = inc;
+            __syncthreads();
+            uint32_t pre = inc - t;
+            for (int w = 0; w < warp; w++) pre += wsum[w];
+            dstart[tid] = pre;
+            __syncthreads();
+        }
+#pragma unroll
+        for (int k = 0; k < DD_SORT_ROWS; k++)
+            if (d[k] < 256) {
+                const uint32_t at = dstart[d[k]] + rk[k];
+                s_hi[at] = h[k]; s_lo[at] = l[k]; s_ord[at] = o[k];
+            }
+        __syncthreads();
+        const uint32_t cnt = (end - t0 < DD_SORT_TILE) ? end - t0 : DD_SORT_TILE;
+        for (uint32_t i = tid; i < cnt; i += DD_THREADS) {
+            const uint64_t hh = s_hi[i], ll = s_lo[i];
+            const unsigned dg = dd_digit(hh, ll, shift);
+            const uint32_t pos = base[dg] + (i - dstart[dg]);
+            hi2[pos] = hh; lo2[pos] = ll; ord2[pos] = s_ord[i];
         }
         __syncthreads();
-        if (act) {
-            const uint32_t pos = wcnt[warp][d] + rank;
-            hi2[pos] = h; lo2[pos] = l; ord2[pos] = o;
-        }
+        base[tid] += tcnt[tid];
         __syncthreads();
     }
 }
@@ -643,7 +688,7 @@ static int dd_sort(tsk_dedup *d)
     uint32_t nblk = (n + 2047) / 2048;
     if (nblk > d->nblk) nblk = d->nblk;
     uint32_t chunk = (n + nblk - 1) / nblk;
-    chunk = (chunk + DD_THREADS - 1) / DD_THREADS * DD_THREADS;
+    chunk = (chunk + DD_SORT_TILE - 1) / DD_SORT_TILE * DD_SORT_TILE;
     nblk = (n + chunk - 1) / chunk;
     /* the first pass reads the uploaded keys, later ones alternate between the two work buffers */
     const uint64_t *shi = d->kin_hi, *slo = d->kin_lo;

@@ -133,7 +133,7 @@ def main(argv=None):
         "stages_ms": {"umi_radix_sort": float(np.mean(ms_sort)), "group_scan_collapse": float(np.mean(ms_col))},
         "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
-                     "note": "algorithmic bytes = 40 B per record + 16 B per group; the 12-pass radix sort moves about 60 B per record and pass"},
+                     "note": "algorithmic bytes = 40 B per record + 16 B per group; the 12-pass radix sort moves about 45 B per record and pass (histogram read + scatter)"},
         "e2e": {"value": n / e2e_s, "unit": "records/s", "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 16 * n + 16 * int(ng)},
         "gpu_launches": int(launches),
     }
