@@ -227,6 +227,9 @@ def main():
                     help="clusters in the bounded CPU sample (reference arm / cpu_baseline)")
     ap.add_argument("--workload", default="import", choices=["import", "dedup"],
                     help="import (default): the north-star path; dedup: the duplicate-collapsing row (tools/dedup_bench.py)")
+    ap.add_argument("--layout", default="miseq", choices=["miseq", "hiseq"],
+                    help="read layout of the synthetic run; miseq (default) is the configuration the metric is quoted on, "
+                         "hiseq = BASELINE.json configs[2] (use --clusters-per-tile 3100000 for its tile size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     if "--workload" in sys.argv and "dedup" in sys.argv:
@@ -255,9 +258,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = stock_config("miseq", phix_match_name="PhiX")
+    cfg = stock_config(args.layout, phix_match_name="PhiX")
     T, L3, bins = cfg.total_cycles, cfg.threep_length, cfg.dist_sampling_bins
     ntiles, N = args.tiles, args.clusters_per_tile
+    workload = WORKLOAD if (args.layout, ntiles, N) == ("miseq", TILES_PER_GPU, CLUSTERS_PER_TILE) else (
+        "%s layout: %d tiles x %d clusters per GPU, %d cycles, 4 exp + 7 spike-in samples, [control] PhiX"
+        % (args.layout, ntiles, N, T))
 
     proc = TileProcessor(cfg, device=local_rank)
     stream = torch.cuda.current_stream()
@@ -454,7 +460,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "tiles_per_gpu": ntiles, "clusters_per_tile": N,
+                "config": {"workload": workload, "tiles_per_gpu": ntiles, "clusters_per_tile": N,
                            "l2": "inputs_larger_than_L2 (2.5 GB per tile, streamed once)",
                            "polya_called_per_step": int(measured) * world,
                            "cutoffs_fitted": int(np.isfinite(fit).sum())},
