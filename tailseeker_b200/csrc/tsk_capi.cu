@@ -338,8 +338,8 @@ static int ensure_cluster_buffers(tsk_ctx *ctx, uint32_t n)
     ctx->rec_cap_words = (size_t)cap * (size_t)(2 + ctx->maxdump);
     TSK_CUDA(cudaMalloc(&ctx->d_records, sizeof(uint32_t) * ctx->rec_cap_words));
     ctx->scratch_cap = (size_t)cap * (size_t)maxinsert;
-    TSK_CUDA(cudaMalloc(&ctx->d_scratch, sizeof(float) * ctx->scratch_cap));
-    TSK_CUDA(cudaMalloc(&ctx->d_lists, sizeof(uint32_t) * (16 + 4 * (size_t)cap)));
+    TSK_CUDA(cudaMalloc(&ctx->d_scratch, sizeof(float) * 2 * ctx->scratch_cap));   /* second half: handed-over clusters */
+    TSK_CUDA(cudaMalloc(&ctx->d_lists, sizeof(uint32_t) * (16 + 6 * (size_t)cap)));      /* tsk_score.cu: six arrays */
     ctx->cap_clusters = cap;
     return 0;
 }

@@ -95,7 +95,7 @@ struct tsk_ctx {
     uint32_t *d_totals;          /* [num_samples+1] */
     uint64_t *d_recbase;         /* [num_samples+1] word offset of each sample's slots */
     uint32_t *d_records;  size_t rec_cap_words;
-    float    *d_scratch;  size_t scratch_cap;   /* [maxinsert][N] scores of KIND_POS clusters */
+    float    *d_scratch;  size_t scratch_cap;   /* 2 x scratch_cap floats: per-cycle scores that are read back (tsk_score.cu) */
     uint32_t *d_pos, *d_neg;     /* [T][bins] */
     uint32_t *d_counters;        /* [num_samples][6] */
     uint32_t *d_fair;            /* [hash_size] candidate counts per bucket */

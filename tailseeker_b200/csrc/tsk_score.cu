@@ -53,11 +53,18 @@ __device__ __forceinline__ int score_bin(float score, int bins)
 }
 
 /* list area layout (u32): [0] undo count, [1] contended count, [2] accepted count,
- * [3] slow-path count, then four arrays of `cap` entries */
+ * [3] slow-path count, then six arrays of `cap` entries */
 __device__ __forceinline__ uint32_t *list_array(uint32_t *lists, int which, uint32_t cap)
 {
     return lists + 16 + (size_t)which * cap;
 }
+
+/* Lists: 0 inline-sampled clusters that aborted later, 1 clusters of over-subscribed
+ * fair-sampling buckets ("contenders"), 2 the contenders that were accepted, 3 clusters handed to
+ * the literal kernel; 4 and 5 run parallel to 1 and 2 and hold the offset (in floats) of the
+ * cluster's score column in the scratch block, or TSK_NO_COLUMN. */
+#define TSK_NO_COLUMN 0xffffffffu
+struct ScoreArgs;
 
 /* ======================================================================================
  * generic path: literal restatement
@@ -207,6 +214,13 @@ struct ScoreArgs {
     uint32_t listcap;
 };
 
+__device__ __forceinline__ void append_contender(const ScoreArgs &A, uint32_t n, uint32_t column)
+{
+    const uint32_t k = atomicAdd(&A.lists[1], 1u);
+    list_array(A.lists, 1, A.listcap)[k] = n;
+    list_array(A.lists, 4, A.listcap)[k] = column;
+}
+
 /* Everything the reference does for one cluster inside process_polya_signal() after the
  * sequence seed, for work item w. */
 __device__ void process_item_generic(const DevParams &P, const ScoreShared &sh, const ScoreArgs &A,
@@ -301,7 +315,7 @@ __device__ void process_item_generic(const DevParams &P, const ScoreShared &sh, 
         if (aborted && neg_inline)
             list_array(A.lists, 0, A.listcap)[atomicAdd(&A.lists[0], 1u)] = n;
         else if (!aborted && !neg_inline)
-            list_array(A.lists, 1, A.listcap)[atomicAdd(&A.lists[1], 1u)] = n;
+            append_contender(A, n, TSK_NO_COLUMN);
     }
 
     if ((kd & KIND_POS) && !aborted && scan_len > 0 && P.cctr_left + P.cctr_right < scan_len) {
@@ -777,7 +791,7 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
         if (aborted && neg_inline)
             list_array(A.lists, 0, A.listcap)[atomicAdd(&A.lists[0], 1u)] = n;
         else if (!aborted && !neg_inline)
-            list_array(A.lists, 1, A.listcap)[atomicAdd(&A.lists[1], 1u)] = n;
+            append_contender(A, n, TSK_NO_COLUMN);
     }
 
     /* ---- contrast test (find_max_cumulative_contrast) and positive sampling ----
@@ -1060,11 +1074,16 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
     double ptotal = 0.;                       /* sum of the scores from the seed start on (KIND_POS lanes) */
     uint32_t dhwin = 0;                       /* bit k = downhill of cycle (c - k); max_mods < 32 */
     /* score of cycle r lives in row (r - start - ps) of the item's scratch block; scr walks one row per cycle */
-    /* columns are handed to the KIND_POS lanes only, packed to the left: a row is then a run of
+    /* columns are handed only to the lanes whose scores are read back, packed to the left: a row is then a run of
      * completely written sectors (a sector with unwritten bytes is first filled from DRAM when it
      * leaves L2: 0.44 GB of reads per tile) and the other lanes' slots cost no traffic at all */
+    /* a KIND_NEG lane of an over-subscribed fair-sampling bucket keeps its scores too: if it is
+     * accepted afterwards they are sampled from here instead of being computed again from
+     * intensities that have long left the caches (k_sample_neg_columns) */
+    const bool negdefer = (kd & KIND_NEG) && !neg_inline;
+    const bool needcol = ispos || negdefer;
     float *const scol = A.scratch + (size_t)(w0 >> 5) * (size_t)(tl + 1) * 32 +
-                        __popc(__ballot_sync(FULL_MASK, ispos) & ((1u << lane) - 1));
+                        __popc(__ballot_sync(FULL_MASK, needcol) & ((1u << lane) - 1));
     float *scr = scol + ((ptrdiff_t)rbeg_w - (start + ps)) * (ptrdiff_t)spitch;
     const uint32_t a_logtab = smem_u32(&sm.sh.logtab[0]), a_tscore = smem_u32(&sm.sh.tscore[0]);
     const uint32_t a_tile = smem_u32(&sm.tile[warp][0][0]);
@@ -1139,10 +1158,8 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
                 s = min(s, TSK_SCORE_MAX);
                 /* packet j = c - ps carries downhill[j], the UN-offset array (spotanalyzer.c:604-606) */
                 word = lit ? ((s << 1) | ((dhwin >> ps) & 1u)) : 0u;
-                if (ispos) {
-                    *scr = score;
-                    ptotal = __dadd_rn(ptotal, (double)score);      /* same order as the reference's cumsum */
-                }
+                if (needcol) *scr = score;
+                if (ispos) ptotal = __dadd_rn(ptotal, (double)score);      /* same order as the reference's cumsum */
                 if (neg_inline && lit && !isinf(score))
                     atomicAdd(&A.neg[(size_t)(ts + r) * bins + score_bin(score, bins)], 1u);
             }
@@ -1194,7 +1211,7 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
         if (aborted && neg_inline)
             list_array(A.lists, 0, A.listcap)[atomicAdd(&A.lists[0], 1u)] = n;
         else if (!aborted && !neg_inline)
-            list_array(A.lists, 1, A.listcap)[atomicAdd(&A.lists[1], 1u)] = n;
+            append_contender(A, n, (uint32_t)(scol - A.scratch));
     }
 
     /* ---- contrast test (find_max_cumulative_contrast) and positive sampling ----
@@ -1276,6 +1293,10 @@ k_fair_insert(uint32_t *__restrict__ slots, int K, const uint32_t *__restrict__ 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
         uint32_t v = cont[i];
         uint32_t *sl = slots + (size_t)bucket[v] * K;
+        /* slots only ever decrease: an entry above the current last slot cannot end up in one.
+         * Saves the same-address atomics of a bucket shared by thousands of low-diversity reads
+         * (4 ns each, serialised: 0.9 ms on a 3.1 M-cluster tile). */
+        if (v > __ldcg(&sl[K - 1])) continue;
         for (int s = 0; s < K && v != 0xffffffffu; s++) {
             const uint32_t old = atomicMin(&sl[s], v);
             v = max(old, v);
@@ -1295,7 +1316,11 @@ k_fair_claim(const uint32_t *__restrict__ slots, int K, const uint32_t *__restri
         const uint32_t *sl = slots + (size_t)bucket[e] * K;
         bool mine = false;
         for (int s = 0; s < K; s++) mine |= sl[s] == e;
-        if (mine) acc[atomicAdd(&lists[2], 1u)] = e;
+        if (mine) {
+            const uint32_t k = atomicAdd(&lists[2], 1u);
+            acc[k] = e;
+            list_array(lists, 5, listcap)[k] = list_array(lists, 4, listcap)[i];
+        }
     }
 }
 
@@ -1346,7 +1371,7 @@ __device__ __forceinline__ void probe_ranges_warp(const DevParams &P, const int1
  * clusters that later aborted on dark cycles (-1).  One CTA per listed cluster: the cycles of
  * a cluster are independent once its signal ranges are known, so the threads take cycles
  * tid, tid+128, ... (the literal arithmetic of the generic path). */
-__global__ void __launch_bounds__(TSK_K2_THREADS)
+__global__ void __launch_bounds__(TSK_K2_THREADS, 6)      /* latency-bound (scattered column reads): warps over registers */
 k_resample_neg(const __grid_constant__ DevParams P, const TileView tv,
                const DevSample *__restrict__ samples, const float *__restrict__ g_tscore,
                const tsk_call *__restrict__ calls, uint32_t *__restrict__ neg,
@@ -1358,7 +1383,9 @@ k_resample_neg(const __grid_constant__ DevParams P, const TileView tv,
     const uint32_t *arr = list_array(const_cast<uint32_t *>(lists), which, listcap);
     const int lane = threadIdx.x & 31;
     /* one CTA per listed cluster: the lists are short, a cluster's latency is what counts */
+    const uint32_t *column = which == 2 ? list_array(const_cast<uint32_t *>(lists), 5, listcap) : nullptr;
     for (uint32_t i = blockIdx.x; i < cnt; i += gridDim.x) {
+        if (column && column[i] != TSK_NO_COLUMN) continue;      /* sampled by k_sample_neg_columns */
         const uint32_t n = arr[i] & 0x7fffffffu;
         const tsk_call call = calls[n];
         const int ts = P.threep_start, tl = P.threep_length, bins = P.bins;
@@ -1378,6 +1405,35 @@ k_resample_neg(const __grid_constant__ DevParams P, const TileView tv,
             const int16_t *p = cifcol + (size_t)(de - ts + c) * 4 * pitch;
             if (score_cycle_generic(P, sh, p, pitch, low, bw, es, score) && !isinf(score))
                 atomicAdd(&neg[(size_t)(de + c) * bins + score_bin(score, bins)], delta);
+        }
+    }
+}
+
+/* Accepted clusters of over-subscribed buckets whose scores the scoring kernel kept: one warp per
+ * cluster walks its scratch column (row i = cycle de + ps + i) and adds the bins, NaN = dark cycle
+ * and infinite scores skipped like in the inline form. */
+__global__ void __launch_bounds__(256)
+k_sample_neg_columns(const __grid_constant__ DevParams P, const DevSample *__restrict__ samples,
+                     const tsk_call *__restrict__ calls, const float *__restrict__ scratch,
+                     uint32_t *__restrict__ neg, const uint32_t *__restrict__ lists, uint32_t listcap)
+{
+    const uint32_t cnt = lists[2];
+    const uint32_t *arr = list_array(const_cast<uint32_t *>(lists), 2, listcap);
+    const uint32_t *column = list_array(const_cast<uint32_t *>(lists), 5, listcap);
+    const int lane = threadIdx.x & 31, bins = P.bins;
+    for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < cnt; i += gridDim.x * (blockDim.x >> 5)) {
+        const uint32_t off = column[i];
+        if (off == TSK_NO_COLUMN) continue;
+        const tsk_call call = calls[arr[i]];
+        const int de = call.delimiter_end, ps = call.terminal_mods;
+        int insert_len = P.threep_start + P.threep_length - de;
+        const int limit = samples[call.sample].limit_threep;
+        if (limit > 0 && limit < insert_len) insert_len = limit;
+        const float *col = scratch + off;
+        for (int k = lane; k < insert_len - ps; k += 32) {
+            const float score = col[(size_t)k * 32];
+            if (score == score && !isinf(score))
+                atomicAdd(&neg[(size_t)(de + ps + k) * bins + score_bin(score, bins)], 1u);
         }
     }
 }
@@ -1559,8 +1615,13 @@ int tsk_launch_score(tsk_ctx *ctx)
             if (make_cif_tensor_map(ctx, &tmap, K2C_W) != 0) return -1;
             k_normalise_score_pack_compact<<<grid, TSK_K2_THREADS, sizeof(K2SmemC), ctx->stream>>>(ctx->dp, a, rcp_maxent, tmap);
         }
-        /* handed-over clusters: usually none, many on tiles that are mostly dropped clusters */
-        k_normalise_score_pack_generic<<<148 * 2, TSK_K2_THREADS, 0, ctx->stream>>>(ctx->dp, a, 0);
+        /* handed-over clusters: usually none, many on tiles that are mostly dropped clusters.
+         * They keep their scores in the second half of the scratch buffer: the first half still
+         * holds the columns of the over-subscribed fair-sampling buckets' clusters, which are
+         * sampled after the fix-ups (k_sample_neg_columns) */
+        ScoreArgs ah = a;
+        ah.scratch = ctx->d_scratch + ctx->scratch_cap;
+        k_normalise_score_pack_generic<<<148 * 2, TSK_K2_THREADS, 0, ctx->stream>>>(ctx->dp, ah, 0);
         ctx->launches += 2;
     }
     TSK_CUDA(cudaGetLastError());
@@ -1588,11 +1649,13 @@ int tsk_launch_fixups(tsk_ctx *ctx)
         k_fair_claim<<<148, 256, 0, st>>>(ctx->d_fairslots, K, ctx->d_bucket, ctx->d_lists, listcap);
         ctx->launches += 3;
     }
+    k_sample_neg_columns<<<148 * 8, 256, 0, st>>>(P, ctx->d_samples, ctx->d_calls, ctx->d_scratch, ctx->d_neg,
+                                                  ctx->d_lists, listcap);
     k_resample_neg<<<148 * 16, TSK_K2_THREADS, 0, st>>>(P, ctx->tile, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
                                                       ctx->d_neg, ctx->d_lists, listcap, 2, 1u);
     k_resample_neg<<<148 * 16, TSK_K2_THREADS, 0, st>>>(P, ctx->tile, ctx->d_samples, ctx->d_tscore, ctx->d_calls,
                                                       ctx->d_neg, ctx->d_lists, listcap, 0, 0xffffffffu);
-    ctx->launches += 2;
+    ctx->launches += 3;
     TSK_CUDA(cudaGetLastError());
     return 0;
 }

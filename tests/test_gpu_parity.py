@@ -175,6 +175,24 @@ def test_nondefault_parameters(oracle):
         p.close()
 
 
+@pytest.mark.parametrize("buckets,maxcount,mode", [(64, 5, 0), (64, 5, 2), (7, 3, 0), (4096, 1, 0), (4096, 1, 1)])
+def test_fair_sampling_contention(oracle, buckets, maxcount, mode):
+    """A tiny hash space: nearly every negative candidate sits in an over-subscribed bucket, so the
+    first `maxcount` of each bucket in cluster order are found by the slot walk and sampled
+    afterwards -- from the scratch columns the compact kernel keeps (mode 0), or re-scored from
+    the intensities (row form, literal kernel)."""
+    from tailseeker_b200.config import stock_config
+    from tailseeker_b200.importer import TileProcessor
+    cfg = stock_config("miseq", fair_sampling_hash_space_size=buckets, fair_sampling_max_count=maxcount)
+    p = TileProcessor(cfg)
+    try:
+        p.force_generic(mode)
+        _, o = _run(p, cfg, oracle, 9000, 31, lowdiv_frac=0.05, dark_cluster_frac=0.02)
+        compare_tile(p, cfg, None, o)
+    finally:
+        p.close()
+
+
 def test_wide_seed_weights(oracle):
     """find_polya weights that do not fit the packed int8 form of the seed scan."""
     from tailseeker_b200.config import stock_config
