@@ -22,6 +22,22 @@
 
 #define MAX_LINE_LEN 511          /* the reference's fgets() buffer (:42,369) */
 
+/* TSK_HOST_TIMING=1: wall time of each phase on stderr */
+#include <time.h>
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+static int timing_on = -1;
+static double t_last;
+static void phase(const char *what)
+{
+    if (timing_on < 0) { timing_on = getenv("TSK_HOST_TIMING") != NULL; t_last = now_s(); }
+    if (timing_on) { const double t = now_s(); fprintf(stderr, "[timing] %-28s %.3f s\n", what, t - t_last); t_last = t; }
+}
+
 struct rec_table {
     const char *buf;
     size_t nlines;
@@ -262,12 +278,6 @@ static void *boot_cuda(void *arg)
     return NULL;
 }
 
-static int cmp_emit(const void *a, const void *b)
-{
-    const uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
-    return x < y ? -1 : x > y;
-}
-
 int main(int argc, char *argv[])
 {
     int sort = 0, argi = 1, rc = -1;
@@ -281,7 +291,6 @@ int main(int argc, char *argv[])
     uint32_t *order = NULL, *group = NULL, *tslot = NULL, *slot_at = NULL, *rep = NULL, *ndup = NULL, *kept = NULL, *emit = NULL;
     int32_t *tval = NULL, *gpolya = NULL;
     uint8_t *lost = NULL;
-    uint64_t *emitkey = NULL;
 
     if (argi < argc && strcmp(argv[argi], "--sort") == 0) { sort = 1; argi++; }
     if (argi < argc) tracefn = argv[argi];
@@ -295,7 +304,9 @@ int main(int argc, char *argv[])
         tracef = fopen(tracefn, "wb");
         if (!tracef) { fprintf(stderr, "ERROR: Cannot open %s.", tracefn); goto done; }
     }
+    phase("start");
     buf = read_all(stdin, &len);
+    phase("read stdin");
     if (!buf) { perror("tailseq-dedup-perfect"); goto done; }
     if (ferror(stdin)) { perror("fgets"); goto done; }
     if (build_table(&t, buf, len) != 0) { perror("tailseq-dedup-perfect"); goto done; }
@@ -305,14 +316,17 @@ int main(int argc, char *argv[])
         fprintf(stderr, "Could not parse line %ld: %.*s%s%s\n", t.bad_line, (int)((e ? e : buf + len) - ln), ln,
                 t.error[0] ? " -- " : "", t.error);
     }
+    phase("index + parse lines");
     if (boot.started) { pthread_join(boot.th, NULL); boot.started = 0; }
     if (boot.rc != 0) { fprintf(stderr, "%s\n", boot.error); goto done; }
+    phase("wait for the CUDA context");
 
     const size_t n = t.nlines;
     uint64_t ngroups = 0;
     if (n > 0) {
         if (tsk_dedup_create(&d, boot.device, n) != 0 || tsk_dedup_upload(d, n, t.khi, t.klo, t.flags, t.polya) != 0 ||
             tsk_dedup_run(d, sort, &ngroups) != 0) { fprintf(stderr, "%s\n", tsk_last_error()); goto done; }
+        phase("upload + sort + collapse");
         order = malloc(4 * n); group = malloc(4 * n); tval = malloc(4 * n); tslot = malloc(4 * n);
         rep = malloc(4 * ngroups); gpolya = malloc(4 * ngroups); ndup = malloc(4 * ngroups); kept = malloc(4 * ngroups);
         emit = malloc(4 * ngroups);
@@ -326,23 +340,29 @@ int main(int argc, char *argv[])
             if (!lost) { perror("tailseq-dedup-perfect"); goto done; }
             for (uint32_t i = 0; i < nlost; i++) lost[order[lostpos[i]]] = 1;
         }
+        phase("fetch results");
         /* stdout order: groups as they come (reference), or by the representative's place in the input */
         if (sort) {
-            emitkey = malloc(8 * ngroups);
-            if (!emitkey) { perror("tailseq-dedup-perfect"); goto done; }
-            for (uint64_t g = 0; g < ngroups; g++) emitkey[g] = ((uint64_t)order[rep[g]] << 32) | g;
-            qsort(emitkey, ngroups, 8, cmp_emit);
-            for (uint64_t g = 0; g < ngroups; g++) emit[g] = (uint32_t)emitkey[g];
+            /* one pass over the input positions: group whose representative sits there, if any */
+            uint32_t *at = calloc(n, 4);
+            if (!at) { perror("tailseq-dedup-perfect"); goto done; }
+            for (uint64_t g = 0; g < ngroups; g++) at[order[rep[g]]] = (uint32_t)g + 1;
+            uint64_t k = 0;
+            for (size_t i = 0; i < n; i++) if (at[i]) emit[k++] = at[i] - 1;
+            free(at);
         } else
             for (uint64_t g = 0; g < ngroups; g++) emit[g] = (uint32_t)g;
+        phase("output order");
         struct fmt_ctx c = {&t, order, group, NULL, tval, rep, ndup, kept, emit, gpolya, lost};
         if (emit_all(&c, ngroups, 0, stdout) != 0) { perror("tailseq-dedup-perfect"); goto done; }
+        phase("format + write stdout");
         if (tracef) {
             slot_at = malloc(4 * n);
             if (!slot_at) { perror("tailseq-dedup-perfect"); goto done; }
             for (size_t p = 0; p < n; p++) slot_at[tslot[p]] = (uint32_t)p;
             c.slot_at = slot_at;
             if (emit_all(&c, n, 1, tracef) != 0) { perror("tailseq-dedup-perfect"); goto done; }
+            phase("format + compress trace");
         }
     }
     if (tracef && n == 0) {                                   /* an empty gzip stream, like bgzf_close() on nothing */
@@ -357,8 +377,9 @@ done:
     if (tracef && fclose(tracef) != 0) rc = -1;
     if (d) tsk_dedup_destroy(d);
     free(order); free(group); free(tval); free(tslot); free(slot_at); free(rep); free(gpolya); free(ndup); free(kept);
-    free(emit); free(emitkey); free(lost);
+    free(emit); free(lost);
     free_table(&t);
     free(buf);
+    phase("clean up");
     return rc;
 }

@@ -17,7 +17,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
 hi, lo, flags, polya = dedup_bench.synth_keys(n, seed=3)
 text = dedup_bench.keys_to_text(hi, lo, flags, polya)
 threads = os.cpu_count() or 1
-env = dict(os.environ, LC_ALL="C", TSK_SHIM_GZ_LEVEL="1", TSK_GZ_LEVEL="1")
+env = dict(os.environ, LC_ALL="C", TSK_SHIM_GZ_LEVEL="1", TSK_GZ_LEVEL="1", TSK_HOST_TIMING="1")
 with tempfile.TemporaryDirectory(dir="/dev/shm") as d:
     src = os.path.join(d, "in.txt")
     open(src, "wb").write(text)
