@@ -1158,8 +1158,10 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
                 s = min(s, TSK_SCORE_MAX);
                 /* packet j = c - ps carries downhill[j], the UN-offset array (spotanalyzer.c:604-606) */
                 word = lit ? ((s << 1) | ((dhwin >> ps) & 1u)) : 0u;
-                if (needcol) *scr = score;
-                if (ispos) ptotal = __dadd_rn(ptotal, (double)score);      /* same order as the reference's cumsum */
+                if (needcol) {      /* one predicate: the sum is only used by the KIND_POS lanes */
+                    *scr = score;
+                    ptotal = __dadd_rn(ptotal, (double)score);      /* same order as the reference's cumsum */
+                }
                 if (neg_inline && lit && !isinf(score))
                     atomicAdd(&A.neg[(size_t)(ts + r) * bins + score_bin(score, bins)], 1u);
             }
