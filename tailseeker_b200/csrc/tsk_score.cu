@@ -1077,11 +1077,13 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
     /* columns are handed only to the lanes whose scores are read back, packed to the left: a row is then a run of
      * completely written sectors (a sector with unwritten bytes is first filled from DRAM when it
      * leaves L2: 0.44 GB of reads per tile) and the other lanes' slots cost no traffic at all */
-    /* a KIND_NEG lane of an over-subscribed fair-sampling bucket keeps its scores too: if it is
-     * accepted afterwards they are sampled from here instead of being computed again from
-     * intensities that have long left the caches (k_sample_neg_columns) */
-    const bool negdefer = (kd & KIND_NEG) && !neg_inline;
-    const bool needcol = ispos || negdefer;
+    /* KIND_NEG lanes keep their scores too.  Those that may be sampled at once (neg_inline) are
+     * sampled after the loop by the whole warp, 32 cycles of one cluster at a time: inside the
+     * loop the bin + RED sequence ran every cycle for the one lane in five that needed it (5.6 %
+     * of the kernel's instructions), and a cluster that aborted on dark cycles had to be taken
+     * out again afterwards.  Those of over-subscribed fair-sampling buckets are sampled after
+     * the fix-ups, if accepted (k_sample_neg_columns). */
+    const bool needcol = ispos || (kd & KIND_NEG) != 0;
     float *const scol = A.scratch + (size_t)(w0 >> 5) * (size_t)(tl + 1) * 32 +
                         __popc(__ballot_sync(FULL_MASK, needcol) & ((1u << lane) - 1));
     float *scr = scol + ((ptrdiff_t)rbeg_w - (start + ps)) * (ptrdiff_t)spitch;
@@ -1162,8 +1164,6 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
                     *scr = score;
                     ptotal = __dadd_rn(ptotal, (double)score);      /* same order as the reference's cumsum */
                 }
-                if (neg_inline && lit && !isinf(score))
-                    atomicAdd(&A.neg[(size_t)(ts + r) * bins + score_bin(score, bins)], 1u);
             }
         }
         /* ---- stage the packed word; every 8 cycles the emitting lanes' records are written four
@@ -1196,6 +1196,26 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
     /* ---- scored cycles ---- */
     stream(rbeg_w, rend_w, rdata_w, cycle, flush);
 
+    /* ---- negative sampling (spotanalyzer.c:589-599) of the lanes that need no fair-sampling
+     *      decision and did not abort: the warp walks each such lane's column ---- */
+    __syncwarp();                                   /* the columns were written by other lanes */
+    for (unsigned todo = __ballot_sync(FULL_MASK, alive && neg_inline && !(ndark > 0 && ndark >= P.max_dark_cycles)); todo; todo &= todo - 1) {
+        const int src = __ffs(todo) - 1;
+        const float *col = reinterpret_cast<const float *>((uintptr_t)__shfl_sync(FULL_MASK, (unsigned long long)(uintptr_t)scol, src));
+        const int len = __shfl_sync(FULL_MASK, scan_len, src);
+        const int row0 = __shfl_sync(FULL_MASK, de + ps, src);
+        for (int k0 = lane; k0 < len; k0 += 256) {
+            float sc[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++)             /* eight independent loads in flight */
+                sc[j] = (k0 + 32 * j < len) ? col[(size_t)(k0 + 32 * j) * spitch] : CUDART_NAN_F;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (sc[j] == sc[j] && !isinf(sc[j]))    /* NaN = dark cycle */
+                    atomicAdd(&A.neg[(size_t)(row0 + k0 + 32 * j) * bins + score_bin(sc[j], bins)], 1u);
+        }
+    }
+
     if (!alive) return;
     bool aborted = false;
     if (ndark > 0) {
@@ -1209,12 +1229,7 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
         }
         *reinterpret_cast<uint4 *>(&A.calls[n]) = *reinterpret_cast<const uint4 *>(&call);
     }
-    if (kd & KIND_NEG) {
-        if (aborted && neg_inline)
-            list_array(A.lists, 0, A.listcap)[atomicAdd(&A.lists[0], 1u)] = n;
-        else if (!aborted && !neg_inline)
-            append_contender(A, n, (uint32_t)(scol - A.scratch));
-    }
+    if ((kd & KIND_NEG) && !aborted && !neg_inline) append_contender(A, n, (uint32_t)(scol - A.scratch));
 
     /* ---- contrast test (find_max_cumulative_contrast) and positive sampling ----
      * f(i) = cum_i/i - (total-cum_i)/(len-i).  The divisions are replaced by table reciprocals
