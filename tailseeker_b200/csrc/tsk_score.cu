@@ -1122,7 +1122,10 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
                 nrm[ch] = fmaxf(div_by_rcp(__fsub_rn(sig[ch], low[ch]), bw[ch], ybw[ch]), 0.f);
             const float sum = __fadd_rn(__fadd_rn(__fadd_rn(nrm[0], nrm[1]), nrm[2]), nrm[3]);
             float prob[4];
-            if (__builtin_expect(in_exp_range(sum, -60, 60), 1)) {
+            /* sum == 0 (every channel at or below its floor: a dark cycle) takes the fast path too:
+             * rcp(0) = inf, the refinement turns it into NaN, and so does 0 x NaN in the division --
+             * the NaN that IEEE 0/0 gives, which is all that is looked at */
+            if (__builtin_expect(in_exp_range(sum, -60, 60) || sum == 0.f, 1)) {
                 const float ys = rcp_rn_fast(sum);
 #pragma unroll
                 for (int ch = 0; ch < 4; ch++) prob[ch] = div_by_rcp(nrm[ch], sum, ys);
