@@ -1219,6 +1219,9 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
         }
     }
 
+    /* the rest is per lane; the lanes meet again for the positive sampling */
+    bool do_pos = false;
+    [&]() {
     if (!alive) return;
     bool aborted = false;
     if (ndark > 0) {
@@ -1275,8 +1278,27 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
             } else {
                 atpos = contrast_exact(col, spitch, scan_len, left, P.cctr_right, total, &contrast);
             }
-            if (atpos >= P.boundary_pos && contrast >= P.required_contrast)
-                sample_positive(P, col, spitch, scan_len, ps, de + ps, A.pos);
+            do_pos = atpos >= P.boundary_pos && contrast >= P.required_contrast;
+        }
+    }
+    }();
+
+    /* ---- positive sampling (add_polya_score_sample, spotanalyzer.c:441-457) of the lanes whose
+     *      contrast test passed: like the negative one, the warp walks one cluster at a time ---- */
+    for (unsigned todo = __ballot_sync(FULL_MASK, do_pos); todo; todo &= todo - 1) {
+        const int src = __ffs(todo) - 1;
+        const float *col = reinterpret_cast<const float *>((uintptr_t)__shfl_sync(FULL_MASK, (unsigned long long)(uintptr_t)scol, src));
+        const int take = __shfl_sync(FULL_MASK, -ps + min(scan_len, P.boundary_pos - P.sampling_gap), src);
+        const int row0 = __shfl_sync(FULL_MASK, de + ps, src);
+        for (int k0 = lane; k0 < take; k0 += 128) {
+            float sc[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                sc[j] = (k0 + 32 * j < take) ? col[(size_t)(k0 + 32 * j) * spitch] : CUDART_NAN_F;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (sc[j] == sc[j] && !isinf(sc[j]))
+                    atomicAdd(&A.pos[(size_t)(row0 + k0 + 32 * j) * bins + score_bin(sc[j], bins)], 1u);
         }
     }
 }
