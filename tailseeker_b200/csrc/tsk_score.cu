@@ -1249,24 +1249,38 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
         if (total == total) {        /* a NaN anywhere makes the first candidate NaN: no sampling */
             double cum = 0., m1 = -CUDART_INF, m2 = -CUDART_INF, cum1 = 0.;
             int at = left - 1;
-            for (int i0 = 0; i0 <= last; i0 += 16) {
-                float v8[16];
+            /* three stretches, so that the long one carries no per-element range tests (they cost
+             * a third of the scan's instructions): positions before the first candidate only add
+             * up; whole batches of sixteen candidates; the ragged end */
+            int i0 = 0;
+            for (; i0 < left - 1; i0 += 8) {
+                float x[8];
 #pragma unroll
-                for (int k = 0; k < 16; k++)      /* sixteen independent loads in flight */
-                    v8[k] = (i0 + k <= last) ? col[(size_t)(i0 + k) * spitch] : 0.f;
+                for (int k = 0; k < 8; k++) x[k] = (i0 + k < left - 1) ? col[(size_t)(i0 + k) * spitch] : 0.f;
 #pragma unroll
-                for (int k = 0; k < 16; k++) {
-                    const int i = i0 + k;
-                    if (i <= last) {
-                        cum = __dadd_rn(cum, (double)v8[k]);
-                        if (i >= left - 1) {
-                            const double v = __dsub_rn(__dmul_rn(cum, __ldg(A.rcp + i)),
-                                                       __dmul_rn(__dsub_rn(total, cum), __ldg(A.rcp + (scan_len - i))));
-                            if (v > m1) { m2 = m1; m1 = v; at = i; cum1 = cum; }
-                            else if (v > m2) m2 = v;
-                        }
-                    }
-                }
+                for (int k = 0; k < 8; k++) if (i0 + k < left - 1) cum = __dadd_rn(cum, (double)x[k]);
+            }
+            auto candidate = [&](const int i, const float x) {
+                cum = __dadd_rn(cum, (double)x);
+                const double v = __dsub_rn(__dmul_rn(cum, __ldg(A.rcp + i)),
+                                           __dmul_rn(__dsub_rn(total, cum), __ldg(A.rcp + (scan_len - i))));
+                if (v > m1) { m2 = m1; m1 = v; at = i; cum1 = cum; }
+                else if (v > m2) m2 = v;
+            };
+            for (i0 = left - 1; i0 + 15 <= last; i0 += 16) {
+                const float *p = col + (size_t)i0 * spitch;
+                float x[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) x[k] = p[(size_t)k * spitch];      /* sixteen independent loads in flight */
+#pragma unroll
+                for (int k = 0; k < 16; k++) candidate(i0 + k, x[k]);
+            }
+            if (i0 <= last) {
+                float x[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) x[k] = (i0 + k <= last) ? col[(size_t)(i0 + k) * spitch] : 0.f;
+#pragma unroll
+                for (int k = 0; k < 16; k++) if (i0 + k <= last) candidate(i0 + k, x[k]);
             }
             float contrast;
             int atpos;
