@@ -34,6 +34,8 @@ __device__ __forceinline__ int mismatch3(uint32_t a, uint32_t b)
     return __popc(x);
 }
 
+template <int N> struct tsk_int { static constexpr int value = N; };
+
 __global__ void __launch_bounds__(TSK_K1_THREADS)
 k_decode_demux_seed(const __grid_constant__ DevParams P, const TileView tv,
                     const DevSample *__restrict__ g_samples,
@@ -202,27 +204,43 @@ k_decode_demux_seed(const __grid_constant__ DevParams P, const TileView tv,
                          * descending i with >= ends on the smallest maximiser, like the ascending
                          * strict > of the reference. */
                         const int DL = mlen - 1;
-                        int dS[8], dJ[8], bestg = INT_MIN, Vsuf = 0;
+                        int bestg = INT_MIN, Vsuf = 0;
+                        /* one instance per register depth: with the depth a compile-time constant
+                         * the tap is a plain register and only DL - 1 moves are left (the
+                         * run-time select over eight taps was 11 % of this kernel's instructions
+                         * and 21 % of its stall samples) */
+                        auto lower = [&](auto depth) {
+                            constexpr int D = decltype(depth)::value;
+                            int dS[D > 0 ? D : 1], dJ[D > 0 ? D : 1];
 #pragma unroll
-                        for (int k = 0; k < 8; k++) { dS[k] = 0; dJ[k] = -1; }
-                        for (; j >= 0; j--) {
-                            const uint32_t code = tsk_base_code(rd(de + j));
-                            if (Srun <= minS) { minS = Srun; argj = j; }
-                            int cS = minS, cJ = argj;
+                            for (int k = 0; k < (D > 0 ? D : 1); k++) { dS[k] = 0; dJ[k] = -1; }
+                            for (; j >= 0; j--) {
+                                const uint32_t code = tsk_base_code(rd(de + j));
+                                if (Srun <= minS) { minS = Srun; argj = j; }
+                                const int cS = D > 0 ? dS[D > 0 ? D - 1 : 0] : minS, cJ = D > 0 ? dJ[D > 0 ? D - 1 : 0] : argj;
 #pragma unroll
-                            for (int k = 0; k < 8; k++)
-                                if (k == DL - 1) { cS = dS[k]; cJ = dJ[k]; }
-#pragma unroll
-                            for (int k = 7; k > 0; k--) { dS[k] = dS[k - 1]; dJ[k] = dJ[k - 1]; }
-                            dS[0] = minS; dJ[0] = argj;
-                            Srun += P.w_polyA[code];
-                            if (j < M) {
-                                Vsuf += P.w_nonA[code];
-                                if (j + DL <= L - 1) {
-                                    const int g = Srun - cS - Vsuf;
-                                    if (g >= bestg) { bestg = g; bi = j; bj = cJ; }
+                                for (int k = (D > 0 ? D : 1) - 1; k > 0; k--) { dS[k] = dS[k - 1]; dJ[k] = dJ[k - 1]; }
+                                dS[0] = minS; dJ[0] = argj;
+                                Srun += P.w_polyA[code];
+                                if (j < M) {
+                                    Vsuf += P.w_nonA[code];
+                                    if (j + D <= L - 1) {
+                                        const int g = Srun - cS - Vsuf;
+                                        if (g >= bestg) { bestg = g; bi = j; bj = cJ; }
+                                    }
                                 }
                             }
+                        };
+                        switch (DL) {
+                        case 0: lower(tsk_int<0>{}); break;
+                        case 1: lower(tsk_int<1>{}); break;
+                        case 2: lower(tsk_int<2>{}); break;
+                        case 3: lower(tsk_int<3>{}); break;
+                        case 4: lower(tsk_int<4>{}); break;
+                        case 5: lower(tsk_int<5>{}); break;
+                        case 6: lower(tsk_int<6>{}); break;
+                        case 7: lower(tsk_int<7>{}); break;
+                        default: lower(tsk_int<8>{}); break;
                         }
                         if (bi >= 0) bscore = Vsuf + bestg;       /* Vsuf is V(M) now */
                     } else {
