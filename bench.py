@@ -55,7 +55,7 @@ def measured_peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -70,13 +70,26 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "200"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    @staticmethod
+    def _when(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, t0=None, t1=None):
+        """Median SM clock and throttle reasons of the samples taken in [t0, t1] (host clock), the
+        timed region; the sampler is started before the warm-up steps because nvidia-smi needs a
+        few hundred ms to deliver its first sample and the timed region of the device-resident run
+        is shorter than that.  Without a sample inside the window the ones taken during the
+        warm-up steps (same kernels, same load) are reported and `window` says so."""
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": "timed"}
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -88,6 +101,13 @@ class ClockSampler:
             os.unlink(self.path)
         except OSError:
             rows = []
+        if t0 is not None and t1 is not None:
+            inside = [r for r in rows if len(r) >= 9 and (self._when(r[0]) or 0) >= t0 and (self._when(r[0]) or 0) <= t1]
+            if inside:
+                rows = inside
+            else:
+                out["window"] = "warmup+timed"
+                rows = [r for r in rows if len(r) >= 9 and (self._when(r[0]) or t1 + 1) <= t1]
         sm, reasons = [], set()
         for r in rows:
             if len(r) < 9:
@@ -321,6 +341,8 @@ def main():
 
     # ---- warm-up, then K timed steps (device-resident inputs) --------------------------------
     proc.ruler_reset(T)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         measured, fit = device_step()
     # byte accounting + per-stage timing from a representative pass (tile 0 calls)
@@ -334,16 +356,15 @@ def main():
 
     proc.profile(True)
     launches0 = proc.launch_count()
-    sampler = ClockSampler(local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    sampler.start()
+    t_begin = time.time()
     e0.record(stream)
     for _ in range(args.steps):
         measured, fit = device_step()
     e1.record(stream)
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, time.time())
     ms_total = e0.elapsed_time(e1)
     launches = proc.launch_count() - launches0
     stage_ms, stage_runs = proc.profile_get()
