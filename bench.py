@@ -487,7 +487,8 @@ def main():
                            "cutoffs_fitted": int(np.isfinite(fit).sum())},
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"],
-                           "reasons": clocks["reasons"], "samples": clocks["samples"]}}
+                           "reasons": clocks["reasons"], "samples": clocks["samples"],
+                           "window": clocks.get("window", "timed")}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
