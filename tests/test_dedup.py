@@ -77,3 +77,35 @@ def test_parse_taginfo_columns():
     assert c["flags"].tolist() == [9, 17] and c["polya"].tolist() == [30, -1]
     assert c["mods"] == [b"TT", b""] and c["umi"] == [b"ACGT", b"NNNN"]
     assert c["head"] == [b"a1101\t7\t9\t30\tTT", b"b2101\t12\t17\t-1\t"]
+
+
+def test_c_umi_packing_matches_the_python_mirror():
+    """tsk_dedup_pack_umi() is a host function of the library: no GPU needed."""
+    import ctypes
+    from tailseeker_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(9)
+    umis = [bytes(rng.choice(np.frombuffer(b"ACGNT", np.uint8), int(rng.integers(0, 43)))) for _ in range(300)]
+    hi, lo = dedup.pack_umis(umis)
+    key = (ctypes.c_uint64 * 2)()
+    for i, u in enumerate(umis):
+        assert L.tsk_dedup_pack_umi(u, len(u), key) == 0
+        assert (key[0], key[1]) == (int(hi[i]), int(lo[i])), u
+    assert L.tsk_dedup_pack_umi(b"A" * 43, 43, key) == -1 and b"42" in L.tsk_last_error()
+    assert L.tsk_dedup_pack_umi(b"ACGU", 4, key) == -1 and b"ACGNT" in L.tsk_last_error()
+
+
+def test_dedup_has_no_cpu_path(tmp_path):
+    """Without a B200 the library entry points and the drop-in program fail with a message."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from tailseeker_b200 import _lib
+    with pytest.raises(_lib.TskError):
+        dedup.Deduplicator(16)
+    prog = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tailseeker_b200", "bin",
+                        "tailseq-dedup-perfect")
+    if os.access(prog, os.X_OK):
+        r = subprocess.run([prog], input=b"a1101\t1\t1\t30\tTT\tACGT\n", capture_output=True)
+        assert r.returncode != 0 and r.stdout == b"" and b"no CPU path" in r.stderr
