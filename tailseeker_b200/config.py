@@ -218,6 +218,8 @@ class ImporterConfig:
     signal: str = "signals/{name}_{tile}.sigpack"
     signal_dists: str = "sigdists-r00/{posneg}_{tile}.sigdists"
     stats: str = "stats/signal-proc-{tile}.csv"
+    # [alternative_calls]: (first cycle, 1-based; FASTQ path) in INI order (parseconfig.c:153-185)
+    alternative_calls: Tuple[Tuple[int, str], ...] = ()
     # [control]
     phix_match_name: str = ""          # "" = no control (parseconfig.c:576)
     phix_match_start: int = 6
@@ -284,7 +286,8 @@ class ImporterConfig:
                  "stats = %s\n" % (self._tile(self.seqqual), self._tile(self.taginfo),
                                    self._tile(self.signal), self._tile(self.signal_dists),
                                    self._tile(self.stats)))
-        o.append("[alternative_calls]\n")
+        o.append("[alternative_calls]\n" +
+                 "".join("%d = %s\n" % (first, path) for first, path in self.alternative_calls))
         if self.phix_match_name:
             o.append("[control]\nphix-match-name = %s\nphix-match-start = %d\n"
                      "phix-match-length = %d\n" % (self.phix_match_name, self.phix_match_start,

@@ -108,8 +108,13 @@ static int feed(void *user, const char *section, const char *name, const char *v
         else if (IS("length-dists")) c->length_dists_output = strdup(value);
         else UNKNOWN("output");
     } else if (SEC("alternative_calls")) {
+        struct host_altcall *ac;
         if (atoi(name) <= 0) { fprintf(stderr, "Alternative call position is out of range.\n"); return -1; }
-        c->altcalls_given = 1;
+        ac = calloc(1, sizeof(*ac));
+        if (!ac || !(ac->filename = strdup(value))) { perror("alternative_calls"); free(ac); return -1; }
+        ac->first_cycle = atoi(name) - 1;
+        ac->next = c->altcalls;
+        c->altcalls = ac;
     } else if (SEC("control")) {
         if (IS("phix-match-name")) { strncpy(c->control_name, value, TSK_NAME_MAX - 1); }
         else if (IS("phix-match-start")) c->control_first_cycle = atoi(value) - 1;
@@ -260,6 +265,11 @@ void tsk_free_config(struct host_config *c)
     free(c->datadir); free(c->laneid); free(c->threep_colormatrix_filename);
     free(c->seqqual_output); free(c->taginfo_output); free(c->signal_output);
     free(c->signal_dists_output); free(c->stats_output); free(c->length_dists_output);
+    while (c->altcalls) {
+        struct host_altcall *n = c->altcalls->next;
+        free(c->altcalls->filename); free(c->altcalls);
+        c->altcalls = n;
+    }
     while (c->samples) {
         struct host_sample *n = c->samples->next;
         free(c->samples->index); free(c->samples->delimiter); free(c->samples->fingerprint);

@@ -140,6 +140,7 @@ static int process(struct host_config *cfg, struct ctx_boot *boot, const float *
         togo -= count;
     }
     printf("%sClearing\n", msgprefix);
+    if (tsk_check_tile_end(tf) < 0) goto done;
     if (!ctx && !(ctx = await_context(boot))) goto done;      /* a tile without clusters */
     if (cfg->stats_output) {
         if (tsk_get_counters(ctx, counters) != 0) { fprintf(stderr, "%s\n", tsk_last_error()); goto done; }
@@ -172,10 +173,6 @@ int main(int argc, char *argv[])
     phase("start");
     cfg = tsk_parse_config(argv[1]);
     if (cfg == NULL) return -1;
-    if (cfg->altcalls_given) {
-        fprintf(stderr, "[alternative_calls] (third-party base-caller override, altcalls.c) is not supported.\n");
-        return -1;
-    }
     if (tsk_load_color_matrix(inv, cfg->threep_colormatrix_filename) < 0) return -1;
     params = malloc(sizeof(*params));
     if (!params || tsk_build_params(cfg, params) < 0) return -1;

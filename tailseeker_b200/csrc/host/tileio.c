@@ -4,6 +4,10 @@
  *        int16[N] (A,C,G,T)              (reference src/importer/cifreader.c:38-102,118-170,235)
  *   BCL  u32 N, u8[N]; ".bcl" or ".bcl.gz" (reference src/importer/bclreader.c:43-80,95-119,206)
  * Blocks are read straight into bcl[T][count] / cif[L3][4][count]: no AoS transpose.
+ *   [alternative_calls]  gzip'ed or plain FASTQ, one record per cluster in tile order, overriding the
+ *        base-call bytes of cycles first_cycle .. first_cycle+readlength-1; the BCL files of those
+ *        cycles are never opened      (reference src/importer/altcalls.c:51-196, bclreader.c:185-191,
+ *        tailseq-import.c:203-230)
  * Colour matrix: 16 numbers, inverted like src/contrib/misc.c:11-58 (float cofactors, same order).
  */
 #include <endian.h>
@@ -12,12 +16,86 @@
 #include <string.h>
 #include "tsk_host.h"
 
+struct fastq_override {
+    gzFile fp;
+    const char *filename;               /* owned by the configuration */
+    int first_cycle, ncycles;
+};
+
 struct tile_files {
     int T, L3;
     uint32_t nclusters, read;
     FILE **cif;
-    gzFile *bcl;
+    gzFile *bcl;                        /* NULL for a cycle taken from a FASTQ override */
+    struct fastq_override *alt;         /* in the configuration's list order */
+    int nalt;
 };
+
+/* One FASTQ line into buf (BUFSIZ like the reference, which therefore splits longer lines too).
+ * Returns the length without the last character -- the reference takes strlen - 1 whether or not
+ * that character is a newline (altcalls.c:72,154,177) -- or -1 at the end of the file. */
+static int fastq_line(gzFile fp, char *buf)
+{
+    if (gzgets(fp, buf, BUFSIZ) == NULL) return -1;
+    return (int)strlen(buf) - 1;
+}
+
+static int open_fastq_override(struct fastq_override *o, const struct host_altcall *ac)
+{
+    char line[BUFSIZ];
+    o->filename = ac->filename;
+    o->first_cycle = ac->first_cycle;
+    o->fp = gzopen(ac->filename, "rt");
+    if (!o->fp) { fprintf(stderr, "open_alternative_calls: Can't open file %s.\n", ac->filename); return -1; }
+    /* the read length is that of the first record */
+    if (fastq_line(o->fp, line) < 0) { fprintf(stderr, "No sequence available in %s.\n", ac->filename); return -1; }
+    if (line[0] != '@') { fprintf(stderr, "%s is not in FASTQ format.\n", ac->filename); return -1; }
+    if ((o->ncycles = fastq_line(o->fp, line)) < 0) {
+        fprintf(stderr, "Unexpected EOF while reading %s\n", ac->filename);
+        return -1;
+    }
+    if (gzrewind(o->fp) < 0) { fprintf(stderr, "Failed to rewind the FASTQ reader for %s\n", ac->filename); return -1; }
+    return 0;
+}
+
+/* base-call byte of one FASTQ position: C 1, G 2, T/U 3, everything else (A, N, ...) 0 in bits 0-1,
+ * phred in bits 2-7 truncated to a byte (altcalls.c:35-44,186-188) */
+static inline uint8_t fastq_call(char base, char qual)
+{
+    uint8_t code = 0;
+    switch (base) {
+    case 'C': case 'c': code = 1; break;
+    case 'G': case 'g': code = 2; break;
+    case 'T': case 't': case 'U': case 'u': code = 3; break;
+    }
+    return (uint8_t)(code | (uint8_t)((uint8_t)(qual - 33) << 2));
+}
+
+/* the next `count` records of one override into rows first_cycle.. of bcl[T][count] */
+static int read_fastq_override(struct fastq_override *o, uint32_t count, uint8_t *bcl)
+{
+    char head[BUFSIZ], seq[BUFSIZ], qual[BUFSIZ];
+    for (uint32_t k = 0; k < count; k++) {
+        int n;
+        if (fastq_line(o->fp, head) < 0) { fprintf(stderr, "Not enough sequences from %s\n", o->filename); return -1; }
+        if (head[0] != '@') { fprintf(stderr, "%s is not in FASTQ format.\n", o->filename); return -1; }
+        if ((n = fastq_line(o->fp, seq)) < 0) goto eof;
+        if (n != o->ncycles) goto ragged;
+        if (fastq_line(o->fp, head) < 0) goto eof;
+        if (head[0] != '+') { fprintf(stderr, "%s is not in FASTQ format.\n", o->filename); return -1; }
+        if ((n = fastq_line(o->fp, qual)) < 0) goto eof;
+        if (n != o->ncycles) goto ragged;
+        for (int j = 0; j < n; j++)
+            bcl[(size_t)(o->first_cycle + j) * count + k] = fastq_call(seq[j], qual[j]);
+    }
+    return 0;
+eof:
+    fprintf(stderr, "Unexpected EOF while reading %s\n", o->filename);
+    return -1;
+ragged:
+    fprintf(stderr, "Sequence length in the FASTQ is inconsistent.\n");
+    return -1;
+}
 
 static float cofactor_entry(int i, int j, const float *m)
 {
@@ -88,6 +166,26 @@ struct tile_files *tsk_open_tile(const struct host_config *cfg, const char *msgp
     tf->T = cfg->total_cycles; tf->L3 = cfg->threep_length;
     tf->cif = calloc(tf->L3, sizeof(FILE *));
     tf->bcl = calloc(tf->T, sizeof(gzFile));
+    unsigned char *overridden = calloc(tf->T > 0 ? tf->T : 1, 1);
+    for (const struct host_altcall *ac = cfg->altcalls; ac; ac = ac->next) tf->nalt++;
+    tf->alt = calloc(tf->nalt ? tf->nalt : 1, sizeof(*tf->alt));
+    if (!tf->cif || !tf->bcl || !overridden || !tf->alt) { perror("tsk_open_tile"); free(overridden); tsk_close_tile(tf); return NULL; }
+    {
+        int a = 0;
+        for (const struct host_altcall *ac = cfg->altcalls; ac; ac = ac->next, a++) {
+            struct fastq_override *o = &tf->alt[a];
+            if (open_fastq_override(o, ac) < 0) { free(overridden); tsk_close_tile(tf); return NULL; }
+            printf("%sUsing FASTQ %s for cycles %d-%d.\n", msgprefix, o->filename, o->first_cycle + 1,
+                   o->first_cycle + o->ncycles);
+            /* the reference writes past its cycle array here (tailseq-import.c:212-214) */
+            if (o->first_cycle + o->ncycles > tf->T) {
+                fprintf(stderr, "Alternative calls in %s run past the last cycle (%d).\n", o->filename, tf->T);
+                free(overridden); tsk_close_tile(tf);
+                return NULL;
+            }
+            memset(overridden + o->first_cycle, 1, o->ncycles);
+        }
+    }
     printf("%sUsing cluster intensities for cycle %d-%d from %s.\n", msgprefix, cfg->threep_start + 1,
            cfg->threep_start + cfg->threep_length, cfg->datadir);
     for (int i = 0; i < tf->L3; i++) {
@@ -95,16 +193,22 @@ struct tile_files *tsk_open_tile(const struct host_config *cfg, const char *msgp
         snprintf(path, PATH_MAX, "%s/L%03d/C%d.1/s_%d_%04d.cif", cfg->datadir, cfg->lane,
                  cfg->threep_start + i + 1, cfg->lane, cfg->tile);
         tf->cif[i] = open_cif(path, &n);
-        if (!tf->cif[i]) { tsk_close_tile(tf); return NULL; }
+        if (!tf->cif[i]) { free(overridden); tsk_close_tile(tf); return NULL; }
         if (i == 0) tf->nclusters = n;
         else if (n != tf->nclusters) {
             fprintf(stderr, "Inconsistent number of clusters in CIF cycle %d.\n", cfg->threep_length + i + 1);
-            tsk_close_tile(tf);
+            free(overridden); tsk_close_tile(tf);
             return NULL;
         }
     }
-    for (int c = 0; c < tf->T; c++) {
+    /* one message per stretch of cycles that still comes from BCL files (bclreader.c:193-228) */
+    for (int c = 0, run = -1; c <= tf->T; c++) {
         uint32_t n;
+        if (c == tf->T || overridden[c]) {
+            if (run >= 0) printf("%sUsing BCL base calls for cycle %d-%d.\n", msgprefix, run + 1, c);
+            run = -1;
+            continue;
+        }
         snprintf(path, PATH_MAX, "%s/BaseCalls/L%03d/C%d.1/s_%d_%04d.bcl", cfg->datadir, cfg->lane, c + 1,
                  cfg->lane, cfg->tile);
         tf->bcl[c] = gzopen(path, "rb");
@@ -112,17 +216,18 @@ struct tile_files *tsk_open_tile(const struct host_config *cfg, const char *msgp
             strncat(path, ".gz", PATH_MAX - strlen(path) - 1);
             tf->bcl[c] = gzopen(path, "rb");
         }
-        if (!tf->bcl[c]) { fprintf(stderr, "load_bcl_file: Can't open file %s.\n", path); tsk_close_tile(tf); return NULL; }
-        if (gzread(tf->bcl[c], &n, 4) < 4) { fprintf(stderr, "Unexpected EOF %s.\n", path); tsk_close_tile(tf); return NULL; }
+        if (!tf->bcl[c]) { fprintf(stderr, "load_bcl_file: Can't open file %s.\n", path); goto bad_bcl; }
+        if (gzread(tf->bcl[c], &n, 4) < 4) { fprintf(stderr, "Unexpected EOF %s.\n", path); goto bad_bcl; }
         n = le32toh(n);
-        if (n != tf->nclusters) {
-            fprintf(stderr, "Inconsistent number of clusters in cycle %d.\n", c + 1);
-            tsk_close_tile(tf);
-            return NULL;
-        }
+        if (n != tf->nclusters) { fprintf(stderr, "Inconsistent number of clusters in cycle %d.\n", c + 1); goto bad_bcl; }
+        if (run < 0) run = c;
     }
-    printf("%sUsing BCL base calls for cycle %d-%d.\n", msgprefix, 1, tf->T);
+    free(overridden);
     return tf;
+bad_bcl:
+    free(overridden);
+    tsk_close_tile(tf);
+    return NULL;
 }
 
 uint32_t tsk_tile_nclusters(const struct tile_files *tf) { return tf->nclusters; }
@@ -145,9 +250,13 @@ int tsk_read_block(struct tile_files *tf, uint32_t count, uint8_t *bcl, int16_t 
             for (uint32_t k = 0; k < count; k++) dst[k] = (int16_t)le16toh((uint16_t)dst[k]);
 #endif
         }
+    /* overrides first, in list order: where two of them overlap the later entry of the list wins */
+    for (int a = 0; a < tf->nalt; a++)
+        if (read_fastq_override(&tf->alt[a], count, bcl) < 0) return -1;
     for (int c = 0; c < tf->T; c++) {
         uint8_t *dst = bcl + (size_t)c * count;
         uint32_t got = 0;
+        if (!tf->bcl[c]) continue;
         while (got < count) {          /* gzread takes an unsigned int length */
             const uint32_t want = count - got > (1u << 30) ? (1u << 30) : count - got;
             const int r = gzread(tf->bcl[c], dst + got, want);
@@ -159,9 +268,23 @@ int tsk_read_block(struct tile_files *tf, uint32_t count, uint8_t *bcl, int16_t 
     return 0;
 }
 
+/* after the last block: a FASTQ override must be used up (altcalls.c:116-124, tailseq-import.c:648) */
+int tsk_check_tile_end(struct tile_files *tf)
+{
+    char line[BUFSIZ];
+    for (int a = 0; a < tf->nalt; a++)
+        if (gzgets(tf->alt[a].fp, line, BUFSIZ) != NULL) {
+            fprintf(stderr, "Extra sequences found in %s\n", tf->alt[a].filename);
+            return -1;
+        }
+    return 0;
+}
+
 void tsk_close_tile(struct tile_files *tf)
 {
     if (!tf) return;
+    if (tf->alt) for (int a = 0; a < tf->nalt; a++) if (tf->alt[a].fp) gzclose(tf->alt[a].fp);
+    free(tf->alt);
     if (tf->cif) for (int i = 0; i < tf->L3; i++) if (tf->cif[i]) fclose(tf->cif[i]);
     if (tf->bcl) for (int c = 0; c < tf->T; c++) if (tf->bcl[c]) gzclose(tf->bcl[c]);
     free(tf->cif); free(tf->bcl); free(tf);

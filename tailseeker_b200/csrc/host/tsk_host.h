@@ -34,6 +34,12 @@ struct host_sample {
     struct host_sample *next;
 };
 
+struct host_altcall {
+    char *filename;
+    int first_cycle;                    /* 0-based */
+    struct host_altcall *next;
+};
+
 struct host_config {
     /* [source] */
     char *datadir, *laneid, *threep_colormatrix_filename;
@@ -48,8 +54,9 @@ struct host_config {
     /* [output] */
     char *seqqual_output, *taginfo_output, *signal_output, *signal_dists_output, *stats_output,
          *length_dists_output;
-    /* [alternative_calls] */
-    int altcalls_given;
+    /* [alternative_calls]: FASTQ files that override the base calls from `first_cycle` on; newest
+     * entry first, like the reference's list (parseconfig.c:153-185) */
+    struct host_altcall *altcalls;
     /* [control] */
     char control_name[TSK_NAME_MAX];
     int control_first_cycle, control_read_length;
@@ -90,6 +97,8 @@ struct tile_files *tsk_open_tile(const struct host_config *cfg, const char *msgp
 uint32_t tsk_tile_nclusters(const struct tile_files *tf);
 /* read the next `count` clusters of every cycle into bcl[T][count], cif[L3][4][count] */
 int tsk_read_block(struct tile_files *tf, uint32_t count, uint8_t *bcl, int16_t *cif);
+/* after the last block: -1 when a FASTQ override still holds records */
+int tsk_check_tile_end(struct tile_files *tf);
 void tsk_close_tile(struct tile_files *tf);
 
 /* writers.c */
