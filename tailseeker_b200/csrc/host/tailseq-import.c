@@ -29,7 +29,7 @@ static void usage(const char *prog)
 {
     printf("tailseq-import 3.0 (B200)"
            "\n - Import Illumina .cif and .bcl files into TAIL-seq internal formats"
-           "\n\nUsage: %s {config.ini}\n\n", prog);
+           "\n\nUsage: %s {config.ini} [more config.ini ...]\n\n", prog);
 }
 
 /* The CUDA context (0.7 s to create) comes up on its own thread while the main thread opens the
@@ -159,24 +159,21 @@ done:
     return rc;
 }
 
-int main(int argc, char *argv[])
+/* one tile: the body of the reference's main() (tailseq-import.c:736-757) */
+static int run_tile(const char *inifile, int device)
 {
     struct host_config *cfg;
     tsk_params *params;
     tsk_ctx *ctx = NULL;
     struct ctx_boot boot;
     float inv[16];
-    int r, device = 0;
-    const char *dev = getenv("TAILSEEKER_DEVICE");
+    int r;
 
-    if (argc < 2) { usage(argv[0]); return 0; }
-    phase("start");
-    cfg = tsk_parse_config(argv[1]);
+    cfg = tsk_parse_config(inifile);
     if (cfg == NULL) return -1;
-    if (tsk_load_color_matrix(inv, cfg->threep_colormatrix_filename) < 0) return -1;
+    if (tsk_load_color_matrix(inv, cfg->threep_colormatrix_filename) < 0) { tsk_free_config(cfg); return -1; }
     params = malloc(sizeof(*params));
-    if (!params || tsk_build_params(cfg, params) < 0) return -1;
-    if (dev) device = atoi(dev);
+    if (!params || tsk_build_params(cfg, params) < 0) { free(params); tsk_free_config(cfg); return -1; }
     memset(&boot, 0, sizeof(boot));
     boot.params = params; boot.device = device;
     if (pthread_create(&boot.thread, NULL, boot_context, &boot) == 0) boot.started = 1;
@@ -188,4 +185,22 @@ int main(int argc, char *argv[])
     free(params);
     tsk_free_config(cfg);
     return r;
+}
+
+/* `tailseq-import {config.ini}` as in the reference.  Further configuration files are processed one
+ * after the other in the same process, so a lane's tiles pay for the CUDA start-up (0.4-2 s) once
+ * instead of once per tile; the run stops at the first tile that fails, like a chain of commands. */
+int main(int argc, char *argv[])
+{
+    int device = 0;
+    const char *dev = getenv("TAILSEEKER_DEVICE");
+
+    if (argc < 2) { usage(argv[0]); return 0; }
+    phase("start");
+    if (dev) device = atoi(dev);
+    for (int i = 1; i < argc; i++) {
+        const int r = run_tile(argv[i], device);
+        if (r != 0) return r;
+    }
+    return 0;
 }
