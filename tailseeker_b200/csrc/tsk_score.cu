@@ -10,7 +10,7 @@
  * Two code paths, both exact:
  *   k_normalise_score_pack          the fast path: one thread per cluster, a branch-free
  *       cycle step; the nine IEEE divisions per cycle become multiplications by hoisted
- *       correctly rounded reciprocals plus two FMA residual corrections (Markstein), logf is
+ *       correctly rounded reciprocals plus one FMA residual correction (Markstein), logf is
  *       the host's table algorithm in fp64 FMAs, packed record words are transposed through
  *       shared memory so every record is written with full 128-byte lines.
  *   k_normalise_score_pack_generic  the literal operation-by-operation restatement
@@ -345,17 +345,24 @@ k_normalise_score_pack_generic(const __grid_constant__ DevParams P, const ScoreA
 /* ======================================================================================
  * fast path
  * ==================================================================================== */
-/* a / b given y = RN(1/b): two residual corrections (Markstein).  After the first, q is a
- * faithful quotient; the second then yields RN(a/b) exactly [Markstein 1990; Cornea, Harrison,
- * Tang 2002, thm. on q' = RN(q + r*y) with r = a - b*q exact].  Preconditions (checked by the
- * caller): b, y normal and finite, |a/b| far from the overflow/underflow thresholds.
- * tests/test_gpu_parity.py::test_division_exact compares against __fdiv_rn on 2^31 pairs. */
+/* a / b given y = RN(1/b): q0 = RN(a*y), the exact residual r = a - b*q0 (one FMA), and
+ * q = RN(q0 + r*y) -- the sequence the compiler's own IEEE division runs after its range check
+ * (FCHK; MUFU.RCP + Newton step; FFMA q0; FFMA r; FFMA q), with the reciprocal hoisted out of the
+ * cycle loop.  q0 + r*y = a/b + (a/b - q0)(b*y - 1) misses a/b by less than 1.5 * 2^-24 ulp, so the
+ * final rounding can only go wrong for quotients that close to a rounding midpoint; those are the
+ * solutions of X*B + k = 2^S * A for small |k| (X odd, A and B the 24-bit significands), and
+ * tools/div_onestep_proof.c enumerates them for EVERY divisor significand B and |k| <= 33 * 2^ctz(B)
+ * (2.3e9 quotients, none rounds differently from a / b; the GPU self-test's 2^31 pairs and 1.2e10
+ * random and structured pairs besides), whereas the same search finds 6.1e6 failures as soon as y
+ * is one ulp off.  A second
+ * correction step, which earlier versions ran, is therefore redundant.
+ * Preconditions (checked by the caller): b and y normal and finite, y correctly rounded, |a/b| and
+ * the residual far from the overflow/underflow thresholds.
+ * tests/test_gpu_parity.py::test_fast_arithmetic_sweeps compares against __fdiv_rn on 2^31 pairs. */
 __device__ __forceinline__ float div_by_rcp(float a, float b, float y)
 {
-    float q = __fmul_rn(a, y);
-    float r = __fmaf_rn(-b, q, a);
-    q = __fmaf_rn(r, y, q);
-    r = __fmaf_rn(-b, q, a);
+    const float q = __fmul_rn(a, y);
+    const float r = __fmaf_rn(-b, q, a);
     return __fmaf_rn(r, y, q);
 }
 

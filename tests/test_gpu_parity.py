@@ -56,7 +56,8 @@ def test_logf_exact(proc, oracle):
 
 def test_fast_arithmetic_sweeps(proc):
     """(1) FMA logf == separately-rounded logf on every normal float in (0,1];
-    (2) reciprocal-multiply + 2 residual corrections == IEEE division on 2^31 operand pairs."""
+    (2) reciprocal-multiply + one residual correction == IEEE division on 2^31 operand pairs
+    (tools/div_onestep_proof.c holds the exhaustive hard-case search behind that step)."""
     logf_bad, div_bad = proc.selftest_sweeps(1 << 31)
     assert logf_bad == 0
     assert div_bad == 0
