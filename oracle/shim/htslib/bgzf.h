@@ -1,7 +1,7 @@
 /* TEST INFRASTRUCTURE ONLY.
  * Stand-in for htslib's <htslib/bgzf.h>, which is not installed in this image.
  * The reference's hot path uses exactly three BGZF symbols, all pure compression
- * (no arithmetic): bgzf_open / bgzf_write / bgzf_close
+ * (no arithmetic): bgzf_open / bgzf_write / bgzf_close (+ bgzf_mt in the exporter)
  * (reference src/importer/tailseq-import.c:55,68,83,110,282,294-297;
  *  src/importer/spotanalyzer.c:373,419-428; src/utils.c:56-76).
  * They are mapped onto zlib's gz* API; every consumer of these files reads them with
@@ -36,6 +36,13 @@ static inline ssize_t bgzf_write(BGZF *fp, const void *data, size_t length)
         return 0;
     r = gzwrite((gzFile)fp, data, (unsigned)length);
     return (r <= 0) ? -1 : (ssize_t)r;
+}
+
+/* tailseq-writefastq.c:387,399 asks for BGZF worker threads; the zlib stand-in has none */
+static inline int bgzf_mt(BGZF *fp, int n_threads, int n_sub_blks)
+{
+    (void)fp; (void)n_threads; (void)n_sub_blks;
+    return 0;
 }
 
 static inline int bgzf_close(BGZF *fp)
