@@ -26,8 +26,18 @@
 #define FULL_MASK 0xffffffffu
 #define CONTRAST_MAXLEN 288          /* reciprocal table length (scan_len <= threep_length + 1) */
 
+/* TSK_LOGF_KI (off by default; build with TSK_NVCC_EXTRA=-DTSK_LOGF_KI=1): the (exponent, index)
+ * table form of logf, V2 of tools/logf_variants.c -- prepared on the CPU, not yet run on a GPU. */
+#ifdef TSK_LOGF_KI
+#define LOGF_KI_KMIN  15                                           /* table rows for k = -15 .. 0 */
+#define LOGF_KI_FIRST (0x3f330000u - ((uint32_t)LOGF_KI_KMIN << 23)) /* smallest bit pattern it covers */
+#endif
+
 struct ScoreShared {
     double2 logtab[16];
+#ifdef TSK_LOGF_KI
+    double2 logki[16 * 16];            /* [(k & 15) * 16 + i] = {invc[i] * 2^-k, fma(k, ln2, logc[i])} */
+#endif
     float   tscore[TSK_T_SCORE_BINS + 1];
     int16_t limit[TSK_MAX_SAMPLES];
     int16_t dump[TSK_MAX_SAMPLES];
@@ -38,6 +48,13 @@ __device__ __forceinline__ void load_score_shared(ScoreShared &sh, const float *
 {
     for (int i = threadIdx.x; i < 16; i += blockDim.x)
         sh.logtab[i] = make_double2(c_logf_tab[i][0], c_logf_tab[i][1]);
+#ifdef TSK_LOGF_KI
+    for (int e = threadIdx.x; e < 16 * 16; e += blockDim.x) {
+        const int k = (e >> 4) ? (e >> 4) - 16 : 0, i = e & 15;
+        sh.logki[e] = make_double2(scalbn(c_logf_tab[i][0], -k),
+                                   __fma_rn((double)k, 0x1.62e42fefa39efp-1, c_logf_tab[i][1]));
+    }
+#endif
     for (int i = threadIdx.x; i <= TSK_T_SCORE_BINS; i += blockDim.x) sh.tscore[i] = tscore[i];
     for (int i = threadIdx.x; i < S; i += blockDim.x) {
         sh.limit[i] = samples[i].limit_threep;
@@ -410,6 +427,26 @@ __device__ __forceinline__ float logf_core_t(uint32_t ix, TabLoad tabload)
     return (float)y;
 }
 
+#ifdef TSK_LOGF_KI
+/* the same logarithm for LOGF_KI_FIRST <= ix <= 0x3f800000 from one table entry per (k, i): the
+ * entry's reciprocal carries 2^-k, so p itself is the multiplicand (no mantissa extraction), and
+ * its second half is the finished y0 = k*ln2 + logc (no int -> double, no FMA).  Every operation
+ * left is one the form above performs on the same values, hence the same float; other bit
+ * patterns give a finite meaningless number from an in-bounds entry (callers discard it). */
+template <typename TabLoad>
+__device__ __forceinline__ float logf_ki_t(uint32_t ix, TabLoad tabload)
+{
+    const uint32_t tmp = ix - 0x3f330000u;
+    const double2 t = tabload((tmp >> 15) & 0xff0u);              /* byte offset of entry (k & 15, i) */
+    const double r = __fma_rn((double)__uint_as_float(ix), t.x, -1.0);
+    const double r2 = __dmul_rn(r, r);
+    double y = __fma_rn(c_logf_k[1], r, c_logf_k[2]);
+    y = __fma_rn(c_logf_k[3], r2, y);
+    y = __fma_rn(y, r2, __dadd_rn(t.y, r));
+    return (float)y;
+}
+#endif
+
 __device__ __forceinline__ float logf_core(uint32_t ix, const double2 *__restrict__ tab)
 {
     return logf_core_t(ix, [tab](uint32_t ofs) { return *reinterpret_cast<const double2 *>(
@@ -658,6 +695,9 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
     /* score of cycle r lives at scratch[(r - start - ps) * spitch + n]; scr walks one row per cycle */
     float *scr = A.scratch + n + ((ptrdiff_t)rbeg_w - (start + ps)) * (ptrdiff_t)spitch;
     const uint32_t a_logtab = smem_u32(&sm.sh.logtab[0]), a_tscore = smem_u32(&sm.sh.tscore[0]);
+#ifdef TSK_LOGF_KI
+    const uint32_t a_logki = smem_u32(&sm.sh.logki[0]);
+#endif
     const uint32_t a_tile = smem_u32(&sm.tile[warp][0][0]);
     const uint32_t a_mytile = a_tile + lane * ((K2_TILE_CYC + 1) * 4);
     const uint32_t colofs = (uint32_t)lane * 2;
@@ -705,15 +745,36 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
             lit = lit && (prob[0] == prob[0]);
             /* ---- Shannon entropy: h -= p*logf(p) for p > 0 (the skipped terms are 0) ---- */
             float h = 0.f;
+#ifdef TSK_LOGF_KI
+            /* a positive p below the table's first row (p < 1.07e-5, rare) sends this lane down the
+             * general form; zero and NaN stay here, their terms are discarded below */
+            bool tiny = false;
 #pragma unroll
-            for (int ch = 0; ch < 4; ch++) {
-                const float lg = logf_core_t(__float_as_uint(prob[ch]), [a_logtab](uint32_t ofs) {
-                    double2 t;
-                    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(a_logtab + ofs));
-                    return t;
-                });
-                const float term = __fmul_rn(prob[ch], lg);
-                h = __fsub_rn(h, prob[ch] > 0.f ? term : 0.f);
+            for (int ch = 0; ch < 4; ch++) tiny = tiny || (__float_as_uint(prob[ch]) - 1u) < (LOGF_KI_FIRST - 1u);
+            if (__builtin_expect(!tiny, 1)) {
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) {
+                    const float lg = logf_ki_t(__float_as_uint(prob[ch]), [a_logki](uint32_t ofs) {
+                        double2 t;
+                        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(a_logki + ofs));
+                        return t;
+                    });
+                    const float term = __fmul_rn(prob[ch], lg);
+                    h = __fsub_rn(h, prob[ch] > 0.f ? term : 0.f);
+                }
+            } else
+#endif
+            {
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) {
+                    const float lg = logf_core_t(__float_as_uint(prob[ch]), [a_logtab](uint32_t ofs) {
+                        double2 t;
+                        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(a_logtab + ofs));
+                        return t;
+                    });
+                    const float term = __fmul_rn(prob[ch], lg);
+                    h = __fsub_rn(h, prob[ch] > 0.f ? term : 0.f);
+                }
             }
             const float es = __fsub_rn(1.f, div_by_rcp(h, P.maximum_entropy, rcp_maxent));
             const uint32_t ti = min((uint32_t)__float2int_rz(__fmul_rn(prob[3], (float)TSK_T_SCORE_BINS)),
@@ -1095,6 +1156,9 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
                         __popc(__ballot_sync(FULL_MASK, needcol) & ((1u << lane) - 1));
     float *scr = scol + ((ptrdiff_t)rbeg_w - (start + ps)) * (ptrdiff_t)spitch;
     const uint32_t a_logtab = smem_u32(&sm.sh.logtab[0]), a_tscore = smem_u32(&sm.sh.tscore[0]);
+#ifdef TSK_LOGF_KI
+    const uint32_t a_logki = smem_u32(&sm.sh.logki[0]);
+#endif
     const uint32_t a_tile = smem_u32(&sm.tile[warp][0][0]);
     const uint32_t a_mytile = a_tile + lane * ((K2_TILE_CYC + 1) * 4);
 
@@ -1144,15 +1208,36 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
             lit = lit && (prob[0] == prob[0]);
             /* ---- Shannon entropy: h -= p*logf(p) for p > 0 (the skipped terms are 0) ---- */
             float h = 0.f;
+#ifdef TSK_LOGF_KI
+            /* a positive p below the table's first row (p < 1.07e-5, rare) sends this lane down the
+             * general form; zero and NaN stay here, their terms are discarded below */
+            bool tiny = false;
 #pragma unroll
-            for (int ch = 0; ch < 4; ch++) {
-                const float lg = logf_core_t(__float_as_uint(prob[ch]), [a_logtab](uint32_t ofs) {
-                    double2 t;
-                    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(a_logtab + ofs));
-                    return t;
-                });
-                const float term = __fmul_rn(prob[ch], lg);
-                h = __fsub_rn(h, prob[ch] > 0.f ? term : 0.f);
+            for (int ch = 0; ch < 4; ch++) tiny = tiny || (__float_as_uint(prob[ch]) - 1u) < (LOGF_KI_FIRST - 1u);
+            if (__builtin_expect(!tiny, 1)) {
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) {
+                    const float lg = logf_ki_t(__float_as_uint(prob[ch]), [a_logki](uint32_t ofs) {
+                        double2 t;
+                        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(a_logki + ofs));
+                        return t;
+                    });
+                    const float term = __fmul_rn(prob[ch], lg);
+                    h = __fsub_rn(h, prob[ch] > 0.f ? term : 0.f);
+                }
+            } else
+#endif
+            {
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) {
+                    const float lg = logf_core_t(__float_as_uint(prob[ch]), [a_logtab](uint32_t ofs) {
+                        double2 t;
+                        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(a_logtab + ofs));
+                        return t;
+                    });
+                    const float term = __fmul_rn(prob[ch], lg);
+                    h = __fsub_rn(h, prob[ch] > 0.f ? term : 0.f);
+                }
             }
             const float es = __fsub_rn(1.f, div_by_rcp(h, P.maximum_entropy, rcp_maxent));
             const uint32_t ti = min((uint32_t)__float2int_rz(__fmul_rn(prob[3], (float)TSK_T_SCORE_BINS)),

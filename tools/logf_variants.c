@@ -2,7 +2,8 @@
  * logf_variants.c -- CPU sweep over EVERY normal float in (0, 1] of cheaper forms of K2's logf
  * (tailseeker_b200/csrc/tsk_score.cu: logf_core_t, the host libm's table algorithm in fp64 FMAs,
  * shannon_entropy in signalproc.c:39-51).  Prepared for the next round: none of these is in the
- * kernel yet.
+ * default build yet; V2 is in the kernels behind -DTSK_LOGF_KI=1 (TSK_NVCC_EXTRA), waiting for its
+ * first GPU run.
  *
  *   gcc -O2 -mfma -ffp-contract=off -o logf_variants tools/logf_variants.c -lm -lpthread && ./logf_variants
  *
@@ -65,15 +66,28 @@ static inline float v2(uint32_t ix)
     return tail(fma((double)u2f(ix), e[0], -1.0), e[1]);
 }
 
-struct job { int id; uint64_t bad[3]; };
+/* V2 as the kernel has it behind TSK_LOGF_KI: 16 rows (k = -15 .. 0), byte offset (tmp >> 15) & 0xff0,
+ * used for LOGF_KI_FIRST <= ix <= 0x3f800000; below that the kernel form runs */
+#define LOGF_KI_FIRST (0x3f330000u - (15u << 23))
+static double KI16[16 * 16][2];
+static inline float v2_kernel(uint32_t ix)
+{
+    if (ix - 1u < LOGF_KI_FIRST - 1u) return kernel_form(ix);
+    const uint32_t tmp = ix - 0x3f330000u;
+    const double *e = KI16[((tmp >> 15) & 0xff0u) >> 4];
+    return tail(fma((double)u2f(ix), e[0], -1.0), e[1]);
+}
+
+struct job { int id; uint64_t bad[4]; };
 static void *run(void *p)
 {
     struct job *j = p;
-    for (uint64_t ix = 0x00800000u + j->id; ix < 0x3f800000u; ix += 8) {
+    for (uint64_t ix = 0x00800000u + j->id; ix <= 0x3f800000u; ix += 8) {
         const uint32_t want = f2u(logf(u2f((uint32_t)ix)));
         j->bad[0] += f2u(kernel_form((uint32_t)ix)) != want;
         j->bad[1] += f2u(v1((uint32_t)ix)) != want;
         j->bad[2] += f2u(v2((uint32_t)ix)) != want;
+        j->bad[3] += f2u(v2_kernel((uint32_t)ix)) != want;
     }
     return NULL;
 }
@@ -82,16 +96,22 @@ int main(void)
 {
     pthread_t t[8];
     struct job j[8];
-    uint64_t bad[3] = {0, 0, 0};
+    uint64_t bad[4] = {0, 0, 0, 0};
     for (int k = 0; k < 128; k++) KLN2[k] = (double)(-k) * LN2;
     for (int k = -127; k <= 0; k++)
         for (int i = 0; i < 16; i++) {
             KI[(k & 127) * 16 + i][0] = ldexp(T[i][0], -k);
             KI[(k & 127) * 16 + i][1] = fma((double)k, LN2, T[i][1]);
         }
+    for (int e = 0; e < 256; e++) {                      /* as load_score_shared() fills sh.logki */
+        const int k = (e >> 4) ? (e >> 4) - 16 : 0, i = e & 15;
+        KI16[e][0] = scalbn(T[i][0], -k);
+        KI16[e][1] = fma((double)k, LN2, T[i][1]);
+    }
     for (int i = 0; i < 8; i++) { memset(&j[i], 0, sizeof(j[i])); j[i].id = i; pthread_create(&t[i], NULL, run, &j[i]); }
-    for (int i = 0; i < 8; i++) { pthread_join(t[i], NULL); for (int v = 0; v < 3; v++) bad[v] += j[i].bad[v]; }
-    printf("normal floats in (0,1): %u; differing from the host logf: kernel form %llu, V1 %llu, V2 %llu\n",
-           0x3f800000u - 0x00800000u, (unsigned long long)bad[0], (unsigned long long)bad[1], (unsigned long long)bad[2]);
-    return bad[0] || bad[1] || bad[2];
+    for (int i = 0; i < 8; i++) { pthread_join(t[i], NULL); for (int v = 0; v < 4; v++) bad[v] += j[i].bad[v]; }
+    printf("normal floats in (0,1]: %u; differing from the host logf: kernel form %llu, V1 %llu, V2 %llu, "
+           "V2 as compiled under TSK_LOGF_KI %llu\n", 0x3f800000u - 0x00800000u + 1, (unsigned long long)bad[0],
+           (unsigned long long)bad[1], (unsigned long long)bad[2], (unsigned long long)bad[3]);
+    return bad[0] || bad[1] || bad[2] || bad[3];
 }
