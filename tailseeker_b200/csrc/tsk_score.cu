@@ -1610,6 +1610,13 @@ __global__ void k_logf_sweep(uint32_t first, uint64_t count, unsigned long long 
 {
     __shared__ double2 tab[16];
     if (threadIdx.x < 16) tab[threadIdx.x] = make_double2(c_logf_tab[threadIdx.x][0], c_logf_tab[threadIdx.x][1]);
+#ifdef TSK_LOGF_KI
+    __shared__ double2 ki[16 * 16];                 /* filled exactly like ScoreShared::logki */
+    for (int e = threadIdx.x; e < 16 * 16; e += blockDim.x) {
+        const int k = (e >> 4) ? (e >> 4) - 16 : 0, i = e & 15;
+        ki[e] = make_double2(scalbn(c_logf_tab[i][0], -k), __fma_rn((double)k, 0x1.62e42fefa39efp-1, c_logf_tab[i][1]));
+    }
+#endif
     __syncthreads();
     unsigned long long bad = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -1617,6 +1624,12 @@ __global__ void k_logf_sweep(uint32_t first, uint64_t count, unsigned long long 
         const float a = tsk_logf(__uint_as_float(ix), tab);
         const float b = logf_core(ix, tab);
         bad += __float_as_uint(a) != __float_as_uint(b);
+#ifdef TSK_LOGF_KI
+        if (ix >= LOGF_KI_FIRST) {                  /* the table form wherever the kernels use it */
+            const float c = logf_ki_t(ix, [&ki](uint32_t ofs) { return ki[ofs >> 4]; });
+            bad += __float_as_uint(a) != __float_as_uint(c);
+        }
+#endif
     }
     if (bad) atomicAdd(mismatches, bad);
 }
