@@ -1626,7 +1626,8 @@ __global__ void k_logf_sweep(uint32_t first, uint64_t count, unsigned long long 
         bad += __float_as_uint(a) != __float_as_uint(b);
 #ifdef TSK_LOGF_KI
         if (ix >= LOGF_KI_FIRST) {                  /* the table form wherever the kernels use it */
-            const float c = logf_ki_t(ix, [&ki](uint32_t ofs) { return ki[ofs >> 4]; });
+            const double2 *kip = ki;
+            const float c = logf_ki_t(ix, [kip](uint32_t ofs) { return kip[ofs >> 4]; });
             bad += __float_as_uint(a) != __float_as_uint(c);
         }
 #endif
