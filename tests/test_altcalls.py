@@ -104,6 +104,11 @@ def test_reference_with_overrides_equals_reference_on_rewritten_bcl(tmp_path):
     b = refrun.run_import(cfg, tile2, workdir=wb)
     _same(a, b)
     assert a["taginfo"] != refrun.run_import(cfg, tile)["taginfo"]        # the overrides do matter
+    # the drop-in's reader on the very same INI: same source messages, in the same order
+    r = subprocess.run([DUMP, a["ini"], str(tmp_path / "d.bcl")], capture_output=True, cwd=wa)
+    assert r.returncode == 0, r.stderr.decode()
+    using = lambda text: [l for l in text.splitlines() if "Using " in l]
+    assert using(r.stdout.decode()) == using(a["stdout"]) and len(using(a["stdout"])) == 6
 
 
 def _dump(cfg, data, mpath, workdir, read_buffer_size=None):
