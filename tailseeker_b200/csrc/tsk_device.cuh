@@ -8,7 +8,11 @@
 #ifndef TSK_DEVICE_CUH
 #define TSK_DEVICE_CUH
 
+#ifdef TSK_HOST_CHECK
+#include "tsk_hostcheck.h"            /* CPU checks of this very source (tests/exact_check.cpp) */
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 /* {invc, logc} table of the logf the host libm implements (glibc >= 2.28,

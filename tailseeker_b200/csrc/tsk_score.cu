@@ -21,17 +21,11 @@
 #include <math_constants.h>
 #include "tsk_internal.h"
 #include "tsk_device.cuh"
+#include "tsk_exact.cuh"
 #include "tsk_tma.cuh"
 
 #define FULL_MASK 0xffffffffu
 #define CONTRAST_MAXLEN 288          /* reciprocal table length (scan_len <= threep_length + 1) */
-
-/* TSK_LOGF_KI (off by default; build with TSK_NVCC_EXTRA=-DTSK_LOGF_KI=1): the (exponent, index)
- * table form of logf, V2 of tools/logf_variants.c -- prepared on the CPU, not yet run on a GPU. */
-#ifdef TSK_LOGF_KI
-#define LOGF_KI_KMIN  15                                           /* table rows for k = -15 .. 0 */
-#define LOGF_KI_FIRST (0x3f330000u - ((uint32_t)LOGF_KI_KMIN << 23)) /* smallest bit pattern it covers */
-#endif
 
 struct ScoreShared {
     double2 logtab[16];
@@ -362,27 +356,6 @@ k_normalise_score_pack_generic(const __grid_constant__ DevParams P, const ScoreA
 /* ======================================================================================
  * fast path
  * ==================================================================================== */
-/* a / b given y = RN(1/b): q0 = RN(a*y), the exact residual r = a - b*q0 (one FMA), and
- * q = RN(q0 + r*y) -- the sequence the compiler's own IEEE division runs after its range check
- * (FCHK; MUFU.RCP + Newton step; FFMA q0; FFMA r; FFMA q), with the reciprocal hoisted out of the
- * cycle loop.  q0 + r*y = a/b + (a/b - q0)(b*y - 1) misses a/b by less than 1.5 * 2^-24 ulp, so the
- * final rounding can only go wrong for quotients that close to a rounding midpoint; those are the
- * solutions of X*B + k = 2^S * A for small |k| (X odd, A and B the 24-bit significands), and
- * tools/div_onestep_proof.c enumerates them for EVERY divisor significand B and |k| <= 33 * 2^ctz(B)
- * (2.3e9 quotients, none rounds differently from a / b; the GPU self-test's 2^31 pairs and 1.2e10
- * random and structured pairs besides), whereas the same search finds 6.1e6 failures as soon as y
- * is one ulp off.  A second
- * correction step, which earlier versions ran, is therefore redundant.
- * Preconditions (checked by the caller): b and y normal and finite, y correctly rounded, |a/b| and
- * the residual far from the overflow/underflow thresholds.
- * tests/test_gpu_parity.py::test_fast_arithmetic_sweeps compares against __fdiv_rn on 2^31 pairs. */
-__device__ __forceinline__ float div_by_rcp(float a, float b, float y)
-{
-    const float q = __fmul_rn(a, y);
-    const float r = __fmaf_rn(-b, q, a);
-    return __fmaf_rn(r, y, q);
-}
-
 /* RN(1/x) for x in [2^-60, 2^60): the reciprocal approximation plus one Newton step, the very
  * sequence __frcp_rn() runs on its fast path (checked against it in k_div_sweep) without its
  * range test, which the caller has already made. */
@@ -393,59 +366,6 @@ __device__ __forceinline__ float rcp_rn_fast(float x)
     const float e = -__fmaf_rn(x, y0, -1.0f);
     return __fmaf_rn(y0, e, y0);
 }
-
-/* host-libm logf in fp64 FMAs for a NORMAL x in (0, 1] given as raw bits.  For zero, negative
- * or subnormal bit patterns the result is a finite meaningless number: callers either discard
- * it (p <= 0) or multiply it by a subnormal p, a term < 2^-119 that cannot reach the float sum
- * it feeds (h is 0 or >= 2^-24 * |log|, and 1 - h/maxent rounds to 1 for h < 2^-25). */
-/* The polynomial's fp64 constants live in constant memory: DFMA / DADD take a constant-bank
- * operand directly, whereas 64-bit literals are rebuilt with two moves each on every use. */
-__device__ __constant__ double c_logf_k[5] = {
-    0x1.62e42fefa39efp-1,        /* ln 2 */
-    0x1.5575b0be00b6ap-2,        /* A[1] */
-    -0x1.ffffef20a4123p-2,       /* A[2] */
-    -0x1.00ea348b88334p-2,       /* A[0] */
-    4503601774854144.0,          /* 2^52 + 2^31 */
-};
-
-template <typename TabLoad>
-__device__ __forceinline__ float logf_core_t(uint32_t ix, TabLoad tabload)
-{
-    const uint32_t tmp = ix - 0x3f330000u;
-    const int k = (int32_t)tmp >> 23;
-    const uint32_t iz = ix - (tmp & 0xff800000u);
-    const double2 t = tabload((tmp >> 15) & 0xf0u);          /* byte offset of entry (tmp >> 19) & 15 */
-    const double z = (double)__uint_as_float(iz);
-    /* (double)k without the conversion unit: 2^52 + 2^31 + k, minus the bias */
-    const double kd = __dsub_rn(__hiloint2double(0x43300000, (int)(0x80000000u ^ (uint32_t)k)), c_logf_k[4]);
-    const double r = __fma_rn(z, t.x, -1.0);
-    const double y0 = __fma_rn(kd, c_logf_k[0], t.y);
-    const double r2 = __dmul_rn(r, r);
-    double y = __fma_rn(c_logf_k[1], r, c_logf_k[2]);
-    y = __fma_rn(c_logf_k[3], r2, y);
-    y = __fma_rn(y, r2, __dadd_rn(y0, r));
-    return (float)y;
-}
-
-#ifdef TSK_LOGF_KI
-/* the same logarithm for LOGF_KI_FIRST <= ix <= 0x3f800000 from one table entry per (k, i): the
- * entry's reciprocal carries 2^-k, so p itself is the multiplicand (no mantissa extraction), and
- * its second half is the finished y0 = k*ln2 + logc (no int -> double, no FMA).  Every operation
- * left is one the form above performs on the same values, hence the same float; other bit
- * patterns give a finite meaningless number from an in-bounds entry (callers discard it). */
-template <typename TabLoad>
-__device__ __forceinline__ float logf_ki_t(uint32_t ix, TabLoad tabload)
-{
-    const uint32_t tmp = ix - 0x3f330000u;
-    const double2 t = tabload((tmp >> 15) & 0xff0u);              /* byte offset of entry (k & 15, i) */
-    const double r = __fma_rn((double)__uint_as_float(ix), t.x, -1.0);
-    const double r2 = __dmul_rn(r, r);
-    double y = __fma_rn(c_logf_k[1], r, c_logf_k[2]);
-    y = __fma_rn(c_logf_k[3], r2, y);
-    y = __fma_rn(y, r2, __dadd_rn(t.y, r));
-    return (float)y;
-}
-#endif
 
 __device__ __forceinline__ float logf_core(uint32_t ix, const double2 *__restrict__ tab)
 {

@@ -1,0 +1,71 @@
+// CPU check of the scoring kernels' exact-arithmetic helpers, compiled from THEIR OWN SOURCE
+// (tailseeker_b200/csrc/tsk_exact.cuh, tsk_device.cuh through tsk_hostcheck.h):
+//   div_by_rcp(a, b, RN(1/b))  ==  a / b                      (signalproc.c:246-266,329 divisions)
+//   tsk_logf, logf_core_t, logf_ki_t  ==  the host's logf     (shannon_entropy, signalproc.c:39-51)
+// g++ -O2 -mfma -ffp-contract=off -DTSK_HOST_CHECK -DTSK_LOGF_KI=1 -I tailseeker_b200/csrc
+//     usage: exact_check [stride over the floats in (0,1], default 1 = every one] [division pairs]
+#include <cstdio>
+#include <cstdlib>
+#include <pthread.h>
+#include "tsk_exact.cuh"
+
+#define NT 8
+static double2 TAB[16], KI[16 * 16];
+struct job { int id; uint32_t stride; uint64_t pairs, n, bad_logf[3], bad_div; };
+
+static void *run(void *p)
+{
+    job *j = (job *)p;
+    const double2 *tab = TAB, *ki = KI;
+    for (uint64_t ix = 0x00800000u + (uint64_t)j->id * j->stride; ix <= 0x3f800000u; ix += (uint64_t)NT * j->stride) {
+        const uint32_t u = (uint32_t)ix;
+        const uint32_t want = __float_as_uint(logf(__uint_as_float(u)));
+        j->n++;
+        j->bad_logf[0] += __float_as_uint(tsk_logf(__uint_as_float(u), tab)) != want;
+        j->bad_logf[1] += __float_as_uint(logf_core_t(u, [tab](uint32_t ofs) { return tab[ofs >> 4]; })) != want;
+        if (u >= LOGF_KI_FIRST)
+            j->bad_logf[2] += __float_as_uint(logf_ki_t(u, [ki](uint32_t ofs) { return ki[ofs >> 4]; })) != want;
+    }
+    // the operand pairs of the GPU self-test (k_div_sweep, both modes), a stretch per thread
+    for (int mode = 0; mode < 2; mode++)
+        for (uint64_t i = j->id; i < j->pairs; i += NT) {
+            uint64_t x = (i + (mode ? 98765 : 12345)) * 0x9E3779B97F4A7C15ull;
+            x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull; x ^= x >> 32;
+            const uint32_t ab = (uint32_t)x, bb = (uint32_t)(x >> 32);
+            float a, b;
+            if (mode == 0) {
+                b = __uint_as_float(((127 - 40 + (bb >> 23) % 80) << 23) | (bb & 0x7fffffu));
+                a = __uint_as_float((ab & 0x80000000u) | ((127 - 60 + ((ab >> 23) & 0xff) % 120) << 23) | (ab & 0x7fffffu));
+            } else {
+                b = __uint_as_float(((124 + (bb >> 23) % 6) << 23) | (bb & 0x7fffffu));
+                a = __fmul_rn(b, __uint_as_float(0x3f800000u | (ab & 0x7fffffu)) - 1.0f);
+            }
+            const float q = div_by_rcp(a, b, 1.0f / b), want = a / b;
+            j->bad_div += __float_as_uint(q) != __float_as_uint(want) && !(q == 0.f && want == 0.f);
+        }
+    return NULL;
+}
+
+int main(int argc, char **argv)
+{
+    const uint32_t stride = argc > 1 ? (uint32_t)strtoul(argv[1], NULL, 10) : 1;
+    const uint64_t pairs = argc > 2 ? strtoull(argv[2], NULL, 10) : (1ull << 30);
+    for (int i = 0; i < 16; i++) TAB[i] = make_double2(c_logf_tab[i][0], c_logf_tab[i][1]);
+    for (int e = 0; e < 256; e++) {                       // as load_score_shared() fills ScoreShared::logki
+        const int k = (e >> 4) ? (e >> 4) - 16 : 0, i = e & 15;
+        KI[e] = make_double2(scalbn(c_logf_tab[i][0], -k), __fma_rn((double)k, 0x1.62e42fefa39efp-1, c_logf_tab[i][1]));
+    }
+    pthread_t t[NT];
+    job j[NT];
+    uint64_t n = 0, bl[3] = {0, 0, 0}, bd = 0;
+    for (int i = 0; i < NT; i++) { j[i] = job(); j[i].id = i; j[i].stride = stride ? stride : 1; j[i].pairs = pairs; pthread_create(&t[i], NULL, run, &j[i]); }
+    for (int i = 0; i < NT; i++) {
+        pthread_join(t[i], NULL);
+        n += j[i].n; bd += j[i].bad_div;
+        for (int v = 0; v < 3; v++) bl[v] += j[i].bad_logf[v];
+    }
+    printf("{\"floats\": %llu, \"tsk_logf\": %llu, \"logf_core_t\": %llu, \"logf_ki_t\": %llu, \"division_pairs\": %llu, \"div_by_rcp\": %llu}\n",
+           (unsigned long long)n, (unsigned long long)bl[0], (unsigned long long)bl[1], (unsigned long long)bl[2],
+           (unsigned long long)(2 * pairs), (unsigned long long)bd);
+    return (bl[0] || bl[1] || bl[2] || bd) ? 1 : 0;
+}
