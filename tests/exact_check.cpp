@@ -4,6 +4,9 @@
 //   tsk_logf, logf_core_t, logf_ki_t  ==  the host's logf     (shannon_entropy, signalproc.c:39-51)
 // g++ -O2 -mfma -ffp-contract=off -DTSK_HOST_CHECK -DTSK_LOGF_KI=1 -I tailseeker_b200/csrc
 //     usage: exact_check [stride over the floats in (0,1], default 1 = every one] [division pairs]
+//                        [stride over the divisor significands of the hard-case search, default 17]
+// Hard cases of the division (see tools/div_onestep_proof.c): the quotients nearest to a rounding
+// midpoint, X*B + k = 2^S * A with X odd and |k| <= 33 * 2^ctz(B), for the chosen divisors B.
 #include <cstdio>
 #include <cstdlib>
 #include <pthread.h>
@@ -11,7 +14,34 @@
 
 #define NT 8
 static double2 TAB[16], KI[16 * 16];
-struct job { int id; uint32_t stride; uint64_t pairs, n, bad_logf[3], bad_div; };
+struct job { int id; uint32_t stride, bstride; uint64_t pairs, n, bad_logf[3], bad_div, hard, bad_hard; };
+
+static uint64_t inv_odd(uint64_t b) { uint64_t x = b; for (int i = 0; i < 6; i++) x *= 2 - b * x; return x; }
+
+static void hard_cases(job *j)
+{
+    for (uint64_t B = (1u << 23) + (uint64_t)j->id * j->bstride; B < (1u << 24); B += (uint64_t)NT * j->bstride) {
+        const int t = __builtin_ctzll(B);
+        const uint64_t iB = inv_odd(B >> t);
+        for (int S = 24; S <= 25; S++) {
+            if (S - t < 2) continue;
+            const uint64_t M = 1ull << (S - t);
+            for (int kk = -33; kk <= 33; kk++) {
+                if (kk == 0) continue;
+                for (uint64_t X = ((uint64_t)(-(int64_t)kk) * iB) & (M - 1); X < (1ull << 25); X += M) {
+                    if (X <= (1ull << 24) || !(X & 1)) continue;
+                    const int64_t num = (int64_t)(X * B) + (int64_t)kk * (int64_t)(1ull << t);
+                    if (num <= 0 || (num & ((1ll << S) - 1))) continue;
+                    const uint64_t A = (uint64_t)num >> S;
+                    if (A < (1u << 23) || A >= (1u << 24)) continue;
+                    const float a = ldexpf((float)A, -10), b = ldexpf((float)B, -7);
+                    j->hard++;
+                    j->bad_hard += __float_as_uint(div_by_rcp(a, b, 1.0f / b)) != __float_as_uint(a / b);
+                }
+            }
+        }
+    }
+}
 
 static void *run(void *p)
 {
@@ -43,6 +73,7 @@ static void *run(void *p)
             const float q = div_by_rcp(a, b, 1.0f / b), want = a / b;
             j->bad_div += __float_as_uint(q) != __float_as_uint(want) && !(q == 0.f && want == 0.f);
         }
+    hard_cases(j);
     return NULL;
 }
 
@@ -55,17 +86,18 @@ int main(int argc, char **argv)
         const int k = (e >> 4) ? (e >> 4) - 16 : 0, i = e & 15;
         KI[e] = make_double2(scalbn(c_logf_tab[i][0], -k), __fma_rn((double)k, 0x1.62e42fefa39efp-1, c_logf_tab[i][1]));
     }
+    const uint32_t bstride = argc > 3 ? (uint32_t)strtoul(argv[3], NULL, 10) : 17;
     pthread_t t[NT];
     job j[NT];
-    uint64_t n = 0, bl[3] = {0, 0, 0}, bd = 0;
-    for (int i = 0; i < NT; i++) { j[i] = job(); j[i].id = i; j[i].stride = stride ? stride : 1; j[i].pairs = pairs; pthread_create(&t[i], NULL, run, &j[i]); }
+    uint64_t n = 0, bl[3] = {0, 0, 0}, bd = 0, hard = 0, bh = 0;
+    for (int i = 0; i < NT; i++) { j[i] = job(); j[i].id = i; j[i].stride = stride ? stride : 1; j[i].pairs = pairs; j[i].bstride = bstride ? bstride : 1; pthread_create(&t[i], NULL, run, &j[i]); }
     for (int i = 0; i < NT; i++) {
         pthread_join(t[i], NULL);
-        n += j[i].n; bd += j[i].bad_div;
+        n += j[i].n; bd += j[i].bad_div; hard += j[i].hard; bh += j[i].bad_hard;
         for (int v = 0; v < 3; v++) bl[v] += j[i].bad_logf[v];
     }
-    printf("{\"floats\": %llu, \"tsk_logf\": %llu, \"logf_core_t\": %llu, \"logf_ki_t\": %llu, \"division_pairs\": %llu, \"div_by_rcp\": %llu}\n",
+    printf("{\"floats\": %llu, \"tsk_logf\": %llu, \"logf_core_t\": %llu, \"logf_ki_t\": %llu, \"division_pairs\": %llu, \"div_by_rcp\": %llu, \"hard_quotients\": %llu, \"div_by_rcp_hard\": %llu}\n",
            (unsigned long long)n, (unsigned long long)bl[0], (unsigned long long)bl[1], (unsigned long long)bl[2],
-           (unsigned long long)(2 * pairs), (unsigned long long)bd);
-    return (bl[0] || bl[1] || bl[2] || bd) ? 1 : 0;
+           (unsigned long long)(2 * pairs), (unsigned long long)bd, (unsigned long long)hard, (unsigned long long)bh);
+    return (bl[0] || bl[1] || bl[2] || bd || bh) ? 1 : 0;
 }

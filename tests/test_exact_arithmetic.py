@@ -26,9 +26,11 @@ def test_kernel_helpers_are_exact_on_the_host(tmp_path):
     subprocess.check_call(["g++", "-O2", "-mfma", "-ffp-contract=off", "-DTSK_HOST_CHECK", "-DTSK_LOGF_KI=1",
                            "-I", os.path.join(ROOT, "tailseeker_b200", "csrc"), "-o", exe,
                            os.path.join(ROOT, "tests", "exact_check.cpp"), "-lm", "-lpthread"])
-    r = subprocess.run([exe, "1", str(1 << 26)], capture_output=True, timeout=600)
+    r = subprocess.run([exe, "1", str(1 << 26), "17"], capture_output=True, timeout=600)
     out = json.loads(r.stdout.decode())
     assert r.returncode == 0, out
     assert out["floats"] == 0x3f800000 - 0x00800000 + 1          # every normal float in (0, 1]
     assert out["tsk_logf"] == out["logf_core_t"] == out["logf_ki_t"] == out["div_by_rcp"] == 0
     assert out["division_pairs"] == 2 << 26
+    # quotients nearest to a rounding midpoint, for every 17th divisor significand
+    assert out["hard_quotients"] > 20_000_000 and out["div_by_rcp_hard"] == 0
