@@ -28,6 +28,8 @@ static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline int __double2int_rz(double a) { return (int)a; }
 static inline double __hiloint2double(int hi, int lo)
 {
     const uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;

@@ -10,6 +10,7 @@
  * (:154-172).
  */
 #include "tsk_internal.h"
+#include "tsk_scorebin.cuh"
 
 #define FULL_MASK 0xffffffffu
 #define RULER_THREADS 256
@@ -23,26 +24,6 @@ struct RulerSegs {
     unsigned long long base[TSK_MAX_SAMPLES];
     int dump[TSK_MAX_SAMPLES];
 };
-
-/* floor((sc - 1) * bins / 16777214) of add_polya_score_sample() (polyaruler.c:163-168). */
-__device__ __forceinline__ int score_bin(uint32_t sc, int bins, int intbins)
-{
-    int b;
-    if (intbins) {
-        /* in integers: with x = a*2^24 + b0 and 2^24 = 16777214 + 2, x = a*16777214 + (2a + b0),
-         * 2a + b0 < 2*16777214.  Equals the reference's fp64 expression whenever bins shares no
-         * factor with 2^23-1 (the host checks): the exact value is then an integer only for
-         * sc-1 in {0, 8388607, 16777214}, which fp64 evaluates exactly, and is otherwise
-         * >= 2^-24 away from one, far beyond the fp64 rounding error. */
-        const unsigned long long x = (unsigned long long)(sc - 1) * (unsigned)bins;
-        const uint32_t a = (uint32_t)(x >> 24), b0 = (uint32_t)x & 0xffffffu;
-        b = (int)(a + ((2 * a + b0) >= 16777214u ? 1u : 0u));
-    } else {
-        b = __double2int_rz(__dmul_rn(__ddiv_rn(__dsub_rn((double)sc, 1.0), (double)(TSK_SCORE_MAX - 1)),
-                                      (double)bins));
-    }
-    return b >= bins ? bins - 1 : b;
-}
 
 /* Records longer than 256 cycles: the same steps with the packets re-read through L1. */
 __device__ __noinline__ int ruler_long_record(const uint32_t *__restrict__ rec, int first, int valid,

@@ -3,6 +3,8 @@
 //   div_by_rcp(a, b, RN(1/b))  ==  a / b                      (signalproc.c:246-266,329 divisions)
 //   tsk_logf, logf_core_t, logf_ki_t  ==  the host's logf     (shannon_entropy, signalproc.c:39-51)
 // g++ -O2 -mfma -ffp-contract=off -DTSK_HOST_CHECK -DTSK_LOGF_KI=1 -I tailseeker_b200/csrc
+//   score_bin(sc, bins, integer form) == min(bins - 1, (int)(((sc - 1.) / 16777214) * bins)) in fp64
+//                                          for every packed score (polyaruler.c:163-168)
 //     usage: exact_check [stride over the floats in (0,1], default 1 = every one] [division pairs]
 //                        [stride over the divisor significands of the hard-case search, default 17]
 // Hard cases of the division (see tools/div_onestep_proof.c): the quotients nearest to a rounding
@@ -11,10 +13,11 @@
 #include <cstdlib>
 #include <pthread.h>
 #include "tsk_exact.cuh"
+#include "tsk_scorebin.cuh"
 
 #define NT 8
 static double2 TAB[16], KI[16 * 16];
-struct job { int id; uint32_t stride, bstride; uint64_t pairs, n, bad_logf[3], bad_div, hard, bad_hard; };
+struct job { int id; uint32_t stride, bstride; uint64_t pairs, n, bad_logf[3], bad_div, hard, bad_hard, nbins, bad_bins; };
 
 static uint64_t inv_odd(uint64_t b) { uint64_t x = b; for (int i = 0; i < 6; i++) x *= 2 - b * x; return x; }
 
@@ -74,6 +77,17 @@ static void *run(void *p)
             j->bad_div += __float_as_uint(q) != __float_as_uint(want) && !(q == 0.f && want == 0.f);
         }
     hard_cases(j);
+    // every packed score 1 .. 2^24 - 1, for bin counts the launcher sends down the integer form
+    // (tsk_ruler.cu: bins <= 65536 sharing no factor with 2^23 - 1 = 47 * 178481)
+    static const int BINS[] = {1000, 470 + 1, 64, 30000, 65536, 1, 2, 3, 999, 1024, 4096, 46, 48, 12345};
+    for (unsigned b = j->id; b < sizeof(BINS) / sizeof(BINS[0]); b += NT)
+        for (uint32_t sc = 1; sc <= TSK_SCORE_MAX; sc++) {
+            const int bins = BINS[b];
+            int want = (int)((((double)sc - 1.) / 16777214) * bins);
+            if (want >= bins) want = bins - 1;
+            j->nbins++;
+            j->bad_bins += score_bin(sc, bins, 1) != want || score_bin(sc, bins, 0) != want;
+        }
     return NULL;
 }
 
@@ -89,15 +103,16 @@ int main(int argc, char **argv)
     const uint32_t bstride = argc > 3 ? (uint32_t)strtoul(argv[3], NULL, 10) : 17;
     pthread_t t[NT];
     job j[NT];
-    uint64_t n = 0, bl[3] = {0, 0, 0}, bd = 0, hard = 0, bh = 0;
+    uint64_t n = 0, bl[3] = {0, 0, 0}, bd = 0, hard = 0, bh = 0, nb = 0, bb = 0;
     for (int i = 0; i < NT; i++) { j[i] = job(); j[i].id = i; j[i].stride = stride ? stride : 1; j[i].pairs = pairs; j[i].bstride = bstride ? bstride : 1; pthread_create(&t[i], NULL, run, &j[i]); }
     for (int i = 0; i < NT; i++) {
         pthread_join(t[i], NULL);
-        n += j[i].n; bd += j[i].bad_div; hard += j[i].hard; bh += j[i].bad_hard;
+        n += j[i].n; bd += j[i].bad_div; hard += j[i].hard; bh += j[i].bad_hard; nb += j[i].nbins; bb += j[i].bad_bins;
         for (int v = 0; v < 3; v++) bl[v] += j[i].bad_logf[v];
     }
-    printf("{\"floats\": %llu, \"tsk_logf\": %llu, \"logf_core_t\": %llu, \"logf_ki_t\": %llu, \"division_pairs\": %llu, \"div_by_rcp\": %llu, \"hard_quotients\": %llu, \"div_by_rcp_hard\": %llu}\n",
+    printf("{\"floats\": %llu, \"tsk_logf\": %llu, \"logf_core_t\": %llu, \"logf_ki_t\": %llu, \"division_pairs\": %llu, \"div_by_rcp\": %llu, \"hard_quotients\": %llu, \"div_by_rcp_hard\": %llu, \"score_bins\": %llu, \"score_bin\": %llu}\n",
            (unsigned long long)n, (unsigned long long)bl[0], (unsigned long long)bl[1], (unsigned long long)bl[2],
-           (unsigned long long)(2 * pairs), (unsigned long long)bd, (unsigned long long)hard, (unsigned long long)bh);
-    return (bl[0] || bl[1] || bl[2] || bd || bh) ? 1 : 0;
+           (unsigned long long)(2 * pairs), (unsigned long long)bd, (unsigned long long)hard, (unsigned long long)bh,
+           (unsigned long long)nb, (unsigned long long)bb);
+    return (bl[0] || bl[1] || bl[2] || bd || bh || bb) ? 1 : 0;
 }

@@ -1,7 +1,8 @@
 """CPU: the scoring kernels' exact-arithmetic helpers, compiled for the host FROM THEIR OWN SOURCE
 (tailseeker_b200/csrc/tsk_exact.cuh + tsk_device.cuh, intrinsics mapped by tsk_hostcheck.h), against
 IEEE division and the host libm's logf -- the two things the reference's scores are made of
-(signalproc.c:39-51 shannon_entropy, :246-266 normalize_signals).  Exhaustive over every normal float
+(signalproc.c:39-51 shannon_entropy, :246-266 normalize_signals) -- and the ruler's histogram bin
+(tsk_scorebin.cuh) against the fp64 expression of polyaruler.c:163-168.  Exhaustive over every normal float
 in (0, 1] for the three logf forms; the GPU self-test's own operand pairs for the division."""
 import json
 import os
@@ -34,3 +35,5 @@ def test_kernel_helpers_are_exact_on_the_host(tmp_path):
     assert out["division_pairs"] == 2 << 26
     # quotients nearest to a rounding midpoint, for every 17th divisor significand
     assert out["hard_quotients"] > 20_000_000 and out["div_by_rcp_hard"] == 0
+    # the ruler's integer histogram bin against the reference's fp64 expression, every packed score
+    assert out["score_bins"] == 14 * ((1 << 24) - 1) and out["score_bin"] == 0
