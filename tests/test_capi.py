@@ -41,6 +41,31 @@ def test_no_gpu_means_loud_failure():
         TileProcessor(stock_config("miseq"))
 
 
+def test_programs_fail_loudly_without_gpu(tmp_path):
+    """The drop-in importer (one or several tiles per process) has no CPU path either: it reads the tile,
+    then stops with the library's message and the reference's failure status (-1 -> 255)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from tailseeker_b200.config import stock_config
+    from tailseeker_b200.synth import make_tile, write_tile_files
+    exe = os.path.join(ROOT, "tailseeker_b200", "bin", "tailseq-import")
+    assert os.access(exe, os.X_OK), "host programs not built (__graft_entry__.build())"
+    cfg = stock_config("miseq")
+    tile = make_tile(cfg, 50, seed=1)
+    data = str(tmp_path / "data")
+    mpath = write_tile_files(tile, cfg, data)
+    for sub in ("seqqual", "taginfo", "signals", "sigdists-r00", "stats"):
+        os.makedirs(str(tmp_path / sub))
+    ini = str(tmp_path / "t.ini")
+    with open(ini, "w") as f:
+        f.write(cfg.replace(data_dir=data, threep_colormatrix=mpath).to_ini())
+    r = subprocess.run([exe, ini, ini], cwd=str(tmp_path), capture_output=True)
+    assert r.returncode == 255
+    assert b"no CPU path" in r.stderr and b"Finished." not in r.stdout
+    assert r.stdout.count(b"Opening input sources") == 1          # the chain stops at the first tile
+
+
 def test_ctypes_layout_matches_header(tmp_path):
     from tailseeker_b200.config import CCall, CParams, CSample
     src = tmp_path / "sz.c"
