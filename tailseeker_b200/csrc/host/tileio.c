@@ -29,6 +29,7 @@ struct tile_files {
     gzFile *bcl;                        /* NULL for a cycle taken from a FASTQ override */
     struct fastq_override *alt;         /* in the configuration's list order */
     int nalt;
+    int threads;                        /* [options] threads: cycle files read side by side */
 };
 
 /* One FASTQ line into buf (BUFSIZ like the reference, which therefore splits longer lines too).
@@ -164,6 +165,7 @@ struct tile_files *tsk_open_tile(const struct host_config *cfg, const char *msgp
     struct tile_files *tf = calloc(1, sizeof(*tf));
     if (!tf) return NULL;
     tf->T = cfg->total_cycles; tf->L3 = cfg->threep_length;
+    tf->threads = cfg->threads > 0 ? cfg->threads : 1;
     tf->cif = calloc(tf->L3, sizeof(FILE *));
     tf->bcl = calloc(tf->T, sizeof(gzFile));
     unsigned char *overridden = calloc(tf->T > 0 ? tf->T : 1, 1);
@@ -232,38 +234,81 @@ bad_bcl:
 
 uint32_t tsk_tile_nclusters(const struct tile_files *tf) { return tf->nclusters; }
 
+/* One cycle file is one task: every file has its own handle and its own rows of the block, so the
+ * [options] threads read them side by side (a page-cached 1 M-cluster tile is 2.5 GB of copying,
+ * the longest host phase of the importer after start-up when it runs on one thread). */
+struct read_job {
+    struct tile_files *tf;
+    uint32_t count;
+    uint8_t *bcl;
+    int16_t *cif;
+    int index;                          /* CIF cycle, BCL cycle, or unused for the overrides */
+};
+
+static int read_cif_cycle(void *arg)
+{
+    const struct read_job *j = arg;
+    struct tile_files *tf = j->tf;
+    const int i = j->index;
+    for (int ch = 0; ch < 4; ch++) {
+        const long at = 13 + ((long)tf->nclusters * ch + tf->read) * 2;
+        int16_t *dst = j->cif + ((size_t)i * 4 + ch) * j->count;
+        if (fseek(tf->cif[i], at, SEEK_SET) != 0) {
+            fprintf(stderr, "Failed to seek cluster intensity values in a CIF.\n");
+            return -1;
+        }
+        if (fread(dst, 2, j->count, tf->cif[i]) != j->count) {
+            fprintf(stderr, "Not all data were loaded from a CIF.\n");
+            return -1;
+        }
+#if __BYTE_ORDER != __LITTLE_ENDIAN
+        for (uint32_t k = 0; k < j->count; k++) dst[k] = (int16_t)le16toh((uint16_t)dst[k]);
+#endif
+    }
+    return 0;
+}
+
+static int read_bcl_cycle(void *arg)
+{
+    const struct read_job *j = arg;
+    const int c = j->index;
+    uint8_t *dst = j->bcl + (size_t)c * j->count;
+    uint32_t got = 0;
+    while (got < j->count) {          /* gzread takes an unsigned int length */
+        const uint32_t want = j->count - got > (1u << 30) ? (1u << 30) : j->count - got;
+        const int r = gzread(j->tf->bcl[c], dst + got, want);
+        if (r < 1) { fprintf(stderr, "Unexpected EOF in a BCL (cycle %d).\n", c + 1); return -1; }
+        got += (uint32_t)r;
+    }
+    return 0;
+}
+
+/* the overrides stay on one thread, in list order: where two of them overlap the later entry of
+ * the list wins (their cycles have no BCL task, so nothing else writes those rows) */
+static int read_overrides(void *arg)
+{
+    const struct read_job *j = arg;
+    for (int a = 0; a < j->tf->nalt; a++)
+        if (read_fastq_override(&j->tf->alt[a], j->count, j->bcl) < 0) return -1;
+    return 0;
+}
+
 int tsk_read_block(struct tile_files *tf, uint32_t count, uint8_t *bcl, int16_t *cif)
 {
-    for (int i = 0; i < tf->L3; i++)
-        for (int ch = 0; ch < 4; ch++) {
-            const long at = 13 + ((long)tf->nclusters * ch + tf->read) * 2;
-            int16_t *dst = cif + ((size_t)i * 4 + ch) * count;
-            if (fseek(tf->cif[i], at, SEEK_SET) != 0) {
-                fprintf(stderr, "Failed to seek cluster intensity values in a CIF.\n");
-                return -1;
-            }
-            if (fread(dst, 2, count, tf->cif[i]) != count) {
-                fprintf(stderr, "Not all data were loaded from a CIF.\n");
-                return -1;
-            }
-#if __BYTE_ORDER != __LITTLE_ENDIAN
-            for (uint32_t k = 0; k < count; k++) dst[k] = (int16_t)le16toh((uint16_t)dst[k]);
-#endif
-        }
-    /* overrides first, in list order: where two of them overlap the later entry of the list wins */
-    for (int a = 0; a < tf->nalt; a++)
-        if (read_fastq_override(&tf->alt[a], count, bcl) < 0) return -1;
-    for (int c = 0; c < tf->T; c++) {
-        uint8_t *dst = bcl + (size_t)c * count;
-        uint32_t got = 0;
-        if (!tf->bcl[c]) continue;
-        while (got < count) {          /* gzread takes an unsigned int length */
-            const uint32_t want = count - got > (1u << 30) ? (1u << 30) : count - got;
-            const int r = gzread(tf->bcl[c], dst + got, want);
-            if (r < 1) { fprintf(stderr, "Unexpected EOF in a BCL (cycle %d).\n", c + 1); return -1; }
-            got += (uint32_t)r;
-        }
-    }
+    const int maxtasks = tf->L3 + tf->T + 1;
+    struct read_job *jobs = calloc(maxtasks, sizeof(*jobs));
+    struct tsk_task *tasks = calloc(maxtasks, sizeof(*tasks));
+    int n = 0, rc;
+    if (!jobs || !tasks) { perror("tsk_read_block"); free(jobs); free(tasks); return -1; }
+#define ADD_TASK(function, idx) do { jobs[n] = (struct read_job){tf, count, bcl, cif, (idx)}; \
+                                     tasks[n].fn = (function); tasks[n].arg = &jobs[n]; n++; } while (0)
+    if (tf->nalt > 0) ADD_TASK(read_overrides, 0);          /* the slowest task first */
+    for (int i = 0; i < tf->L3; i++) ADD_TASK(read_cif_cycle, i);
+    for (int c = 0; c < tf->T; c++) if (tf->bcl[c]) ADD_TASK(read_bcl_cycle, c);
+#undef ADD_TASK
+    rc = tsk_run_tasks(tasks, n, tf->threads);
+    free(jobs); free(tasks);
+    if (rc != 0) return -1;
     tf->read += count;
     return 0;
 }

@@ -111,8 +111,8 @@ def test_reference_with_overrides_equals_reference_on_rewritten_bcl(tmp_path):
     assert using(r.stdout.decode()) == using(a["stdout"]) and len(using(a["stdout"])) == 6
 
 
-def _dump(cfg, data, mpath, workdir, read_buffer_size=None):
-    rcfg = cfg.replace(data_dir=data, threep_colormatrix=mpath,
+def _dump(cfg, data, mpath, workdir, read_buffer_size=None, threads=1):
+    rcfg = cfg.replace(data_dir=data, threep_colormatrix=mpath, threads=threads,
                        read_buffer_size=read_buffer_size or 2147483648)
     ini = os.path.join(workdir, "dump.ini")
     with open(ini, "w") as f:
@@ -156,8 +156,10 @@ def test_host_reader_hands_over_the_mirror_bytes(tmp_path):
             shutil.copyfileobj(f, g)
         os.remove(p)
     want = altcalls.overlay(tile.bcl, entries)
-    for bufsize, minblocks in ((None, 1), (4 * 1024 * 1024, 3)):
-        r, blocks, cifs = _dump(cfg.replace(alternative_calls=entries), data, mpath, str(tmp_path), bufsize)
+    # [options] threads: the cycle files of a block are read side by side
+    for bufsize, minblocks, threads in ((None, 1, 1), (4 * 1024 * 1024, 3, 1), (None, 1, 6), (4 * 1024 * 1024, 3, 16)):
+        r, blocks, cifs = _dump(cfg.replace(alternative_calls=entries), data, mpath, str(tmp_path), bufsize,
+                                threads)
         assert r.returncode == 0, r.stderr.decode()
         assert len(blocks) >= minblocks
         assert (np.concatenate(blocks, axis=1) == want).all()
