@@ -174,13 +174,22 @@ int tsk_ctx_destroy(tsk_ctx *ctx);
  * AoS transpose of cifreader.c:163-164: data stay in the files' native layouts,
  *   bcl[total_cycles][bcl_pitch] u8,   cif[threep_length][4][cif_pitch] i16  (A,C,G,T planes)
  * pitches in ELEMENTS, >= nclusters.  on_device != 0: the pointers are device pointers that
- * the caller keeps alive until the next upload (zero copy) -- bcl must then be 16-byte aligned
+ * the caller keeps alive AND UNMODIFIED until that tile has been processed and the device has
+ * finished with it, i.e. until a getter or tsk_synchronize() has returned after the tile's
+ * tsk_tile_process[_async]() -- not merely until the next upload: two tiles may be pending and
+ * tsk_tile_process_async() returns before its kernels run (zero copy) -- bcl must then be 16-byte aligned
  * with bcl_pitch a multiple of 16 (the rows are fetched by TMA tensor copies; refused otherwise),
  * and cif 16-byte aligned with cif_pitch a multiple of 8 for the fast scoring kernel; otherwise
  * they are host pointers (pinned or pageable) and are copied to HBM on the context's stream.
  * invmatrix = inverse colour matrix (load_color_matrix(), signalproc.c:345-375).
  * Up to two tiles may be uploaded ahead of tsk_tile_process(), which takes them in order: the
- * copy of tile t+1 (on its own stream) then overlaps the kernels of tile t. */
+ * copy of tile t+1 (on its own stream) then overlaps the kernels of tile t; the copy into an
+ * upload slot waits (on the device) for the kernels of the tile that used the slot before.
+ * An upload larger than every tile before it re-allocates the per-cluster result buffers: the
+ * call then waits for everything queued on the device, and results of the previous tile that
+ * have not been read by then (records, calls, lengths) are discarded -- histograms and counters
+ * are kept.  Upload the largest tile first, or read each tile's results before the next upload,
+ * when tile sizes vary. */
 int tsk_tile_upload(tsk_ctx *ctx, const uint8_t *bcl, size_t bcl_pitch,
                     const int16_t *cif, size_t cif_pitch,
                     const float invmatrix[16],

@@ -78,7 +78,8 @@ static uint32_t *read_sigpack(const char *filename, uint32_t *total_clusters, ui
 }
 
 /* output_corrected_polya_measurements(), polyaruler.c:316-388 */
-static int rewrite_taginfo(const char *taginfo_file, const int16_t *meas, const char *tile_id, FILE *out)
+static int rewrite_taginfo(const char *taginfo_file, const int16_t *meas, uint32_t total_clusters,
+                           const char *tile_id, FILE *out)
 {
     gzFile fp = gzopen(taginfo_file, "rt");
     if (!fp) return -1;
@@ -98,6 +99,12 @@ static int rewrite_taginfo(const char *taginfo_file, const int16_t *meas, const 
         tok = strsep(&bptr, "\t\n\r");
         if (!tok) continue;
         clusterno = atoi(tok);
+        if (clusterno >= total_clusters) {          /* a taginfo of another tile (the reference reads out of bounds) */
+            fprintf(stderr, "Cluster %u in %s is beyond the %u clusters of the signal pack.\n",
+                    clusterno, taginfo_file, total_clusters);
+            gzclose(fp);
+            return -1;
+        }
         if (meas[clusterno] < 0) {                 /* not revised: pass the line through */
             size_t term;
             tok[strlen(tok)] = '\t';
@@ -196,8 +203,15 @@ static int run_job(struct ctx_boot *boot, char *const a[9], FILE *out)
             fprintf(stderr, "%s\n", tsk_last_error());
             goto done;
         }
-        for (size_t r = 0; r < nrecords; r++)
-            if (lens[r] >= 0) meas[recs[r * (2 + (size_t)max_cycles)]] = lens[r];
+        for (size_t r = 0; r < nrecords; r++) {
+            const uint32_t clusterno = recs[r * (2 + (size_t)max_cycles)];
+            if (clusterno >= total_clusters) {     /* truncated header / records of another tile */
+                fprintf(stderr, "Cluster %u in %s is beyond the %u clusters of its header.\n",
+                        clusterno, signals_file, total_clusters);
+                goto done;
+            }
+            if (lens[r] >= 0) meas[clusterno] = lens[r];
+        }
     }
     {
         const uint32_t h[3] = {4, (uint32_t)ncycles, (uint32_t)bins};
@@ -210,7 +224,7 @@ static int run_job(struct ctx_boot *boot, char *const a[9], FILE *out)
         }
         gzclose(f);
     }
-    rc = rewrite_taginfo(taginfo_file, meas, tile_id, out) < 0 ? 3 : 0;
+    rc = rewrite_taginfo(taginfo_file, meas, total_clusters, tile_id, out) < 0 ? 3 : 0;
 done:
     free(recs); free(lens); free(meas); free(hist);
     return rc;

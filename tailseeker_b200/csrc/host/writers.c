@@ -151,7 +151,10 @@ static int ob_compress(struct outbuf *b)
     unsigned char *z = NULL;
     size_t zn = 0;
     if (b->n == 0) return 0;
-    if (b->n > GZ_MEMBER_MAX) return -1;           /* chunks are far smaller */
+    if (b->n > GZ_MEMBER_MAX) {                    /* chunks are far smaller (<= 32768 clusters) */
+        fprintf(stderr, "write_block_outputs: a text chunk of %zu bytes exceeds one gzip member\n", b->n);
+        return -1;
+    }
     if (gz_member(b->p, b->n, &z, &zn) != 0) return -1;
     free(b->p);
     b->p = (char *)z; b->n = zn; b->cap = zn;
@@ -270,8 +273,11 @@ int tsk_write_block_outputs(struct host_config *cfg, const tsk_call *calls, uint
 {
     const int S = cfg->num_samples;
     const int nthreads = cfg->threads > 0 ? cfg->threads : 1;
-    /* a few chunks per thread even out samples of very different sizes */
+    /* a few chunks per thread even out samples of very different sizes; and never more than 32768
+     * clusters in a chunk, so that one sample's text of a chunk (< 700 B a line) stays far below
+     * what a single gzip member may hold, whatever [options] threads and read-buffer-size are */
     int nchunks = nthreads > 1 ? nthreads * 4 : 1;
+    if ((uint32_t)nchunks < (nclusters + 32767u) / 32768u) nchunks = (int)((nclusters + 32767u) / 32768u);
     struct host_sample **byidx = calloc(S, sizeof(*byidx));
     struct fmt_job *jobs = NULL;
     struct rec_job *recs = NULL;
@@ -289,7 +295,10 @@ int tsk_write_block_outputs(struct host_config *cfg, const tsk_call *calls, uint
     nparts = 2 * (size_t)S * nchunks + nrec;
     parts = calloc(nparts ? nparts : 1, sizeof(*parts));
     tasks = calloc((size_t)nchunks + nrec + 3 * S, sizeof(*tasks));
-    if (!byidx || !jobs || !recs || !outs || !parts || !tasks) goto done;
+    if (!byidx || !jobs || !recs || !outs || !parts || !tasks) {
+        fprintf(stderr, "write_block_outputs: out of memory\n");
+        goto done;
+    }
     for (struct host_sample *s = cfg->samples; s; s = s->next) byidx[s->numindex] = s;
 
     /* phase 1, all threads: format + deflate the text chunks, deflate the record chunks */
@@ -316,7 +325,10 @@ int tsk_write_block_outputs(struct host_config *cfg, const tsk_call *calls, uint
             tasks[ntask].fn = compress_records; tasks[ntask].arg = j; ntask++;
         }
     }
-    if (run_tasks(tasks, ntask, nthreads) != 0) goto done;
+    if (run_tasks(tasks, ntask, nthreads) != 0) {
+        fprintf(stderr, "write_block_outputs: formatting / compressing the block's outputs failed\n");
+        goto done;
+    }
 
     /* phase 2: append the members to each file in cluster order (one task per file) */
     nrec = 0;
@@ -342,7 +354,10 @@ int tsk_write_block_outputs(struct host_config *cfg, const tsk_call *calls, uint
             tasks[nout].fn = write_stream; tasks[nout].arg = o; nout++;
         }
     }
-    if (run_tasks(tasks, nout, nthreads) != 0) goto done;
+    if (run_tasks(tasks, nout, nthreads) != 0) {
+        fprintf(stderr, "write_block_outputs: writing the block's outputs failed\n");
+        goto done;
+    }
     rc = 0;
 done:
     if (jobs)

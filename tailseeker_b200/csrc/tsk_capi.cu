@@ -234,6 +234,9 @@ extern "C" int tsk_ctx_create(tsk_ctx **out, int device, const tsk_params *param
     TSK_CUDA(cudaStreamCreateWithFlags(&ctx->cstream, cudaStreamNonBlocking));
     TSK_CUDA(cudaEventCreateWithFlags(&ctx->ev_up[0], cudaEventDisableTiming));
     TSK_CUDA(cudaEventCreateWithFlags(&ctx->ev_up[1], cudaEventDisableTiming));
+    TSK_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[0], cudaEventDisableTiming));
+    TSK_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[1], cudaEventDisableTiming));
+    ctx->tile_slot = -1;
     const int S = params->num_samples;
     const size_t histbytes = sizeof(uint32_t) * (size_t)params->total_cycles * params->dist_sampling_bins;
     TSK_CUDA(cudaMalloc(&ctx->d_samples, sizeof(DevSample) * S));
@@ -298,6 +301,7 @@ extern "C" int tsk_ctx_destroy(tsk_ctx *ctx)
     cudaStreamDestroy(ctx->cstream);
     if (ctx->xstream) { cudaStreamDestroy(ctx->xstream); cudaEventDestroy(ctx->ev_ctl[0]); cudaEventDestroy(ctx->ev_ctl[1]); }
     cudaEventDestroy(ctx->ev_up[0]); cudaEventDestroy(ctx->ev_up[1]);
+    cudaEventDestroy(ctx->ev_done[0]); cudaEventDestroy(ctx->ev_done[1]);
     if (ctx->profile) prof_destroy(ctx);
     free(ctx);
     return 0;
@@ -378,6 +382,12 @@ extern "C" int tsk_tile_upload(tsk_ctx *ctx, const uint8_t *bcl, size_t bcl_pitc
     const size_t cpitch = ((size_t)nclusters + 127) & ~(size_t)127;
     if (ensure(&ctx->d_bcl_own[u], &ctx->bcl_cap[u], bpitch * T + 128) != 0) return -1;
     if (ensure(&ctx->d_cif_own[u], &ctx->cif_cap[u], cpitch * 4 * L3 + 128) != 0) return -1;
+    /* the kernels of the tile that last lived in this slot (two uploads ago) may still be queued or
+     * running on the main stream: the copy must not overwrite what they read */
+    if (ctx->slot_busy[u]) {
+        TSK_CUDA(cudaStreamWaitEvent(ctx->cstream, ctx->ev_done[u], 0));
+        ctx->slot_busy[u] = 0;
+    }
     if (nclusters) {
         TSK_CUDA(cudaMemcpy2DAsync(ctx->d_bcl_own[u], bpitch, bcl, bcl_pitch, nclusters, T,
                                    cudaMemcpyHostToDevice, ctx->cstream));
@@ -406,6 +416,7 @@ static int next_tile(tsk_ctx *ctx)
     memcpy(ctx->dp.inv, ctx->pending[0].inv, sizeof(float) * 16);
     if (ctx->pending[0].slot >= 0)
         TSK_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_up[ctx->pending[0].slot], 0));
+    ctx->tile_slot = ctx->pending[0].slot;
     ctx->pending[0] = ctx->pending[1];
     ctx->npending--;
     ctx->tile_valid = 1;

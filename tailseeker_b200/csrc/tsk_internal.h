@@ -82,6 +82,9 @@ struct tsk_ctx {
     int16_t *d_cif_own[2];  size_t cif_cap[2];
     cudaStream_t cstream;
     cudaEvent_t ev_up[2];
+    cudaEvent_t ev_done[2];      /* recorded on the main stream after the last kernel that reads slot u */
+    int slot_busy[2];            /* ev_done[u] has been recorded and not yet waited for by an upload */
+    int tile_slot;               /* upload slot the resident tile lives in (-1: caller's device memory) */
     int up_slot;                 /* slot of the next host upload */
     struct { TileView tv; float inv[16]; int slot; /* -1: caller's device memory */ } pending[2];
     int npending, tile_valid;
@@ -131,6 +134,8 @@ struct tsk_ctx {
     uint64_t h_recbase[TSK_MAX_SAMPLES + 1];
     int processed;
     uint64_t launches;
+    size_t k1_smem_configured;   /* cudaFuncSetAttribute state of this context's device */
+    int k2_attr_set;
 
     /* optional per-stage device timing (tsk_profile_enable) */
     int profile, own_stream, force_generic;

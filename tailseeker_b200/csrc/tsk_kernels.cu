@@ -477,10 +477,10 @@ int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev)
         }
         const size_t smem1 = (size_t)slab_rows * TSK_K1_THREADS + 16 + sizeof(DevSample) * S +
                              sizeof(uint32_t) * (S * TSK_NCOUNT + (TSK_K1_THREADS / 32) * (S + 1));
-        static size_t configured = 0;
-        if (smem1 > configured) {
+        /* the attribute is per device: remembered in the context, not in a process-wide static */
+        if (smem1 > ctx->k1_smem_configured) {
             TSK_CUDA(cudaFuncSetAttribute(k_decode_demux_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-            configured = smem1;
+            ctx->k1_smem_configured = smem1;
         }
         k_decode_demux_seed<<<nblk, TSK_K1_THREADS, smem1, st>>>(
             P, tv, ctx->d_samples, ctx->d_calls, ctx->d_kind, ctx->d_bucket, ctx->d_blkcnt,
@@ -514,6 +514,12 @@ int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev)
     if (ev) TSK_CUDA(cudaEventRecord(ev[3], st));
     if (tsk_launch_fixups(ctx) != 0) return -1;
     if (ev) TSK_CUDA(cudaEventRecord(ev[4], st));
+    /* nothing after this point reads the tile's base calls or intensities: its upload slot may be
+     * refilled (tsk_tile_upload waits for this event on the copy stream) */
+    if (ctx->tile_slot >= 0) {
+        TSK_CUDA(cudaEventRecord(ctx->ev_done[ctx->tile_slot], st));
+        ctx->slot_busy[ctx->tile_slot] = 1;
+    }
     TSK_CUDA(cudaGetLastError());
     return 0;
 }

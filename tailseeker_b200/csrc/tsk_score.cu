@@ -1678,13 +1678,12 @@ int tsk_launch_score(tsk_ctx *ctx)
         k_normalise_score_pack_generic<<<grid, TSK_K2_THREADS, 0, ctx->stream>>>(ctx->dp, a, 1);
         ctx->launches += 1;
     } else {
-        static bool attr_set = false;
-        if (!attr_set) {
+        if (!ctx->k2_attr_set) {            /* per device, hence per context */
             TSK_CUDA(cudaFuncSetAttribute(k_normalise_score_pack, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(K2Smem)));
             TSK_CUDA(cudaFuncSetAttribute(k_normalise_score_pack_compact, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(K2SmemC)));
-            attr_set = true;
+            ctx->k2_attr_set = 1;
         }
         const float rcp_maxent = 1.0f / ctx->dp.maximum_entropy;      /* IEEE RN on the host */
         /* at most N work items, whose number is only known on the device: surplus warps return */

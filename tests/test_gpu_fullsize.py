@@ -2,8 +2,8 @@
 size-independent properties: the three scoring kernels (compact work-list form, row form,
 literal form -- independent code paths) must agree bit for bit on every output, a second pass
 must reproduce the first, the counters must account for every cluster, and the ruler's three
-entry points must agree.  The oracle itself is too slow at this size; its parity with the CUDA
-path is pinned on smaller tiles in test_gpu_parity.py."""
+entry points must agree.  Parity with the oracle and with the reference binaries at these sizes
+is test_gpu_fullsize_oracle.py."""
 import numpy as np
 import pytest
 

@@ -472,3 +472,41 @@ def test_device_pointer_requirements(stock_cfg):
                      bcl_pitch=pitch, cif_pitch=pitch)
     finally:
         p.close()
+
+
+def test_streamed_host_uploads_reuse_slots(stock_cfg, oracle):
+    """Five host tiles through the two upload slots with nothing read in between: the copy of tile
+    t+2 must wait for the kernels of tile t (same slot).  Pinned buffers and tiles whose copy is
+    much shorter than their kernels make the overwrite visible if the wait is missing: the ruler
+    histogram accumulated over all tiles, the counters and the last tile must equal the blocking run."""
+    import torch
+    from tailseeker_b200.synth import make_tile
+    from tailseeker_b200.importer import TileProcessor, invert_colormatrix
+    cfg = stock_cfg
+    T = cfg.total_cycles
+    tiles = [make_tile(cfg, n, seed=sd) for n, sd in ((6000, 41), (5000, 42), (6500, 43), (5500, 44), (6000, 45))]
+    pinned = [(torch.from_numpy(t.bcl.copy()).pin_memory(), torch.from_numpy(t.cif.copy()).pin_memory()) for t in tiles]
+    p = TileProcessor(cfg)
+    try:
+        packed = p.cutoffs_to_packed(np.full(T, 0.25))
+        p.ruler_reset(T)
+        for t in tiles:
+            p.upload(t.bcl, t.cif, invert_colormatrix(t.matrix))
+            p.process()
+            p.ruler_tile_all(packed)
+        want_hist, want_counters, want_called = p.ruler_hist(), p.counters(), p.ruler_called()
+        for rep in range(3):
+            p.reset_counters()
+            p.ruler_reset(T)
+            for t, (pb, pc) in zip(tiles, pinned):
+                p.upload(pb.numpy(), pc.numpy(), invert_colormatrix(t.matrix))
+                p.process_async()
+                p.ruler_tile_all_async(packed)
+            assert p.ruler_called() == want_called
+            assert (p.ruler_hist() == want_hist).all()
+            assert (p.counters() == want_counters).all()
+        o = oracle.process(cfg, tiles[-1].bcl, tiles[-1].cif, oracle.invert_matrix(tiles[-1].matrix))
+        for s in range(p.params.num_samples):
+            assert (p.records(s) == o["records"][s]).all()
+    finally:
+        p.close()
