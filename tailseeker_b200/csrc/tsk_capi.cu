@@ -251,6 +251,7 @@ extern "C" int tsk_ctx_create(tsk_ctx **out, int device, const tsk_params *param
         TSK_CUDA(cudaMalloc(&ctx->d_rcp, sizeof(rcp)));
         TSK_CUDA(cudaMemcpy(ctx->d_rcp, rcp, sizeof(rcp), cudaMemcpyHostToDevice));
     }
+    if (tsk_score_setup(ctx) != 0) return -1;
     TSK_CUDA(cudaMalloc(&ctx->d_pos, histbytes));
     TSK_CUDA(cudaMalloc(&ctx->d_neg, histbytes));
     TSK_CUDA(cudaMemset(ctx->d_pos, 0, histbytes));
@@ -289,7 +290,7 @@ extern "C" int tsk_ctx_destroy(tsk_ctx *ctx)
         cudaStreamDestroy(ctx->rstream);
         cudaEventDestroy(ctx->ev_rul[0]); cudaEventDestroy(ctx->ev_rul[1]);
     }
-    void *ptrs[] = {ctx->d_rtotals, ctx->d_rrecbase, ctx->d_samples, ctx->d_tscore, ctx->d_rcp, ctx->d_bcl_own[0], ctx->d_cif_own[0], ctx->d_bcl_own[1],
+    void *ptrs[] = {ctx->d_logki, ctx->d_rtotals, ctx->d_rrecbase, ctx->d_samples, ctx->d_tscore, ctx->d_rcp, ctx->d_bcl_own[0], ctx->d_cif_own[0], ctx->d_bcl_own[1],
                     ctx->d_cif_own[1], ctx->d_calls, ctx->d_kind,
                     ctx->d_bucket, ctx->d_worklist, ctx->d_blkcnt, ctx->d_totals, ctx->d_recbase,
                     ctx->d_records, ctx->d_scratch, ctx->d_pos, ctx->d_neg, ctx->d_counters, ctx->d_fair, ctx->d_fairslots,

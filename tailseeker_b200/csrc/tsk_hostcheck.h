@@ -29,6 +29,7 @@ static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
+/* scalbn: libm's */
 static inline int __double2int_rz(double a) { return (int)a; }
 static inline double __hiloint2double(int hi, int lo)
 {

@@ -73,6 +73,7 @@ struct tsk_ctx {
     DevSample *d_samples;        /* [num_samples] */
     float *d_tscore;             /* [201] */
     double *d_rcp;               /* [288] 1.0 / i for the contrast scan */
+    void *d_logki;               /* double2 [2048]: (exponent, index) table of the fast kernel's logf (tsk_exact.cuh) */
     int maxdump;                 /* max signal_dump_length over samples */
 
     /* resident tile */
@@ -161,6 +162,7 @@ void tsk_set_error(const char *fmt, ...);
 /* kernel launchers (tsk_kernels.cu / tsk_ruler.cu / tsk_fit.cu) */
 int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev /* optional [5] */);
 int tsk_launch_score(tsk_ctx *ctx);
+int tsk_score_setup(tsk_ctx *ctx);        /* per-context tables of the scoring kernels */
 int tsk_launch_fixups(tsk_ctx *ctx);
 int tsk_control_setup(tsk_ctx *ctx);      /* builds the PhiX index (tsk_control.cu) */
 int tsk_launch_control(tsk_ctx *ctx);

@@ -29,9 +29,6 @@
 
 struct ScoreShared {
     double2 logtab[16];
-#ifdef TSK_LOGF_KI
-    double2 logki[16 * 16];            /* [(k & 15) * 16 + i] = {invc[i] * 2^-k, fma(k, ln2, logc[i])} */
-#endif
     float   tscore[TSK_T_SCORE_BINS + 1];
     int16_t limit[TSK_MAX_SAMPLES];
     int16_t dump[TSK_MAX_SAMPLES];
@@ -42,13 +39,6 @@ __device__ __forceinline__ void load_score_shared(ScoreShared &sh, const float *
 {
     for (int i = threadIdx.x; i < 16; i += blockDim.x)
         sh.logtab[i] = make_double2(c_logf_tab[i][0], c_logf_tab[i][1]);
-#ifdef TSK_LOGF_KI
-    for (int e = threadIdx.x; e < 16 * 16; e += blockDim.x) {
-        const int k = (e >> 4) ? (e >> 4) - 16 : 0, i = e & 15;
-        sh.logki[e] = make_double2(scalbn(c_logf_tab[i][0], -k),
-                                   __fma_rn((double)k, 0x1.62e42fefa39efp-1, c_logf_tab[i][1]));
-    }
-#endif
     for (int i = threadIdx.x; i <= TSK_T_SCORE_BINS; i += blockDim.x) sh.tscore[i] = tscore[i];
     for (int i = threadIdx.x; i < S; i += blockDim.x) {
         sh.limit[i] = samples[i].limit_threep;
@@ -208,6 +198,7 @@ __device__ __forceinline__ void sample_positive(const DevParams &P, const float 
 struct ScoreArgs {
     TileView tv;
     const double *rcp;            /* [CONTRAST_MAXLEN] 1.0 / i, correctly rounded */
+    const double2 *logki;         /* [LOGF_KI_ENTRIES] (exponent, index) table of logf_ki_t */
     const DevSample *samples;
     const float *tscore;
     tsk_call *calls;
@@ -615,9 +606,6 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
     /* score of cycle r lives at scratch[(r - start - ps) * spitch + n]; scr walks one row per cycle */
     float *scr = A.scratch + n + ((ptrdiff_t)rbeg_w - (start + ps)) * (ptrdiff_t)spitch;
     const uint32_t a_logtab = smem_u32(&sm.sh.logtab[0]), a_tscore = smem_u32(&sm.sh.tscore[0]);
-#ifdef TSK_LOGF_KI
-    const uint32_t a_logki = smem_u32(&sm.sh.logki[0]);
-#endif
     const uint32_t a_tile = smem_u32(&sm.tile[warp][0][0]);
     const uint32_t a_mytile = a_tile + lane * ((K2_TILE_CYC + 1) * 4);
     const uint32_t colofs = (uint32_t)lane * 2;
@@ -665,25 +653,6 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
             lit = lit && (prob[0] == prob[0]);
             /* ---- Shannon entropy: h -= p*logf(p) for p > 0 (the skipped terms are 0) ---- */
             float h = 0.f;
-#ifdef TSK_LOGF_KI
-            /* a positive p below the table's first row (p < 1.07e-5, rare) sends this lane down the
-             * general form; zero and NaN stay here, their terms are discarded below */
-            bool tiny = false;
-#pragma unroll
-            for (int ch = 0; ch < 4; ch++) tiny = tiny || (__float_as_uint(prob[ch]) - 1u) < (LOGF_KI_FIRST - 1u);
-            if (__builtin_expect(!tiny, 1)) {
-#pragma unroll
-                for (int ch = 0; ch < 4; ch++) {
-                    const float lg = logf_ki_t(__float_as_uint(prob[ch]), [a_logki](uint32_t ofs) {
-                        double2 t;
-                        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(a_logki + ofs));
-                        return t;
-                    });
-                    const float term = __fmul_rn(prob[ch], lg);
-                    h = __fsub_rn(h, prob[ch] > 0.f ? term : 0.f);
-                }
-            } else
-#endif
             {
 #pragma unroll
                 for (int ch = 0; ch < 4; ch++) {
@@ -1076,12 +1045,10 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
                         __popc(__ballot_sync(FULL_MASK, needcol) & ((1u << lane) - 1));
     float *scr = scol + ((ptrdiff_t)rbeg_w - (start + ps)) * (ptrdiff_t)spitch;
     const uint32_t a_logtab = smem_u32(&sm.sh.logtab[0]), a_tscore = smem_u32(&sm.sh.tscore[0]);
-#ifdef TSK_LOGF_KI
-    const uint32_t a_logki = smem_u32(&sm.sh.logki[0]);
-#endif
     const uint32_t a_tile = smem_u32(&sm.tile[warp][0][0]);
     const uint32_t a_mytile = a_tile + lane * ((K2_TILE_CYC + 1) * 4);
 
+#ifdef TSK_K2_V1
     /* one cycle of this lane: r = 3'-read cycle, arow = shared address of the cycle's [4][32] rows */
     auto cycle = [&](const int r, const uint32_t arow) {
         uint32_t word = 0;
@@ -1128,25 +1095,6 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
             lit = lit && (prob[0] == prob[0]);
             /* ---- Shannon entropy: h -= p*logf(p) for p > 0 (the skipped terms are 0) ---- */
             float h = 0.f;
-#ifdef TSK_LOGF_KI
-            /* a positive p below the table's first row (p < 1.07e-5, rare) sends this lane down the
-             * general form; zero and NaN stay here, their terms are discarded below */
-            bool tiny = false;
-#pragma unroll
-            for (int ch = 0; ch < 4; ch++) tiny = tiny || (__float_as_uint(prob[ch]) - 1u) < (LOGF_KI_FIRST - 1u);
-            if (__builtin_expect(!tiny, 1)) {
-#pragma unroll
-                for (int ch = 0; ch < 4; ch++) {
-                    const float lg = logf_ki_t(__float_as_uint(prob[ch]), [a_logki](uint32_t ofs) {
-                        double2 t;
-                        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(a_logki + ofs));
-                        return t;
-                    });
-                    const float term = __fmul_rn(prob[ch], lg);
-                    h = __fsub_rn(h, prob[ch] > 0.f ? term : 0.f);
-                }
-            } else
-#endif
             {
 #pragma unroll
                 for (int ch = 0; ch < 4; ch++) {
@@ -1210,6 +1158,155 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
 
     /* ---- scored cycles ---- */
     stream(rbeg_w, rend_w, rdata_w, cycle, flush);
+
+#else
+    /* ---- scored cycles: one TMA group (four cycles) per step, straight-line and branch-free.
+     * Every lane runs every cycle of the warp's range [rbeg_w, rend_w); `act` (this lane is inside
+     * its own [start, start + insert_len)) gates what the cycle may change, so there is no per-lane
+     * branch, no range test per cycle and the addresses inside a group are immediates.  A cycle
+     * whose channel sum leaves the range the reciprocal division is proved for (never on stock
+     * data; a zero sum is a dark cycle and is fine) hands the cluster to the literal kernel after
+     * the loop instead of taking an IEEE-division branch inside it.
+     * Entropy terms: p * logf(p) with p = +0 is 0 * (finite) = -0, and h - (-0) == h, so the
+     * "skip p <= 0" select of shannon_entropy() (signalproc.c:39-51) is implicit; h starts as -t0
+     * instead of 0 - t0 (differs only in the sign of a zero, which 1 - h/maxent absorbs). ---- */
+    const unsigned ilen_a = alive ? (unsigned)insert_len : 0u;
+    const char *const logki = reinterpret_cast<const char *>(A.logki);
+    bool handover = false;
+    auto cycle = [&](const int c, const uint32_t ap, const uint32_t atile, float *const scr) {
+        const bool act = (unsigned)c < ilen_a;
+        /* ---- decrosstalk (signalproc.c:85-103); exact int16 -> float through 2^23+2^22 ---- */
+#ifdef TSK_K2_I2FP
+        const float v0 = (float)lds_s16(ap), v1 = (float)lds_s16(ap + K2C_CHB), v2 = (float)lds_s16(ap + 2 * K2C_CHB),
+                    v3 = (float)lds_s16(ap + 3 * K2C_CHB);
+#else
+        const float v0 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap)), 12582912.f);
+        const float v1 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap + K2C_CHB)), 12582912.f);
+        const float v2 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap + 2 * K2C_CHB)), 12582912.f);
+        const float v3 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap + 3 * K2C_CHB)), 12582912.f);
+#endif
+        float sig[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float a = __fmul_rn(P.inv[4 * j + 0], v0);
+            a = __fadd_rn(a, __fmul_rn(P.inv[4 * j + 1], v1));
+            a = __fadd_rn(a, __fmul_rn(P.inv[4 * j + 2], v2));
+            sig[j] = __fadd_rn(a, __fmul_rn(P.inv[4 * j + 3], v3));
+        }
+        /* ---- dark test: sum of the positive channels (x + 0 == x, so max(.,0) is exact) ---- */
+        float tot = fmaxf(sig[0], 0.f);
+        tot = __fadd_rn(tot, fmaxf(sig[1], 0.f));
+        tot = __fadd_rn(tot, fmaxf(sig[2], 0.f));
+        tot = __fadd_rn(tot, fmaxf(sig[3], 0.f));
+        /* ---- normalise into the cluster's dynamic range (signalproc.c:246-266) ---- */
+        float nrm[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++)
+            nrm[ch] = fmaxf(div_by_rcp(__fsub_rn(sig[ch], low[ch]), bw[ch], ybw[ch]), 0.f);
+        const float sum = __fadd_rn(__fadd_rn(__fadd_rn(nrm[0], nrm[1]), nrm[2]), nrm[3]);
+        /* sum == 0 (every channel at or below its floor: a dark cycle): rcp(0) = inf, the
+         * refinement turns it into NaN, and so does 0 x NaN in the division -- the NaN that IEEE
+         * 0/0 gives, which is all that is looked at */
+        handover |= act & ((__float_as_uint(sum) - 0x21800000u) >= 0x3c000000u) & (sum != 0.f);
+        const float ys = rcp_rn_fast(sum);
+        float prob[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++) prob[ch] = div_by_rcp(nrm[ch], sum, ys);
+        const bool good = act && !(tot < P.dark_threshold) && (prob[0] == prob[0]);
+        /* ---- Shannon entropy ---- */
+        float term[4];
+#pragma unroll
+        for (int ch = 0; ch < 4; ch++) {
+#ifdef TSK_K2_LOGTAB_SMEM
+            const float lg = logf_core_t(__float_as_uint(prob[ch]), [a_logtab](uint32_t ofs) {
+                double2 t;
+                asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(a_logtab + ofs));
+                return t;
+            });
+#else
+            /* one 16-byte entry per (exponent, index) from a 32 KB table in global memory: the few
+             * rows probabilities really fall into (k = 0 ... -12, 3 KB) stay in L1 */
+            const float lg = logf_ki_t(__float_as_uint(prob[ch]), [logki](uint32_t ofs) {
+                double2 t;
+                asm("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "l"(logki + ofs));
+                return t;
+            });
+#endif
+            term[ch] = __fmul_rn(prob[ch], lg);
+        }
+        const float h = __fsub_rn(__fsub_rn(__fsub_rn(-term[0], term[1]), term[2]), term[3]);
+        const float es = __fsub_rn(1.f, div_by_rcp(h, P.maximum_entropy, rcp_maxent));
+        const uint32_t ti = min((uint32_t)__float2int_rz(__fmul_rn(prob[3], (float)TSK_T_SCORE_BINS)),
+                                (uint32_t)TSK_T_SCORE_BINS);
+        float tsc;
+        asm("ld.shared.f32 %0, [%1];" : "=f"(tsc) : "r"(a_tscore + ti * 4));
+        const float score = good ? __fmul_rn(es, tsc) : CUDART_NAN_F;
+        const uint32_t dh = (good && es < prev_entropy) ? 1u : 0u;
+        prev_entropy = good ? es : CUDART_NAN_F;
+        ndark += (act && !good) ? 1 : 0;
+        dhwin = (dhwin << 1) | dh;
+        /* packet j = c - ps carries downhill[j], the UN-offset array (spotanalyzer.c:604-606) */
+        const bool inrec = act && c >= ps;
+        uint32_t sp = 1u + (uint32_t)__float2int_rz(__fmul_rn(score, (float)(TSK_SCORE_MAX - 1)));
+        sp = min(sp, TSK_SCORE_MAX);
+        const uint32_t word = (good && c >= ps) ? ((sp << 1) | ((dhwin >> ps) & 1u)) : 0u;
+        if (needcol && inrec) {       /* one predicate: the sum is only used by the KIND_POS lanes */
+            *scr = score;
+            ptotal = __dadd_rn(ptotal, (double)score);      /* same order as the reference's cumsum */
+        }
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(atile), "r"(word) : "memory");
+    };
+    /* after every second group (8 cycles) and after the last one: r = last cycle staged */
+    auto flush = [&](const int g, const int ng, const int r) {
+        if (!(g & 1) && g != ng - 1) return;
+        const int rbase = r - ((r - rbeg_w) & (K2_TILE_CYC - 1));     /* cycle in tile column 0 */
+        const int l8 = lane & 7;
+        for (int it = 0; it < nflush; it++) {
+            /* next (up to) four emitting lanes: this quarter-warp's is in flushpick */
+            const int p6 = (int)(flushpick >> (6 * it)) & 63;
+            const int pick = p6 == 63 ? -1 : p6;
+            const int src = pick < 0 ? 0 : pick;
+            const unsigned long long ra = __shfl_sync(FULL_MASK, recaddr, src);
+            const int ri = __shfl_sync(FULL_MASK, recinfo, src);
+            const int j = rbase + l8 - (ri & 0xffff);
+            if (pick >= 0 && j >= 0 && j < (ri >> 16) && rbase + l8 <= r) {
+                uint32_t wv;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv) : "r"(a_tile + (pick * (K2_TILE_CYC + 1) + l8) * 4));
+                reinterpret_cast<uint32_t *>((uintptr_t)ra)[2 + j] = wv;
+            }
+        }
+        __syncwarp();
+    };
+    {
+        const int c0 = rbeg_w, c1 = rend_w;
+        const int ng = c1 > c0 ? (c1 - c0 + K2_GROUP - 1) / K2_GROUP : 0;
+        const int ngd = rdata_w > c0 ? min(ng, (rdata_w - c0 + K2_GROUP - 1) / K2_GROUP) : 0;
+        if (lane == 0)
+            for (int g = 0; g < min(K2_NGROUP, ngd); g++) issue_group(G + g, c0 + g * K2_GROUP);
+        int cidx = c0 - start;                 /* this lane's score index of the group's first cycle */
+        float *scrg = scr;                     /* row of the group's first cycle in the lane's scratch column */
+        for (int g = 0; g < ng; g++) {
+            const int slot = (G + g) % K2_NGROUP;
+            if (g < ngd) mbar_wait(a_full + 8 * slot, ((G + g) / K2_NGROUP) & 1);
+            /* groups past the data (record padding only) run on whatever the slot holds: act is false */
+            const uint32_t ap = a_stage + slot * (K2_GROUP * K2C_ROWB) + colofs;
+            const uint32_t atile = a_mytile + (g & 1) * (K2_GROUP * 4);
+#pragma unroll
+            for (int k = 0; k < K2_GROUP; k++)
+                cycle(cidx + k, ap + k * K2C_ROWB, atile + 4 * k, scrg + (size_t)k * spitch);
+            cidx += K2_GROUP;
+            scrg += K2_GROUP * spitch;
+            __syncwarp();
+            if (lane == 0 && g + K2_NGROUP < ngd) issue_group(G + g + K2_NGROUP, c0 + (g + K2_NGROUP) * K2_GROUP);
+            flush(g, ng, min(c0 + g * K2_GROUP + K2_GROUP, c1) - 1);
+        }
+        G += ngd;
+    }
+    if (handover && alive) {        /* the literal kernel redoes this cluster from scratch (list 3) */
+        list_array(A.lists, 3, A.listcap)[atomicAdd(&A.lists[3], 1u)] = n;
+        alive = false;
+    }
+#endif
 
     /* ---- negative sampling (spotanalyzer.c:589-599) of the lanes that need no fair-sampling
      *      decision and did not abort: the warp walks each such lane's column ---- */
@@ -1506,6 +1603,22 @@ k_sample_neg_columns(const __grid_constant__ DevParams P, const DevSample *__res
     }
 }
 
+/* the (exponent, index) table of logf_ki_t, built once per context with the device's own FMA */
+__global__ void k_fill_logki(double2 *__restrict__ tab)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < LOGF_KI_ENTRIES) tab[e] = logf_ki_entry(e, c_logf_tab[e & 15][0], c_logf_tab[e & 15][1]);
+}
+
+int tsk_score_setup(tsk_ctx *ctx)
+{
+    TSK_CUDA(cudaMalloc(&ctx->d_logki, sizeof(double2) * LOGF_KI_ENTRIES));
+    k_fill_logki<<<LOGF_KI_ENTRIES / 256, 256, 0, ctx->stream>>>(reinterpret_cast<double2 *>(ctx->d_logki));
+    ctx->launches++;
+    TSK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 /* ======================================================================================
  * self-test hooks
  * ==================================================================================== */
@@ -1526,17 +1639,10 @@ __global__ void k_logf_probe(const float *__restrict__ in, float *__restrict__ o
 
 /* all floats with bit patterns [first, first+count): counts where the FMA core differs from
  * the separately-rounded restatement (must be 0 on normal inputs in (0,1]) */
-__global__ void k_logf_sweep(uint32_t first, uint64_t count, unsigned long long *mismatches)
+__global__ void k_logf_sweep(uint32_t first, uint64_t count, unsigned long long *mismatches, const double2 *__restrict__ logki)
 {
     __shared__ double2 tab[16];
     if (threadIdx.x < 16) tab[threadIdx.x] = make_double2(c_logf_tab[threadIdx.x][0], c_logf_tab[threadIdx.x][1]);
-#ifdef TSK_LOGF_KI
-    __shared__ double2 ki[16 * 16];                 /* filled exactly like ScoreShared::logki */
-    for (int e = threadIdx.x; e < 16 * 16; e += blockDim.x) {
-        const int k = (e >> 4) ? (e >> 4) - 16 : 0, i = e & 15;
-        ki[e] = make_double2(scalbn(c_logf_tab[i][0], -k), __fma_rn((double)k, 0x1.62e42fefa39efp-1, c_logf_tab[i][1]));
-    }
-#endif
     __syncthreads();
     unsigned long long bad = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -1544,13 +1650,10 @@ __global__ void k_logf_sweep(uint32_t first, uint64_t count, unsigned long long 
         const float a = tsk_logf(__uint_as_float(ix), tab);
         const float b = logf_core(ix, tab);
         bad += __float_as_uint(a) != __float_as_uint(b);
-#ifdef TSK_LOGF_KI
-        if (ix >= LOGF_KI_FIRST) {                  /* the table form wherever the kernels use it */
-            const double2 *kip = ki;
-            const float c = logf_ki_t(ix, [kip](uint32_t ofs) { return kip[ofs >> 4]; });
+        {                                           /* the (exponent, index) table form of the fast kernel */
+            const float c = logf_ki_t(ix, [logki](uint32_t ofs) { return __ldg(logki + (ofs >> 4)); });
             bad += __float_as_uint(a) != __float_as_uint(c);
         }
-#endif
     }
     if (bad) atomicAdd(mismatches, bad);
 }
@@ -1605,7 +1708,8 @@ extern "C" int tsk_selftest_sweeps(tsk_ctx *ctx, uint64_t div_pairs, uint64_t *l
     TSK_CUDA(cudaMalloc(&d, sizeof(h)));
     TSK_CUDA(cudaMemsetAsync(d, 0, sizeof(h), ctx->stream));
     /* every normal float in (0, 1] */
-    k_logf_sweep<<<148 * 16, 256, 0, ctx->stream>>>(0x00800000u, (uint64_t)(0x3f800000u - 0x00800000u) + 1, d);
+    k_logf_sweep<<<148 * 16, 256, 0, ctx->stream>>>(0x00800000u, (uint64_t)(0x3f800000u - 0x00800000u) + 1, d,
+                                                    reinterpret_cast<const double2 *>(ctx->d_logki));
     k_div_sweep<<<148 * 16, 256, 0, ctx->stream>>>(12345, div_pairs / 2, 0, d + 1);
     k_div_sweep<<<148 * 16, 256, 0, ctx->stream>>>(98765, div_pairs / 2, 1, d + 1);
     ctx->launches += 3;
@@ -1628,6 +1732,7 @@ static ScoreArgs make_args(tsk_ctx *ctx)
     a.recbase = ctx->d_recbase; a.records = ctx->d_records; a.scratch = ctx->d_scratch;
     a.spitch = (size_t)ctx->cap_clusters; a.pos = ctx->d_pos; a.neg = ctx->d_neg; a.fair = ctx->d_fair;
     a.lists = ctx->d_lists; a.listcap = ctx->cap_clusters; a.rcp = ctx->d_rcp;
+    a.logki = reinterpret_cast<const double2 *>(ctx->d_logki);
     return a;
 }
 
@@ -1670,7 +1775,11 @@ int tsk_launch_score(tsk_ctx *ctx)
     const int head = fast_head_cycles(ctx);
     /* the TMA bulk copies need 16-byte aligned 256-byte rows, and the CTA windows must stay inside
      * the row pitch; the downhill window is 32 bits */
-    const bool fast_ok = ctx->force_generic != 1 && head <= K2_HEAD_MAX && ctx->dp.max_mods < 32 &&
+    /* |inverse colour matrix| < 2^40 keeps every de-crosstalked signal, quotient and residual of the
+     * fast division far from overflow (|signal - low| / bandwidth < 2^58 * 2^40) */
+    bool inv_ok = true;
+    for (int i = 0; i < 16; i++) inv_ok = inv_ok && fabsf(ctx->dp.inv[i]) < 0x1p40f;
+    const bool fast_ok = ctx->force_generic != 1 && inv_ok && head <= K2_HEAD_MAX && ctx->dp.max_mods < 32 &&
                          ctx->dp.npos == 2 && ctx->dp.nneg == 4 &&
                          (ctx->tile.cif_pitch % 8) == 0 && ((uintptr_t)ctx->tile.cif % 16) == 0;
     if (!fast_ok) {

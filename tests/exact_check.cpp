@@ -2,7 +2,7 @@
 // (tailseeker_b200/csrc/tsk_exact.cuh, tsk_device.cuh through tsk_hostcheck.h):
 //   div_by_rcp(a, b, RN(1/b))  ==  a / b                      (signalproc.c:246-266,329 divisions)
 //   tsk_logf, logf_core_t, logf_ki_t  ==  the host's logf     (shannon_entropy, signalproc.c:39-51)
-// g++ -O2 -mfma -ffp-contract=off -DTSK_HOST_CHECK -DTSK_LOGF_KI=1 -I tailseeker_b200/csrc
+// g++ -O2 -mfma -ffp-contract=off -DTSK_HOST_CHECK -I tailseeker_b200/csrc
 //   score_bin(sc, bins, integer form) == min(bins - 1, (int)(((sc - 1.) / 16777214) * bins)) in fp64
 //                                          for every packed score (polyaruler.c:163-168)
 //     usage: exact_check [stride over the floats in (0,1], default 1 = every one] [division pairs]
@@ -16,7 +16,7 @@
 #include "tsk_scorebin.cuh"
 
 #define NT 8
-static double2 TAB[16], KI[16 * 16];
+static double2 TAB[16], KI[LOGF_KI_ENTRIES];
 struct job { int id; uint32_t stride, bstride; uint64_t pairs, n, bad_logf[3], bad_div, hard, bad_hard, nbins, bad_bins; };
 
 static uint64_t inv_odd(uint64_t b) { uint64_t x = b; for (int i = 0; i < 6; i++) x *= 2 - b * x; return x; }
@@ -56,8 +56,7 @@ static void *run(void *p)
         j->n++;
         j->bad_logf[0] += __float_as_uint(tsk_logf(__uint_as_float(u), tab)) != want;
         j->bad_logf[1] += __float_as_uint(logf_core_t(u, [tab](uint32_t ofs) { return tab[ofs >> 4]; })) != want;
-        if (u >= LOGF_KI_FIRST)
-            j->bad_logf[2] += __float_as_uint(logf_ki_t(u, [ki](uint32_t ofs) { return ki[ofs >> 4]; })) != want;
+        j->bad_logf[2] += __float_as_uint(logf_ki_t(u, [ki](uint32_t ofs) { return ki[ofs >> 4]; })) != want;
     }
     // the operand pairs of the GPU self-test (k_div_sweep, both modes), a stretch per thread
     for (int mode = 0; mode < 2; mode++)
@@ -96,9 +95,15 @@ int main(int argc, char **argv)
     const uint32_t stride = argc > 1 ? (uint32_t)strtoul(argv[1], NULL, 10) : 1;
     const uint64_t pairs = argc > 2 ? strtoull(argv[2], NULL, 10) : (1ull << 30);
     for (int i = 0; i < 16; i++) TAB[i] = make_double2(c_logf_tab[i][0], c_logf_tab[i][1]);
-    for (int e = 0; e < 256; e++) {                       // as load_score_shared() fills ScoreShared::logki
-        const int k = (e >> 4) ? (e >> 4) - 16 : 0, i = e & 15;
-        KI[e] = make_double2(scalbn(c_logf_tab[i][0], -k), __fma_rn((double)k, 0x1.62e42fefa39efp-1, c_logf_tab[i][1]));
+    for (int e = 0; e < LOGF_KI_ENTRIES; e++)             // as k_fill_logki fills the device table
+        KI[e] = logf_ki_entry(e, c_logf_tab[e & 15][0], c_logf_tab[e & 15][1]);
+    // what the kernels rely on for the bit patterns outside (0, 1]: +0 gives a finite value
+    {
+        const double2 *ki = KI;
+        const float z = logf_ki_t(0u, [ki](uint32_t ofs) { return ki[ofs >> 4]; });
+        if (!(z == z) || z - z != 0.f) { printf("logf_ki_t(+0) is not finite\n"); return 1; }
+        for (uint32_t u = 0; u < 0x7f800000u; u += 9973)          // any non-NaN pattern: in bounds and finite
+            if (!(logf_ki_t(u, [ki](uint32_t ofs) { return ki[ofs >> 4]; }) - 0.f == logf_ki_t(u, [ki](uint32_t ofs) { return ki[ofs >> 4]; }))) { printf("logf_ki_t(%08x) is NaN\n", u); return 1; }
     }
     const uint32_t bstride = argc > 3 ? (uint32_t)strtoul(argv[3], NULL, 10) : 17;
     pthread_t t[NT];

@@ -24,7 +24,7 @@ def _cpu_has_fma():
 @pytest.mark.skipif(shutil.which("g++") is None or not _cpu_has_fma(), reason="needs g++ and a CPU with FMA")
 def test_kernel_helpers_are_exact_on_the_host(tmp_path):
     exe = str(tmp_path / "exact_check")
-    subprocess.check_call(["g++", "-O2", "-mfma", "-ffp-contract=off", "-DTSK_HOST_CHECK", "-DTSK_LOGF_KI=1",
+    subprocess.check_call(["g++", "-O2", "-mfma", "-ffp-contract=off", "-DTSK_HOST_CHECK",
                            "-I", os.path.join(ROOT, "tailseeker_b200", "csrc"), "-o", exe,
                            os.path.join(ROOT, "tests", "exact_check.cpp"), "-lm", "-lpthread"])
     r = subprocess.run([exe, "1", str(1 << 26), "17"], capture_output=True, timeout=600)
