@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TSK_ABI_VERSION          2
+#define TSK_ABI_VERSION          3
 
 #define TSK_NUM_CHANNELS         4      /* tailseq-import.h:40 */
 #define TSK_MAX_SAMPLES          64
@@ -226,6 +226,45 @@ int tsk_get_hist(tsk_ctx *ctx, uint32_t *pos, uint32_t *neg);
 int tsk_get_device_ptrs(tsk_ctx *ctx, void **pos_hist, void **neg_hist, void **counters,
                         void **ruler_pos_hist);
 
+/* ---- output encoding on the device ----------------------------------------------------- */
+/* Replaces what the reference's workers do after the per-cluster analysis: format_basecalls()
+ * (bclreader.c:146-166), write_seqqual_entry() / write_taginfo_entry() (spotanalyzer.c:206-307),
+ * the record bytes of write_polya_score() (:389-438) and the BGZF compression of all three
+ * (sync_write_out_buffer() -> bgzf_write(), :355-386, :419-428) -- 71 % of the reference's
+ * single-thread time.  The tile's text is formatted from the resident calls and base calls and
+ * every stream is deflated on the GPU as a series of BGZF blocks (RFC 1952 members with the `BC`
+ * extra field, one dynamic-Huffman block each); the host only write()s the bytes it gets back.
+ * Decompressed, a stream is byte for byte what the reference writes with threads = 1. */
+#define TSK_ENCODE_MAX_UMI 8
+typedef struct tsk_encode_sample {
+    int32_t want_seqqual, want_taginfo, want_signal;   /* which of the sample's files exist (none for
+                                                          Unknown / control, tailseq-import.c:46-48) */
+    int32_t umi_count;                                 /* [sample:*] umi ranges, absolute 0-based cycles */
+    int32_t umi_start[TSK_ENCODE_MAX_UMI], umi_length[TSK_ENCODE_MAX_UMI];
+} tsk_encode_sample;
+typedef struct tsk_encode_layout {
+    int32_t fivep_start, fivep_length;                 /* 0-based */
+    int32_t threep_seqqual_output_length;              /* parseconfig.c:491 */
+    tsk_encode_sample samples[TSK_MAX_SAMPLES];        /* list order of tsk_params.samples */
+} tsk_encode_layout;
+enum { TSK_STREAM_SEQQUAL = 0, TSK_STREAM_TAGINFO = 1, TSK_STREAM_SIGNAL = 2 };
+int tsk_encode_configure(tsk_ctx *ctx, const tsk_encode_layout *layout);
+/* Encodes the outputs of the tile last processed (any block of it: cluster numbers start at the
+ * block's firstclusterno) and brings the compressed streams to pinned host memory. */
+int tsk_tile_encode(tsk_ctx *ctx);
+/* One stream of the last tsk_tile_encode(): *data (host memory owned by the context, valid until
+ * the next tsk_tile_encode()) holds *nbytes bytes of whole BGZF blocks to append to the sample's
+ * file; 0 bytes when the sample wrote nothing.  The signal stream holds the records only: the
+ * 12-byte header {4, total clusters, dump length} (tailseq-import.c:106-110) is the caller's. */
+int tsk_tile_get_encoded(tsk_ctx *ctx, int sample, int stream, const uint8_t **data, size_t *nbytes);
+/* Device time of the last tsk_tile_encode() (CUDA events around its kernels). */
+int tsk_encode_elapsed_ms(tsk_ctx *ctx, double *ms);
+/* Self-test: `n` arbitrary host bytes deflated by the same kernels as one stream; the BGZF blocks
+ * (<= n + n / 1000 + 64 bytes per started 32 KB) are written to out[0 .. *outn). */
+int tsk_selftest_deflate(tsk_ctx *ctx, const uint8_t *data, size_t n, uint8_t *out, size_t capacity, size_t *outn);
+/* The 28-byte empty BGZF block that ends a file (htslib's end-of-file marker). */
+int tsk_bgzf_eof_block(const uint8_t **data, size_t *nbytes);
+
 /* ---- ruler path -------------------------------------------------------------------- */
 /* load_score_cutoffs()'s float->24-bit conversion (polyaruler.c:93-96) for one value. */
 uint32_t tsk_cutoff_to_packed(double cutoff);
@@ -277,6 +316,48 @@ int tsk_fit_cutoffs(tsk_ctx *ctx, const uint64_t *pos, const uint64_t *neg,
                     int cycles, int bins, uint64_t min_spots, double kde_bandwidth,
                     double search_low, const double *search_high, int nsearch_high,
                     double *cutoffs_out);
+
+/* ---- cross-tile sums on the devices (one tile set per GPU) ----------------------------- */
+/* Replaces the sums the reference forms over per-tile files: pos/neg histograms before cutoff
+ * estimation (scripts/calculate-optimal-parameters.py:139-140), the ruler histogram per round
+ * (scripts/measure-polya-lengths.py:64-70), the demultiplexing counters
+ * (scripts/stats-merge-demultiplexing-counts.py:33-53).  Integer sums: the result equals the
+ * single-device one bit for bit.
+ *
+ * NCCL communicators are passed as void* (an ncclComm_t).  Callers that have none can make one
+ * here; NCCL is loaded at run time ("libnccl.so.2", or the file named by TSK_NCCL_LIB). */
+#define TSK_NCCL_ID_BYTES 128
+int tsk_nccl_unique_id(uint8_t id[TSK_NCCL_ID_BYTES]);                 /* rank 0, then hand to all */
+int tsk_nccl_init_rank(void **comm, int device, int nranks, int rank, const uint8_t id[TSK_NCCL_ID_BYTES]);
+int tsk_nccl_init_all(void **comms, int ndev, const int *devices);    /* one process driving ndev GPUs */
+int tsk_nccl_destroy(void *comm);
+int tsk_nccl_group_start(void);      /* one thread issuing the collective for several devices */
+int tsk_nccl_group_end(void);
+/* The context's pos / neg histograms, demultiplexing counters and ruler histogram summed over
+ * the communicator's ranks, in place, as ONE grouped collective on the context's stream. */
+int tsk_hist_allreduce(tsk_ctx *ctx, void *nccl_comm);
+
+/* Run-wide accumulators (u64, like the Python's int64 sums) on one device, fed tile by tile without
+ * leaving the device; with max_tiles > 0 the tiles' own histograms are kept too (per-tile fits). */
+typedef struct tsk_merge tsk_merge;
+int tsk_merge_create(tsk_merge **out, int device, int cycles, int bins, int nsamples, int max_tiles);
+void tsk_merge_destroy(tsk_merge *m);
+/* pos / neg of the tile last processed by ctx (enqueued on its stream: may follow tsk_tile_process_async) */
+int tsk_merge_add_tile(tsk_merge *m, tsk_ctx *ctx);
+/* the context's ruler histogram and counters (they accumulate inside the context): once, at the end */
+int tsk_merge_add_totals(tsk_merge *m, tsk_ctx *ctx);
+/* ONE ncclAllReduce(uint64, sum) over the packed accumulators */
+int tsk_merge_allreduce(tsk_merge *m, tsk_ctx *ctx, void *nccl_comm);
+/* host copies: u64 [cycles][bins] x 3, u64 [nsamples][6] (tsk_counters order); any may be NULL */
+int tsk_merge_get(tsk_merge *m, tsk_ctx *ctx, uint64_t *pos, uint64_t *neg, uint64_t *ruler_pos, uint64_t *counters);
+/* what: 1 pos/neg + kept tiles, 2 ruler histogram, 4 counters */
+int tsk_merge_reset(tsk_merge *m, tsk_ctx *ctx, int what);
+int tsk_merge_tile_count(tsk_merge *m);
+/* find_all_eqodds_point() on device memory: cutoffs of the run-wide histograms (first `cycles`
+ * values) and of every kept tile (then `cycles` per tile, in the order they were added).
+ * positive = 0: importer positives; 1: the ruler's run-wide positives (main.py:214-215). */
+int tsk_merge_fit(tsk_merge *m, tsk_ctx *ctx, int positive, uint64_t min_spots, double kde_bandwidth,
+                  double search_low, const double *search_high, int nsearch_high, double *cutoffs_out);
 
 /* ---- duplicate collapsing: tailseq-dedup-perfect ------------------------------------- */
 /* Replaces the per-UMI-group loop of src/deduplicator/tailseq-dedup-perfect.c (main()

@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes
 import os
 
-from .config import CCall, CParams
+from .config import CCall, CEncodeLayout, CParams
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtailseeker_b200.so")
@@ -24,6 +24,10 @@ SYMBOLS = [
     "tsk_ruler_tile_all_async", "tsk_ruler_get_lengths", "tsk_ruler_get_called",
     "tsk_dedup_pack_umi", "tsk_dedup_create", "tsk_dedup_destroy", "tsk_dedup_upload", "tsk_dedup_run",
     "tsk_dedup_get_records", "tsk_dedup_get_groups", "tsk_dedup_get_lost", "tsk_dedup_elapsed_ms", "tsk_dedup_launch_count",
+    "tsk_encode_configure", "tsk_tile_encode", "tsk_tile_get_encoded", "tsk_encode_elapsed_ms", "tsk_bgzf_eof_block", "tsk_selftest_deflate",
+    "tsk_nccl_unique_id", "tsk_nccl_init_rank", "tsk_nccl_init_all", "tsk_nccl_destroy", "tsk_nccl_group_start",
+    "tsk_nccl_group_end", "tsk_hist_allreduce", "tsk_merge_create", "tsk_merge_destroy", "tsk_merge_add_tile",
+    "tsk_merge_add_totals", "tsk_merge_allreduce", "tsk_merge_get", "tsk_merge_reset", "tsk_merge_tile_count", "tsk_merge_fit",
 ]
 
 _lib = None
@@ -81,6 +85,27 @@ def load():
     L.tsk_dedup_elapsed_ms.argtypes = [vp, ctypes.POINTER(f32), ctypes.POINTER(f32)]
     L.tsk_dedup_launch_count.argtypes = [vp]
     L.tsk_dedup_launch_count.restype = u64
+    L.tsk_encode_configure.argtypes = [vp, ctypes.POINTER(CEncodeLayout)]
+    L.tsk_tile_encode.argtypes = [vp]
+    L.tsk_tile_get_encoded.argtypes = [vp, i32, i32, ctypes.POINTER(vp), ctypes.POINTER(sz)]
+    L.tsk_encode_elapsed_ms.argtypes = [vp, ctypes.POINTER(f64)]
+    L.tsk_selftest_deflate.argtypes = [vp, vp, sz, vp, sz, ctypes.POINTER(sz)]
+    L.tsk_nccl_unique_id.argtypes = [vp]
+    L.tsk_nccl_init_rank.argtypes = [ctypes.POINTER(vp), i32, i32, i32, vp]
+    L.tsk_nccl_init_all.argtypes = [ctypes.POINTER(vp), i32, ctypes.POINTER(i32)]
+    L.tsk_nccl_destroy.argtypes = [vp]
+    L.tsk_hist_allreduce.argtypes = [vp, vp]
+    L.tsk_merge_create.argtypes = [ctypes.POINTER(vp), i32, i32, i32, i32, i32]
+    L.tsk_merge_destroy.argtypes = [vp]
+    L.tsk_merge_destroy.restype = None
+    L.tsk_merge_add_tile.argtypes = [vp, vp]
+    L.tsk_merge_add_totals.argtypes = [vp, vp]
+    L.tsk_merge_allreduce.argtypes = [vp, vp, vp]
+    L.tsk_merge_get.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.tsk_merge_reset.argtypes = [vp, vp, i32]
+    L.tsk_merge_tile_count.argtypes = [vp]
+    L.tsk_merge_fit.argtypes = [vp, vp, i32, ctypes.c_uint64, f64, f64, vp, i32, vp]
+    L.tsk_bgzf_eof_block.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(sz)]
     L.tsk_fit_cutoffs.argtypes = [vp, vp, vp, i32, i32, ctypes.c_uint64, f64, f64, vp, i32, vp]
     L.tsk_synchronize.argtypes = [vp]
     L.tsk_tile_process_timed.argtypes = [vp, i32, vp]

@@ -22,7 +22,7 @@ from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
-TSK_ABI_VERSION = 2
+TSK_ABI_VERSION = 3
 TSK_MAX_SAMPLES = 64
 TSK_MAX_SEQ = 32
 TSK_T_SCORE_BINS = 200
@@ -106,6 +106,23 @@ class CParams(ctypes.Structure):
         ("num_samples", ctypes.c_int32),
         ("samples", CSample * TSK_MAX_SAMPLES),
     ]
+
+
+TSK_ENCODE_MAX_UMI = 8
+
+
+class CEncodeSample(ctypes.Structure):
+    """tsk_encode_sample (include/tailseeker_b200.h)."""
+    _fields_ = [("want_seqqual", ctypes.c_int32), ("want_taginfo", ctypes.c_int32), ("want_signal", ctypes.c_int32),
+                ("umi_count", ctypes.c_int32),
+                ("umi_start", ctypes.c_int32 * TSK_ENCODE_MAX_UMI), ("umi_length", ctypes.c_int32 * TSK_ENCODE_MAX_UMI)]
+
+
+class CEncodeLayout(ctypes.Structure):
+    """tsk_encode_layout (include/tailseeker_b200.h)."""
+    _fields_ = [("fivep_start", ctypes.c_int32), ("fivep_length", ctypes.c_int32),
+                ("threep_seqqual_output_length", ctypes.c_int32),
+                ("samples", CEncodeSample * TSK_MAX_SAMPLES)]
 
 
 class CCall(ctypes.Structure):
@@ -395,6 +412,22 @@ class ImporterConfig:
             if d["delimiter"] is None:
                 d["delimiter"] = ""
         return out
+
+    def to_encode_layout(self, taginfo: bool = True) -> "CEncodeLayout":
+        """What tsk_encode_configure() needs besides the parameters: the 5' read, the seqqual
+        output length and every sample's files and UMI ranges (parseconfig.c:244-262,491)."""
+        lay = CEncodeLayout()
+        lay.fivep_start = self.fivep_start - 1
+        lay.fivep_length = self.fivep_length
+        lay.threep_seqqual_output_length = self.threep_seqqual_output_length
+        for i, d in enumerate(self.sample_list()):
+            es = lay.samples[i]
+            es.want_seqqual = es.want_signal = 1 if d["has_streams"] else 0
+            es.want_taginfo = 1 if (d["has_streams"] and taginfo) else 0
+            es.umi_count = len(d["umi"])
+            for u, (st, ln) in enumerate(d["umi"]):
+                es.umi_start[u], es.umi_length[u] = st, ln
+        return lay
 
     def min_bases_passes(self) -> int:
         frac = np.float32(float(self.balancer_minimum_qcpass_percent) * 0.01)

@@ -367,3 +367,26 @@ int tsk_build_params(const struct host_config *c, tsk_params *p)
     }
     return 0;
 }
+
+/* What tsk_encode_configure() needs besides the parameters: which files each sample has (none for
+ * the 'X...' pseudo-samples, tailseq-import.c:46-48), the 5' read and the UMI ranges. */
+int tsk_build_encode_layout(const struct host_config *cfg, tsk_encode_layout *out)
+{
+    memset(out, 0, sizeof(*out));
+    out->fivep_start = cfg->fivep_start;
+    out->fivep_length = cfg->fivep_length;
+    out->threep_seqqual_output_length = cfg->threep_seqqual_output_length;
+    for (const struct host_sample *s = cfg->samples; s; s = s->next) {
+        tsk_encode_sample *e;
+        if (s->numindex < 0 || s->numindex >= TSK_MAX_SAMPLES) return -1;
+        e = &out->samples[s->numindex];
+        if (s->index && s->index[0] == 'X') continue;
+        e->want_seqqual = 1;
+        e->want_taginfo = cfg->taginfo_output != NULL;
+        e->want_signal = 1;
+        if (s->umi_count > TSK_ENCODE_MAX_UMI) return -1;
+        e->umi_count = s->umi_count;
+        for (int i = 0; i < s->umi_count; i++) { e->umi_start[i] = s->umi[i].start; e->umi_length[i] = s->umi[i].length; }
+    }
+    return 0;
+}

@@ -71,6 +71,13 @@ static int process(struct host_config *cfg, struct ctx_boot *boot, const float *
     uint32_t nclusters, togo, blocksize, blockno, totalblocks;
     int rc = -1;
 
+    /* The block's text and records are formatted and deflated on the GPU (tsk_tile_encode) and the
+     * host only appends the BGZF blocks; TSK_HOST_WRITERS=1 keeps the host formatter + zlib, for
+     * timing one against the other. */
+    const int device_encode = getenv("TSK_HOST_WRITERS") == NULL;
+    int encoder_ready = 0;
+
+    tsk_writers_device_encoding(device_encode);
     snprintf(msgprefix, BUFSIZ, "[%s%d] ", cfg->laneid, cfg->tile);
     if (tsk_open_writers(cfg) < 0) return -1;
     printf("%sOpening input sources\n", msgprefix);
@@ -109,12 +116,28 @@ static int process(struct host_config *cfg, struct ctx_boot *boot, const float *
         phase("wait for the CUDA context");
 
         printf("%sAnalyzing and writing out\n", msgprefix);
+        if (device_encode && !encoder_ready) {
+            tsk_encode_layout *layout = malloc(sizeof(*layout));
+            if (!layout || tsk_build_encode_layout(cfg, layout) != 0 || tsk_encode_configure(ctx, layout) != 0) {
+                fprintf(stderr, "%s\n", layout ? tsk_last_error() : "out of memory");
+                free(layout);
+                goto done;
+            }
+            free(layout);
+            encoder_ready = 1;
+        }
         if (tsk_tile_upload(ctx, bcl, count, cif, count, invmatrix, count, nclusters - togo, 0) != 0 ||
-            tsk_tile_process(ctx) != 0 || tsk_tile_get_calls(ctx, calls) != 0) {
+            tsk_tile_process(ctx) != 0 || (!device_encode && tsk_tile_get_calls(ctx, calls) != 0)) {
             fprintf(stderr, "%s\n", tsk_last_error());
             goto done;
         }
         phase("upload + kernels + calls");
+        if (device_encode) {
+            if (tsk_tile_encode(ctx) != 0) { fprintf(stderr, "%s\n", tsk_last_error()); goto done; }
+            phase("format + deflate on the GPU");
+            if (tsk_write_encoded_outputs(cfg, ctx) < 0) goto done;
+            phase("write");
+        } else {
         for (struct host_sample *s = cfg->samples; s; s = s->next) {
             const int i = s->numindex;
             free(records[i]); records[i] = NULL; nslots[i] = 0;
@@ -130,6 +153,7 @@ static int process(struct host_config *cfg, struct ctx_boot *boot, const float *
         phase("fetch records");
         if (tsk_write_block_outputs(cfg, calls, count, nclusters - togo, bcl, records, nslots) < 0) goto done;
         phase("format + compress + write");
+        }
         /* like the reference, the pos/neg distributions are rewritten after every block
          * (tailseq-import.c:358-370,559): a multi-block tile keeps its last block's */
         if (cfg->signal_dists_output) {

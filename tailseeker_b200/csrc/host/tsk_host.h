@@ -108,6 +108,11 @@ int tsk_write_signal_headers(struct host_config *cfg, uint32_t total_clusters);
 int tsk_write_block_outputs(struct host_config *cfg, const tsk_call *calls, uint32_t nclusters,
                             uint32_t firstclusterno, const uint8_t *bcl, uint32_t **records,
                             const uint32_t *nslots);
+/* device-encoded outputs (tsk_tile_encode): the files become series of BGZF blocks; the host adds
+ * the signal header block and the end-of-file block and appends what the GPU hands back */
+void tsk_writers_device_encoding(int on);
+int tsk_write_encoded_outputs(struct host_config *cfg, tsk_ctx *ctx);
+int tsk_build_encode_layout(const struct host_config *cfg, tsk_encode_layout *out);
 int tsk_write_sigdists(const char *filename_format, const char *type, const uint32_t *counts,
                        int total_cycles, int bins);
 int tsk_write_stats(const char *output, const struct host_config *cfg, const tsk_counters *counters);

@@ -98,6 +98,27 @@ static int put_member(FILE *f, const void *src, size_t n)
     return ok ? 0 : -1;
 }
 
+/* ---- BGZF framing for the few bytes the host itself adds to device-encoded files ---- */
+static int device_encoding = 0;      /* files are series of BGZF blocks made by tsk_tile_encode() */
+
+void tsk_writers_device_encoding(int on) { device_encoding = on; }
+
+/* src[0..n) (n <= 65000) as one BGZF member holding a stored deflate block */
+static int put_bgzf_stored(FILE *f, const void *src, size_t n)
+{
+    unsigned char m[18 + 5 + 65000 + 8];
+    static const unsigned char hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+    const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), src, (uInt)n), len = (uint32_t)n;
+    const size_t total = 18 + 5 + n + 8;
+    if (n > 65000) return -1;
+    memcpy(m, hdr, 16);
+    m[16] = (unsigned char)((total - 1) & 0xff); m[17] = (unsigned char)((total - 1) >> 8);
+    m[18] = 1; m[19] = len & 0xff; m[20] = len >> 8; m[21] = ~len & 0xff; m[22] = (~len >> 8) & 0xff;
+    memcpy(m + 23, src, n);
+    for (int k = 0; k < 4; k++) { m[23 + n + k] = (crc >> (8 * k)) & 0xff; m[27 + n + k] = (len >> (8 * k)) & 0xff; }
+    return fwrite(m, 1, total, f) == total ? 0 : -1;
+}
+
 int tsk_open_writers(struct host_config *cfg)
 {
     for (struct host_sample *s = cfg->samples; s; s = s->next) {
@@ -115,7 +136,10 @@ void tsk_close_writers(struct host_config *cfg)
         FILE **fs[3] = {&s->stream_seqqual, &s->stream_taginfo, &s->stream_signal};
         for (int w = 0; w < 3; w++)
             if (*fs[w]) {
-                if (ftell(*fs[w]) == 0) put_member(*fs[w], "", 0);   /* an empty stream is still a gzip file */
+                if (device_encoding) {                      /* htslib's end-of-file marker block */
+                    const uint8_t *eof; size_t n;
+                    if (tsk_bgzf_eof_block(&eof, &n) == 0) fwrite(eof, 1, n, *fs[w]);
+                } else if (ftell(*fs[w]) == 0) put_member(*fs[w], "", 0);   /* an empty stream is still a gzip file */
                 fclose(*fs[w]);
                 *fs[w] = NULL;
             }
@@ -127,7 +151,10 @@ int tsk_write_signal_headers(struct host_config *cfg, uint32_t total_clusters)
     for (struct host_sample *s = cfg->samples; s; s = s->next)
         if (s->stream_signal) {
             const uint32_t h[3] = {4, total_clusters, (uint32_t)s->signal_dump_length};
-            if (put_member(s->stream_signal, h, sizeof(h)) != 0) { perror("write_output_file_headers"); return -1; }
+            if ((device_encoding ? put_bgzf_stored(s->stream_signal, h, sizeof(h)) : put_member(s->stream_signal, h, sizeof(h))) != 0) {
+                perror("write_output_file_headers");
+                return -1;
+            }
         }
     return 0;
 }
@@ -368,6 +395,47 @@ done:
         }
     if (recs) for (int i = 0; i < nrec; i++) free(recs[i].z.p);
     free(jobs); free(recs); free(outs); free(parts); free(tasks); free(byidx);
+    return rc;
+}
+
+/* The block's outputs as the GPU encoded them (tsk_tile_encode): whole BGZF blocks per stream,
+ * appended to the sample's files, one writer task per file. */
+struct enc_job { FILE *f; const uint8_t *data; size_t n; };
+
+static int write_encoded(void *arg)
+{
+    struct enc_job *j = arg;
+    if (j->n && fwrite(j->data, 1, j->n, j->f) != j->n) { perror("write_block_outputs"); return -1; }
+    return 0;
+}
+
+int tsk_write_encoded_outputs(struct host_config *cfg, tsk_ctx *ctx)
+{
+    const int S = cfg->num_samples;
+    struct enc_job *jobs = calloc(3 * (size_t)S, sizeof(*jobs));
+    struct task *tasks = calloc(3 * (size_t)S, sizeof(*tasks));
+    int n = 0, rc = -1;
+    if (!jobs || !tasks) { fprintf(stderr, "write_block_outputs: out of memory\n"); goto done; }
+    for (struct host_sample *s = cfg->samples; s; s = s->next) {
+        FILE *fs[3] = {s->stream_seqqual, s->stream_taginfo, s->stream_signal};
+        for (int kind = 0; kind < 3; kind++) {
+            if (!fs[kind]) continue;
+            jobs[n].f = fs[kind];
+            if (tsk_tile_get_encoded(ctx, s->numindex, kind, &jobs[n].data, &jobs[n].n) != 0) {
+                fprintf(stderr, "%s\n", tsk_last_error());
+                goto done;
+            }
+            tasks[n].fn = write_encoded; tasks[n].arg = &jobs[n];
+            n++;
+        }
+    }
+    if (n && run_tasks(tasks, n, cfg->threads > 0 ? cfg->threads : 1) != 0) {
+        fprintf(stderr, "write_block_outputs: writing the block's outputs failed\n");
+        goto done;
+    }
+    rc = 0;
+done:
+    free(jobs); free(tasks);
     return rc;
 }
 

@@ -285,6 +285,7 @@ extern "C" int tsk_ctx_destroy(tsk_ctx *ctx)
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    tsk_encode_free(ctx);
     if (ctx->rstream) {
         cudaStreamSynchronize(ctx->rstream);
         cudaStreamDestroy(ctx->rstream);

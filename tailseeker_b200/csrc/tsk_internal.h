@@ -65,8 +65,11 @@ struct TileView {
     uint32_t nclusters, firstclusterno;
 };
 
+struct EncState;
+
 struct tsk_ctx {
     int device;
+    EncState *enc;               /* device-side output encoding (tsk_encode.cu), NULL until configured */
     cudaStream_t stream;
     tsk_params hp;               /* host copy of the parameters */
     DevParams dp;
@@ -162,7 +165,8 @@ void tsk_set_error(const char *fmt, ...);
 /* kernel launchers (tsk_kernels.cu / tsk_ruler.cu / tsk_fit.cu) */
 int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev /* optional [5] */);
 int tsk_launch_score(tsk_ctx *ctx);
-int tsk_score_setup(tsk_ctx *ctx);        /* per-context tables of the scoring kernels */
+int tsk_score_setup(tsk_ctx *ctx);
+void tsk_encode_free(tsk_ctx *ctx);       /* tsk_encode.cu */        /* per-context tables of the scoring kernels */
 int tsk_launch_fixups(tsk_ctx *ctx);
 int tsk_control_setup(tsk_ctx *ctx);      /* builds the PhiX index (tsk_control.cu) */
 int tsk_launch_control(tsk_ctx *ctx);

@@ -443,8 +443,14 @@ __device__ __forceinline__ int lds_s16(uint32_t addr)
 #define K2_HEAD_MAX  24                  /* resident cycles [0, head): balancer + first scored cycles */
 #define K2_ROWB      (4 * 32 * 2)        /* bytes per cycle and warp: four channel rows of 32 int16 */
 #define K2_TILE_CYC  8                   /* record words staged per lane between flushes */
+/* Measured on a 1.07 M-cluster tile (tools/k2_variants.sh, profiles/r2_k2_variants.txt): 4 CTAs per SM
+ * at 119 registers and two cycles swept together 2.53 ms; 5 CTAs at 96 registers 2.59 ms; the
+ * round-1 loop 2.79 ms. */
 #ifndef K2_MIN_CTAS
-#define K2_MIN_CTAS  5
+#define K2_MIN_CTAS  4
+#endif
+#ifndef K2_SWEEP
+#define K2_SWEEP     2                   /* cycles of a group whose phases are swept together (1, 2 or 4) */
 #endif
 
 struct __align__(128) K2Smem {
@@ -1173,7 +1179,8 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
     const unsigned ilen_a = alive ? (unsigned)insert_len : 0u;
     const char *const logki = reinterpret_cast<const char *>(A.logki);
     bool handover = false;
-    auto cycle = [&](const int c, const uint32_t ap, const uint32_t atile, float *const scr) {
+    /* phase A of a cycle: intensities -> the four channel probabilities and whether the cycle is lit */
+    auto cycle_a = [&](const int c, const uint32_t ap, float prob[4], bool &good) {
         const bool act = (unsigned)c < ilen_a;
         /* ---- decrosstalk (signalproc.c:85-103); exact int16 -> float through 2^23+2^22 ---- */
 #ifdef TSK_K2_I2FP
@@ -1209,15 +1216,20 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
          * 0/0 gives, which is all that is looked at */
         handover |= act & ((__float_as_uint(sum) - 0x21800000u) >= 0x3c000000u) & (sum != 0.f);
         const float ys = rcp_rn_fast(sum);
-        float prob[4];
 #pragma unroll
         for (int ch = 0; ch < 4; ch++) prob[ch] = div_by_rcp(nrm[ch], sum, ys);
-        const bool good = act && !(tot < P.dark_threshold) && (prob[0] == prob[0]);
+        good = act && !(tot < P.dark_threshold) && (prob[0] == prob[0]);
+    };
+    /* phase B: entropy -> score -> packed word, sampling columns, dark-cycle count */
+    auto cycle_b = [&](const int c, const float prob[4], const bool good, const uint32_t atile, float *const scr) {
+        const bool act = (unsigned)c < ilen_a;
         /* ---- Shannon entropy ---- */
         float term[4];
 #pragma unroll
         for (int ch = 0; ch < 4; ch++) {
-#ifdef TSK_K2_LOGTAB_SMEM
+#ifndef TSK_K2_LOGTAB_GLOBAL
+            /* 16-entry core table in shared memory: 21 more instructions per cycle than the (exponent, index)
+             * table below, yet 4 % faster -- the 32 KB table's L1 latency (long-scoreboard stalls 3x) costs more */
             const float lg = logf_core_t(__float_as_uint(prob[ch]), [a_logtab](uint32_t ofs) {
                 double2 t;
                 asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(a_logtab + ofs));
@@ -1291,9 +1303,37 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
             /* groups past the data (record padding only) run on whatever the slot holds: act is false */
             const uint32_t ap = a_stage + slot * (K2_GROUP * K2C_ROWB) + colofs;
             const uint32_t atile = a_mytile + (g & 1) * (K2_GROUP * 4);
+            /* the group's cycles in two sweeps: the four probability chains are independent of each
+             * other, and so are the sixteen logarithms that follow -- fewer issue slots lost to
+             * waiting on the previous instruction of one chain */
+#if K2_SWEEP == 4
+            {
+                float prob[K2_GROUP][4];
+                bool good[K2_GROUP];
 #pragma unroll
-            for (int k = 0; k < K2_GROUP; k++)
-                cycle(cidx + k, ap + k * K2C_ROWB, atile + 4 * k, scrg + (size_t)k * spitch);
+                for (int k = 0; k < K2_GROUP; k++) cycle_a(cidx + k, ap + k * K2C_ROWB, prob[k], good[k]);
+#pragma unroll
+                for (int k = 0; k < K2_GROUP; k++) cycle_b(cidx + k, prob[k], good[k], atile + 4 * k, scrg + (size_t)k * spitch);
+            }
+#elif K2_SWEEP == 2
+#pragma unroll
+            for (int k2 = 0; k2 < K2_GROUP; k2 += 2) {
+                float prob[2][4];
+                bool good[2];
+#pragma unroll
+                for (int k = 0; k < 2; k++) cycle_a(cidx + k2 + k, ap + (k2 + k) * K2C_ROWB, prob[k], good[k]);
+#pragma unroll
+                for (int k = 0; k < 2; k++) cycle_b(cidx + k2 + k, prob[k], good[k], atile + 4 * (k2 + k), scrg + (size_t)(k2 + k) * spitch);
+            }
+#else
+#pragma unroll
+            for (int k = 0; k < K2_GROUP; k++) {
+                float prob[4];
+                bool good;
+                cycle_a(cidx + k, ap + k * K2C_ROWB, prob, good);
+                cycle_b(cidx + k, prob, good, atile + 4 * k, scrg + (size_t)k * spitch);
+            }
+#endif
             cidx += K2_GROUP;
             scrg += K2_GROUP * spitch;
             __syncwarp();

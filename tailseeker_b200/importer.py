@@ -248,6 +248,40 @@ class TileProcessor:
         _lib.check(self.lib.tsk_ruler_get_hist(self._ctx, _ptr(out)))
         return out
 
+    # ---- output encoding on the device (tsk_encode.cu) ----
+    def encode_configure(self, layout=None):
+        lay = layout if layout is not None else self.cfg.to_encode_layout()
+        _lib.check(self.lib.tsk_encode_configure(self._ctx, ctypes.byref(lay)))
+
+    def encode(self):
+        """Formats and deflates the outputs of the tile last processed.  Returns
+        {(sample index, stream): bytes} with stream 0 seqqual, 1 taginfo, 2 signal records; each value
+        is a run of whole BGZF blocks."""
+        _lib.check(self.lib.tsk_tile_encode(self._ctx))
+        out = {}
+        for s in range(self.params.num_samples):
+            for kind in range(3):
+                ptr, n = ctypes.c_void_p(), ctypes.c_size_t()
+                _lib.check(self.lib.tsk_tile_get_encoded(self._ctx, s, kind, ctypes.byref(ptr), ctypes.byref(n)))
+                out[(s, kind)] = ctypes.string_at(ptr.value, n.value) if n.value else b""
+        return out
+
+    def encode_ms(self) -> float:
+        ms = ctypes.c_double()
+        _lib.check(self.lib.tsk_encode_elapsed_ms(self._ctx, ctypes.byref(ms)))
+        return ms.value
+
+    def selftest_deflate(self, data: bytes) -> bytes:
+        out = ctypes.create_string_buffer(len(data) + len(data) // 500 + 4096 + 64 * (len(data) // 32768 + 1))
+        n = ctypes.c_size_t()
+        _lib.check(self.lib.tsk_selftest_deflate(self._ctx, data, len(data), out, len(out), ctypes.byref(n)))
+        return out.raw[:n.value]
+
+    def bgzf_eof(self) -> bytes:
+        ptr, n = ctypes.c_void_p(), ctypes.c_size_t()
+        _lib.check(self.lib.tsk_bgzf_eof_block(ctypes.byref(ptr), ctypes.byref(n)))
+        return ctypes.string_at(ptr.value, n.value)
+
     def selftest_logf(self, x: np.ndarray) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float32)
         out = np.empty_like(x)
