@@ -346,7 +346,8 @@ void tsk_merge_destroy(tsk_merge *m);
 int tsk_merge_add_tile(tsk_merge *m, tsk_ctx *ctx);
 /* the context's ruler histogram and counters (they accumulate inside the context): once, at the end */
 int tsk_merge_add_totals(tsk_merge *m, tsk_ctx *ctx);
-/* ONE ncclAllReduce(uint64, sum) over the packed accumulators */
+/* ONE ncclAllReduce(uint64, sum) over the packed accumulators.  ctx may be NULL here and in
+ * tsk_merge_get() (the contexts of a run are gone by then): the device is synchronised first. */
 int tsk_merge_allreduce(tsk_merge *m, tsk_ctx *ctx, void *nccl_comm);
 /* host copies: u64 [cycles][bins] x 3, u64 [nsamples][6] (tsk_counters order); any may be NULL */
 int tsk_merge_get(tsk_merge *m, tsk_ctx *ctx, uint64_t *pos, uint64_t *neg, uint64_t *ruler_pos, uint64_t *counters);

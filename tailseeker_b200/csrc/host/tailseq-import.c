@@ -57,7 +57,43 @@ static tsk_ctx *await_context(struct ctx_boot *b)
     return b->ctx;
 }
 
-static int process(struct host_config *cfg, struct ctx_boot *boot, const float *invmatrix)
+/* --devices: one worker (host thread + CUDA context) per GPU, the configuration files dealt round
+ * robin (one tile set per GPU); every device sums the histograms and counters of its tiles in a
+ * tsk_merge accumulator and the sums are all-reduced over NCCL at the end of the run. */
+struct run_merge {
+    tsk_merge *m;
+    int cycles, bins, nsamples;
+    char **sample_names;         /* list order, taken from the first tile */
+    char **sample_rows;          /* the constant CSV columns of each sample */
+};
+
+static int merge_tile(struct run_merge *rm, const struct host_config *cfg, tsk_ctx *ctx, int device, int per_block)
+{
+    if (!rm) return 0;
+    if (!rm->m) {
+        if (tsk_merge_create(&rm->m, device, cfg->total_cycles, cfg->bins, cfg->num_samples, 0) != 0) {
+            fprintf(stderr, "%s\n", tsk_last_error());
+            return -1;
+        }
+        rm->cycles = cfg->total_cycles; rm->bins = cfg->bins; rm->nsamples = cfg->num_samples;
+        rm->sample_names = calloc(cfg->num_samples, sizeof(char *));
+        rm->sample_rows = calloc(cfg->num_samples, sizeof(char *));
+        for (const struct host_sample *s = cfg->samples; s; s = s->next) {
+            char row[512];
+            snprintf(row, sizeof(row), "%s,%d,%s,%d,%d", s->index ? s->index : "(null)", s->maximum_index_mismatches,
+                     s->delimiter ? s->delimiter : "(null)", s->delimiter_pos, s->maximum_delimiter_mismatches);
+            rm->sample_names[s->numindex] = strdup(s->name);
+            rm->sample_rows[s->numindex] = strdup(row);
+        }
+    }
+    if ((per_block ? tsk_merge_add_tile(rm->m, ctx) : tsk_merge_add_totals(rm->m, ctx)) != 0) {
+        fprintf(stderr, "%s\n", tsk_last_error());
+        return -1;
+    }
+    return 0;
+}
+
+static int process(struct host_config *cfg, struct ctx_boot *boot, const float *invmatrix, struct run_merge *rm)
 {
     tsk_ctx *ctx = NULL;
     char msgprefix[BUFSIZ];
@@ -170,6 +206,9 @@ static int process(struct host_config *cfg, struct ctx_boot *boot, const float *
         if (tsk_get_counters(ctx, counters) != 0) { fprintf(stderr, "%s\n", tsk_last_error()); goto done; }
         if (tsk_write_stats(cfg->stats_output, cfg, counters) < 0) goto done;
     }
+    /* run-wide sums: what the tile's .sigdists files hold (the LAST block's histograms, like the
+     * reference's per-block rewrite, tailseq-import.c:358-370,559) and its counters */
+    if (merge_tile(rm, cfg, ctx, boot->device, 1) != 0 || merge_tile(rm, cfg, ctx, boot->device, 0) != 0) goto done;
     phase("sigdists + stats");
     printf("[%s%d] Finished.\n", cfg->laneid, cfg->tile);
     rc = 0;
@@ -184,7 +223,7 @@ done:
 }
 
 /* one tile: the body of the reference's main() (tailseq-import.c:736-757) */
-static int run_tile(const char *inifile, int device)
+static int run_tile(const char *inifile, int device, struct run_merge *rm)
 {
     struct host_config *cfg;
     tsk_params *params;
@@ -202,7 +241,7 @@ static int run_tile(const char *inifile, int device)
     boot.params = params; boot.device = device;
     if (pthread_create(&boot.thread, NULL, boot_context, &boot) == 0) boot.started = 1;
     else boot_context(&boot);
-    r = process(cfg, &boot, inv);
+    r = process(cfg, &boot, inv, rm);
     phase("close files");
     ctx = await_context(&boot);
     if (ctx) tsk_ctx_destroy(ctx);
@@ -211,19 +250,135 @@ static int run_tile(const char *inifile, int device)
     return r;
 }
 
+/* ---- several devices ---- */
+struct dev_worker {
+    pthread_t thread;
+    int device, index, ndev, nfiles, rc;
+    char **files;
+    struct run_merge rm;
+};
+
+static void *device_worker(void *arg)
+{
+    struct dev_worker *w = arg;
+    for (int i = w->index; i < w->nfiles; i += w->ndev) {
+        w->rc = run_tile(w->files[i], w->device, &w->rm);
+        if (w->rc != 0) break;
+    }
+    return NULL;
+}
+
+static int write_merged(const struct run_merge *rm, const char *sigdists_fmt, const char *stats_file)
+{
+    const size_t hw = (size_t)rm->cycles * rm->bins;
+    uint64_t *pos = malloc(sizeof(uint64_t) * hw), *neg = malloc(sizeof(uint64_t) * hw);
+    uint64_t *cnt = malloc(sizeof(uint64_t) * 6 * (size_t)rm->nsamples);
+    uint32_t *h32 = malloc(sizeof(uint32_t) * hw);
+    int rc = -1;
+    if (!pos || !neg || !cnt || !h32) { perror("write_merged"); goto done; }
+    if (tsk_merge_get(rm->m, NULL, pos, neg, NULL, cnt) != 0) { fprintf(stderr, "%s\n", tsk_last_error()); goto done; }
+    if (sigdists_fmt) {
+        /* the .sigdists layout holds u32 counts (tailseq-import.c:290-296); a run-wide count beyond that saturates */
+        for (int k = 0; k < 2; k++) {
+            const uint64_t *src = k ? neg : pos;
+            for (size_t i = 0; i < hw; i++) h32[i] = src[i] > 0xffffffffull ? 0xffffffffu : (uint32_t)src[i];
+            if (tsk_write_sigdists(sigdists_fmt, k ? "neg" : "pos", h32, rm->cycles, rm->bins) != 0) goto done;
+        }
+    }
+    if (stats_file) {
+        /* the "(total)" rows of scripts/stats-merge-demultiplexing-counts.py:33-53 (sorted by name) */
+        FILE *fp = fopen(stats_file, "w");
+        int *order = malloc(sizeof(int) * rm->nsamples);
+        if (!fp || !order) { perror("write_merged"); if (fp) fclose(fp); free(order); goto done; }
+        for (int i = 0; i < rm->nsamples; i++) order[i] = i;
+        for (int i = 1; i < rm->nsamples; i++)
+            for (int j = i; j > 0 && strcmp(rm->sample_names[order[j - 1]], rm->sample_names[order[j]]) > 0; j--) {
+                const int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t;
+            }
+        fprintf(fp, "tile,name,index,max_index_mm,delim,delim_pos,max_delim_mm,cln_no_index_mm,cln_1_index_mm,"
+                    "cln_2+_index_mm,cln_fp_mm,cln_qc_fail,cln_no_delim,cln_passed\n");
+        for (int k = 0; k < rm->nsamples; k++) {
+            const int i = order[k];
+            const uint64_t *c = cnt + 6 * (size_t)i;      /* mm0 mm1 mm2+ nodelim fpmm qcfail */
+            fprintf(fp, "(total),%s,%s,%llu,%llu,%llu,%llu,%llu,%llu,%lld\n", rm->sample_names[i], rm->sample_rows[i],
+                    (unsigned long long)c[0], (unsigned long long)c[1], (unsigned long long)c[2], (unsigned long long)c[4],
+                    (unsigned long long)c[5], (unsigned long long)c[3],
+                    (long long)(c[0] + c[1] + c[2]) - (long long)(c[3] + c[4] + c[5]));
+        }
+        free(order);
+        fclose(fp);
+    }
+    rc = 0;
+done:
+    free(pos); free(neg); free(cnt); free(h32);
+    return rc;
+}
+
+static int run_devices(const char *devlist, char **files, int nfiles, const char *sigdists_fmt, const char *stats_file)
+{
+    struct dev_worker w[64];
+    int devices[64], ndev = 0, rc = 0;
+    void *comms[64];
+    char *list = strdup(devlist), *save = NULL;
+    for (char *tok = strtok_r(list, ",", &save); tok && ndev < 64; tok = strtok_r(NULL, ",", &save)) devices[ndev++] = atoi(tok);
+    free(list);
+    if (ndev < 1) { fprintf(stderr, "--devices needs a comma-separated list of GPU numbers\n"); return 2; }
+    memset(w, 0, sizeof(w));
+    for (int d = 0; d < ndev; d++) {
+        w[d].device = devices[d]; w[d].index = d; w[d].ndev = ndev; w[d].nfiles = nfiles; w[d].files = files;
+        if (pthread_create(&w[d].thread, NULL, device_worker, &w[d]) != 0) { perror("pthread_create"); return -1; }
+    }
+    for (int d = 0; d < ndev; d++) { pthread_join(w[d].thread, NULL); if (w[d].rc != 0 && rc == 0) rc = w[d].rc; }
+    if (rc != 0 || (!sigdists_fmt && !stats_file)) return rc;
+    /* the run-wide sums: one all-reduce over the devices that processed tiles, written by the first */
+    int nact = 0, act[64];
+    for (int d = 0; d < ndev; d++) if (w[d].rm.m) { act[nact] = d; devices[nact] = w[d].device; nact++; }
+    if (nact == 0) return 0;
+    for (int k = 1; k < nact; k++)
+        if (w[act[k]].rm.cycles != w[act[0]].rm.cycles || w[act[k]].rm.bins != w[act[0]].rm.bins ||
+            w[act[k]].rm.nsamples != w[act[0]].rm.nsamples) {
+            fprintf(stderr, "The tiles of a merged run must share cycles, bins and sample list.\n");
+            return -1;
+        }
+    if (nact > 1) {
+        if (tsk_nccl_init_all(comms, nact, devices) != 0 || tsk_nccl_group_start() != 0) { fprintf(stderr, "%s\n", tsk_last_error()); return -1; }
+        for (int k = 0; k < nact; k++)
+            if (tsk_merge_allreduce(w[act[k]].rm.m, NULL, comms[k]) != 0) { fprintf(stderr, "%s\n", tsk_last_error()); return -1; }
+        if (tsk_nccl_group_end() != 0) { fprintf(stderr, "%s\n", tsk_last_error()); return -1; }
+    }
+    rc = write_merged(&w[act[0]].rm, sigdists_fmt, stats_file);
+    if (nact > 1) for (int k = 0; k < nact; k++) tsk_nccl_destroy(comms[k]);
+    for (int d = 0; d < ndev; d++) tsk_merge_destroy(w[d].rm.m);
+    return rc;
+}
+
 /* `tailseq-import {config.ini}` as in the reference.  Further configuration files are processed one
  * after the other in the same process, so a lane's tiles pay for the CUDA start-up (0.4-2 s) once
- * instead of once per tile; the run stops at the first tile that fails, like a chain of commands. */
+ * instead of once per tile; the run stops at the first tile that fails, like a chain of commands.
+ * `tailseq-import --devices 0,1,...,7 [--merged-sigdists FMT{posneg}] [--merged-stats FILE] a.ini b.ini ...`
+ * deals the tiles over several GPUs and writes the run-wide sums next to the per-tile outputs. */
 int main(int argc, char *argv[])
 {
-    int device = 0;
-    const char *dev = getenv("TAILSEEKER_DEVICE");
+    int device = 0, first = 1;
+    const char *dev = getenv("TAILSEEKER_DEVICE"), *devlist = NULL, *msig = NULL, *mstats = NULL;
 
     if (argc < 2) { usage(argv[0]); return 0; }
     phase("start");
     if (dev) device = atoi(dev);
-    for (int i = 1; i < argc; i++) {
-        const int r = run_tile(argv[i], device);
+    while (first + 1 < argc && argv[first][0] == '-' && argv[first][1] == '-') {
+        if (!strcmp(argv[first], "--devices")) devlist = argv[first + 1];
+        else if (!strcmp(argv[first], "--merged-sigdists")) msig = argv[first + 1];
+        else if (!strcmp(argv[first], "--merged-stats")) mstats = argv[first + 1];
+        else { usage(argv[0]); return 2; }
+        first += 2;
+    }
+    if (devlist || msig || mstats) {
+        char one[16];
+        snprintf(one, sizeof(one), "%d", device);
+        return run_devices(devlist ? devlist : one, argv + first, argc - first, msig, mstats);
+    }
+    for (int i = first; i < argc; i++) {
+        const int r = run_tile(argv[i], device, NULL);
         if (r != 0) return r;
     }
     return 0;

@@ -144,6 +144,7 @@ struct tsk_merge {
     /* per-tile histograms of the tiles this device processed, for the per-tile fits */
     unsigned long long *d_tile_pos, *d_tile_neg;          /* [max_tiles][cycles][bins] */
     double *d_fit;  size_t fit_cap;
+    cudaStream_t own;                /* used when a call is made without a context (end of a run) */
 };
 
 __global__ void k_merge_add_u32(unsigned long long *__restrict__ acc, unsigned long long *__restrict__ keep,
@@ -172,6 +173,7 @@ extern "C" int tsk_merge_create(tsk_merge **out, int device, int cycles, int bin
     m->device = device; m->cycles = cycles; m->bins = bins; m->nsamples = nsamples; m->max_tiles = max_tiles;
     m->hw = (size_t)cycles * bins;
     m->acc_words = 3 * m->hw + (size_t)nsamples * TSK_NCOUNT + 2;
+    TSK_CUDA(cudaStreamCreateWithFlags(&m->own, cudaStreamNonBlocking));
     TSK_CUDA(cudaMalloc(&m->d_acc, sizeof(unsigned long long) * m->acc_words));
     TSK_CUDA(cudaMemset(m->d_acc, 0, sizeof(unsigned long long) * m->acc_words));
     if (max_tiles > 0) {
@@ -190,12 +192,25 @@ extern "C" void tsk_merge_destroy(tsk_merge *m)
     if (m->d_tile_pos) cudaFree(m->d_tile_pos);
     if (m->d_tile_neg) cudaFree(m->d_tile_neg);
     if (m->d_fit) cudaFree(m->d_fit);
+    if (m->own) cudaStreamDestroy(m->own);
     free(m);
 }
 
-static int merge_matches(const tsk_merge *m, const tsk_ctx *ctx)
+/* stream of a call that may come without a context (ctx == NULL: everything the device still has
+ * queued is waited for first, then the accumulator's own stream is used) */
+static int merge_stream(tsk_merge *m, tsk_ctx *ctx, cudaStream_t *st)
 {
-    if (!m || !ctx) { tsk_set_error("null argument"); return -1; }
+    if (ctx) { *st = ctx->stream; return 0; }
+    TSK_CUDA(cudaSetDevice(m->device));
+    TSK_CUDA(cudaDeviceSynchronize());
+    *st = m->own;
+    return 0;
+}
+
+static int merge_matches(const tsk_merge *m, const tsk_ctx *ctx, bool ctx_optional = false)
+{
+    if (!m || (!ctx && !ctx_optional)) { tsk_set_error("null argument"); return -1; }
+    if (!ctx) return 0;
     if (m->device != ctx->device || m->cycles != ctx->dp.total_cycles || m->bins != ctx->dp.bins ||
         m->nsamples != ctx->dp.num_samples) { tsk_set_error("accumulator and context differ in device or shape"); return -1; }
     return 0;
@@ -245,24 +260,28 @@ extern "C" int tsk_merge_allreduce(tsk_merge *m, tsk_ctx *ctx, void *nccl_comm)
 {
     NcclApi *a = nccl_api();
     if (!a) return -1;
-    if (merge_matches(m, ctx) != 0 || !nccl_comm) { if (!nccl_comm) tsk_set_error("null communicator"); return -1; }
+    if (merge_matches(m, ctx, true) != 0 || !nccl_comm) { if (!nccl_comm) tsk_set_error("null communicator"); return -1; }
     TSK_CUDA(cudaSetDevice(m->device));
-    TSK_NCCL(a, a->AllReduce(m->d_acc, m->d_acc, m->acc_words, ncclUint64, ncclSum, (ncclComm_t)nccl_comm, ctx->stream));
-    ctx->launches++;
+    cudaStream_t st;
+    if (merge_stream(m, ctx, &st) != 0) return -1;
+    TSK_NCCL(a, a->AllReduce(m->d_acc, m->d_acc, m->acc_words, ncclUint64, ncclSum, (ncclComm_t)nccl_comm, st));
+    if (ctx) ctx->launches++;
     return 0;
 }
 
 extern "C" int tsk_merge_get(tsk_merge *m, tsk_ctx *ctx, uint64_t *pos, uint64_t *neg, uint64_t *ruler_pos, uint64_t *counters)
 {
-    if (merge_matches(m, ctx) != 0) return -1;
+    if (merge_matches(m, ctx, true) != 0) return -1;
     TSK_CUDA(cudaSetDevice(m->device));
+    cudaStream_t st;
+    if (merge_stream(m, ctx, &st) != 0) return -1;
     const size_t hb = sizeof(uint64_t) * m->hw;
-    if (pos) TSK_CUDA(cudaMemcpyAsync(pos, m->d_acc, hb, cudaMemcpyDeviceToHost, ctx->stream));
-    if (neg) TSK_CUDA(cudaMemcpyAsync(neg, m->d_acc + m->hw, hb, cudaMemcpyDeviceToHost, ctx->stream));
-    if (ruler_pos) TSK_CUDA(cudaMemcpyAsync(ruler_pos, m->d_acc + 2 * m->hw, hb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pos) TSK_CUDA(cudaMemcpyAsync(pos, m->d_acc, hb, cudaMemcpyDeviceToHost, st));
+    if (neg) TSK_CUDA(cudaMemcpyAsync(neg, m->d_acc + m->hw, hb, cudaMemcpyDeviceToHost, st));
+    if (ruler_pos) TSK_CUDA(cudaMemcpyAsync(ruler_pos, m->d_acc + 2 * m->hw, hb, cudaMemcpyDeviceToHost, st));
     if (counters) TSK_CUDA(cudaMemcpyAsync(counters, m->d_acc + 3 * m->hw, sizeof(uint64_t) * m->nsamples * TSK_NCOUNT,
-                                           cudaMemcpyDeviceToHost, ctx->stream));
-    TSK_CUDA(cudaStreamSynchronize(ctx->stream));
+                                           cudaMemcpyDeviceToHost, st));
+    TSK_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
 

@@ -63,6 +63,7 @@ class TileProcessor:
         self.cfg = cfg
         self.params = params if params is not None else cfg.to_cparams()
         self.lib = _lib.load()
+        self.device = device
         self._ctx = ctypes.c_void_p()
         _lib.check(self.lib.tsk_ctx_create(ctypes.byref(self._ctx), device, ctypes.byref(self.params)))
         self.nclusters = 0          # clusters of the tile last taken by process()
@@ -299,7 +300,7 @@ class TileProcessor:
         _lib.check(self.lib.tsk_debug_force_generic(self._ctx, int(on)))
 
     # ------------------------------------------------------------------ estimator
-    def fit_cutoffs(self, pos: np.ndarray, neg: np.ndarray) -> np.ndarray:
+    def fit_cutoffs(self, pos: np.ndarray, neg: np.ndarray, min_spots: Optional[int] = None) -> np.ndarray:
         """Per-cycle equal-odds cutoffs (NaN where undetermined) for one histogram pair."""
         pos = np.ascontiguousarray(pos, dtype=np.uint64)
         neg = np.ascontiguousarray(neg, dtype=np.uint64)
@@ -308,7 +309,7 @@ class TileProcessor:
         out = np.zeros(cycles, dtype=np.float64)
         _lib.check(self.lib.tsk_fit_cutoffs(
             self._ctx, _ptr(pos), _ptr(neg), cycles, bins,
-            ctypes.c_uint64(self.cfg.minimum_spots_for_dist_sampling),
+            ctypes.c_uint64(self.cfg.minimum_spots_for_dist_sampling if min_spots is None else min_spots),
             float(self.cfg.kde_bandwidth_for_dist), float(self.cfg.cutoff_score_search_low),
             _ptr(highs), highs.size, _ptr(out)))
         return out
