@@ -142,7 +142,7 @@ def reference_sample_run(cfg, bcl, cif, matrix_text, threads, cutoffs):
     base = "/dev/shm" if os.path.isdir("/dev/shm") else None
     work = tempfile.mkdtemp(prefix="tskbench_", dir=base)
     try:
-        r = refrun.run_import(cfg, tile, workdir=work, threads=threads, gz_level=1)
+        r = refrun.run_import(cfg, tile, workdir=work, threads=threads, gz_level=1, read_buffer_size=4 << 30)
         secs = r["wall_s"]
         tid = cfg.tile_id
         cpath = os.path.join(work, "cutoffs.txt")
@@ -162,35 +162,46 @@ def default_cutoffs(T):
     return np.full(T, 0.25, dtype=np.float64)
 
 
+def workload_config(layout, ntiles, N, T):
+    """The `config` both arms print (identical keys and values: the driver compares them)."""
+    workload = WORKLOAD if (layout, ntiles, N) == ("miseq", TILES_PER_GPU, CLUSTERS_PER_TILE) else (
+        "%s layout: %d tiles x %d clusters per GPU, %d cycles, 4 exp + 7 spike-in samples, [control] PhiX"
+        % (layout, ntiles, N, T))
+    return {"workload": workload, "tiles_per_gpu": ntiles, "clusters_per_tile": N,
+            "l2": "inputs_larger_than_L2 (2.5 GB per tile, streamed once)",
+            "ruler_rounds": 1}
+
+
 def run_reference_arm(args):
+    """The reference's own CPU implementation of the path (oracle/_ref: the unmodified sources) with
+    every host thread it can use, one FULL tile of the workload per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from oracle import refrun
     from tailseeker_b200.config import stock_config
-    from tailseeker_b200.synth import make_tile
-    cfg = stock_config("miseq", phix_match_name="PhiX")
+    cfg = stock_config(args.layout, phix_match_name="PhiX")
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD}}
+            "config": workload_config(args.layout, args.tiles, args.clusters_per_tile, cfg.total_cycles)}
     if not refrun.available():
         line["unavailable"] = "oracle/_ref binaries are not built (run __graft_entry__.build() where /root/reference exists)"
         print(json.dumps(line))
         return 0
     cores = os.cpu_count() or 1
-    nsample = args.ref_clusters
-    tile = make_tile(cfg, nsample, seed=1234, phix_frac=PHIX_FRAC)
+    nsample = args.ref_clusters if args.ref_clusters > 0 else args.clusters_per_tile
+    bcl, cif, mtext = host_tile(cfg, nsample, seed=1000)
     cut = default_cutoffs(cfg.total_cycles)
     times = []
     for it in range(args.warmup + args.steps):
-        n, secs = reference_sample_run(cfg, tile.bcl, tile.cif, tile.matrix_text, cores, cut)
+        n, secs = reference_sample_run(cfg, bcl, cif, mtext, cores, cut)
         if it >= args.warmup:
             times.append(secs)
     value = nsample / (sum(times) / len(times))
-    sample = ("%d-cluster MiSeq-shaped tile per step: tailseq-import (threads=%d, one read block, "
-              "zlib level 1 instead of BGZF) + tailseq-polya-ruler per sample, files on /dev/shm; "
-              "wall time of the binaries (file read + compute + compress + write)" % (nsample, cores))
+    sample = ("one %d-cluster tile of the workload per step (the per-GPU tile set is %d such tiles): tailseq-import "
+              "(threads=%d, one read block, zlib level 1 instead of BGZF) + tailseq-polya-ruler per sample, files on "
+              "/dev/shm; wall time of the binaries (file read + compute + compress + write)" % (nsample, args.tiles, cores))
     line.update({"value": value, "ms_per_step": 1e3 * sum(times) / len(times),
                  "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
                                   "sample": sample},
@@ -198,6 +209,84 @@ def run_reference_arm(args):
                  "gpu_launches": 0})
     print(json.dumps(line))
     return 0
+
+
+def host_tile(cfg, n, seed):
+    """A host tile of the workload's recipe: generated on the GPU when there is one (seconds for a
+    full tile), by the NumPy generator otherwise."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            from tailseeker_b200.synth_torch import make_tile_device
+            bcl, cif, mtext, pitch = make_tile_device(cfg, n, seed=seed, device="cuda", phix_frac=PHIX_FRAC)
+            out = (np.ascontiguousarray(bcl[:, :n].cpu().numpy()), np.ascontiguousarray(cif[:, :, :n].cpu().numpy()), mtext)
+            del bcl, cif
+            torch.cuda.empty_cache()
+            return out
+    except ImportError:
+        pass
+    from tailseeker_b200.synth import make_tile
+    t = make_tile(cfg, n, seed=seed, phix_frac=PHIX_FRAC)
+    return t.bcl, t.cif, t.matrix_text
+
+
+# ------------------------------------------------------------------------------------------
+# the command-line surface: files -> bin/tailseq-import -> files, beside the reference binary
+# ------------------------------------------------------------------------------------------
+def cli_leg(cfg, ntiles, N, threads):
+    """`tailseq-import a.ini b.ini ...` (drop-in: C host + CUDA, text and BGZF blocks made on the GPU)
+    against oracle/_ref/tailseq-import (one process per tile, zlib level 1), same files on /dev/shm,
+    same [options] threads.  Returns clusters/s of both and the drop-in's phase times."""
+    import shutil
+    from oracle import refrun
+    from tailseeker_b200.synth import Tile, write_tile_files
+    exe = os.path.join(ROOT, "tailseeker_b200", "bin", "tailseq-import")
+    if not (os.access(exe, os.X_OK) and refrun.available()):
+        return None
+    base = tempfile.mkdtemp(prefix="tskcli_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        inis = {"ref": [], "our": []}
+        for k in range(ntiles):
+            tcfg = cfg.replace(tile=1101 + k)
+            bcl, cif, mtext = host_tile(tcfg, N, seed=7000 + k)
+            data = os.path.join(base, "data%d" % k)
+            mpath = write_tile_files(Tile(bcl=bcl, cif=cif, matrix_text=mtext, nclusters=N, truth_sample=None), tcfg, data)
+            del bcl, cif
+            for arm in ("ref", "our"):
+                w = os.path.join(base, arm)
+                for sub in ("seqqual", "taginfo", "signals", "sigdists-r00", "stats"):
+                    os.makedirs(os.path.join(w, sub), exist_ok=True)
+                ini = os.path.join(w, "tile%d.ini" % k)
+                with open(ini, "w") as f:
+                    f.write(tcfg.replace(data_dir=data, threep_colormatrix=mpath, threads=threads,
+                                         read_buffer_size=8 << 30).to_ini())
+                inis[arm].append(ini)
+        env = dict(os.environ, TSK_SHIM_GZ_LEVEL="1", TSK_HOST_TIMING="1")
+        t0 = time.perf_counter()
+        for ini in inis["ref"]:
+            subprocess.run([refrun.REF_IMPORT, ini], cwd=os.path.join(base, "ref"), env=env, check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        tref = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        r = subprocess.run([exe] + inis["our"], cwd=os.path.join(base, "our"), env=env, check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+        tour = time.perf_counter() - t0
+        phases = {}
+        for ln in r.stderr.decode().splitlines():
+            if ln.startswith("[timing]"):
+                name, secs = ln[8:].rsplit(None, 2)[0].strip(), float(ln.split()[-2])
+                phases[name] = round(phases.get(name, 0.0) + secs, 3)
+        sizes = {arm: sum(os.path.getsize(os.path.join(dp, f)) for sub in ("seqqual", "taginfo", "signals")
+                          for dp, _, fs in os.walk(os.path.join(base, arm, sub)) for f in fs) for arm in ("ref", "our")}
+        return {"value": ntiles * N / tour, "unit": UNIT, "reference_value": ntiles * N / tref,
+                "speedup": tref / tour, "tiles": ntiles, "clusters_per_tile": N, "threads": threads,
+                "seconds": round(tour, 3), "reference_seconds": round(tref, 3),
+                "output_bytes": sizes["our"], "reference_output_bytes": sizes["ref"], "phases_s": phases,
+                "note": "files on /dev/shm -> tailseq-import (one process, all tiles; CUDA start-up included) -> files; "
+                        "reference: its binary once per tile, zlib level 1; outputs of both decompress to the same bytes "
+                        "(tests/test_gpu_dropin.py, test_gpu_fullsize_oracle.py)"}
+    finally:
+        shutil.rmtree(base, ignore_errors=True)
 
 
 # ------------------------------------------------------------------------------------------
@@ -235,6 +324,19 @@ def algorithmic_bytes(cfg, params, calls, nclusters, slot_counts):
             "processed": int(proc.sum())}
 
 
+def pin_rank_to_cores(local_rank, local_world):
+    """Each rank keeps to its own slice of the host cores: eight ranks that all wander over the same
+    cores (and the same memory controller queues) is what the end-to-end curve of round 1 showed."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(1, local_world))
+        mine = cores[local_rank * per:(local_rank + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return len(mine)
+    except (AttributeError, OSError):
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -243,8 +345,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tiles", type=int, default=TILES_PER_GPU)
     ap.add_argument("--clusters-per-tile", type=int, default=CLUSTERS_PER_TILE)
-    ap.add_argument("--ref-clusters", type=int, default=100_000,
-                    help="clusters in the bounded CPU sample (reference arm / cpu_baseline)")
+    ap.add_argument("--ref-clusters", type=int, default=0,
+                    help="clusters in the CPU sample (reference arm / cpu_baseline); 0 = one full tile")
     ap.add_argument("--workload", default="import", choices=["import", "dedup"],
                     help="import (default): the north-star path; dedup: the duplicate-collapsing row (tools/dedup_bench.py)")
     ap.add_argument("--layout", default="miseq", choices=["miseq", "hiseq"],
@@ -252,6 +354,9 @@ def main():
                          "hiseq = BASELINE.json configs[2] (use --clusters-per-tile 3100000 for its tile size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cli", action="store_true", help="skip the files -> tailseq-import -> files leg (N = 1 only)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the HiSeq-lane and estimator-sweep legs (BASELINE configs 3-5)")
+    ap.add_argument("--cli-tiles", type=int, default=2)
     if "--workload" in sys.argv and "dedup" in sys.argv:
         sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
         import dedup_bench
@@ -266,6 +371,7 @@ def main():
 
     import torch
     import torch.distributed as dist
+    from tailseeker_b200 import merge as M
     from tailseeker_b200.config import stock_config
     from tailseeker_b200.importer import TileProcessor, invert_colormatrix
     from tailseeker_b200.synth_torch import make_tile_device
@@ -273,22 +379,36 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    host_cores = pin_rank_to_cores(local_rank, local_world) if world > 1 else (os.cpu_count() or 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    comm = None
     if world > 1:
+        M.use_torch_nccl()
         dist.init_process_group("nccl", device_id=dev)
+        comm = M.NcclComm.from_torch_distributed(local_rank)       # the library's own collective uses it
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     cfg = stock_config(args.layout, phix_match_name="PhiX")
     T, L3, bins = cfg.total_cycles, cfg.threep_length, cfg.dist_sampling_bins
     ntiles, N = args.tiles, args.clusters_per_tile
-    workload = WORKLOAD if (args.layout, ntiles, N) == ("miseq", TILES_PER_GPU, CLUSTERS_PER_TILE) else (
-        "%s layout: %d tiles x %d clusters per GPU, %d cycles, 4 exp + 7 spike-in samples, [control] PhiX"
-        % (args.layout, ntiles, N, T))
 
     proc = TileProcessor(cfg, device=local_rank)
     stream = torch.cuda.current_stream()
     proc.set_stream(stream.cuda_stream)
     S = proc.params.num_samples
+    merge = M.RunMerge(proc)
 
     # ---- synthetic tile set, generated in HBM (one lane's worth per rank) -------------------
     tiles = []
@@ -300,43 +420,28 @@ def main():
 
     cut = default_cutoffs(T)
     packed = proc.cutoffs_to_packed(cut)
-    acc_pos = torch.zeros((T, bins), dtype=torch.int64, device=dev)
-    acc_neg = torch.zeros((T, bins), dtype=torch.int64, device=dev)
-    ptrs = None
 
-    def lib_views():
-        p = proc.device_ptrs()
-        return (torch.as_tensor(DevView(p["pos"], (T, bins), "<i4"), device=dev),
-                torch.as_tensor(DevView(p["neg"], (T, bins), "<i4"), device=dev),
-                torch.as_tensor(DevView(p["counters"], (S, 6), "<i4"), device=dev))
-
-    def finish_step(host_fit: bool):
-        """run-wide statistics: all-reduce (N>1) + cutoff fit on the summed histograms"""
-        cnt = lib_views()[2].to(torch.int64)
-        if world > 1:
-            dist.all_reduce(acc_pos)
-            dist.all_reduce(acc_neg)
-            dist.all_reduce(cnt)
-        hp = acc_pos.cpu().numpy().astype(np.uint64)
-        hn = acc_neg.cpu().numpy().astype(np.uint64)
-        return proc.fit_cutoffs(hp, hn), cnt
-
-    views = lib_views()          # the library's histograms / counters live at fixed device addresses
+    def finish_step():
+        """run-wide statistics: ONE all-reduce (N > 1) of the packed histograms + counters on the device,
+        then the cutoff fit reads the summed histograms where they are (no trip through the host)"""
+        merge.add_totals()
+        merge.allreduce(comm)
+        return merge.fit(positive=0, with_tiles=False)[0]
 
     def device_step():
         """One pass over the rank's tiles, queued back to back on the stream: nothing about a
-        tile is read on the host until the end of the step (histogram sums for the fit and the
-        number of measured tails)."""
-        acc_pos.zero_(); acc_neg.zero_()
+        tile is read on the host until the end of the step (the fitted cutoffs and the number of
+        measured tails)."""
+        merge.reset(7)
         proc.reset_counters()
         proc.ruler_reset(T)
         for (bcl, cif, inv, pitch, _) in tiles:
             proc.upload(bcl.data_ptr(), cif.data_ptr(), inv, nclusters=N, on_device=True,
                         bcl_pitch=pitch, cif_pitch=pitch)
             proc.process_async()
-            acc_pos.add_(views[0]); acc_neg.add_(views[1])
+            merge.add_tile()
             proc.ruler_tile_all_async(packed)
-        fit, _ = finish_step(True)
+        fit = finish_step()
         return proc.ruler_called(), fit
 
     # ---- warm-up, then K timed steps (device-resident inputs) --------------------------------
@@ -348,11 +453,6 @@ def main():
     # byte accounting + per-stage timing from a representative pass (tile 0 calls)
     calls0 = proc.calls()       # last tile processed
     ab = algorithmic_bytes(cfg, proc.params, calls0, N, [proc.record_count(s) for s in range(S)])
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     proc.profile(True)
     launches0 = proc.launch_count()
@@ -369,10 +469,7 @@ def main():
     launches = proc.launch_count() - launches0
     stage_ms, stage_runs = proc.profile_get()
     proc.profile(False)
-    tms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_step = float(tms.item()) / args.steps
+    ms_step = max_over_ranks(ms_total) / args.steps
     clusters_step = ntiles * N * world
     value = clusters_step / (ms_step * 1e-3)
 
@@ -401,14 +498,24 @@ def main():
     tfile = os.path.join(ROOT, "profiles", "k2_traffic.json")
     if os.path.exists(tfile):
         try:
-            roof["traffic"] = json.load(open(tfile)).get("dram_bytes_per_launch")
+            tj = json.load(open(tfile))
+            roof["traffic"] = tj.get("dram_bytes_per_launch")
+            # the bound this kernel really runs against: instruction issue.  Warp-instructions of one
+            # launch (ncu smsp__inst_executed.sum of the same build, scaled to this tile's work items)
+            # over what 148 SMs x 4 schedulers can issue in the measured launch time.
+            wi = tj.get("warp_instructions_per_launch")
+            if wi and clocks.get("sm_mhz") and k2_ms > 0:
+                wi = wi * ab["processed"] / max(1, tj.get("processed_clusters", ab["processed"]))
+                cap = 148 * 4 * clocks["sm_mhz"] * 1e6 * k2_ms * 1e-3
+                roof["issue"] = {"bound": "issue", "warp_instructions_per_launch": int(wi), "issue_slots_per_launch": int(cap),
+                                 "frac": wi / cap, "source": tj.get("source")}
         except Exception:
             pass
 
     # ---- end-to-end: host (pinned) buffers through the C ABI ----------------------------------
     e2e = None
     if not args.no_e2e:
-        nhost = min(2, ntiles)
+        nhost = min(4, ntiles)               # staging ring of this rank: four distinct pinned tiles (10 GB)
         host_tiles = []
         for i in range(nhost):
             bcl, cif, inv, pitch, _ = tiles[i]
@@ -419,8 +526,9 @@ def main():
         torch.cuda.synchronize()
 
         def e2e_step():
-            acc_pos.zero_(); acc_neg.zero_()
+            merge.reset(7)
             proc.reset_counters()
+            proc.ruler_reset(T)
             d2h = 0
             hb, hc, inv = host_tiles[0]
             proc.upload(hb, hc, inv)                         # H2D of tile 0 (pinned -> HBM)
@@ -429,15 +537,14 @@ def main():
                     hb, hc, inv = host_tiles[(t + 1) % nhost]
                     proc.upload(hb, hc, inv)
                 proc.process()
+                merge.add_tile()
                 calls = proc.calls()                          # D2H 16 B / cluster
                 d2h += calls.nbytes
-                vp, vn, _ = lib_views()
-                acc_pos.add_(vp); acc_neg.add_(vn)
                 lens, _ = proc.ruler_tile_all(packed)         # D2H 2 B / record slot
                 d2h += lens.nbytes
-            fit, cnt = finish_step(True)                      # D2H of the two histograms
-            cnt.cpu()
-            d2h += 2 * T * bins * 8 + S * 6 * 8
+            fit = finish_step()                               # D2H of the fitted cutoffs
+            got = merge.get()                                 # and of the run-wide histograms / counters
+            d2h += fit.nbytes + sum(v.nbytes for v in got.values())
             return d2h
 
         for _ in range(1):
@@ -450,50 +557,176 @@ def main():
             d2h_bytes = e2e_step()
         e3.record(stream)
         barrier()
-        dt = e2.elapsed_time(e3) * 1e-3 / esteps
-        tdt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
-        e2e = {"value": clusters_step / float(tdt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(ntiles * N * (T + 8 * L3)) * world,      # whole job, like value
+        dt = max_over_ranks(e2.elapsed_time(e3) * 1e-3 / esteps)
+        h2d = int(ntiles * N * (T + 8 * L3))
+        e2e = {"value": clusters_step / dt, "unit": UNIT,
+               "h2d_bytes_per_step": h2d * world,      # whole job, like value
                "d2h_bytes_per_step": int(d2h_bytes) * world, "steps": esteps,
-               "note": "H2D of tile t+1 (copy stream) overlaps the kernels of tile t; results read back per tile; 2 distinct pinned host tiles cycled"}
+               "h2d_gbs_per_gpu": h2d / dt / 1e9, "host_cores_per_rank": host_cores,
+               "note": "H2D of tile t+1 (copy stream) overlaps the kernels of tile t; results read back per tile; "
+                       "%d distinct pinned host tiles per rank cycled; ranks pinned to disjoint core sets. The copies "
+                       "run at the PCIe rate (54 GB/s per GPU) while a host can feed them: N x that is the ceiling" % nhost}
+        del host_tiles
 
     # ---- CPU baseline beside it (rank 0, N=1 only) --------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import refrun
         if refrun.available():
-            ns = args.ref_clusters
+            ns = args.ref_clusters if args.ref_clusters > 0 else N
             bcl, cif, inv, pitch, mtext = tiles[0]
             hb = bcl[:, :ns].contiguous().cpu().numpy()
             hc = cif[:, :, :ns].contiguous().cpu().numpy()
             cores = os.cpu_count() or 1
             n, secs = reference_sample_run(cfg, hb, hc, mtext, cores, cut)
             cpu = {"value": n / secs, "unit": UNIT, "cores": cores, "kind": "reference",
-                   "sample": "first %d clusters of tile 0: reference tailseq-import (threads=%d, zlib level 1) "
-                             "+ tailseq-polya-ruler per sample, files on /dev/shm, binaries' wall time" % (ns, cores)}
+                   "sample": "%d clusters of tile 0 (%s): reference tailseq-import (threads=%d, zlib level 1) "
+                             "+ tailseq-polya-ruler per sample, files on /dev/shm, binaries' wall time"
+                             % (ns, "one full tile" if ns == N else "a part of one tile", cores)}
+            del hb, hc
         else:
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
                    "sample": "oracle/_ref not built"}
 
+    # ---- device-side output encoding of one tile (what the drop-in program's write path runs) ----
+    encode = None
     if rank == 0:
+        proc.encode_configure()
+        bcl, cif, inv, pitch, _ = tiles[0]
+        proc.upload(bcl.data_ptr(), cif.data_ptr(), inv, nclusters=N, on_device=True, bcl_pitch=pitch, cif_pitch=pitch)
+        proc.process()
+        enc_ms = []
+        for _ in range(4):
+            t0 = time.perf_counter()
+            proc.encode_only()
+            wall = time.perf_counter() - t0
+            enc_ms.append((proc.encode_ms(), wall * 1e3))
+        streams = proc.encode()
+        out_bytes = sum(len(v) for v in streams.values())
+        encode = {"kernels_ms_per_tile": min(e[0] for e in enc_ms), "with_d2h_ms_per_tile": min(e[1] for e in enc_ms),
+                  "compressed_bytes_per_tile": out_bytes,
+                  "note": "taginfo + seqqual text formatted and all three streams deflated as BGZF blocks on the GPU; "
+                          "second figure includes the copy of the compressed streams to pinned host memory"}
+        del streams
+
+    # free the MiSeq set before the other legs
+    merge.close()
+    proc.close()
+    del tiles
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs 3 - 5: HiSeq lane tiles (one lane per GPU), estimator sweep -----------
+    extra = None
+    if not args.no_extra:
+        extra = extra_configs(args, torch, dist, M, dev, rank, world, local_rank, comm, barrier, max_over_ranks)
+
+    cli = None
+    if rank == 0 and world == 1 and not args.no_cli:
+        try:
+            cli = cli_leg(cfg, args.cli_tiles, N, os.cpu_count() or 1)
+        except Exception as exc:          # the leg must not take the headline numbers down with it
+            cli = {"error": repr(exc)[:300]}
+
+    if rank == 0:
+        config = workload_config(args.layout, ntiles, N, T)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload, "tiles_per_gpu": ntiles, "clusters_per_tile": N,
-                           "l2": "inputs_larger_than_L2 (2.5 GB per tile, streamed once)",
-                           "polya_called_per_step": int(measured) * world,
-                           "cutoffs_fitted": int(np.isfinite(fit).sum())},
-                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "config": config,
+                "results": {"polya_called_per_step": int(measured) * world,
+                            "cutoffs_fitted": int(np.isfinite(fit).sum()),
+                            "collective": "one ncclAllReduce(uint64) of the packed run-wide histograms + counters per step"
+                                          if world > 1 else "none (one rank)"},
+                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "e2e_cli": cli, "encode": encode,
+                "other_configs": extra, "gpu_launches": int(launches),
                 "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"],
                            "reasons": clocks["reasons"], "samples": clocks["samples"],
                            "window": clocks.get("window", "timed")}}
         print(json.dumps(line))
+    if comm is not None:
+        comm.destroy()
     if world > 1:
         dist.destroy_process_group()
-    proc.close()
     return 0
+
+
+def extra_configs(args, torch, dist, M, dev, rank, world, local_rank, comm, barrier, max_over_ranks):
+    """BASELINE.json configs 3-5 on the same GPUs: (3/4) HiSeq 2500 lane tiles, 309 cycles and 3.1 M
+    clusters each, one lane per GPU -- a sample of `ht` tiles of the lane's 64 per rank; (5) the
+    parameter-estimation sweep: run-wide cutoffs plus the per-tile cutoffs of a lane's 64 tiles."""
+    from tailseeker_b200.config import stock_config
+    from tailseeker_b200.importer import TileProcessor, invert_colormatrix
+    from tailseeker_b200.synth_torch import make_tile_device
+    cfg = stock_config("hiseq", phix_match_name="PhiX")
+    T, HN, ht, lane_tiles = cfg.total_cycles, 3_100_000, 3, 64
+    proc = TileProcessor(cfg, device=local_rank)
+    stream = torch.cuda.current_stream()
+    proc.set_stream(stream.cuda_stream)
+    merge = M.RunMerge(proc, max_tiles=lane_tiles)
+    tiles = []
+    for t in range(ht):
+        bcl, cif, mtext, pitch = make_tile_device(cfg, HN, seed=50000 + 100 * rank + t, device=dev, phix_frac=PHIX_FRAC)
+        mtx = np.array([np.float32(x) for x in mtext.split()], dtype=np.float32)
+        tiles.append((bcl, cif, invert_colormatrix(mtx), pitch))
+    packed = proc.cutoffs_to_packed(default_cutoffs(T))
+
+    def step(keep_tiles):
+        merge.reset(7)
+        proc.reset_counters()
+        proc.ruler_reset(T)
+        for k in range(keep_tiles):
+            bcl, cif, inv, pitch = tiles[k % ht]
+            proc.upload(bcl.data_ptr(), cif.data_ptr(), inv, nclusters=HN, on_device=True, bcl_pitch=pitch, cif_pitch=pitch)
+            proc.process_async()
+            merge.add_tile()
+            proc.ruler_tile_all_async(packed)
+        merge.add_totals()
+        merge.allreduce(comm)
+        return merge.fit(positive=0, with_tiles=False)
+
+    step(ht)
+    proc.profile(True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    nsteps = 2
+    for _ in range(nsteps):
+        step(ht)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / nsteps
+    stage_ms, stage_runs = proc.profile_get()
+    proc.profile(False)
+    hiseq = {"workload": "HiSeq 2500 lane tiles (BASELINE.json configs[2]/[3]): %d tiles x %d clusters per GPU of the lane's 64, "
+                         "309 cycles, one lane per GPU, device-resident" % (ht, HN),
+             "value": ht * HN * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "ms_per_step": ms,
+             "ms_per_tile": {"decode_demux_seed": stage_ms[0] / max(1, int(stage_runs[0])),
+                             "normalise_score_pack": stage_ms[2] / max(1, int(stage_runs[2])),
+                             "fair_sampling_fixups": stage_ms[3] / max(1, int(stage_runs[3])),
+                             "polya_ruler": stage_ms[4] / max(1, int(stage_runs[4]))},
+             "lane_seconds_at_this_rate": lane_tiles * HN / (ht * HN / (ms * 1e-3))}
+    # estimator sweep: a lane's 64 tile histograms on every rank (the sample's tiles re-processed to fill
+    # them), all-reduced run-wide sums, then run-wide + per-tile cutoffs in one call on device memory
+    step(lane_tiles)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    reps = 3
+    t0.record(stream)
+    for _ in range(reps):
+        cutoffs = merge.fit(positive=0, with_tiles=True)
+    t1.record(stream)
+    barrier()
+    fit_ms = max_over_ranks(t0.elapsed_time(t1)) / reps
+    sweep = {"workload": "parameter-estimation sweep (BASELINE.json configs[4]): run-wide + %d per-tile cutoff sets per GPU, "
+                         "%d cycles x 1000 bins each, histograms resident on the device" % (lane_tiles, T),
+             "ms_per_sweep": fit_ms, "tiles_fitted": lane_tiles * world, "n_gpus": world,
+             "cutoff_sets_per_s": (1 + lane_tiles) * world / (fit_ms * 1e-3),
+             "cutoffs_found_run_wide": int(np.isfinite(cutoffs[0]).sum())}
+    merge.close()
+    proc.close()
+    del tiles
+    torch.cuda.empty_cache()
+    return {"hiseq_lane": hiseq, "estimator_sweep": sweep}
 
 
 if __name__ == "__main__":

@@ -42,6 +42,20 @@ struct ctx_boot {
     char error[512];
 };
 
+/* A process that handles several tiles keeps its context -- device buffers, the encoder's pinned
+ * staging buffer -- from one tile to the next when the parameters are the same (they are, within
+ * a run): creating and sizing them again costs more than the tile's kernels.  One per host thread. */
+static __thread tsk_ctx *kept_ctx = NULL;
+static __thread tsk_params *kept_params = NULL;
+static __thread int kept_device = -1;
+
+static void drop_kept_context(void)
+{
+    if (kept_ctx) tsk_ctx_destroy(kept_ctx);
+    free(kept_params);
+    kept_ctx = NULL; kept_params = NULL; kept_device = -1;
+}
+
 static void *boot_context(void *arg)
 {
     struct ctx_boot *b = arg;
@@ -153,12 +167,14 @@ static int process(struct host_config *cfg, struct ctx_boot *boot, const float *
 
         printf("%sAnalyzing and writing out\n", msgprefix);
         if (device_encode && !encoder_ready) {
-            tsk_encode_layout *layout = malloc(sizeof(*layout));
-            if (!layout || tsk_build_encode_layout(cfg, layout) != 0 || tsk_encode_configure(ctx, layout) != 0) {
-                fprintf(stderr, "%s\n", layout ? tsk_last_error() : "out of memory");
+            tsk_encode_layout *layout = calloc(1, sizeof(*layout));
+            if (!layout || tsk_build_encode_layout(cfg, layout) != 0) {
+                fprintf(stderr, "Cannot describe the output layout.\n");
                 free(layout);
                 goto done;
             }
+            /* (a context kept from the previous tile is already set up: the call then returns at once) */
+            if (tsk_encode_configure(ctx, layout) != 0) { fprintf(stderr, "%s\n", tsk_last_error()); free(layout); goto done; }
             free(layout);
             encoder_ready = 1;
         }
@@ -239,12 +255,22 @@ static int run_tile(const char *inifile, int device, struct run_merge *rm)
     if (!params || tsk_build_params(cfg, params) < 0) { free(params); tsk_free_config(cfg); return -1; }
     memset(&boot, 0, sizeof(boot));
     boot.params = params; boot.device = device;
-    if (pthread_create(&boot.thread, NULL, boot_context, &boot) == 0) boot.started = 1;
-    else boot_context(&boot);
+    if (kept_ctx && kept_device == device && memcmp(kept_params, params, sizeof(*params)) == 0) {
+        boot.ctx = kept_ctx;                        /* same parameters as the previous tile */
+        if (tsk_counters_reset(kept_ctx) != 0) { fprintf(stderr, "%s\n", tsk_last_error()); free(params); tsk_free_config(cfg); return -1; }
+    } else {
+        drop_kept_context();
+        if (pthread_create(&boot.thread, NULL, boot_context, &boot) == 0) boot.started = 1;
+        else boot_context(&boot);
+    }
     r = process(cfg, &boot, inv, rm);
     phase("close files");
     ctx = await_context(&boot);
-    if (ctx) tsk_ctx_destroy(ctx);
+    if (ctx && ctx != kept_ctx) {                   /* keep it for the next tile of this thread */
+        kept_ctx = ctx; kept_device = device;
+        kept_params = params; params = NULL;
+    }
+    if (r != 0) drop_kept_context();
     free(params);
     tsk_free_config(cfg);
     return r;
@@ -265,6 +291,7 @@ static void *device_worker(void *arg)
         w->rc = run_tile(w->files[i], w->device, &w->rm);
         if (w->rc != 0) break;
     }
+    drop_kept_context();
     return NULL;
 }
 
@@ -381,5 +408,6 @@ int main(int argc, char *argv[])
         const int r = run_tile(argv[i], device, NULL);
         if (r != 0) return r;
     }
+    drop_kept_context();
     return 0;
 }

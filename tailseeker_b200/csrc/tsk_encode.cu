@@ -11,12 +11,13 @@
  *   k_enc_format    the text: the CTA's [cycles][128 clusters] base-call slab is transposed into
  *                   shared memory once, then a warp writes one line at a time, lane = character
  *   k_enc_live      record slots that were withdrawn after scoring are squeezed out
- *   k_enc_deflate   every stream (seqqual, taginfo, signal records of each sample) is cut into
- *                   32 KB pieces; one CTA turns a piece into one BGZF block: byte histogram,
- *                   length-limited Huffman code, a dynamic-Huffman deflate block WITHOUT matches,
- *                   CRC-32.  On these streams (bases, qualities, noisy 24-bit scores) zlib's
- *                   LZ77 finds next to nothing: level 1 gives 0.394 / 0.497 / 0.782 of the input,
- *                   Huffman only 0.417 / 0.492 / 0.781 (profiles/r2_encode.txt).
+ *   k_enc_hist / k_enc_codes   byte histogram of every stream (seqqual, taginfo, signal records of
+ *                   each sample) and ONE length-limited Huffman code per stream
+ *   k_enc_deflate   every stream is cut into 32 KB pieces; one CTA turns a piece into one BGZF
+ *                   block: a dynamic-Huffman deflate block WITHOUT matches (or a stored block when
+ *                   that is smaller) and its CRC-32.  On these streams (bases, qualities, noisy
+ *                   24-bit scores) zlib's LZ77 finds next to nothing: level 1 gives 0.394 / 0.497 /
+ *                   0.782 of the input, Huffman only 0.417 / 0.492 / 0.781 (profiles/r2_encode.txt).
  *   k_enc_gather    the blocks of a stream are packed back to back
  *
  * The host then only write()s: every stream is a valid BGZF file body (RFC 1952 members with the
@@ -50,6 +51,8 @@ struct DevStream {                             /* one output stream: 3 * sample 
     uint32_t first_block, nblocks;
 };
 
+struct StreamCode;
+
 struct EncState {
     tsk_encode_layout layout;
     DevEncSample *d_samples;
@@ -69,6 +72,8 @@ struct EncState {
     uint64_t *d_streamoff;                     /* [3 S + 1] */
     uint8_t  *d_final;     size_t final_cap;
     uint32_t *d_crctab;                        /* [256] byte table | [256] x^(1024 m) shifts */
+    uint32_t *d_hist;                          /* [3 S][256] byte histogram of every stream */
+    StreamCode *d_codes;                       /* [3 S] */
     uint8_t  *h_final;     size_t h_final_cap; /* pinned */
     uint64_t h_streamoff[3 * TSK_MAX_SAMPLES + 1];
     uint32_t cap_clusters;
@@ -450,51 +455,203 @@ __host__ __device__ static inline uint32_t crc_mulmod(uint32_t a, uint32_t b)
     return p;
 }
 
-/* ---- k_enc_deflate ---------------------------------------------------------------------------- */
+/* ---- deflate: one Huffman code per STREAM, one BGZF block per 32 KB piece ---------------------
+ * A stream's pieces are statistically alike (text of one sample, records of one sample), so the
+ * code is built once per stream from its whole byte histogram (every symbol counted at least once,
+ * so any piece can be written with it) instead of once per piece: the only serial part of the
+ * encoder -- the Huffman merge, a few tens of microseconds on one thread -- runs 3 x samples times
+ * per tile, not 30 000 times.  Each piece still carries its own deflate header (138 bytes), so every
+ * BGZF block stands alone. */
+struct StreamCode {                       /* built by k_enc_codes, read by k_enc_deflate */
+    uint32_t header[(ENC_HDR_BITS + 31) / 32];
+    uint16_t code[ENC_NSYM + 3];          /* bit-reversed: Huffman codes go out MSB first */
+    uint8_t  len[ENC_NSYM + 3];
+};
+
+static size_t enc_codes_bytes(int nstreams) { return sizeof(StreamCode) * (size_t)nstreams; }
+
+__device__ __forceinline__ int stream_of_block(const DevStream *__restrict__ streams, int nstreams, uint32_t b)
+{
+    int s = 0;
+    while (s + 1 < nstreams && b >= streams[s + 1].first_block) s++;
+    while (streams[s].nblocks == 0) s++;                   /* empty streams share first_block with the next one */
+    return s;
+}
+
+/* byte histogram of every stream (global atomics of per-CTA counts) */
+__global__ void __launch_bounds__(ENC_THREADS)
+k_enc_hist(const DevStream *__restrict__ streams, int nstreams, const uint32_t *__restrict__ nblocks,
+           uint32_t *__restrict__ hist /* [nstreams][256] */)
+{
+    __shared__ uint32_t s_hist[ENC_THREADS / 32][256];
+    __shared__ int s_stream;
+    const uint32_t b = blockIdx.x;
+    if (b >= *nblocks) return;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (ENC_THREADS / 32) * 256; i += ENC_THREADS) (&s_hist[0][0])[i] = 0;
+    if (tid == 0) s_stream = stream_of_block(streams, nstreams, b);
+    __syncthreads();
+    const DevStream st = streams[s_stream];
+    const uint64_t off = (uint64_t)(b - st.first_block) * ENC_CHUNK;
+    const uint64_t left = st.nbytes - off;
+    const uint32_t L = left < ENC_CHUNK ? (uint32_t)left : ENC_CHUNK;
+    const uint8_t *src = st.src + off;
+    if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+        const uint32_t *s4 = reinterpret_cast<const uint32_t *>(src);
+        for (uint32_t i = tid; i < (L >> 2); i += ENC_THREADS) {
+            const uint32_t w = s4[i];
+            atomicAdd(&s_hist[warp][w & 0xff], 1u); atomicAdd(&s_hist[warp][(w >> 8) & 0xff], 1u);
+            atomicAdd(&s_hist[warp][(w >> 16) & 0xff], 1u); atomicAdd(&s_hist[warp][w >> 24], 1u);
+        }
+        for (uint32_t i = (L & ~3u) + tid; i < L; i += ENC_THREADS) atomicAdd(&s_hist[warp][src[i]], 1u);
+    } else {
+        for (uint32_t i = tid; i < L; i += ENC_THREADS) atomicAdd(&s_hist[warp][src[i]], 1u);
+    }
+    __syncthreads();
+    uint32_t f = 0;
+    for (int w = 0; w < ENC_THREADS / 32; w++) f += s_hist[w][tid];
+    if (f) atomicAdd(&hist[(size_t)s_stream * 256 + tid], f);
+}
+
+/* one CTA per stream: length-limited Huffman code over {256 literals, end of block}, canonical
+ * codes, and the deflate block header that announces them */
+__global__ void __launch_bounds__(ENC_THREADS)
+k_enc_codes(const DevStream *__restrict__ streams, const uint32_t *__restrict__ hist, StreamCode *__restrict__ codes)
+{
+    __shared__ uint32_t freq[ENC_NSYM + 3];
+    __shared__ uint32_t nodefreq[ENC_NSYM];
+    __shared__ uint16_t order[ENC_NSYM + 3];
+    __shared__ uint16_t parent[2 * ENC_NSYM];
+    __shared__ uint8_t  depth[2 * ENC_NSYM];
+    __shared__ uint8_t  len[ENC_NSYM + 3];
+    __shared__ uint16_t code[ENC_NSYM + 3];
+    __shared__ uint32_t header[(ENC_HDR_BITS + 31) / 32];
+    const int sidx = blockIdx.x, tid = threadIdx.x;
+    if (streams[sidx].nblocks == 0) return;
+    /* every literal counted at least once: a code exists for whatever a piece holds */
+    for (int s = tid; s < ENC_NSYM; s += ENC_THREADS) {
+        freq[s] = s < 256 ? hist[(size_t)sidx * 256 + s] + 1u : streams[sidx].nblocks;
+        len[s] = 0;
+    }
+    for (int i = tid; i < (ENC_HDR_BITS + 31) / 32; i += ENC_THREADS) header[i] = 0;
+    __syncthreads();
+    /* symbols ordered by (frequency, symbol): rank = number of smaller keys */
+    for (int s = tid; s < ENC_NSYM; s += ENC_THREADS) {
+        const uint32_t f = freq[s];
+        int rank = 0;
+        for (int q = 0; q < ENC_NSYM; q++) {
+            const uint32_t g = freq[q];
+            rank += g < f || (g == f && q < s);
+        }
+        order[rank] = (uint16_t)s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int n = ENC_NSYM;
+        /* two queues: sorted leaves and internal nodes in creation order (their weights ascend too) */
+        int li = 0, ni = 0;
+        for (int made = 0; made < n - 1; made++) {
+            uint32_t w = 0;
+            for (int pick = 0; pick < 2; pick++) {
+                const bool leaf = li < n && (ni >= made || freq[order[li]] <= nodefreq[ni]);
+                if (leaf) { w += freq[order[li]]; parent[li] = (uint16_t)(n + made); li++; }
+                else { w += nodefreq[ni]; parent[n + ni] = (uint16_t)(n + made); ni++; }
+            }
+            nodefreq[made] = w;
+        }
+        int count[33];
+        for (int i = 0; i < 33; i++) count[i] = 0;
+        depth[2 * n - 2] = 0;
+        for (int id = 2 * n - 3; id >= 0; id--) {
+            int d = depth[parent[id]] + 1;
+            if (d > 40) d = 40;                               /* everything above 15 is folded below anyway */
+            depth[id] = (uint8_t)d;
+            if (id < n) count[d > 32 ? 32 : d]++;
+        }
+        /* fold the lengths above 15 into 15 and repair the Kraft sum: each step gives one code of
+         * the longest shorter length a sibling, at the cost of one 15-bit code */
+        for (int i = 16; i <= 32; i++) count[15] += count[i];
+        uint32_t total = 0;
+        for (int i = 15; i > 0; i--) total += (uint32_t)count[i] << (15 - i);
+        while (total != (1u << 15)) {
+            count[15]--;
+            for (int i = 14; i > 0; i--)
+                if (count[i]) { count[i]--; count[i + 1] += 2; break; }
+            total--;
+        }
+        /* the most frequent symbols get the shortest codes */
+        int j = n;
+        for (int i = 1; i <= 15; i++)
+            for (int l = count[i]; l > 0; l--) len[order[--j]] = (uint8_t)i;
+        /* canonical codes (RFC 1951 3.2.2) */
+        int blcount[16], next[16];
+        for (int i = 0; i < 16; i++) blcount[i] = 0;
+        for (int s = 0; s < ENC_NSYM; s++) blcount[len[s]]++;
+        blcount[0] = 0;
+        int c = 0;
+        for (int bits = 1; bits < 16; bits++) { c = (c + blcount[bits - 1]) << 1; next[bits] = c; }
+        for (int s = 0; s < ENC_NSYM; s++) {
+            const int l = len[s];
+            code[s] = (uint16_t)(__brev((uint32_t)next[l]++) >> (32 - l));
+        }
+        /* header: BFINAL = 1, BTYPE = dynamic, 257 literal/length codes, 1 distance code of length 0
+         * (no distances are used), the code-length alphabet {0..15} with 4 bits each: 19 three-bit
+         * lengths in the order 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15 from bit 17 */
+        header[0] |= 5u | (0u << 3) | (0u << 8) | (15u << 13);
+        for (int k = 3; k < 19; k++) {
+            const uint32_t bit = 17 + 3 * k;
+            const unsigned long long v = 4ull << (bit & 31);
+            header[bit >> 5] |= (uint32_t)v;
+            if (v >> 32) header[(bit >> 5) + 1] |= (uint32_t)(v >> 32);
+        }
+        for (int s = 0; s < ENC_NSYM + 1; s++) {
+            /* the four-bit code of length value v is v itself, sent MSB first */
+            const uint32_t v = s < ENC_NSYM ? len[s] : 0u;
+            const uint32_t bit = 17 + 57 + 4 * s;
+            const unsigned long long w = (unsigned long long)(__brev(v) >> 28) << (bit & 31);
+            header[bit >> 5] |= (uint32_t)w;
+            if (w >> 32) header[(bit >> 5) + 1] |= (uint32_t)(w >> 32);
+        }
+    }
+    __syncthreads();
+    StreamCode &out = codes[sidx];
+    for (int s = tid; s < ENC_NSYM; s += ENC_THREADS) { out.code[s] = code[s]; out.len[s] = len[s]; }
+    for (int i = tid; i < (ENC_HDR_BITS + 31) / 32; i += ENC_THREADS) out.header[i] = header[i];
+}
+
 struct __align__(16) DeflateSmem {
     uint8_t  in[ENC_CHUNK];
     uint32_t out[ENC_CHUNK / 4 + 8];
-    uint32_t hist[ENC_THREADS / 32][ENC_NSYM + 3];
-    uint32_t freq[ENC_NSYM + 3];
     uint32_t crctab[256];
-    uint32_t nodefreq[ENC_NSYM];
-    uint16_t order[ENC_NSYM + 3];
-    uint16_t parent[2 * ENC_NSYM];
     uint16_t code[ENC_NSYM + 3];
     uint8_t  len[ENC_NSYM + 3];
-    uint8_t  depth[2 * ENC_NSYM];
     uint32_t warpsum[ENC_THREADS / 32];
     uint32_t crcw[ENC_THREADS / 32];
-    uint32_t nused;
-    const uint8_t *src;
-    uint32_t L;
+    int stream;
 };
 
 __global__ void __launch_bounds__(ENC_THREADS)
 k_enc_deflate(const DevStream *__restrict__ streams, int nstreams, const uint32_t *__restrict__ nblocks,
-              const uint32_t *__restrict__ crctab, uint8_t *__restrict__ slots, uint32_t *__restrict__ sizes)
+              const uint32_t *__restrict__ crctab, const StreamCode *__restrict__ codes,
+              uint8_t *__restrict__ slots, uint32_t *__restrict__ sizes)
 {
     extern __shared__ __align__(16) unsigned char deflate_smem[];
     DeflateSmem &sm = *reinterpret_cast<DeflateSmem *>(deflate_smem);
     const uint32_t b = blockIdx.x;
     if (b >= *nblocks) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        int s = 0;
-        while (s + 1 < nstreams && b >= streams[s + 1].first_block) s++;
-        while (streams[s].nblocks == 0) s++;                   /* empty streams share first_block with the next one */
-        const uint64_t off = (uint64_t)(b - streams[s].first_block) * ENC_CHUNK;
-        const uint64_t left = streams[s].nbytes - off;
-        sm.src = streams[s].src + off;
-        sm.L = left < ENC_CHUNK ? (uint32_t)left : ENC_CHUNK;
-        sm.nused = 0;
-    }
-    for (int i = tid; i < (ENC_THREADS / 32) * (ENC_NSYM + 3); i += ENC_THREADS) (&sm.hist[0][0])[i] = 0;
-    for (int i = tid; i < ENC_CHUNK / 4 + 8; i += ENC_THREADS) sm.out[i] = 0;
+    if (tid == 0) sm.stream = stream_of_block(streams, nstreams, b);
     sm.crctab[tid] = crctab[tid];
     __syncthreads();
-    const uint32_t L = sm.L;
-    const uint8_t *src = sm.src;
+    const DevStream st = streams[sm.stream];
+    const StreamCode &sc = codes[sm.stream];
+    const uint64_t off = (uint64_t)(b - st.first_block) * ENC_CHUNK;
+    const uint64_t left = st.nbytes - off;
+    const uint32_t L = left < ENC_CHUNK ? (uint32_t)left : ENC_CHUNK;
+    const uint8_t *src = st.src + off;
+    for (int s = tid; s < ENC_NSYM; s += ENC_THREADS) { sm.code[s] = sc.code[s]; sm.len[s] = sc.len[s]; }
+    /* the output starts as the stream's block header, zeros behind it */
+    for (int i = tid; i < ENC_CHUNK / 4 + 8; i += ENC_THREADS) sm.out[i] = i < (ENC_HDR_BITS + 31) / 32 ? sc.header[i] : 0u;
     /* stage the piece: 4-byte words where the source allows it */
     if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
         const uint32_t nw = L >> 2;
@@ -513,103 +670,22 @@ k_enc_deflate(const DevStream *__restrict__ streams, int nstreams, const uint32_
     const bool holds_first = lo <= 0 && hi > 0;
     if (lo < 0) lo = 0;
 
-    /* ---- byte histogram (per warp) and CRC of the slice ---- */
-    uint32_t crc = holds_first ? 0xffffffffu : 0u;
+    /* ---- CRC of the slice and its size in the Huffman form ---- */
+    uint32_t crc = holds_first ? 0xffffffffu : 0u, bits = 0;
     for (int i = lo; i < hi; i++) {
         const uint32_t v = sm.in[i];
-        atomicAdd(&sm.hist[warp][v], 1u);
+        bits += sm.len[v];
         crc = sm.crctab[(crc ^ v) & 0xffu] ^ (crc >> 8);
     }
     /* move the slice's register to the end of the piece: times x^(8 * bytes after it) */
     crc = crc_mulmod(crc, crctab[256 + (ENC_THREADS - 1 - tid)]);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) crc ^= __shfl_xor_sync(FULL_MASK, crc, d);
-    if (lane == 0) sm.crcw[warp] = crc;
-    __syncthreads();
-    for (int s = tid; s < ENC_NSYM; s += ENC_THREADS) {
-        uint32_t f = 0;
-        if (s < 256) for (int w = 0; w < ENC_THREADS / 32; w++) f += sm.hist[w][s];
-        else f = 1;                                             /* end of block */
-        sm.freq[s] = f;
-        sm.len[s] = 0;
-        if (f) atomicAdd(&sm.nused, 1u);
-    }
-    __syncthreads();
-    /* ---- symbols in use ordered by (frequency, symbol): rank = number of smaller keys ---- */
-    for (int s = tid; s < ENC_NSYM; s += ENC_THREADS) {
-        const uint32_t f = sm.freq[s];
-        if (!f) continue;
-        int rank = 0;
-        for (int q = 0; q < ENC_NSYM; q++) {
-            const uint32_t g = sm.freq[q];
-            rank += (g != 0) && (g < f || (g == f && q < s));
-        }
-        sm.order[rank] = (uint16_t)s;
-    }
-    __syncthreads();
-    /* ---- Huffman code lengths, at most 15 bits ---- */
-    if (tid == 0) {
-        const int n = (int)sm.nused;
-        if (n == 1) {
-            sm.len[sm.order[0]] = 1;
-        } else {
-            /* two queues: sorted leaves and internal nodes in creation order (their weights ascend too) */
-            int li = 0, ni = 0;
-            for (int made = 0; made < n - 1; made++) {
-                uint32_t w = 0;
-                for (int pick = 0; pick < 2; pick++) {
-                    const bool leaf = li < n && (ni >= made || sm.freq[sm.order[li]] <= sm.nodefreq[ni]);
-                    if (leaf) { w += sm.freq[sm.order[li]]; sm.parent[li] = (uint16_t)(n + made); li++; }
-                    else { w += sm.nodefreq[ni]; sm.parent[n + ni] = (uint16_t)(n + made); ni++; }
-                }
-                sm.nodefreq[made] = w;
-            }
-            int count[33];
-            for (int i = 0; i < 33; i++) count[i] = 0;
-            sm.depth[2 * n - 2] = 0;
-            for (int id = 2 * n - 3; id >= 0; id--) {
-                int d = sm.depth[sm.parent[id]] + 1;
-                if (d > 40) d = 40;                           /* everything above 15 is folded below anyway */
-                sm.depth[id] = (uint8_t)d;
-                if (id < n) count[d > 32 ? 32 : d]++;
-            }
-            /* fold the lengths above 15 into 15 and repair the Kraft sum: each step gives one
-             * code of the longest shorter length a sibling, at the cost of one 15-bit code */
-            for (int i = 16; i <= 32; i++) count[15] += count[i];
-            uint32_t total = 0;
-            for (int i = 15; i > 0; i--) total += (uint32_t)count[i] << (15 - i);
-            while (total != (1u << 15)) {
-                count[15]--;
-                for (int i = 14; i > 0; i--)
-                    if (count[i]) { count[i]--; count[i + 1] += 2; break; }
-                total--;
-            }
-            /* the most frequent symbols get the shortest codes */
-            int j = n;
-            for (int i = 1; i <= 15; i++)
-                for (int l = count[i]; l > 0; l--) sm.len[sm.order[--j]] = (uint8_t)i;
-        }
-        /* canonical codes (RFC 1951 3.2.2), stored bit-reversed: Huffman codes go out MSB first */
-        int blcount[16], next[16];
-        for (int i = 0; i < 16; i++) blcount[i] = 0;
-        for (int s = 0; s < ENC_NSYM; s++) blcount[sm.len[s]]++;
-        blcount[0] = 0;
-        int code = 0;
-        for (int bits = 1; bits < 16; bits++) { code = (code + blcount[bits - 1]) << 1; next[bits] = code; }
-        for (int s = 0; s < ENC_NSYM; s++) {
-            const int l = sm.len[s];
-            if (l) sm.code[s] = (uint16_t)(__brev((uint32_t)next[l]++) >> (32 - l));
-        }
-    }
-    __syncthreads();
-
-    /* ---- size of the Huffman form ---- */
-    uint32_t bits = 0;
-    for (int i = lo; i < hi; i++) bits += sm.len[sm.in[i]];
     uint32_t incl = bits;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(FULL_MASK, incl, d); if (lane >= d) incl += o; }
     if (lane == 31) sm.warpsum[warp] = incl;
+    if (lane == 0) sm.crcw[warp] = crc;
     __syncthreads();
     uint32_t before = incl - bits, allbits = 0;
     for (int w = 0; w < ENC_THREADS / 32; w++) { if (w < warp) before += sm.warpsum[w]; allbits += sm.warpsum[w]; }
@@ -641,28 +717,6 @@ k_enc_deflate(const DevStream *__restrict__ streams, int nstreams, const uint32_
         }
         for (uint32_t i = tid; i < L; i += ENC_THREADS) memb[23 + i] = sm.in[i];
         return;
-    }
-
-    /* ---- header: BFINAL = 1, BTYPE = dynamic, 257 literal/length codes, 1 distance code of length
-     *      0 (no distances are used), the code-length alphabet {0..15} with 4 bits each ---- */
-    if (tid == 0) {
-        atomicOr(&sm.out[0], 5u | (0u << 3) | (0u << 8) | (15u << 13));
-        /* 19 three-bit lengths in the order 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15 from bit 17 */
-        for (int k = 3; k < 19; k++) {
-            const uint32_t bit = 17 + 3 * k;
-            const unsigned long long v = 4ull << (bit & 31);
-            atomicOr(&sm.out[bit >> 5], (uint32_t)v);
-            if (v >> 32) atomicOr(&sm.out[(bit >> 5) + 1], (uint32_t)(v >> 32));
-        }
-    }
-    for (int s = tid; s < ENC_NSYM + 1; s += ENC_THREADS) {
-        /* four-bit code of length value v is v itself, sent MSB first */
-        const uint32_t v = s < ENC_NSYM ? sm.len[s] : 0u;
-        const uint32_t r = __brev(v) >> 28;
-        const uint32_t bit = 17 + 57 + 4 * s;
-        const unsigned long long w = (unsigned long long)r << (bit & 31);
-        atomicOr(&sm.out[bit >> 5], (uint32_t)w);
-        if (w >> 32) atomicOr(&sm.out[(bit >> 5) + 1], (uint32_t)(w >> 32));
     }
     /* ---- the literals of this thread's slice ---- */
     {
@@ -770,7 +824,7 @@ void tsk_encode_free(tsk_ctx *ctx)
     if (!e) return;
     void *ptrs[] = {e->d_samples, e->d_lineoff, e->d_ctasum, e->d_texttot, e->d_text, e->d_liverank, e->d_livecta,
                     e->d_livetot, e->d_live, e->d_streams, e->d_nblocks, e->d_slots, e->d_sizes, e->d_offsets,
-                    e->d_streamoff, e->d_final, e->d_crctab};
+                    e->d_streamoff, e->d_final, e->d_crctab, e->d_hist, e->d_codes};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     if (e->h_final) cudaFreeHost(e->h_final);
     cudaEventDestroy(e->ev[0]); cudaEventDestroy(e->ev[1]);
@@ -801,6 +855,7 @@ extern "C" int tsk_encode_configure(tsk_ctx *ctx, const tsk_encode_layout *layou
         }
         if (hs[s].umi_total > umimax) umimax = hs[s].umi_total;
     }
+    if (ctx->enc && memcmp(&ctx->enc->layout, layout, sizeof(*layout)) == 0) return 0;    /* already set up for it */
     if (ctx->enc) tsk_encode_free(ctx);
     EncState *e = (EncState *)calloc(1, sizeof(EncState));
     if (!e) { tsk_set_error("out of memory"); return -1; }
@@ -819,6 +874,8 @@ extern "C" int tsk_encode_configure(tsk_ctx *ctx, const tsk_encode_layout *layou
     TSK_CUDA(cudaMalloc(&e->d_streams, sizeof(DevStream) * (3 * TSK_MAX_SAMPLES + 1)));
     TSK_CUDA(cudaMalloc(&e->d_nblocks, sizeof(uint32_t)));
     TSK_CUDA(cudaMalloc(&e->d_streamoff, sizeof(uint64_t) * (3 * TSK_MAX_SAMPLES + 1)));
+    TSK_CUDA(cudaMalloc(&e->d_hist, sizeof(uint32_t) * 256 * 3 * TSK_MAX_SAMPLES));
+    TSK_CUDA(cudaMalloc((void **)&e->d_codes, enc_codes_bytes(3 * TSK_MAX_SAMPLES)));
     /* CRC tables: the byte table, and x^(8 * 128 * m) mod p for the slices' distances to the end */
     uint32_t tab[512];
     for (uint32_t i = 0; i < 256; i++) {
@@ -927,8 +984,12 @@ extern "C" int tsk_tile_encode(tsk_ctx *ctx)
     size_t recbytes = (size_t)N * (size_t)(2 + ctx->maxdump) * 4;
     size_t nbmax = (textbytes + recbytes) / ENC_CHUNK + 3 * (size_t)S + 4;
     if (nbmax > e->nblk_cap) nbmax = e->nblk_cap;
+    TSK_CUDA(cudaMemsetAsync(e->d_hist, 0, sizeof(uint32_t) * 256 * 3 * S, st));
+    k_enc_hist<<<(unsigned)nbmax, ENC_THREADS, 0, st>>>(e->d_streams, 3 * S, e->d_nblocks, e->d_hist);
+    k_enc_codes<<<3 * S, ENC_THREADS, 0, st>>>(e->d_streams, e->d_hist, e->d_codes);
     k_enc_deflate<<<(unsigned)nbmax, ENC_THREADS, sizeof(DeflateSmem), st>>>(e->d_streams, 3 * S, e->d_nblocks, e->d_crctab,
-                                                                            e->d_slots, e->d_sizes);
+                                                                            e->d_codes, e->d_slots, e->d_sizes);
+    ctx->launches += 2;
     k_enc_offsets<<<1, 1024, 0, st>>>(e->d_sizes, e->d_nblocks, e->d_streams, 3 * S, e->d_offsets, e->d_streamoff);
     k_enc_gather<<<(unsigned)nbmax, 256, 0, st>>>(e->d_slots, e->d_sizes, e->d_nblocks, e->d_offsets, e->d_final);
     ctx->launches += 3;
@@ -1003,7 +1064,8 @@ extern "C" int tsk_selftest_deflate(tsk_ctx *ctx, const uint8_t *data, size_t n,
     TSK_CUDA(cudaSetDevice(ctx->device));
     const size_t nb = (n + ENC_CHUNK - 1) / ENC_CHUNK;
     uint8_t *d_in = NULL, *d_slots = NULL, *d_final = NULL;
-    uint32_t *d_sizes = NULL, *d_nblocks = NULL, *d_crctab = NULL;
+    uint32_t *d_sizes = NULL, *d_nblocks = NULL, *d_crctab = NULL, *d_hist = NULL;
+    StreamCode *d_codes = NULL;
     uint64_t *d_offsets = NULL, *d_streamoff = NULL, h_off[2] = {0, 0};
     DevStream *d_streams = NULL;
     int rc = -1;
@@ -1023,15 +1085,19 @@ extern "C" int tsk_selftest_deflate(tsk_ctx *ctx, const uint8_t *data, size_t n,
             cudaMalloc(&d_final, (nb + 1) * ENC_SLOT) != cudaSuccess || cudaMalloc(&d_sizes, sizeof(uint32_t) * (nb + 1)) != cudaSuccess ||
             cudaMalloc(&d_nblocks, sizeof(uint32_t)) != cudaSuccess || cudaMalloc(&d_crctab, sizeof(tab)) != cudaSuccess ||
             cudaMalloc(&d_offsets, sizeof(uint64_t) * (nb + 2)) != cudaSuccess || cudaMalloc(&d_streamoff, sizeof(uint64_t) * 2) != cudaSuccess ||
-            cudaMalloc(&d_streams, sizeof(DevStream) * 2) != cudaSuccess) { tsk_set_error("cudaMalloc failed"); break; }
+            cudaMalloc(&d_streams, sizeof(DevStream) * 2) != cudaSuccess || cudaMalloc(&d_hist, sizeof(uint32_t) * 256) != cudaSuccess ||
+            cudaMalloc((void **)&d_codes, sizeof(StreamCode)) != cudaSuccess) { tsk_set_error("cudaMalloc failed"); break; }
         if (cudaFuncSetAttribute(k_enc_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DeflateSmem)) != cudaSuccess) break;
         if (n) cudaMemcpyAsync(d_in, data, n, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(d_crctab, tab, sizeof(tab), cudaMemcpyHostToDevice, st);
         k_enc_one_stream<<<1, 1, 0, st>>>(d_in, (uint64_t)n, d_streams, d_nblocks);
-        k_enc_deflate<<<(unsigned)(nb + 1), ENC_THREADS, sizeof(DeflateSmem), st>>>(d_streams, 1, d_nblocks, d_crctab, d_slots, d_sizes);
+        cudaMemsetAsync(d_hist, 0, sizeof(uint32_t) * 256, st);
+        k_enc_hist<<<(unsigned)(nb + 1), ENC_THREADS, 0, st>>>(d_streams, 1, d_nblocks, d_hist);
+        k_enc_codes<<<1, ENC_THREADS, 0, st>>>(d_streams, d_hist, d_codes);
+        k_enc_deflate<<<(unsigned)(nb + 1), ENC_THREADS, sizeof(DeflateSmem), st>>>(d_streams, 1, d_nblocks, d_crctab, d_codes, d_slots, d_sizes);
         k_enc_offsets<<<1, 1024, 0, st>>>(d_sizes, d_nblocks, d_streams, 1, d_offsets, d_streamoff);
         k_enc_gather<<<(unsigned)(nb + 1), 256, 0, st>>>(d_slots, d_sizes, d_nblocks, d_offsets, d_final);
-        ctx->launches += 4;
+        ctx->launches += 6;
         cudaMemcpyAsync(h_off, d_streamoff, sizeof(h_off), cudaMemcpyDeviceToHost, st);
         if (cudaStreamSynchronize(st) != cudaSuccess) { tsk_set_error("deflate self-test: %s", cudaGetErrorString(cudaGetLastError())); break; }
         if (h_off[1] > capacity) { tsk_set_error("output buffer too small"); break; }
@@ -1039,7 +1105,7 @@ extern "C" int tsk_selftest_deflate(tsk_ctx *ctx, const uint8_t *data, size_t n,
         *outn = (size_t)h_off[1];
         rc = 0;
     } while (0);
-    void *ptrs[] = {d_in, d_slots, d_final, d_sizes, d_nblocks, d_crctab, d_offsets, d_streamoff, d_streams};
+    void *ptrs[] = {d_in, d_slots, d_final, d_sizes, d_nblocks, d_crctab, d_offsets, d_streamoff, d_streams, d_hist, d_codes};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     return rc;
 }

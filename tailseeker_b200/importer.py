@@ -258,7 +258,7 @@ class TileProcessor:
         """Formats and deflates the outputs of the tile last processed.  Returns
         {(sample index, stream): bytes} with stream 0 seqqual, 1 taginfo, 2 signal records; each value
         is a run of whole BGZF blocks."""
-        _lib.check(self.lib.tsk_tile_encode(self._ctx))
+        self.encode_only()
         out = {}
         for s in range(self.params.num_samples):
             for kind in range(3):
@@ -266,6 +266,10 @@ class TileProcessor:
                 _lib.check(self.lib.tsk_tile_get_encoded(self._ctx, s, kind, ctypes.byref(ptr), ctypes.byref(n)))
                 out[(s, kind)] = ctypes.string_at(ptr.value, n.value) if n.value else b""
         return out
+
+    def encode_only(self):
+        """tsk_tile_encode() alone: the streams stay in the library's pinned host buffer."""
+        _lib.check(self.lib.tsk_tile_encode(self._ctx))
 
     def encode_ms(self) -> float:
         ms = ctypes.c_double()
