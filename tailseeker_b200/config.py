@@ -531,13 +531,15 @@ def stock_config(layout: str = "miseq", spikeins: bool = True, **overrides) -> I
     else:
         raise ValueError(layout)
     samples = []
-    for name, index in EXPERIMENTAL_MISEQ_V2:
+    # sample sections in the generator's order: experimental, then spike-ins, each sorted by name
+    # (generate-signalproc-conf.py:176, configurations.py:121-131)
+    for name, index in sorted(EXPERIMENTAL_MISEQ_V2):
         samples.append(SampleConf(name=name, index=index, maximum_index_mismatch=2,
                                   delimiter_seq="GTCAG", delimiter_start=16,
                                   maximum_delimiter_mismatch=1,
                                   umi=[(21, 15), (r3, 15)]))
     if spikeins:
-        for name, index, trim, _ in SPIKEINS_STANDARD:
+        for name, index, trim, _ in sorted(SPIKEINS_STANDARD):
             samples.append(SampleConf(name=name, index=index, maximum_index_mismatch=3,
                                       delimiter_seq="GTCAG", delimiter_start=11,
                                       maximum_delimiter_mismatch=1,

@@ -102,6 +102,39 @@ def calculate_optimal_cutoffs(fit, sigdists: Dict[Tuple[str, str], np.ndarray], 
     return result, reports
 
 
+def calculate_optimal_cutoffs_batched(fit, sigdists: Dict[Tuple[str, str], np.ndarray], tile_ids: List[str],
+                                      run_id: str, total_cycles: int, min_spots: int):
+    """calculate_optimal_cutoffs() with ONE call of `fit`: the run-wide histograms and every tile's
+    are stacked row-wise ([(1 + tiles) * cycles][bins]; the fit treats each row on its own), so a run
+    of any size costs one launch and two copies instead of one launch and two copies per tile
+    (the reference spreads the tiles over a process pool, :149-155)."""
+    order = sorted(tile_ids)
+    postotal = np.sum([sigdists[t, "pos"].astype(np.uint64) for t in tile_ids], axis=0)
+    negtotal = np.sum([sigdists[t, "neg"].astype(np.uint64) for t in tile_ids], axis=0)
+    cycles = postotal.shape[0]
+    pos = np.concatenate([postotal] + [sigdists[t, "pos"].astype(np.uint64) for t in order])
+    neg = np.concatenate([negtotal] + [sigdists[t, "neg"].astype(np.uint64) for t in order])
+    roots = np.asarray(fit(pos, neg)).reshape(1 + len(order), cycles)
+
+    def points(k, p, n):
+        return {c: (None if np.isnan(roots[k][c]) else float(roots[k][c])) for c in tried_cycles(p, n, min_spots)}
+
+    all_cycles = np.where(negtotal.sum(axis=1) > 0)[0].tolist()
+    runwide = points(0, postotal, negtotal)
+    runwide_inferred = infer_missing_cutoffs(runwide, all_cycles)
+    reports = {run_id: report_marks(runwide, runwide_inferred, total_cycles)}
+    result = {}
+    for k, t in enumerate(order):
+        own = points(1 + k, sigdists[t, "pos"], sigdists[t, "neg"])
+        merged = dict(own)
+        determined = {c for c, v in own.items() if v is not None}
+        for c in set(all_cycles) - determined:
+            merged[c] = runwide_inferred[c]
+        result[t] = merged
+        reports[t] = report_marks(own, merged, total_cycles)
+    return result, reports
+
+
 def format_cutoffs(cutoffs: Dict[str, Cutoffs], total_cycles: int) -> str:
     """write_outputs(), :173-182: signal-cutoffs.txt."""
     lines = []

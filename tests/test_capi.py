@@ -89,8 +89,9 @@ def test_config_derived_values():
     from tailseeker_b200.config import stock_config
     cfg = stock_config("miseq")
     sl = cfg.sample_list()
-    assert [s["name"] for s in sl][:2] == ["Unknown", "spk128"] and sl[-1]["name"] == "Control1"
-    exp, spk = sl[-1], sl[1]
+    # LIFO of the generator's order (experimental then spike-ins, each sorted by name)
+    assert [s["name"] for s in sl][:2] == ["Unknown", "spkN"] and sl[-1]["name"] == "Control1"
+    exp, spk = sl[-1], next(s for s in sl if s["name"] == "spk128")
     assert exp["delimiter_pos"] == 57 + 15 and exp["signal_dump_length"] == 231
     assert spk["delimiter_pos"] == 57 + 10 and spk["signal_dump_length"] == 182
     assert sl[0]["signal_dump_length"] == 252          # pseudo-sample quirk (delimiter_pos = -1)
