@@ -933,6 +933,7 @@ extern "C" int tsk_tile_encode(tsk_ctx *ctx)
     if (!ctx || !ctx->enc) { tsk_set_error("tsk_encode_configure() has not been called"); return -1; }
     if (!ctx->processed) { tsk_set_error("tsk_tile_process() has not run on this tile"); return -1; }
     TSK_CUDA(cudaSetDevice(ctx->device));
+    TskRange nvtx("tsk:encode_outputs");
     EncState *e = ctx->enc;
     e->have = 0;
     if (enc_buffers(ctx) != 0) return -1;

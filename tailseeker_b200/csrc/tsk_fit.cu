@@ -123,6 +123,7 @@ k_fit_cutoffs(const unsigned long long *__restrict__ pos, const unsigned long lo
 int tsk_launch_fit(tsk_ctx *ctx, const uint64_t *d_pos, const uint64_t *d_neg, int cycles, int bins,
                    uint64_t min_spots, double bw, double low, const double *high, int nhigh, double *d_out)
 {
+    TskRange nvtx("tsk:fit_cutoffs");
     if (bins > FIT_MAX_BINS) { tsk_set_error("too many bins for fit_cutoffs"); return -1; }
     double h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < nhigh; i++) h[i] = high[i];

@@ -4,7 +4,14 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <nvtx3/nvToolsExt.h>          /* header-only: ranges show up in Nsight Systems / ncu --nvtx */
 #include "../../include/tailseeker_b200.h"
+
+/* one NVTX range per stage of the path (host-side bracket around the stage's launches) */
+struct TskRange {
+    explicit TskRange(const char *name) { nvtxRangePushA(name); }
+    ~TskRange() { nvtxRangePop(); }
+};
 
 #define TSK_K1_THREADS   128     /* clusters per decode_demux_seed CTA */
 #define TSK_K1_SLAB      32      /* cycles per TMA copy of its base-call slab */

@@ -457,6 +457,7 @@ int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev)
     if (ev) TSK_CUDA(cudaEventRecord(ev[0], st));
 
     if (N > 0) {
+        TskRange nvtx("tsk:decode_demux_seed");
         /* base calls u8 [T][pitch] as a 2-D tensor: boxes of {128 clusters, TSK_K1_SLAB cycles};
          * rows past T and clusters past N are zero-filled (= no-calls, never looked at) */
         const int slab_rows = (P.total_cycles + TSK_K1_SLAB - 1) / TSK_K1_SLAB * TSK_K1_SLAB;
@@ -494,10 +495,11 @@ int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev)
          * the scan and normalise/score/pack kernels and is joined before the fix-ups. */
         TSK_CUDA(cudaEventRecord(ctx->ev_ctl[0], st));
         TSK_CUDA(cudaStreamWaitEvent(ctx->xstream, ctx->ev_ctl[0], 0));
-        if (tsk_launch_control(ctx) != 0) return -1;
+        { TskRange nvtx("tsk:control_classify"); if (tsk_launch_control(ctx) != 0) return -1; }
         TSK_CUDA(cudaEventRecord(ctx->ev_ctl[1], ctx->xstream));
     }
     if (N > 0) {
+        TskRange nvtx("tsk:slot_scan_assign");
         k_scan_blocks<<<S + 1, SCAN_THREADS, 0, st>>>(ctx->d_blkcnt, ctx->d_totals, nblk, S + 1);
         k_record_bases<<<1, 32, 0, st>>>(ctx->d_totals, ctx->d_samples, ctx->d_recbase, S);
         k_assign<<<(N + 255) / 256, 256, 0, st>>>(tv, ctx->d_calls, ctx->d_kind, ctx->d_blkcnt,
@@ -509,10 +511,10 @@ int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev)
     }
     if (ev) TSK_CUDA(cudaEventRecord(ev[2], st));
     if (tsk_ruler_join(ctx) != 0) return -1;     /* the previous tile's ruler still reads the record slots */
-    if (tsk_launch_score(ctx) != 0) return -1;
+    { TskRange nvtx("tsk:normalise_score_pack"); if (tsk_launch_score(ctx) != 0) return -1; }
     if (N > 0 && control) TSK_CUDA(cudaStreamWaitEvent(st, ctx->ev_ctl[1], 0));
     if (ev) TSK_CUDA(cudaEventRecord(ev[3], st));
-    if (tsk_launch_fixups(ctx) != 0) return -1;
+    { TskRange nvtx("tsk:fair_sampling_fixups"); if (tsk_launch_fixups(ctx) != 0) return -1; }
     if (ev) TSK_CUDA(cudaEventRecord(ev[4], st));
     /* nothing after this point reads the tile's base calls or intensities: its upload slot may be
      * refilled (tsk_tile_upload waits for this event on the copy stream) */

@@ -260,6 +260,7 @@ extern "C" int tsk_merge_allreduce(tsk_merge *m, tsk_ctx *ctx, void *nccl_comm)
 {
     NcclApi *a = nccl_api();
     if (!a) return -1;
+    TskRange nvtx("tsk:merge_allreduce");
     if (merge_matches(m, ctx, true) != 0 || !nccl_comm) { if (!nccl_comm) tsk_set_error("null communicator"); return -1; }
     TSK_CUDA(cudaSetDevice(m->device));
     cudaStream_t st;

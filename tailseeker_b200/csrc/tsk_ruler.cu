@@ -111,18 +111,23 @@ k_polya_ruler(const uint32_t *__restrict__ records, const __grid_constant__ Rule
     for (size_t r = (size_t)blockIdx.x * (RULER_THREADS / 32) + (threadIdx.x >> 5); r < nrecords;
          r += warps_total) {
         while (r >= seg.first[g + 1]) g++;           /* r only grows: segments are visited in order */
-        const uint32_t *rec = records + seg.base[g] + (r - seg.first[g]) * (size_t)(2 + seg.dump[g]);
+        const int dump = seg.dump[g];
+        const uint32_t *rec = records + seg.base[g] + (r - seg.first[g]) * (size_t)(2 + dump);
+        /* the header and all packets of the slot in flight at once: nine independent loads.  The
+         * packet loads do not wait for the header's valid count (a slot always holds `dump`
+         * packets); what lies past the count is masked after the fact -- one memory round trip
+         * per record instead of two. */
         const uint32_t hdr = __ldg(rec + 1);
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) w[k] = (k * 32 + lane < dump) ? __ldg(rec + 2 + k * 32 + lane) : 0u;
         int first = (int16_t)(hdr & 0xffffu);
         const int valid = (int16_t)(hdr >> 16);
         if (first < 0) first = 0;
         if (first > TSK_MAX_CUTOFF_CYCLES) first = TSK_MAX_CUTOFF_CYCLES;
         int len = 0;
-
-        /* all packets of the record in flight at once: eight independent 128-byte loads */
-        uint32_t w[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) w[k] = (k * 32 + lane < valid) ? __ldg(rec + 2 + k * 32 + lane) : 0u;
+        for (int k = 0; k < 8; k++) w[k] = (k * 32 + lane < valid) ? w[k] : 0u;
 
         if (valid > 256) {
             len = ruler_long_record(rec, first, valid, s_cut, weight, lane);
@@ -227,6 +232,7 @@ int tsk_launch_ruler_segs(tsk_ctx *ctx, const uint32_t *d_records, int nseg, con
 int tsk_launch_ruler_resident(tsk_ctx *ctx, cudaStream_t st, int ncutoffs, int min_len, float weight, int bins,
                               float gap, int16_t *d_len_out)
 {
+    TskRange nvtx("tsk:polya_ruler");
     RulerSegs seg;
     seg.nseg = ctx->dp.num_samples;
     size_t blocks = ((size_t)ctx->tile.nclusters + (RULER_THREADS / 32) - 1) / (RULER_THREADS / 32);
@@ -245,6 +251,7 @@ int tsk_launch_ruler_resident(tsk_ctx *ctx, cudaStream_t st, int ncutoffs, int m
 int tsk_launch_ruler(tsk_ctx *ctx, const uint32_t *d_records, size_t nrecords, int dump_len,
                      int ncutoffs, int min_len, float weight, int bins, float gap, int16_t *d_len_out)
 {
+    TskRange nvtx("tsk:polya_ruler");
     const uint32_t first[2] = {0, (uint32_t)nrecords};
     const uint64_t base[1] = {0};
     const int dump[1] = {dump_len};
