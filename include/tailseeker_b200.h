@@ -195,6 +195,23 @@ int tsk_tile_upload(tsk_ctx *ctx, const uint8_t *bcl, size_t bcl_pitch,
                     const float invmatrix[16],
                     uint32_t nclusters, uint32_t firstclusterno, int on_device);
 
+/* The same hand-over cycle file by cycle file (replaces the loops of load_intensities_and_basecalls(),
+ * tailseq-import.c:203-228, and load_cif_data() / load_bcl_data(), cifreader.c:118-170,
+ * bclreader.c:95-119): between tsk_tile_begin() and tsk_tile_end() every row of the tile is sent as
+ * soon as the host has it -- asynchronous copies on the context's copy stream, so file reads,
+ * transfers and the previous tile's kernels overlap; the put calls may come from several reader
+ * threads at once.  A gzip-compressed base-call file (".bcl.gz", bclreader.c:60-72) is handed over
+ * COMPRESSED and inflated on the device: `gz` holds the whole file, `inflated_size` what it inflates
+ * to (4 + clusters in the file), `skip` the offset of this block's first cluster in that stream
+ * (4 + first cluster of the block).  Host buffers passed to the put calls must stay unchanged until
+ * tsk_tile_end() returns; it fails (-1, message names the cycle) for a corrupt or short stream.
+ * The tile then waits for tsk_tile_process() like one given to tsk_tile_upload(). */
+int tsk_tile_begin(tsk_ctx *ctx, uint32_t nclusters, uint32_t firstclusterno, const float invmatrix[16]);
+int tsk_tile_put_bcl(tsk_ctx *ctx, int cycle, const uint8_t *calls /* [nclusters] */);
+int tsk_tile_put_bcl_gz(tsk_ctx *ctx, int cycle, const uint8_t *gz, size_t gzbytes, uint64_t inflated_size, uint64_t skip);
+int tsk_tile_put_cif(tsk_ctx *ctx, int threep_cycle, const int16_t *planes /* [4][plane_pitch] */, size_t plane_pitch);
+int tsk_tile_end(tsk_ctx *ctx);
+
 /* Replaces distribute_processing() (tailseq-import.c:516-565): runs the per-cluster path
  * for the uploaded block.  Like prepare_split_jobs() (:340-392) it starts from zeroed
  * pos/neg histograms and a zeroed fair-sampling table; counters accumulate across calls

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtailseeker_b200.so")
 SOURCES = ["tsk_kernels.cu", "tsk_score.cu", "tsk_capi.cu", "tsk_ruler.cu", "tsk_fit.cu", "tsk_control.cu",
-           "tsk_dedup.cu", "tsk_encode.cu", "tsk_merge.cu"]
+           "tsk_dedup.cu", "tsk_encode.cu", "tsk_merge.cu", "tsk_ingest.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false", "--shared", "-Xcompiler", "-fPIC", "-cudart", "static", "-ldl"]
 

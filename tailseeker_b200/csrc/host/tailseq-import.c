@@ -160,8 +160,18 @@ static int process(struct host_config *cfg, struct ctx_boot *boot, const float *
         const uint32_t count = togo >= blocksize ? blocksize : togo;
         snprintf(msgprefix, BUFSIZ, "[%s%d#%d/%d] ", cfg->laneid, cfg->tile, blockno + 1, totalblocks);
         printf("%sLoading CIF and BCL files\n", msgprefix);
-        if (tsk_read_block(tf, count, bcl, cif) < 0) goto done;
-        phase("read CIF/BCL");
+        /* With a context at hand (a later block, a later tile of this process, or
+         * TSK_DIRECT_INGEST=1) the cycle files go to the device row by row while they are read and
+         * .bcl.gz files are inflated there; the first tile of a process reads into host arrays
+         * while its context is still being created. */
+        int direct = 0;
+        const char *want_direct = getenv("TSK_DIRECT_INGEST");           /* "0": never, anything else: from the first block on */
+        const int never_direct = want_direct && want_direct[0] == '0';
+        if (device_encode && !never_direct && !ctx && ((!boot->started && boot->ctx) || want_direct) &&
+            !(ctx = await_context(boot))) goto done;
+        direct = device_encode && !never_direct && ctx != NULL;
+        if ((direct ? tsk_read_block_to_device(tf, count, bcl, cif, ctx, invmatrix) : tsk_read_block(tf, count, bcl, cif)) < 0) goto done;
+        phase(direct ? "read CIF/BCL -> device" : "read CIF/BCL");
         if (!ctx && !(ctx = await_context(boot))) goto done;
         phase("wait for the CUDA context");
 
@@ -178,7 +188,7 @@ static int process(struct host_config *cfg, struct ctx_boot *boot, const float *
             free(layout);
             encoder_ready = 1;
         }
-        if (tsk_tile_upload(ctx, bcl, count, cif, count, invmatrix, count, nclusters - togo, 0) != 0 ||
+        if ((!direct && tsk_tile_upload(ctx, bcl, count, cif, count, invmatrix, count, nclusters - togo, 0) != 0) ||
             tsk_tile_process(ctx) != 0 || (!device_encode && tsk_tile_get_calls(ctx, calls) != 0)) {
             fprintf(stderr, "%s\n", tsk_last_error());
             goto done;

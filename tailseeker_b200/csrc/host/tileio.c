@@ -27,6 +27,9 @@ struct tile_files {
     uint32_t nclusters, read;
     FILE **cif;
     gzFile *bcl;                        /* NULL for a cycle taken from a FASTQ override */
+    char **bcl_gz_path;                 /* path of the cycle's file when it is a .bcl.gz, else NULL */
+    uint8_t **gz_raw;                   /* the whole compressed file, read once (device-side inflate) */
+    size_t *gz_len;
     struct fastq_override *alt;         /* in the configuration's list order */
     int nalt;
     int threads;                        /* [options] threads: cycle files read side by side */
@@ -168,10 +171,13 @@ struct tile_files *tsk_open_tile(const struct host_config *cfg, const char *msgp
     tf->threads = cfg->threads > 0 ? cfg->threads : 1;
     tf->cif = calloc(tf->L3, sizeof(FILE *));
     tf->bcl = calloc(tf->T, sizeof(gzFile));
+    tf->bcl_gz_path = calloc(tf->T, sizeof(char *));
+    tf->gz_raw = calloc(tf->T, sizeof(uint8_t *));
+    tf->gz_len = calloc(tf->T, sizeof(size_t));
     unsigned char *overridden = calloc(tf->T > 0 ? tf->T : 1, 1);
     for (const struct host_altcall *ac = cfg->altcalls; ac; ac = ac->next) tf->nalt++;
     tf->alt = calloc(tf->nalt ? tf->nalt : 1, sizeof(*tf->alt));
-    if (!tf->cif || !tf->bcl || !overridden || !tf->alt) { perror("tsk_open_tile"); free(overridden); tsk_close_tile(tf); return NULL; }
+    if (!tf->cif || !tf->bcl || !tf->bcl_gz_path || !tf->gz_raw || !tf->gz_len || !overridden || !tf->alt) { perror("tsk_open_tile"); free(overridden); tsk_close_tile(tf); return NULL; }
     {
         int a = 0;
         for (const struct host_altcall *ac = cfg->altcalls; ac; ac = ac->next, a++) {
@@ -217,6 +223,7 @@ struct tile_files *tsk_open_tile(const struct host_config *cfg, const char *msgp
         if (!tf->bcl[c]) {
             strncat(path, ".gz", PATH_MAX - strlen(path) - 1);
             tf->bcl[c] = gzopen(path, "rb");
+            if (tf->bcl[c]) tf->bcl_gz_path[c] = strdup(path);
         }
         if (!tf->bcl[c]) { fprintf(stderr, "load_bcl_file: Can't open file %s.\n", path); goto bad_bcl; }
         if (gzread(tf->bcl[c], &n, 4) < 4) { fprintf(stderr, "Unexpected EOF %s.\n", path); goto bad_bcl; }
@@ -243,7 +250,14 @@ struct read_job {
     uint8_t *bcl;
     int16_t *cif;
     int index;                          /* CIF cycle, BCL cycle, or unused for the overrides */
+    tsk_ctx *ctx;                       /* not NULL: hand the rows to the device as soon as they are read */
 };
+
+static int put_failed(const char *what, int cycle)
+{
+    fprintf(stderr, "%s (cycle %d): %s\n", what, cycle + 1, tsk_last_error());
+    return -1;
+}
 
 static int read_cif_cycle(void *arg)
 {
@@ -265,6 +279,34 @@ static int read_cif_cycle(void *arg)
         for (uint32_t k = 0; k < j->count; k++) dst[k] = (int16_t)le16toh((uint16_t)dst[k]);
 #endif
     }
+    if (j->ctx && tsk_tile_put_cif(j->ctx, i, j->cif + (size_t)i * 4 * j->count, j->count) != 0)
+        return put_failed("tsk_tile_put_cif", tf->T - tf->L3 + i);
+    return 0;
+}
+
+/* a .bcl.gz for the device: the whole compressed file once, then every block names its window */
+static int send_bcl_gz(const struct read_job *j, int c)
+{
+    struct tile_files *tf = j->tf;
+    if (!tf->gz_raw[c]) {
+        FILE *fp = fopen(tf->bcl_gz_path[c], "rb");
+        long size;
+        if (!fp || fseek(fp, 0, SEEK_END) != 0 || (size = ftell(fp)) < 0 || fseek(fp, 0, SEEK_SET) != 0) {
+            fprintf(stderr, "load_bcl_file: Can't read file %s.\n", tf->bcl_gz_path[c]);
+            if (fp) fclose(fp);
+            return -1;
+        }
+        tf->gz_raw[c] = malloc(size > 0 ? (size_t)size : 1);
+        if (!tf->gz_raw[c] || fread(tf->gz_raw[c], 1, (size_t)size, fp) != (size_t)size) {
+            fprintf(stderr, "Unexpected EOF %s.\n", tf->bcl_gz_path[c]);
+            fclose(fp);
+            return -1;
+        }
+        fclose(fp);
+        tf->gz_len[c] = (size_t)size;
+    }
+    if (tsk_tile_put_bcl_gz(j->ctx, c, tf->gz_raw[c], tf->gz_len[c], 4 + (uint64_t)tf->nclusters, 4 + (uint64_t)tf->read) != 0)
+        return put_failed("tsk_tile_put_bcl_gz", c);
     return 0;
 }
 
@@ -274,12 +316,14 @@ static int read_bcl_cycle(void *arg)
     const int c = j->index;
     uint8_t *dst = j->bcl + (size_t)c * j->count;
     uint32_t got = 0;
+    if (j->ctx && j->tf->bcl_gz_path[c]) return send_bcl_gz(j, c);      /* inflated on the device */
     while (got < j->count) {          /* gzread takes an unsigned int length */
         const uint32_t want = j->count - got > (1u << 30) ? (1u << 30) : j->count - got;
         const int r = gzread(j->tf->bcl[c], dst + got, want);
         if (r < 1) { fprintf(stderr, "Unexpected EOF in a BCL (cycle %d).\n", c + 1); return -1; }
         got += (uint32_t)r;
     }
+    if (j->ctx && tsk_tile_put_bcl(j->ctx, c, dst) != 0) return put_failed("tsk_tile_put_bcl", c);
     return 0;
 }
 
@@ -290,17 +334,41 @@ static int read_overrides(void *arg)
     const struct read_job *j = arg;
     for (int a = 0; a < j->tf->nalt; a++)
         if (read_fastq_override(&j->tf->alt[a], j->count, j->bcl) < 0) return -1;
+    if (j->ctx)
+        for (int a = 0; a < j->tf->nalt; a++)
+            for (int c = j->tf->alt[a].first_cycle; c < j->tf->alt[a].first_cycle + j->tf->alt[a].ncycles; c++)
+                if (tsk_tile_put_bcl(j->ctx, c, j->bcl + (size_t)c * j->count) != 0) return put_failed("tsk_tile_put_bcl", c);
     return 0;
 }
 
+static int read_block(struct tile_files *tf, uint32_t count, uint8_t *bcl, int16_t *cif, tsk_ctx *ctx);
+
 int tsk_read_block(struct tile_files *tf, uint32_t count, uint8_t *bcl, int16_t *cif)
+{
+    return read_block(tf, count, bcl, cif, NULL);
+}
+
+/* The same block straight to the device: every cycle file's rows are sent as soon as its reader
+ * thread has them (tsk_tile_put_*), compressed base-call files travel compressed, and the tile is
+ * complete (waiting for tsk_tile_process) when this returns.  The rows of `bcl` that came from
+ * .bcl.gz files are NOT filled on the host. */
+int tsk_read_block_to_device(struct tile_files *tf, uint32_t count, uint8_t *bcl, int16_t *cif, tsk_ctx *ctx,
+                             const float invmatrix[16])
+{
+    if (tsk_tile_begin(ctx, count, tf->read, invmatrix) != 0) { fprintf(stderr, "%s\n", tsk_last_error()); return -1; }
+    const int rc = read_block(tf, count, bcl, cif, ctx);
+    if (tsk_tile_end(ctx) != 0) { fprintf(stderr, "%s\n", tsk_last_error()); return -1; }
+    return rc;
+}
+
+static int read_block(struct tile_files *tf, uint32_t count, uint8_t *bcl, int16_t *cif, tsk_ctx *ctx)
 {
     const int maxtasks = tf->L3 + tf->T + 1;
     struct read_job *jobs = calloc(maxtasks, sizeof(*jobs));
     struct tsk_task *tasks = calloc(maxtasks, sizeof(*tasks));
     int n = 0, rc;
     if (!jobs || !tasks) { perror("tsk_read_block"); free(jobs); free(tasks); return -1; }
-#define ADD_TASK(function, idx) do { jobs[n] = (struct read_job){tf, count, bcl, cif, (idx)}; \
+#define ADD_TASK(function, idx) do { jobs[n] = (struct read_job){tf, count, bcl, cif, (idx), ctx}; \
                                      tasks[n].fn = (function); tasks[n].arg = &jobs[n]; n++; } while (0)
     if (tf->nalt > 0) ADD_TASK(read_overrides, 0);          /* the slowest task first */
     for (int i = 0; i < tf->L3; i++) ADD_TASK(read_cif_cycle, i);
@@ -332,5 +400,8 @@ void tsk_close_tile(struct tile_files *tf)
     free(tf->alt);
     if (tf->cif) for (int i = 0; i < tf->L3; i++) if (tf->cif[i]) fclose(tf->cif[i]);
     if (tf->bcl) for (int c = 0; c < tf->T; c++) if (tf->bcl[c]) gzclose(tf->bcl[c]);
+    if (tf->bcl_gz_path) for (int c = 0; c < tf->T; c++) free(tf->bcl_gz_path[c]);
+    if (tf->gz_raw) for (int c = 0; c < tf->T; c++) free(tf->gz_raw[c]);
+    free(tf->bcl_gz_path); free(tf->gz_raw); free(tf->gz_len);
     free(tf->cif); free(tf->bcl); free(tf);
 }

@@ -97,6 +97,10 @@ struct tile_files *tsk_open_tile(const struct host_config *cfg, const char *msgp
 uint32_t tsk_tile_nclusters(const struct tile_files *tf);
 /* read the next `count` clusters of every cycle into bcl[T][count], cif[L3][4][count] */
 int tsk_read_block(struct tile_files *tf, uint32_t count, uint8_t *bcl, int16_t *cif);
+/* the same, with every cycle file's rows sent to the device as soon as they are read and .bcl.gz files
+ * inflated there (rows of `bcl` that came from .bcl.gz stay unfilled on the host) */
+int tsk_read_block_to_device(struct tile_files *tf, uint32_t count, uint8_t *bcl, int16_t *cif, tsk_ctx *ctx,
+                             const float invmatrix[16]);
 /* after the last block: -1 when a FASTQ override still holds records */
 int tsk_check_tile_end(struct tile_files *tf);
 void tsk_close_tile(struct tile_files *tf);

@@ -286,6 +286,7 @@ extern "C" int tsk_ctx_destroy(tsk_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     tsk_encode_free(ctx);
+    tsk_ingest_free(ctx);
     if (ctx->rstream) {
         cudaStreamSynchronize(ctx->rstream);
         cudaStreamDestroy(ctx->rstream);
@@ -350,6 +351,46 @@ static int ensure_cluster_buffers(tsk_ctx *ctx, uint32_t n)
     return 0;
 }
 
+/* ---- upload slots (shared by tsk_tile_upload and the row-wise ingestion of tsk_ingest.cu) ---- */
+/* Takes the next upload slot for a tile of `nclusters`: sizes the slot's HBM arrays (rows padded to
+ * 128 clusters), makes the copy stream wait for the kernels of the tile that used the slot before,
+ * and fills the pending-tile descriptor.  The tile becomes visible to tsk_tile_process() with
+ * tsk_upload_slot_commit(). */
+int tsk_upload_slot_acquire(tsk_ctx *ctx, uint32_t nclusters, uint32_t firstclusterno, const float invmatrix[16],
+                            int *slot_out, size_t *bpitch_out, size_t *cpitch_out)
+{
+    if (nclusters >= 0x7fffffffu) { tsk_set_error("too many clusters in one block"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->npending >= 2) { tsk_set_error("two tiles are already uploaded; call tsk_tile_process() first"); return -1; }
+    if (ensure_cluster_buffers(ctx, nclusters) != 0) return -1;
+    const int T = ctx->dp.total_cycles, L3 = ctx->dp.threep_length;
+    auto &slot = ctx->pending[ctx->npending];
+    memcpy(slot.inv, invmatrix, sizeof(float) * 16);
+    slot.tv.nclusters = nclusters;
+    slot.tv.firstclusterno = firstclusterno;
+    const int u = ctx->up_slot;
+    const size_t pitch = ((size_t)nclusters + 127) & ~(size_t)127;
+    if (ensure(&ctx->d_bcl_own[u], &ctx->bcl_cap[u], pitch * T + 128) != 0) return -1;
+    if (ensure(&ctx->d_cif_own[u], &ctx->cif_cap[u], pitch * 4 * L3 + 128) != 0) return -1;
+    if (ctx->slot_busy[u]) {
+        TSK_CUDA(cudaStreamWaitEvent(ctx->cstream, ctx->ev_done[u], 0));
+        ctx->slot_busy[u] = 0;
+    }
+    slot.tv.bcl = ctx->d_bcl_own[u]; slot.tv.bcl_pitch = pitch;
+    slot.tv.cif = ctx->d_cif_own[u]; slot.tv.cif_pitch = pitch;
+    slot.slot = u;
+    *slot_out = u; *bpitch_out = pitch; *cpitch_out = pitch;
+    return 0;
+}
+
+int tsk_upload_slot_commit(tsk_ctx *ctx, int u)
+{
+    TSK_CUDA(cudaEventRecord(ctx->ev_up[u], ctx->cstream));
+    ctx->up_slot ^= 1;
+    ctx->npending++;
+    return 0;
+}
+
 /* ---- importer path ----------------------------------------------------------------------- */
 extern "C" int tsk_tile_upload(tsk_ctx *ctx, const uint8_t *bcl, size_t bcl_pitch,
                                const int16_t *cif, size_t cif_pitch, const float invmatrix[16],
@@ -379,17 +420,9 @@ extern "C" int tsk_tile_upload(tsk_ctx *ctx, const uint8_t *bcl, size_t bcl_pitc
     }
     /* own HBM copy (rows padded to 128 clusters), on the copy stream: it overlaps the processing
      * of the previously uploaded tile */
-    const int u = ctx->up_slot;
-    const size_t bpitch = ((size_t)nclusters + 127) & ~(size_t)127;
-    const size_t cpitch = ((size_t)nclusters + 127) & ~(size_t)127;
-    if (ensure(&ctx->d_bcl_own[u], &ctx->bcl_cap[u], bpitch * T + 128) != 0) return -1;
-    if (ensure(&ctx->d_cif_own[u], &ctx->cif_cap[u], cpitch * 4 * L3 + 128) != 0) return -1;
-    /* the kernels of the tile that last lived in this slot (two uploads ago) may still be queued or
-     * running on the main stream: the copy must not overwrite what they read */
-    if (ctx->slot_busy[u]) {
-        TSK_CUDA(cudaStreamWaitEvent(ctx->cstream, ctx->ev_done[u], 0));
-        ctx->slot_busy[u] = 0;
-    }
+    int u;
+    size_t bpitch, cpitch;
+    if (tsk_upload_slot_acquire(ctx, nclusters, firstclusterno, invmatrix, &u, &bpitch, &cpitch) != 0) return -1;
     if (nclusters) {
         TSK_CUDA(cudaMemcpy2DAsync(ctx->d_bcl_own[u], bpitch, bcl, bcl_pitch, nclusters, T,
                                    cudaMemcpyHostToDevice, ctx->cstream));
@@ -397,13 +430,7 @@ extern "C" int tsk_tile_upload(tsk_ctx *ctx, const uint8_t *bcl, size_t bcl_pitc
                                    (size_t)nclusters * sizeof(int16_t), (size_t)4 * L3,
                                    cudaMemcpyHostToDevice, ctx->cstream));
     }
-    TSK_CUDA(cudaEventRecord(ctx->ev_up[u], ctx->cstream));
-    slot.tv.bcl = ctx->d_bcl_own[u]; slot.tv.bcl_pitch = bpitch;
-    slot.tv.cif = ctx->d_cif_own[u]; slot.tv.cif_pitch = cpitch;
-    slot.slot = u;
-    ctx->up_slot ^= 1;
-    ctx->npending++;
-    return 0;
+    return tsk_upload_slot_commit(ctx, u);
 }
 
 /* next uploaded tile becomes the resident one */

@@ -73,10 +73,12 @@ struct TileView {
 };
 
 struct EncState;
+struct IngestState;
 
 struct tsk_ctx {
     int device;
     EncState *enc;               /* device-side output encoding (tsk_encode.cu), NULL until configured */
+    IngestState *ingest;         /* row-wise ingestion + .bcl.gz inflate (tsk_ingest.cu), NULL until used */
     cudaStream_t stream;
     tsk_params hp;               /* host copy of the parameters */
     DevParams dp;
@@ -173,7 +175,11 @@ void tsk_set_error(const char *fmt, ...);
 int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev /* optional [5] */);
 int tsk_launch_score(tsk_ctx *ctx);
 int tsk_score_setup(tsk_ctx *ctx);
-void tsk_encode_free(tsk_ctx *ctx);       /* tsk_encode.cu */        /* per-context tables of the scoring kernels */
+void tsk_encode_free(tsk_ctx *ctx);       /* tsk_encode.cu */
+void tsk_ingest_free(tsk_ctx *ctx);       /* tsk_ingest.cu */
+int tsk_upload_slot_acquire(tsk_ctx *ctx, uint32_t nclusters, uint32_t firstclusterno, const float invmatrix[16],
+                            int *slot_out, size_t *bpitch_out, size_t *cpitch_out);
+int tsk_upload_slot_commit(tsk_ctx *ctx, int slot);        /* per-context tables of the scoring kernels */
 int tsk_launch_fixups(tsk_ctx *ctx);
 int tsk_control_setup(tsk_ctx *ctx);      /* builds the PhiX index (tsk_control.cu) */
 int tsk_launch_control(tsk_ctx *ctx);

@@ -98,6 +98,30 @@ class TileProcessor:
                                             _ptr(inv), nclusters, firstclusterno, int(on_device)))
         self._pending.append((int(nclusters), (bcl, cif)))
 
+    def upload_rows(self, bcl: np.ndarray, cif: np.ndarray, invmatrix: np.ndarray, firstclusterno: int = 0,
+                    gz_rows: Optional[Dict[int, tuple]] = None):
+        """The tile cycle file by cycle file (tsk_tile_begin / put / end).  gz_rows: {cycle: (gzip file
+        bytes, inflated size, skip)} for base-call rows that travel compressed and are inflated on the
+        device; every other row of `bcl` and every cycle of `cif` is sent from the arrays."""
+        inv = np.ascontiguousarray(invmatrix, dtype=np.float32).reshape(16)
+        bcl = np.ascontiguousarray(bcl, dtype=np.uint8)
+        cif = np.ascontiguousarray(cif, dtype=np.int16)
+        n = bcl.shape[1]
+        gz_rows = gz_rows or {}
+        _lib.check(self.lib.tsk_tile_begin(self._ctx, n, firstclusterno, _ptr(inv)))
+        keep = []
+        for c in range(bcl.shape[0]):
+            if c in gz_rows:
+                raw, size, skip = gz_rows[c]
+                keep.append(raw)
+                _lib.check(self.lib.tsk_tile_put_bcl_gz(self._ctx, c, raw, len(raw), size, skip))
+            else:
+                _lib.check(self.lib.tsk_tile_put_bcl(self._ctx, c, _ptr(bcl[c])))
+        for i in range(cif.shape[0]):
+            _lib.check(self.lib.tsk_tile_put_cif(self._ctx, i, _ptr(cif[i]), cif.shape[2]))
+        _lib.check(self.lib.tsk_tile_end(self._ctx))
+        self._pending.append((int(n), (bcl, cif, keep)))
+
     def _take(self):
         if self._pending:
             self.nclusters, self._keep = self._pending.pop(0)
