@@ -134,8 +134,8 @@ def test_sharded_cuda_path_plus_nccl_equals_single_gpu(stock_cfg):
             p.close()
 
 
-@pytest.mark.skipif("_ngpus() < 2")
-def test_program_over_two_devices_writes_the_sums(tmp_path):
+@pytest.mark.parametrize("devices", ["0", pytest.param("0,1", marks=pytest.mark.skipif("_ngpus() < 2"))])
+def test_program_over_devices_writes_the_sums(tmp_path, devices):
     from oracle import refrun
     from tailseeker_b200.config import stock_config
     from tailseeker_b200.synth import make_tile, write_tile_files
@@ -153,7 +153,7 @@ def test_program_over_two_devices_writes_the_sums(tmp_path):
         with open(ini, "w") as f:
             f.write(cfg.replace(data_dir=data, threep_colormatrix=mpath, threads=4).to_ini())
         inis.append(ini); tids.append(cfg.tile_id)
-    r = subprocess.run([exe, "--devices", "0,1", "--merged-sigdists", str(tmp_path / "run_{posneg}.sigdists"),
+    r = subprocess.run([exe, "--devices", devices, "--merged-sigdists", str(tmp_path / "run_{posneg}.sigdists"),
                         "--merged-stats", str(tmp_path / "run_stats.csv")] + inis, cwd=str(tmp_path), capture_output=True)
     assert r.returncode == 0, r.stderr.decode()[-2000:]
     for kind in ("pos", "neg"):
