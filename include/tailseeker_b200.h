@@ -276,6 +276,14 @@ int tsk_tile_encode(tsk_ctx *ctx);
 int tsk_tile_get_encoded(tsk_ctx *ctx, int sample, int stream, const uint8_t **data, size_t *nbytes);
 /* Device time of the last tsk_tile_encode() (CUDA events around its kernels). */
 int tsk_encode_elapsed_ms(tsk_ctx *ctx, double *ms);
+/* The same deflater for any host bytes: `n` bytes -> a run of whole BGZF blocks in pinned host memory
+ * owned by the object (valid until its next call).  tailseq-writefastq's output side: replaces
+ * bgzf_write() on its two FASTQ streams (src/exporter/tailseq-writefastq.c:148-240, bgzf_mt :387,399). */
+typedef struct tsk_bgzf tsk_bgzf;
+int tsk_bgzf_create(tsk_bgzf **out, int device);
+void tsk_bgzf_destroy(tsk_bgzf *z);
+int tsk_bgzf_deflate(tsk_bgzf *z, const void *data, size_t n, const uint8_t **out, size_t *outn);
+uint64_t tsk_bgzf_launch_count(tsk_bgzf *z);
 /* Self-test: `n` arbitrary host bytes deflated by the same kernels as one stream; the BGZF blocks
  * (<= n + n / 1000 + 64 bytes per started 32 KB) are written to out[0 .. *outn). */
 int tsk_selftest_deflate(tsk_ctx *ctx, const uint8_t *data, size_t n, uint8_t *out, size_t capacity, size_t *outn);

@@ -7,12 +7,13 @@
  *
  * Joins the (deduplicated, tile-ordered) taginfo lines `tile cluster flags polyA mods duplicates`
  * with the per-tile seqqual lines `cluster seq5 qual5 seq3 qual3` and writes the two FASTQ files.
- * This is a host program by nature -- the work is inflating two text streams and deflating two --
- * and has no kernel: it is here so that the reference's whole C surface has a counterpart in this
- * build, and because its output side is the same parallel gzip-member writer the importer uses
- * (writers.c): the FASTQ text is cut into 1 MiB pieces that all threads deflate at once, where the
- * reference hands `--threads` to htslib's BGZF writer.  Same options, same record layout, same
- * diagnostics, same exit status; the files decompress to the same bytes.
+ * The join is host work (two text streams inflated and matched line by line, no arithmetic); the
+ * output side -- where the reference hands `--threads` to htslib's BGZF writer -- is the GPU's BGZF
+ * deflater of the importer (tsk_bgzf_deflate, csrc/tsk_encode.cu): the FASTQ text collected for both
+ * mates is deflated on the device and the program appends the blocks.  TSK_HOST_WRITERS=1 keeps the
+ * host path (1 MiB pieces deflated by all threads as gzip members, writers.c) for comparison and
+ * for machines without a GPU.  Same options, same record layout, same diagnostics, same exit
+ * status; the files decompress to the same bytes.
  */
 #include <getopt.h>
 #include <stdlib.h>
@@ -64,11 +65,28 @@ static int deflate_piece(void *arg)
     return tsk_gz_member(pc->src, pc->n, &pc->gz, &pc->gzn);
 }
 
+static tsk_bgzf *gpu_deflater = NULL;       /* NULL: host zlib (TSK_HOST_WRITERS=1) */
+
+static int flush_outputs_gpu(struct outfile *out, int nout)
+{
+    for (int f = 0; f < nout; f++) {
+        const uint8_t *z;
+        size_t zn;
+        if (out[f].used == 0) continue;
+        if (tsk_bgzf_deflate(gpu_deflater, out[f].text, out[f].used, &z, &zn) != 0) { fprintf(stderr, "%s\n", tsk_last_error()); return -1; }
+        if (fwrite(z, 1, zn, out[f].fp) != zn) return -1;
+        out[f].used = 0;
+    }
+    return 0;
+}
+
 static int flush_outputs(struct outfile *out, int nout, int threads)
 {
+    if (gpu_deflater) return flush_outputs_gpu(out, nout);
     struct piece *pcs;
     struct tsk_task *tasks;
     int n = 0, rc = 0;
+    if (nout <= 0) return 0;
     for (int f = 0; f < nout; f++) n += (int)((out[f].used + PIECE_BYTES - 1) / PIECE_BYTES);
     if (n == 0) return 0;
     pcs = calloc(n, sizeof(*pcs));
@@ -208,6 +226,11 @@ int main(int argc, char *argv[])
         fprintf(stderr, "One or more required arguments are not specified.\n");
         return -1;
     }
+    if (!getenv("TSK_HOST_WRITERS")) {
+        const char *dev = getenv("TAILSEEKER_DEVICE");
+        if (tsk_bgzf_create(&gpu_deflater, dev ? atoi(dev) : 0) != 0) { fprintf(stderr, "%s\n", tsk_last_error()); return -1; }
+        if (threads < 16) threads = 16;         /* the device takes 16 MiB of text per stream and call */
+    }
     taginfo = gzopen(taginfo_fn, "rt");
     if (!taginfo) { fprintf(stderr, "Failed to open %s.\n", taginfo_fn); return -1; }
     gzbuffer(taginfo, 1 << 20);
@@ -222,12 +245,16 @@ int main(int argc, char *argv[])
     r = convert(taginfo, seqqual_fn, out, verbose, threads);
     gzclose(taginfo);
     for (int f = 0; f < 2; f++) {
-        if (out[f].used == 0 && ftell(out[f].fp) == 0) {        /* nothing written: an empty gzip member */
+        if (gpu_deflater) {                                     /* htslib's end-of-file marker block */
+            const uint8_t *eof; size_t n;
+            if (tsk_bgzf_eof_block(&eof, &n) == 0) fwrite(eof, 1, n, out[f].fp);
+        } else if (out[f].used == 0 && ftell(out[f].fp) == 0) {        /* nothing written: an empty gzip member */
             unsigned char *gz; size_t gzn;
             if (tsk_gz_member("", 0, &gz, &gzn) == 0) { fwrite(gz, 1, gzn, out[f].fp); free(gz); }
         }
         if (fclose(out[f].fp) != 0) r = -1;
         free(out[f].text);
     }
+    tsk_bgzf_destroy(gpu_deflater);
     return r;
 }

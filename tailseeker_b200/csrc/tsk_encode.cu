@@ -1110,3 +1110,115 @@ extern "C" int tsk_selftest_deflate(tsk_ctx *ctx, const uint8_t *data, size_t n,
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
     return rc;
 }
+
+/* ---- the BGZF deflater on its own: any host bytes -> BGZF blocks (tailseq-writefastq's output side) ---- */
+struct tsk_bgzf {
+    int device;
+    cudaStream_t stream;
+    size_t cap;                       /* input bytes the buffers hold */
+    uint8_t *d_in, *d_slots, *d_final, *h_final;
+    uint32_t *d_sizes, *d_nblocks, *d_crctab, *d_hist;
+    uint64_t *d_offsets, *d_streamoff;
+    DevStream *d_streams;
+    StreamCode *d_codes;
+    uint64_t launches;
+};
+
+static void bgzf_release(tsk_bgzf *z)
+{
+    void *ptrs[] = {z->d_in, z->d_slots, z->d_final, z->d_sizes, z->d_nblocks, z->d_crctab, z->d_hist, z->d_offsets,
+                    z->d_streamoff, z->d_streams, z->d_codes};
+    for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) if (ptrs[i]) cudaFree(ptrs[i]);
+    if (z->h_final) cudaFreeHost(z->h_final);
+    z->d_in = z->d_slots = z->d_final = z->h_final = NULL;
+    z->d_sizes = z->d_nblocks = z->d_crctab = z->d_hist = NULL;
+    z->d_offsets = z->d_streamoff = NULL; z->d_streams = NULL; z->d_codes = NULL;
+}
+
+static int bgzf_reserve(tsk_bgzf *z, size_t n)
+{
+    if (n <= z->cap && z->d_in) return 0;
+    bgzf_release(z);
+    const size_t cap = n + n / 4 + (1u << 20);
+    const size_t nb = cap / ENC_CHUNK + 2;
+    uint32_t tab[512];
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; k++) c = (c & 1u) ? (c >> 1) ^ CRC_POLY : c >> 1;
+        tab[i] = c;
+    }
+    uint32_t x1024 = 0x40000000u;
+    for (int k = 0; k < 10; k++) x1024 = crc_mulmod(x1024, x1024);
+    tab[256] = 0x80000000u;
+    for (int m = 1; m < 256; m++) tab[256 + m] = crc_mulmod(tab[256 + m - 1], x1024);
+    TSK_CUDA(cudaMalloc(&z->d_in, cap + 16));
+    TSK_CUDA(cudaMalloc(&z->d_slots, nb * ENC_SLOT));
+    TSK_CUDA(cudaMalloc(&z->d_final, nb * ENC_SLOT));
+    TSK_CUDA(cudaHostAlloc((void **)&z->h_final, nb * ENC_SLOT, cudaHostAllocDefault));
+    TSK_CUDA(cudaMalloc(&z->d_sizes, sizeof(uint32_t) * nb));
+    TSK_CUDA(cudaMalloc(&z->d_nblocks, sizeof(uint32_t)));
+    TSK_CUDA(cudaMalloc(&z->d_crctab, sizeof(tab)));
+    TSK_CUDA(cudaMalloc(&z->d_hist, sizeof(uint32_t) * 256));
+    TSK_CUDA(cudaMalloc(&z->d_offsets, sizeof(uint64_t) * (nb + 1)));
+    TSK_CUDA(cudaMalloc(&z->d_streamoff, sizeof(uint64_t) * 2));
+    TSK_CUDA(cudaMalloc(&z->d_streams, sizeof(DevStream) * 2));
+    TSK_CUDA(cudaMalloc((void **)&z->d_codes, sizeof(StreamCode)));
+    TSK_CUDA(cudaMemcpy(z->d_crctab, tab, sizeof(tab), cudaMemcpyHostToDevice));
+    TSK_CUDA(cudaFuncSetAttribute(k_enc_deflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DeflateSmem)));
+    z->cap = cap;
+    return 0;
+}
+
+extern "C" int tsk_bgzf_create(tsk_bgzf **out, int device)
+{
+    if (!out) { tsk_set_error("null argument"); return -1; }
+    *out = NULL;
+    if (tsk_probe(device) < 0) return -1;
+    TSK_CUDA(cudaSetDevice(device));
+    tsk_bgzf *z = (tsk_bgzf *)calloc(1, sizeof(tsk_bgzf));
+    if (!z) { tsk_set_error("out of memory"); return -1; }
+    z->device = device;
+    TSK_CUDA(cudaStreamCreateWithFlags(&z->stream, cudaStreamNonBlocking));
+    *out = z;
+    return 0;
+}
+
+extern "C" void tsk_bgzf_destroy(tsk_bgzf *z)
+{
+    if (!z) return;
+    cudaSetDevice(z->device);
+    bgzf_release(z);
+    if (z->stream) cudaStreamDestroy(z->stream);
+    free(z);
+}
+
+extern "C" int tsk_bgzf_deflate(tsk_bgzf *z, const void *data, size_t n, const uint8_t **out, size_t *outn)
+{
+    if (!z || (n && !data) || !out || !outn) { tsk_set_error("null argument"); return -1; }
+    TSK_CUDA(cudaSetDevice(z->device));
+    *out = NULL; *outn = 0;
+    if (n == 0) return 0;
+    if (bgzf_reserve(z, n) != 0) return -1;
+    const size_t nb = (n + ENC_CHUNK - 1) / ENC_CHUNK;
+    cudaStream_t st = z->stream;
+    uint64_t h_off[2] = {0, 0};
+    TSK_CUDA(cudaMemcpyAsync(z->d_in, data, n, cudaMemcpyHostToDevice, st));
+    TSK_CUDA(cudaMemsetAsync(z->d_hist, 0, sizeof(uint32_t) * 256, st));
+    k_enc_one_stream<<<1, 1, 0, st>>>(z->d_in, (uint64_t)n, z->d_streams, z->d_nblocks);
+    k_enc_hist<<<(unsigned)nb, ENC_THREADS, 0, st>>>(z->d_streams, 1, z->d_nblocks, z->d_hist);
+    k_enc_codes<<<1, ENC_THREADS, 0, st>>>(z->d_streams, z->d_hist, z->d_codes);
+    k_enc_deflate<<<(unsigned)nb, ENC_THREADS, sizeof(DeflateSmem), st>>>(z->d_streams, 1, z->d_nblocks, z->d_crctab, z->d_codes,
+                                                                         z->d_slots, z->d_sizes);
+    k_enc_offsets<<<1, 1024, 0, st>>>(z->d_sizes, z->d_nblocks, z->d_streams, 1, z->d_offsets, z->d_streamoff);
+    k_enc_gather<<<(unsigned)nb, 256, 0, st>>>(z->d_slots, z->d_sizes, z->d_nblocks, z->d_offsets, z->d_final);
+    z->launches += 6;
+    TSK_CUDA(cudaGetLastError());
+    TSK_CUDA(cudaMemcpyAsync(h_off, z->d_streamoff, sizeof(h_off), cudaMemcpyDeviceToHost, st));
+    TSK_CUDA(cudaStreamSynchronize(st));
+    if (h_off[1]) TSK_CUDA(cudaMemcpyAsync(z->h_final, z->d_final, (size_t)h_off[1], cudaMemcpyDeviceToHost, st));
+    TSK_CUDA(cudaStreamSynchronize(st));
+    *out = z->h_final; *outn = (size_t)h_off[1];
+    return 0;
+}
+
+extern "C" uint64_t tsk_bgzf_launch_count(tsk_bgzf *z) { return z ? z->launches : 0; }

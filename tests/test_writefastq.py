@@ -47,6 +47,14 @@ def tiles(tmp_path_factory):
     return work, base, paths, merged
 
 
+@pytest.fixture(autouse=True)
+def host_writers(monkeypatch, request):
+    """The CPU suite runs the program's host output path (TSK_HOST_WRITERS=1: zlib members); its default,
+    the GPU's BGZF deflater, is tests/test_gpu_writefastq.py, which re-runs these tests on a GPU box."""
+    if "gpu" not in request.keywords:
+        monkeypatch.setenv("TSK_HOST_WRITERS", "1")
+
+
 def _run(binary, work, taginfo, sample, tag, extra=()):
     r5, r3 = os.path.join(work, "%s_%s_R5.fastq.gz" % (sample, tag)), os.path.join(work, "%s_%s_R3.fastq.gz" % (sample, tag))
     r = subprocess.run([binary, "--taginfo", taginfo, "--seqqual", "seqqual/%s_@tile@.txt.gz" % sample,
