@@ -997,7 +997,6 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
     const int valid = min(scan_len, dump);
     const bool emit = (kd & KIND_EMIT) != 0;
     const bool ispos = (kd & KIND_POS) != 0;
-    const int rscore_end = alive ? rdata_end : 0;
 
     uint32_t *rec = nullptr;
     if (emit) {
@@ -1061,118 +1060,6 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
     const uint32_t a_tile = smem_u32(&sm.tile[warp][0][0]);
     const uint32_t a_mytile = a_tile + lane * ((K2_TILE_CYC + 1) * 4);
 
-#ifdef TSK_K2_V1
-    /* one cycle of this lane: r = 3'-read cycle, arow = shared address of the cycle's [4][32] rows */
-    auto cycle = [&](const int r, const uint32_t arow) {
-        uint32_t word = 0;
-        if (r >= start && r < rscore_end) {
-            /* ---- decrosstalk (signalproc.c:85-103); exact int16 -> float through 2^23+2^22 ---- */
-            const uint32_t ap = arow + colofs;
-            const float v0 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap)), 12582912.f);
-            const float v1 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap + K2C_CHB)), 12582912.f);
-            const float v2 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap + 2 * K2C_CHB)), 12582912.f);
-            const float v3 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap + 3 * K2C_CHB)), 12582912.f);
-            float sig[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                float a = __fmul_rn(P.inv[4 * j + 0], v0);
-                a = __fadd_rn(a, __fmul_rn(P.inv[4 * j + 1], v1));
-                a = __fadd_rn(a, __fmul_rn(P.inv[4 * j + 2], v2));
-                sig[j] = __fadd_rn(a, __fmul_rn(P.inv[4 * j + 3], v3));
-            }
-            /* ---- dark test: sum of the positive channels (x + 0 == x, so max(.,0) is exact) ---- */
-            float tot = fmaxf(sig[0], 0.f);
-            tot = __fadd_rn(tot, fmaxf(sig[1], 0.f));
-            tot = __fadd_rn(tot, fmaxf(sig[2], 0.f));
-            tot = __fadd_rn(tot, fmaxf(sig[3], 0.f));
-            bool lit = !(tot < P.dark_threshold);
-            /* ---- normalise into the cluster's dynamic range (signalproc.c:246-266) ---- */
-            float nrm[4];
-#pragma unroll
-            for (int ch = 0; ch < 4; ch++)
-                nrm[ch] = fmaxf(div_by_rcp(__fsub_rn(sig[ch], low[ch]), bw[ch], ybw[ch]), 0.f);
-            const float sum = __fadd_rn(__fadd_rn(__fadd_rn(nrm[0], nrm[1]), nrm[2]), nrm[3]);
-            float prob[4];
-            /* sum == 0 (every channel at or below its floor: a dark cycle) takes the fast path too:
-             * rcp(0) = inf, the refinement turns it into NaN, and so does 0 x NaN in the division --
-             * the NaN that IEEE 0/0 gives, which is all that is looked at */
-            if (__builtin_expect(in_exp_range(sum, -60, 60) || sum == 0.f, 1)) {
-                const float ys = rcp_rn_fast(sum);
-#pragma unroll
-                for (int ch = 0; ch < 4; ch++) prob[ch] = div_by_rcp(nrm[ch], sum, ys);
-            } else {
-                /* sum == 0 (0/0 -> NaN -> dark) or a pathological magnitude: IEEE division */
-#pragma unroll
-                for (int ch = 0; ch < 4; ch++) prob[ch] = __fdiv_rn(nrm[ch], sum);
-            }
-            lit = lit && (prob[0] == prob[0]);
-            /* ---- Shannon entropy: h -= p*logf(p) for p > 0 (the skipped terms are 0) ---- */
-            float h = 0.f;
-            {
-#pragma unroll
-                for (int ch = 0; ch < 4; ch++) {
-                    const float lg = logf_core_t(__float_as_uint(prob[ch]), [a_logtab](uint32_t ofs) {
-                        double2 t;
-                        asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t.x), "=d"(t.y) : "r"(a_logtab + ofs));
-                        return t;
-                    });
-                    const float term = __fmul_rn(prob[ch], lg);
-                    h = __fsub_rn(h, prob[ch] > 0.f ? term : 0.f);
-                }
-            }
-            const float es = __fsub_rn(1.f, div_by_rcp(h, P.maximum_entropy, rcp_maxent));
-            const uint32_t ti = min((uint32_t)__float2int_rz(__fmul_rn(prob[3], (float)TSK_T_SCORE_BINS)),
-                                    (uint32_t)TSK_T_SCORE_BINS);
-            float tsc;
-            asm("ld.shared.f32 %0, [%1];" : "=f"(tsc) : "r"(a_tscore + ti * 4));
-            const float score = lit ? __fmul_rn(es, tsc) : CUDART_NAN_F;
-            const uint32_t dh = (lit && es < prev_entropy) ? 1u : 0u;
-            prev_entropy = lit ? es : CUDART_NAN_F;
-            ndark += lit ? 0 : 1;
-            dhwin = (dhwin << 1) | dh;
-
-            if (r >= start + ps) {
-                uint32_t s = 1u + (uint32_t)__float2int_rz(__fmul_rn(score, (float)(TSK_SCORE_MAX - 1)));
-                s = min(s, TSK_SCORE_MAX);
-                /* packet j = c - ps carries downhill[j], the UN-offset array (spotanalyzer.c:604-606) */
-                word = lit ? ((s << 1) | ((dhwin >> ps) & 1u)) : 0u;
-                if (needcol) {      /* one predicate: the sum is only used by the KIND_POS lanes */
-                    *scr = score;
-                    ptotal = __dadd_rn(ptotal, (double)score);      /* same order as the reference's cumsum */
-                }
-            }
-        }
-        /* ---- stage the packed word; every 8 cycles the emitting lanes' records are written four
-         *      at a time, 8 consecutive words (one 32-byte sector) each ---- */
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_mytile + ((r - rbeg_w) & (K2_TILE_CYC - 1)) * 4), "r"(word) : "memory");
-        scr += spitch;
-    };
-    /* after every second group (8 cycles) and after the last one: r = last cycle staged */
-    auto flush = [&](const int g, const int ng, const int r) {
-        if (!(g & 1) && g != ng - 1) return;
-        const int rbase = r - ((r - rbeg_w) & (K2_TILE_CYC - 1));     /* cycle in tile column 0 */
-        const int l8 = lane & 7;
-        for (int it = 0; it < nflush; it++) {
-            /* next (up to) four emitting lanes: this quarter-warp's is in flushpick */
-            const int p6 = (int)(flushpick >> (6 * it)) & 63;
-            const int pick = p6 == 63 ? -1 : p6;
-            const int src = pick < 0 ? 0 : pick;
-            const unsigned long long ra = __shfl_sync(FULL_MASK, recaddr, src);
-            const int ri = __shfl_sync(FULL_MASK, recinfo, src);
-            const int j = rbase + l8 - (ri & 0xffff);
-            if (pick >= 0 && j >= 0 && j < (ri >> 16) && rbase + l8 <= r) {
-                uint32_t wv;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv) : "r"(a_tile + (pick * (K2_TILE_CYC + 1) + l8) * 4));
-                reinterpret_cast<uint32_t *>((uintptr_t)ra)[2 + j] = wv;
-            }
-        }
-        __syncwarp();
-    };
-
-    /* ---- scored cycles ---- */
-    stream(rbeg_w, rend_w, rdata_w, cycle, flush);
-
-#else
     /* ---- scored cycles: one TMA group (four cycles) per step, straight-line and branch-free.
      * Every lane runs every cycle of the warp's range [rbeg_w, rend_w); `act` (this lane is inside
      * its own [start, start + insert_len)) gates what the cycle may change, so there is no per-lane
@@ -1354,7 +1241,6 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
         list_array(A.lists, 3, A.listcap)[atomicAdd(&A.lists[3], 1u)] = n;
         alive = false;
     }
-#endif
 
     /* ---- negative sampling (spotanalyzer.c:589-599) of the lanes that need no fair-sampling
      *      decision and did not abort: the warp walks each such lane's column ---- */
