@@ -118,11 +118,6 @@ static int build_device_params(const tsk_params *p, DevParams *d, DevSample *ds)
     for (int i = 0; i < 5; i++) { d->w_polyA[i] = p->weights_polyA[i]; d->w_nonA[i] = p->weights_nonA[i]; }
     d->w_small = 1;
     for (int i = 0; i < 5; i++) d->w_small = d->w_small && p->weights_polyA[i] >= -128 && p->weights_polyA[i] <= 127;
-    d->wpk_lo = d->wpk_hi = 0;
-    if (d->w_small) {
-        for (int i = 0; i < 4; i++) d->wpk_lo |= (uint32_t)(uint8_t)(int8_t)p->weights_polyA[i] << (8 * i);
-        d->wpk_hi = (uint32_t)(uint8_t)(int8_t)p->weights_polyA[4];
-    }
     d->max_mods = p->max_terminal_modifications; d->min_polya_len = p->min_polya_length;
     d->sigproc_trigger = p->sigproc_trigger_polya_length;
     d->dark_threshold = p->dark_cycles_threshold; d->max_dark_cycles = p->max_dark_cycles;

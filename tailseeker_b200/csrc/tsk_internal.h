@@ -53,8 +53,7 @@ struct DevParams {
     int32_t boundary_pos, sampling_gap, bins;
     int32_t fair_fp_len, fair_hash_size, fair_max_count;
     int32_t w_polyA[5], w_nonA[5];
-    uint32_t wpk_lo, wpk_hi;     /* w_polyA as five int8 (A,C,G,T | N) when they all fit: w_small */
-    int32_t w_small;
+    int32_t w_small;             /* every w_polyA fits int8: the seed scan's packed-key long stretch applies */
     int32_t max_mods, min_polya_len, sigproc_trigger;
     float   dark_threshold;
     int32_t max_dark_cycles;

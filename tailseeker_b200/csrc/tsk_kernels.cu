@@ -54,6 +54,9 @@ k_decode_demux_seed(const __grid_constant__ DevParams P, const TileView tv,
     uint32_t *s_wcnt = s_cnt + S * TSK_NCOUNT;       /* [warps][S+1] */
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarps = TSK_K1_THREADS / 32;
+    /* per base-call BYTE: poly(A) weight of its base * 512 - 1, the step of the packed
+     * (running sum, position) key of the seed scan's long stretch */
+    int32_t *s_wkey = reinterpret_cast<int32_t *>(s_wcnt + nwarps * (S + 1));
 
     if (tid == 0) {
         const uint32_t bar = smem_u32(s_bar);
@@ -68,6 +71,8 @@ k_decode_demux_seed(const __grid_constant__ DevParams P, const TileView tv,
         reinterpret_cast<uint32_t *>(s_samples)[i] = reinterpret_cast<const uint32_t *>(g_samples)[i];
     for (int i = tid; i < S * TSK_NCOUNT + nwarps * (S + 1); i += TSK_K1_THREADS)
         s_cnt[i] = 0;
+    if (P.w_small)
+        for (int b = tid; b < 256; b += TSK_K1_THREADS) s_wkey[b] = P.w_polyA[tsk_base_code(b)] * 512 - 1;
     __syncthreads();
 
     const uint32_t n = blockIdx.x * TSK_K1_THREADS + tid;
@@ -182,18 +187,23 @@ k_decode_demux_seed(const __grid_constant__ DevParams P, const TileView tv,
                     int Srun = 0, minS = 0x3fffffff, argj = -1;
                     const int captop = M + mlen - 1;        /* j below this may be a j_min(i) */
                     int j = L - 1;
-                    if (P.w_small) {
-                        /* the long stretch above the captured region only carries the running
-                         * sum and its minimum: weights from a byte-permute of five packed int8
-                         * (selector nibbles 8+code replicate the sign) instead of a table load */
+                    if (P.w_small && j >= captop) {
+                        /* the long stretch above the captured region only carries the running sum
+                         * and its minimum.  Both live in ONE register: key = sum * 512 + position
+                         * (positions < 512, |sum| < 2^15), so "smaller sum, then smaller position" --
+                         * the update rule `sum <= min` of a scan that walks downwards -- is a plain
+                         * integer minimum, and a step adds weight * 512 - 1, looked up by the raw
+                         * base-call byte: five instructions a cycle (two shared loads, address,
+                         * minimum, add) instead of ten (base code, byte-permuted weight, compare,
+                         * select, two adds). */
+                        int key = j, minkey = INT_MAX;         /* Srun = 0 so far */
 #pragma unroll 4
                         for (; j >= captop; j--) {
-                            const uint32_t code = tsk_base_code(rd(de + j));
-                            if (Srun <= minS) { minS = Srun; argj = j; }
-                            int wv;     /* prmt, default mode: nibble 8+k = sign of byte k replicated */
-                            asm("prmt.b32 %0, %1, %2, %3;" : "=r"(wv) : "r"(P.wpk_lo), "r"(P.wpk_hi), "r"(code * 0x1111u + 0x8880u));
-                            Srun += wv;
+                            minkey = min(minkey, key);
+                            key += s_wkey[rd(de + j)];
                         }
+                        minS = minkey >> 9; argj = minkey & 511;
+                        Srun = (key - j) >> 9;                 /* key == Srun * 512 + j, exactly */
                     }
                     if (mlen - 1 <= 8) {
                         /* Candidate start i = j is complete at step j: S(i) has just been formed, and
@@ -477,7 +487,7 @@ int tsk_launch_import(tsk_ctx *ctx, cudaEvent_t *ev)
             if (r != CUDA_SUCCESS) { tsk_set_error("cuTensorMapEncodeTiled (base calls) failed (%d)", (int)r); return -1; }
         }
         const size_t smem1 = (size_t)slab_rows * TSK_K1_THREADS + 16 + sizeof(DevSample) * S +
-                             sizeof(uint32_t) * (S * TSK_NCOUNT + (TSK_K1_THREADS / 32) * (S + 1));
+                             sizeof(uint32_t) * (S * TSK_NCOUNT + (TSK_K1_THREADS / 32) * (S + 1)) + 256 * sizeof(int32_t);
         /* the attribute is per device: remembered in the context, not in a process-wide static */
         if (smem1 > ctx->k1_smem_configured) {
             TSK_CUDA(cudaFuncSetAttribute(k_decode_demux_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));

@@ -627,7 +627,7 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
     auto cycle = [&](const int r, const uint32_t arow) {
         uint32_t word = 0;
         if (r >= start && r < rscore_end) {
-            /* ---- decrosstalk (signalproc.c:85-103); exact int16 -> float through 2^23+2^22 ---- */
+            /* ---- decrosstalk (signalproc.c:85-103) ---- */
             const uint32_t ap = arow + colofs;
             const float v0 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap)), 12582912.f);
             const float v1 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap + 64)), 12582912.f);
@@ -829,6 +829,9 @@ struct __align__(128) K2SmemC {
     uint32_t tile[K2_WARPS][32][K2_TILE_CYC + 1];
     ScoreShared sh;
     uint64_t bar_full[K2_WARPS][K2_NGROUP];
+    /* record flush plan: round `it`, quarter-warp q writes eight words of ONE record:
+     * {record address lo, hi, first cycle | words << 16, byte offset of the lane's row in tile[warp]} */
+    uint4 plan[K2_WARPS][8][4];
 };
 
 __global__ void __launch_bounds__(TSK_K2_THREADS, K2_MIN_CTAS)
@@ -1035,8 +1038,24 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
             flushpick = (flushpick & ~(63ull << (6 * it))) | ((unsigned long long)pick << (6 * it));
         }
     }
-    const unsigned long long recaddr = (unsigned long long)(uintptr_t)rec;
-    const int recinfo = ((start + ps) & 0xffff) | (max(dump, 0) << 16);
+    {
+        /* who writes what is the same at every flush: worked out once (three shuffles a round),
+         * kept in shared memory and read back with one broadcast load a round */
+        const unsigned long long recaddr = (unsigned long long)(uintptr_t)rec;
+        const int recinfo = ((start + ps) & 0xffff) | (max(dump, 0) << 16);
+        for (int it = 0; it < 8; it++) {
+            const int p6 = it < nflush ? (int)(flushpick >> (6 * it)) & 63 : 63;
+            const int src = p6 == 63 ? 0 : p6;
+            const unsigned long long ra = __shfl_sync(FULL_MASK, recaddr, src);
+            const int ri = __shfl_sync(FULL_MASK, recinfo, src);
+            if ((lane & 7) == 0)
+                sm.plan[warp][it][lane >> 3] = make_uint4((uint32_t)ra, (uint32_t)(ra >> 32),
+                                                          p6 == 63 ? 0u : (uint32_t)ri,
+                                                          (uint32_t)(src * (K2_TILE_CYC + 1) * 4));
+        }
+        __syncwarp();
+    }
+    const uint32_t a_plan = smem_u32(&sm.plan[warp][0][lane >> 3]);
 
     int ndark = 0;
     float prev_entropy = CUDART_NAN_F;
@@ -1077,16 +1096,11 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
     /* phase A of a cycle: intensities -> the four channel probabilities and whether the cycle is lit */
     auto cycle_a = [&](const int c, const uint32_t ap, float prob[4], bool &good) {
         const bool act = (unsigned)c < ilen_a;
-        /* ---- decrosstalk (signalproc.c:85-103); exact int16 -> float through 2^23+2^22 ---- */
-#ifdef TSK_K2_I2FP
+        /* ---- decrosstalk (signalproc.c:85-103) ---- */
+        /* I2FP (one instruction, exact for int16); the two-instruction integer-add + FADD route
+         * through 2^23 + 2^22 measured 1 % slower */
         const float v0 = (float)lds_s16(ap), v1 = (float)lds_s16(ap + K2C_CHB), v2 = (float)lds_s16(ap + 2 * K2C_CHB),
                     v3 = (float)lds_s16(ap + 3 * K2C_CHB);
-#else
-        const float v0 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap)), 12582912.f);
-        const float v1 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap + K2C_CHB)), 12582912.f);
-        const float v2 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap + 2 * K2C_CHB)), 12582912.f);
-        const float v3 = __fsub_rn(__int_as_float(0x4B400000 + lds_s16(ap + 3 * K2C_CHB)), 12582912.f);
-#endif
         float sig[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -1168,19 +1182,21 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
         if (!(g & 1) && g != ng - 1) return;
         const int rbase = r - ((r - rbeg_w) & (K2_TILE_CYC - 1));     /* cycle in tile column 0 */
         const int l8 = lane & 7;
-        for (int it = 0; it < nflush; it++) {
-            /* next (up to) four emitting lanes: this quarter-warp's is in flushpick */
-            const int p6 = (int)(flushpick >> (6 * it)) & 63;
-            const int pick = p6 == 63 ? -1 : p6;
-            const int src = pick < 0 ? 0 : pick;
-            const unsigned long long ra = __shfl_sync(FULL_MASK, recaddr, src);
-            const int ri = __shfl_sync(FULL_MASK, recinfo, src);
-            const int j = rbase + l8 - (ri & 0xffff);
-            if (pick >= 0 && j >= 0 && j < (ri >> 16) && rbase + l8 <= r) {
-                uint32_t wv;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv) : "r"(a_tile + (pick * (K2_TILE_CYC + 1) + l8) * 4));
-                reinterpret_cast<uint32_t *>((uintptr_t)ra)[2 + j] = wv;
-            }
+        const int rb = rbase + l8;
+        const uint32_t a_src = a_tile + l8 * 4;
+        /* two rounds at a time: four independent shared loads, then the two stores */
+        for (int it = 0; it < nflush; it += 2) {
+            uint4 e0, e1;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e0.x), "=r"(e0.y), "=r"(e0.z), "=r"(e0.w) : "r"(a_plan + it * 64));
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e1.x), "=r"(e1.y), "=r"(e1.z), "=r"(e1.w) : "r"(a_plan + it * 64 + 64));
+            uint32_t w0, w1;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(a_src + e0.w));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(a_src + e1.w));
+            const uint32_t j0 = (uint32_t)(rb - (int)(e0.z & 0xffffu)), j1 = (uint32_t)(rb - (int)(e1.z & 0xffffu));
+            if (rb <= r && j0 < (e0.z >> 16))
+                reinterpret_cast<uint32_t *>((uintptr_t)(((unsigned long long)e0.y << 32) | e0.x))[2 + j0] = w0;
+            if (rb <= r && j1 < (e1.z >> 16))
+                reinterpret_cast<uint32_t *>((uintptr_t)(((unsigned long long)e1.y << 32) | e1.x))[2 + j1] = w1;
         }
         __syncwarp();
     };

@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of scoring-kernel builds on one GPU box: for every variant (extra nvcc flags) rebuild the
 # library, run the parity tests that pin the fast kernel, then time it (stage times of bench.py).
-#   gpurun --timeout 1500 -- 'bash tools/k2_variants.sh "" "-DTSK_K2_V1" "-DTSK_K2_I2FP"'
+#   gpurun --timeout 1500 -- 'bash tools/k2_variants.sh "" "-DK2_SWEEP=4" "-DK2_MIN_CTAS=5"'
 set -u
 mkdir -p gpurun_out
 : > gpurun_out/k2_variants.txt
