@@ -820,12 +820,13 @@ k_normalise_score_pack(const __grid_constant__ DevParams P, const ScoreArgs A, c
  * than K2C_W from there (an item spanning > 121 clusters, i.e. under ~30 % kept) go to the literal kernel.  Nothing is
  * resident: the balancer cycles and then the scored cycles stream through the same ring of two
  * 4-cycle groups (the few cycles both passes need are fetched twice, from L2). ---- */
-#define K2C_W     128                    /* clusters per TMA box */
-#define K2C_CHB   (K2C_W * 2)            /* bytes per channel row */
-#define K2C_ROWB  (4 * K2C_CHB)          /* bytes per cycle and warp */
+#define K2C_NARROW 64                    /* clusters per TMA box of the narrow instance */
+#define K2C_WIDE   128                   /* ... of the wide one */
+#define K2_WIDE_ITEMS 8                  /* lists[8]: items the narrow instance left to the wide one (zeroed with the list counters) */
 
+template <int W>
 struct __align__(128) K2SmemC {
-    int16_t  stage[K2_WARPS][K2_NGROUP * K2_GROUP][4][K2C_W];
+    int16_t  stage[K2_WARPS][K2_NGROUP * K2_GROUP][4][W];
     uint32_t tile[K2_WARPS][32][K2_TILE_CYC + 1];
     ScoreShared sh;
     uint64_t bar_full[K2_WARPS][K2_NGROUP];
@@ -834,12 +835,23 @@ struct __align__(128) K2SmemC {
     uint4 plan[K2_WARPS][8][4];
 };
 
+/* Two instances are launched over the same work list and every item is taken by exactly one of them:
+ * the narrow one (64-cluster box) if all 32 clusters of the item lie within 64 of its first -- any tile
+ * that keeps more than ~60 % of its clusters -- the wide one (128) otherwise.  A box twice as wide as
+ * needed doubles the L2 -> shared-memory traffic of the kernel (8.1 GB per tile with 128 for 2.0 GB
+ * used) and cost 3.6 % of its time. */
+template <int W>
 __global__ void __launch_bounds__(TSK_K2_THREADS, K2_MIN_CTAS)
 k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreArgs A, const float rcp_maxent,
                                const __grid_constant__ CUtensorMap tmap)
 {
+    constexpr int K2C_W = W;                     /* clusters per TMA box */
+    constexpr int K2C_CHB = K2C_W * 2;           /* bytes per channel row */
+    constexpr int K2C_ROWB = 4 * K2C_CHB;        /* bytes per cycle and warp */
+    /* the wide instance runs second: nothing was left for it on most tiles */
+    if (W == K2C_WIDE && A.lists[K2_WIDE_ITEMS] == 0) return;
     extern __shared__ __align__(128) unsigned char k2_smem_raw[];
-    K2SmemC &sm = *reinterpret_cast<K2SmemC *>(k2_smem_raw);
+    K2SmemC<W> &sm = *reinterpret_cast<K2SmemC<W> *>(k2_smem_raw);
     const ScoreShared &sh = sm.sh;
     const int S = P.num_samples;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -870,6 +882,11 @@ k_normalise_score_pack_compact(const __grid_constant__ DevParams P, const ScoreA
     /* window start: a tiled TMA copy must begin on a 16-byte boundary of the plane (8 clusters);
      * a box starting elsewhere faults with "illegal instruction" */
     const int x0 = (int)(__shfl_sync(FULL_MASK, n, 0) & ~7u);
+    /* which instance owns the item (warp-uniform); the narrow one counts what it leaves */
+    if (__all_sync(FULL_MASK, !alive || n - (uint32_t)x0 < K2C_NARROW) != (W == K2C_NARROW)) {
+        if (W == K2C_NARROW && lane == 0) atomicAdd(&A.lists[K2_WIDE_ITEMS], 1u);
+        return;
+    }
     if (alive && n - (uint32_t)x0 >= K2C_W) {
         /* the window does not reach this far (long run of dropped clusters): literal kernel */
         list_array(A.lists, 3, A.listcap)[atomicAdd(&A.lists[3], 1u)] = n;
@@ -1740,8 +1757,10 @@ int tsk_launch_score(tsk_ctx *ctx)
         if (!ctx->k2_attr_set) {            /* per device, hence per context */
             TSK_CUDA(cudaFuncSetAttribute(k_normalise_score_pack, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(K2Smem)));
-            TSK_CUDA(cudaFuncSetAttribute(k_normalise_score_pack_compact, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)sizeof(K2SmemC)));
+            TSK_CUDA(cudaFuncSetAttribute(k_normalise_score_pack_compact<K2C_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(K2SmemC<K2C_NARROW>)));
+            TSK_CUDA(cudaFuncSetAttribute(k_normalise_score_pack_compact<K2C_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(K2SmemC<K2C_WIDE>)));
             ctx->k2_attr_set = 1;
         }
         const float rcp_maxent = 1.0f / ctx->dp.maximum_entropy;      /* IEEE RN on the host */
@@ -1752,8 +1771,11 @@ int tsk_launch_score(tsk_ctx *ctx)
             if (make_cif_tensor_map(ctx, &tmap, 32) != 0) return -1;
             k_normalise_score_pack<<<grid, TSK_K2_THREADS, sizeof(K2Smem), ctx->stream>>>(ctx->dp, a, rcp_maxent, head, tmap);
         } else {
-            if (make_cif_tensor_map(ctx, &tmap, K2C_W) != 0) return -1;
-            k_normalise_score_pack_compact<<<grid, TSK_K2_THREADS, sizeof(K2SmemC), ctx->stream>>>(ctx->dp, a, rcp_maxent, tmap);
+            CUtensorMap tmapw;
+            if (make_cif_tensor_map(ctx, &tmap, K2C_NARROW) != 0 || make_cif_tensor_map(ctx, &tmapw, K2C_WIDE) != 0) return -1;
+            k_normalise_score_pack_compact<K2C_NARROW><<<grid, TSK_K2_THREADS, sizeof(K2SmemC<K2C_NARROW>), ctx->stream>>>(ctx->dp, a, rcp_maxent, tmap);
+            k_normalise_score_pack_compact<K2C_WIDE><<<grid, TSK_K2_THREADS, sizeof(K2SmemC<K2C_WIDE>), ctx->stream>>>(ctx->dp, a, rcp_maxent, tmapw);
+            ctx->launches += 1;
         }
         /* handed-over clusters: usually none, many on tiles that are mostly dropped clusters.
          * They keep their scores in the second half of the scratch buffer: the first half still

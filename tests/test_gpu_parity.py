@@ -88,10 +88,11 @@ def test_row_form_of_fast_kernel(stock_cfg, oracle):
         p.close()
 
 
-@pytest.mark.parametrize("unknown_frac", [0.5, 0.9])
+@pytest.mark.parametrize("unknown_frac", [0.3, 0.5, 0.9])
 def test_sparse_work_list(proc, stock_cfg, oracle, unknown_frac):
-    """Mostly dropped clusters: work items span more clusters than the TMA window and hand their
-    far lanes to the literal kernel."""
+    """Many dropped clusters: 0.3 mixes work items of the narrow (64-cluster box) and the wide (128)
+    instance of the scoring kernel, 0.5 is all wide, at 0.9 items span more clusters than the wide box
+    and hand their far lanes to the literal kernel."""
     _, o = _run(proc, stock_cfg, oracle, 15000, 23, unknown_frac=unknown_frac)
     compare_tile(proc, stock_cfg, None, o)
 
