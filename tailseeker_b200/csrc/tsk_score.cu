@@ -446,7 +446,7 @@ __device__ __forceinline__ int lds_s16(uint32_t addr)
 #define K2_CL        TSK_K2_THREADS      /* clusters per CTA */
 #define K2_WARPS     (TSK_K2_THREADS / 32)
 #define K2_GROUP     4                   /* cycles per TMA copy */
-#define K2_NGROUP    2                   /* groups in each warp's ring (4-7 cycles of look-ahead; 3 groups were 2 % slower) */
+#define K2_NGROUP    2                   /* groups in each warp's ring (4-7 cycles of look-ahead; 3 groups were 2 % slower, 4 groups 3 %) */
 #define K2_HEAD_MAX  24                  /* resident cycles [0, head): balancer + first scored cycles */
 #define K2_ROWB      (4 * 32 * 2)        /* bytes per cycle and warp: four channel rows of 32 int16 */
 #define K2_TILE_CYC  8                   /* record words staged per lane between flushes */
