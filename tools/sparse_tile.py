@@ -11,7 +11,7 @@ from tailseeker_b200.synth_torch import make_tile_device
 cfg = stock_config("miseq", phix_match_name="PhiX")
 N = 1070000
 names = ["decode", "scan", "score", "fixups"]
-for unk in (0.03, 0.3, 0.5, 0.7):
+for unk in (0.03, 0.15, 0.3, 0.4, 0.5, 0.7):
     bcl, cif, mtext, pitch = make_tile_device(cfg, N, seed=77, device="cuda", unknown_frac=unk, phix_frac=0.8)
     mtx = np.array([np.float32(x) for x in mtext.split()], dtype=np.float32)
     p = TileProcessor(cfg)
