@@ -272,10 +272,18 @@ def cli_leg(cfg, ntiles, N, threads):
                            stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
         tour = time.perf_counter() - t0
         phases = {}
+        if os.environ.get("TSK_CLI_RAW_TIMING"):                 # per-tile lines, for tools/cli_time.py
+            sys.stderr.write(r.stderr.decode())
+        per_tile = []                       # a tile's phases start with "open files + buffers"
         for ln in r.stderr.decode().splitlines():
             if ln.startswith("[timing]"):
                 name, secs = ln[8:].rsplit(None, 2)[0].strip(), float(ln.split()[-2])
                 phases[name] = round(phases.get(name, 0.0) + secs, 3)
+                if name == "open files + buffers":
+                    per_tile.append(0.0)
+                if per_tile:
+                    per_tile[-1] += secs
+        later = per_tile[1:] if len(per_tile) > 1 else []
         sizes = {arm: sum(os.path.getsize(os.path.join(dp, f)) for sub in ("seqqual", "taginfo", "signals")
                           for dp, _, fs in os.walk(os.path.join(base, arm, sub)) for f in fs) for arm in ("ref", "our")}
         start = phases.get("wait for the CUDA context", 0.0)
@@ -284,8 +292,11 @@ def cli_leg(cfg, ntiles, N, threads):
                 "speedup": tref / tour, "tiles": ntiles, "clusters_per_tile": N, "threads": threads,
                 "seconds": round(tour, 3), "reference_seconds": round(tref, 3),
                 "output_bytes": sizes["our"], "reference_output_bytes": sizes["ref"], "phases_s": phases,
+                "seconds_per_tile": [round(x, 3) for x in per_tile],
+                "steady_state_value": (N * len(later) / sum(later)) if later and sum(later) > 0 else None,
                 "note": "files on /dev/shm -> tailseq-import (one process, all tiles; CUDA start-up included: creating the "
-                        "context takes 0.2 - 3 s on these boxes, the phase 'wait for the CUDA context' says how much) -> files; "
+                        "context takes 0.2 - 3 s on these boxes, the phase 'wait for the CUDA context' says how much; the first tile also "
+                        "pays the first-use allocations, steady_state_value = clusters/s over the later tiles) -> files; "
                         "reference: its binary once per tile, zlib level 1; outputs of both decompress to the same bytes "
                         "(tests/test_gpu_dropin.py, test_gpu_fullsize_oracle.py)"}
     finally:

@@ -210,6 +210,13 @@ int tsk_tile_begin(tsk_ctx *ctx, uint32_t nclusters, uint32_t firstclusterno, co
 int tsk_tile_put_bcl(tsk_ctx *ctx, int cycle, const uint8_t *calls /* [nclusters] */);
 int tsk_tile_put_bcl_gz(tsk_ctx *ctx, int cycle, const uint8_t *gz, size_t gzbytes, uint64_t inflated_size, uint64_t skip);
 int tsk_tile_put_cif(tsk_ctx *ctx, int threep_cycle, const int16_t *planes /* [4][plane_pitch] */, size_t plane_pitch);
+/* Page-locked staging for the readers of the cycle files (the reference reads each file into its row of
+ * one big pageable array, bclreader.c:95-119 / cifreader.c): a slot of at least `bytes`, to be filled, passed
+ * to tsk_tile_put_bcl / tsk_tile_put_cif and released; the library hands it out again only after that
+ * copy has completed, so a released slot needs no further care (unlike caller-owned buffers, above).
+ * Thread-safe; blocks while all slots (24) are in use. */
+int tsk_tile_stage_acquire(tsk_ctx *ctx, size_t bytes, void **ptr, int *slot);
+int tsk_tile_stage_release(tsk_ctx *ctx, int slot);
 int tsk_tile_end(tsk_ctx *ctx);
 
 /* Replaces distribute_processing() (tailseq-import.c:516-565): runs the per-cluster path

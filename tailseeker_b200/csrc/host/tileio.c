@@ -264,24 +264,35 @@ static int read_cif_cycle(void *arg)
     const struct read_job *j = arg;
     struct tile_files *tf = j->tf;
     const int i = j->index;
-    for (int ch = 0; ch < 4; ch++) {
+    /* on the way to the device the planes are read into a page-locked staging slot of the library
+     * (copied at the PCIe rate, and the reader thread is free at once); otherwise into the block array */
+    int16_t *planes = j->cif + (size_t)i * 4 * j->count;
+    int slot = -1, rc = 0;
+    if (j->ctx) {
+        void *p = NULL;
+        if (tsk_tile_stage_acquire(j->ctx, sizeof(int16_t) * 4 * (size_t)j->count, &p, &slot) != 0)
+            return put_failed("tsk_tile_stage_acquire", tf->T - tf->L3 + i);
+        planes = p;
+    }
+    for (int ch = 0; ch < 4 && rc == 0; ch++) {
         const long at = 13 + ((long)tf->nclusters * ch + tf->read) * 2;
-        int16_t *dst = j->cif + ((size_t)i * 4 + ch) * j->count;
+        int16_t *dst = planes + (size_t)ch * j->count;
         if (fseek(tf->cif[i], at, SEEK_SET) != 0) {
             fprintf(stderr, "Failed to seek cluster intensity values in a CIF.\n");
-            return -1;
-        }
-        if (fread(dst, 2, j->count, tf->cif[i]) != j->count) {
+            rc = -1;
+        } else if (fread(dst, 2, j->count, tf->cif[i]) != j->count) {
             fprintf(stderr, "Not all data were loaded from a CIF.\n");
-            return -1;
+            rc = -1;
         }
 #if __BYTE_ORDER != __LITTLE_ENDIAN
-        for (uint32_t k = 0; k < j->count; k++) dst[k] = (int16_t)le16toh((uint16_t)dst[k]);
+        for (uint32_t k = 0; rc == 0 && k < j->count; k++) dst[k] = (int16_t)le16toh((uint16_t)dst[k]);
 #endif
     }
-    if (j->ctx && tsk_tile_put_cif(j->ctx, i, j->cif + (size_t)i * 4 * j->count, j->count) != 0)
-        return put_failed("tsk_tile_put_cif", tf->T - tf->L3 + i);
-    return 0;
+    if (j->ctx) {
+        if (rc == 0 && tsk_tile_put_cif(j->ctx, i, planes, j->count) != 0) rc = put_failed("tsk_tile_put_cif", tf->T - tf->L3 + i);
+        if (tsk_tile_stage_release(j->ctx, slot) != 0 && rc == 0) rc = put_failed("tsk_tile_stage_release", tf->T - tf->L3 + i);
+    }
+    return rc;
 }
 
 /* a .bcl.gz for the device: the whole compressed file once, then every block names its window */
@@ -316,15 +327,24 @@ static int read_bcl_cycle(void *arg)
     const int c = j->index;
     uint8_t *dst = j->bcl + (size_t)c * j->count;
     uint32_t got = 0;
+    int slot = -1, rc = 0;
     if (j->ctx && j->tf->bcl_gz_path[c]) return send_bcl_gz(j, c);      /* inflated on the device */
+    if (j->ctx) {                                                       /* see read_cif_cycle() */
+        void *p = NULL;
+        if (tsk_tile_stage_acquire(j->ctx, j->count ? j->count : 1, &p, &slot) != 0) return put_failed("tsk_tile_stage_acquire", c);
+        dst = p;
+    }
     while (got < j->count) {          /* gzread takes an unsigned int length */
         const uint32_t want = j->count - got > (1u << 30) ? (1u << 30) : j->count - got;
         const int r = gzread(j->tf->bcl[c], dst + got, want);
-        if (r < 1) { fprintf(stderr, "Unexpected EOF in a BCL (cycle %d).\n", c + 1); return -1; }
+        if (r < 1) { fprintf(stderr, "Unexpected EOF in a BCL (cycle %d).\n", c + 1); rc = -1; break; }
         got += (uint32_t)r;
     }
-    if (j->ctx && tsk_tile_put_bcl(j->ctx, c, dst) != 0) return put_failed("tsk_tile_put_bcl", c);
-    return 0;
+    if (j->ctx) {
+        if (rc == 0 && tsk_tile_put_bcl(j->ctx, c, dst) != 0) rc = put_failed("tsk_tile_put_bcl", c);
+        if (tsk_tile_stage_release(j->ctx, slot) != 0 && rc == 0) rc = put_failed("tsk_tile_stage_release", c);
+    }
+    return rc;
 }
 
 /* the overrides stay on one thread, in list order: where two of them overlap the later entry of
@@ -350,8 +370,9 @@ int tsk_read_block(struct tile_files *tf, uint32_t count, uint8_t *bcl, int16_t 
 
 /* The same block straight to the device: every cycle file's rows are sent as soon as its reader
  * thread has them (tsk_tile_put_*), compressed base-call files travel compressed, and the tile is
- * complete (waiting for tsk_tile_process) when this returns.  The rows of `bcl` that came from
- * .bcl.gz files are NOT filled on the host. */
+ * complete (waiting for tsk_tile_process) when this returns.  The block arrays are NOT filled on the
+ * host (the rows pass through the library's page-locked staging slots); only the rows of FASTQ
+ * overrides are written to `bcl`. */
 int tsk_read_block_to_device(struct tile_files *tf, uint32_t count, uint8_t *bcl, int16_t *cif, tsk_ctx *ctx,
                              const float invmatrix[16])
 {

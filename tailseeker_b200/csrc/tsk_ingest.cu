@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <mutex>
+#include <condition_variable>
 #include "tsk_internal.h"
 
 #define INF_FAST_BITS 9
@@ -33,8 +34,19 @@ struct InflateRow {
     uint32_t pad_;
 };
 
+/* page-locked staging slots of the file readers (tsk_tile_stage_acquire / _release) */
+#define STAGE_SLOTS 24
+struct StageSlot {
+    uint8_t *p;
+    size_t cap;
+    cudaEvent_t done;        /* the copy out of the slot, recorded on the copy stream at release */
+    int busy, has_event;
+};
+
 struct IngestState {
     std::mutex lock;
+    std::condition_variable slot_free;
+    StageSlot stage[STAGE_SLOTS];
     int open, slot;
     uint32_t nclusters;
     size_t bpitch, cpitch;
@@ -292,8 +304,74 @@ void tsk_ingest_free(tsk_ctx *ctx)
     if (g->d_status) cudaFree(g->d_status);
     free(g->h_rows);
     if (g->h_gz) cudaFreeHost(g->h_gz);
+    for (int i = 0; i < STAGE_SLOTS; i++) {
+        if (g->stage[i].has_event) cudaEventDestroy(g->stage[i].done);
+        if (g->stage[i].p) cudaFreeHost(g->stage[i].p);
+    }
     delete g;
     ctx->ingest = NULL;
+}
+
+/* A page-locked buffer of at least `bytes` for one cycle file's rows: the reader fills it, passes it to
+ * tsk_tile_put_bcl / tsk_tile_put_cif and releases it; the slot goes to the next reader once that copy
+ * has completed.  From pageable memory the same copies are staged by the driver at a fifth of the
+ * PCIe rate and hold the calling thread meanwhile.  Blocks while all slots are taken. */
+extern "C" int tsk_tile_stage_acquire(tsk_ctx *ctx, size_t bytes, void **ptr, int *slot)
+{
+    if (!ctx || !ptr || !slot) { tsk_set_error("null argument"); return -1; }
+    IngestState *g = ingest_state(ctx);
+    int s = -1;
+    {
+        std::unique_lock<std::mutex> guard(g->lock);
+        for (;;) {
+            s = -1;
+            for (int i = 0; i < STAGE_SLOTS; i++) {
+                if (g->stage[i].busy) continue;
+                /* a slot that is large enough already, else any free one */
+                if (s < 0 || (g->stage[s].cap < bytes && g->stage[i].cap >= bytes)) s = i;
+            }
+            if (s >= 0) break;
+            g->slot_free.wait(guard);
+        }
+        g->stage[s].busy = 1;
+    }
+    StageSlot &t = g->stage[s];
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e == cudaSuccess && t.has_event) e = cudaEventSynchronize(t.done);
+    if (e == cudaSuccess && !t.has_event) {
+        e = cudaEventCreateWithFlags(&t.done, cudaEventDisableTiming);
+        if (e == cudaSuccess) t.has_event = 1;
+    }
+    if (e == cudaSuccess && t.cap < bytes) {
+        if (t.p) cudaFreeHost(t.p);
+        t.p = NULL; t.cap = 0;
+        e = cudaHostAlloc((void **)&t.p, bytes, cudaHostAllocDefault);
+        if (e == cudaSuccess) t.cap = bytes;
+    }
+    if (e != cudaSuccess) {
+        tsk_set_error("staging slot: %s", cudaGetErrorString(e));
+        std::lock_guard<std::mutex> guard(g->lock);
+        t.busy = 0;
+        g->slot_free.notify_one();
+        return -1;
+    }
+    *ptr = t.p; *slot = s;
+    return 0;
+}
+
+extern "C" int tsk_tile_stage_release(tsk_ctx *ctx, int slot)
+{
+    IngestState *g = ctx ? ctx->ingest : NULL;
+    if (!g || slot < 0 || slot >= STAGE_SLOTS || !g->stage[slot].busy) { tsk_set_error("bad staging slot"); return -1; }
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e == cudaSuccess) e = cudaEventRecord(g->stage[slot].done, ctx->cstream);
+    {
+        std::lock_guard<std::mutex> guard(g->lock);
+        g->stage[slot].busy = 0;
+    }
+    g->slot_free.notify_one();
+    if (e != cudaSuccess) { tsk_set_error("staging slot: %s", cudaGetErrorString(e)); return -1; }
+    return 0;
 }
 
 extern "C" int tsk_tile_begin(tsk_ctx *ctx, uint32_t nclusters, uint32_t firstclusterno, const float invmatrix[16])

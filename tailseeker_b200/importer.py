@@ -99,10 +99,11 @@ class TileProcessor:
         self._pending.append((int(nclusters), (bcl, cif)))
 
     def upload_rows(self, bcl: np.ndarray, cif: np.ndarray, invmatrix: np.ndarray, firstclusterno: int = 0,
-                    gz_rows: Optional[Dict[int, tuple]] = None):
+                    gz_rows: Optional[Dict[int, tuple]] = None, staged: bool = False):
         """The tile cycle file by cycle file (tsk_tile_begin / put / end).  gz_rows: {cycle: (gzip file
         bytes, inflated size, skip)} for base-call rows that travel compressed and are inflated on the
-        device; every other row of `bcl` and every cycle of `cif` is sent from the arrays."""
+        device; every other row of `bcl` and every cycle of `cif` is sent from the arrays -- through the
+        library's page-locked staging slots when `staged` (what the file readers of tailseq-import do)."""
         inv = np.ascontiguousarray(invmatrix, dtype=np.float32).reshape(16)
         bcl = np.ascontiguousarray(bcl, dtype=np.uint8)
         cif = np.ascontiguousarray(cif, dtype=np.int16)
@@ -110,15 +111,27 @@ class TileProcessor:
         gz_rows = gz_rows or {}
         _lib.check(self.lib.tsk_tile_begin(self._ctx, n, firstclusterno, _ptr(inv)))
         keep = []
+
+        def put(row: np.ndarray, send):
+            if not staged:
+                return send(_ptr(row))
+            p, slot = ctypes.c_void_p(), ctypes.c_int32()
+            _lib.check(self.lib.tsk_tile_stage_acquire(self._ctx, max(1, row.nbytes), ctypes.byref(p), ctypes.byref(slot)))
+            ctypes.memmove(p, _ptr(row), row.nbytes)
+            try:
+                send(p)
+            finally:
+                _lib.check(self.lib.tsk_tile_stage_release(self._ctx, slot.value))
+
         for c in range(bcl.shape[0]):
             if c in gz_rows:
                 raw, size, skip = gz_rows[c]
                 keep.append(raw)
                 _lib.check(self.lib.tsk_tile_put_bcl_gz(self._ctx, c, raw, len(raw), size, skip))
             else:
-                _lib.check(self.lib.tsk_tile_put_bcl(self._ctx, c, _ptr(bcl[c])))
+                put(bcl[c], lambda p, c=c: _lib.check(self.lib.tsk_tile_put_bcl(self._ctx, c, p)))
         for i in range(cif.shape[0]):
-            _lib.check(self.lib.tsk_tile_put_cif(self._ctx, i, _ptr(cif[i]), cif.shape[2]))
+            put(cif[i], lambda p, i=i: _lib.check(self.lib.tsk_tile_put_cif(self._ctx, i, p, cif.shape[2])))
         _lib.check(self.lib.tsk_tile_end(self._ctx))
         self._pending.append((int(n), (bcl, cif, keep)))
 

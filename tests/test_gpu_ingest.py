@@ -86,6 +86,30 @@ def test_gz_rows_equal_array_upload(stock_cfg, oracle):
         p.close()
 
 
+def test_staged_rows_equal_array_upload(stock_cfg, oracle):
+    """Every row through the library's page-locked staging slots (553 rows over 24 slots: each slot is
+    reused ~23 times while earlier copies may still be in flight), twice through the same context, with
+    a row length that changes in between (slots grow)."""
+    from tailseeker_b200.synth import make_tile
+    from tailseeker_b200.importer import TileProcessor, invert_colormatrix
+    cfg = stock_cfg
+    p = TileProcessor(cfg)
+    try:
+        for n, seed in ((9000, 5), (31000, 6), (1, 7)):
+            tile = make_tile(cfg, n, seed=seed)
+            inv = invert_colormatrix(tile.matrix)
+            p.reset_counters()
+            p.upload_rows(tile.bcl, tile.cif, inv, staged=True)
+            # the arrays may change as soon as upload_rows() has returned: the slots hold the data
+            want = oracle.process(cfg, tile.bcl.copy(), tile.cif.copy(), oracle.invert_matrix(tile.matrix))
+            tile.bcl[:] = 0
+            tile.cif[:] = 0
+            p.process()
+            compare_tile(p, cfg, None, want)
+    finally:
+        p.close()
+
+
 def test_bad_streams_fail_loudly(stock_cfg):
     from tailseeker_b200 import _lib
     from tailseeker_b200.synth import make_tile
