@@ -273,6 +273,10 @@ typedef struct tsk_encode_layout {
 } tsk_encode_layout;
 enum { TSK_STREAM_SEQQUAL = 0, TSK_STREAM_TAGINFO = 1, TSK_STREAM_SIGNAL = 2 };
 int tsk_encode_configure(tsk_ctx *ctx, const tsk_encode_layout *layout);
+/* Optional: page-lock the host buffer of the encoded streams for blocks of `nclusters` clusters now (on a
+ * start-up thread beside the first tile's upload, say) rather than inside the first tsk_tile_encode().
+ * Not to be called while tsk_encode_configure() / tsk_tile_encode() run on the same context. */
+int tsk_encode_reserve(tsk_ctx *ctx, uint32_t nclusters);
 /* Encodes the outputs of the tile last processed (any block of it: cluster numbers start at the
  * block's firstclusterno) and brings the compressed streams to pinned host memory. */
 int tsk_tile_encode(tsk_ctx *ctx);

@@ -24,7 +24,7 @@ SYMBOLS = [
     "tsk_ruler_tile_all_async", "tsk_ruler_get_lengths", "tsk_ruler_get_called",
     "tsk_dedup_pack_umi", "tsk_dedup_create", "tsk_dedup_destroy", "tsk_dedup_upload", "tsk_dedup_run",
     "tsk_dedup_get_records", "tsk_dedup_get_groups", "tsk_dedup_get_lost", "tsk_dedup_elapsed_ms", "tsk_dedup_launch_count",
-    "tsk_encode_configure", "tsk_tile_encode", "tsk_tile_get_encoded", "tsk_encode_elapsed_ms", "tsk_bgzf_eof_block", "tsk_selftest_deflate", "tsk_bgzf_create", "tsk_bgzf_destroy", "tsk_bgzf_deflate", "tsk_bgzf_launch_count", "tsk_tile_begin", "tsk_tile_put_bcl", "tsk_tile_put_bcl_gz", "tsk_tile_put_cif", "tsk_tile_end", "tsk_tile_stage_acquire", "tsk_tile_stage_release",
+    "tsk_encode_configure", "tsk_encode_reserve", "tsk_tile_encode", "tsk_tile_get_encoded", "tsk_encode_elapsed_ms", "tsk_bgzf_eof_block", "tsk_selftest_deflate", "tsk_bgzf_create", "tsk_bgzf_destroy", "tsk_bgzf_deflate", "tsk_bgzf_launch_count", "tsk_tile_begin", "tsk_tile_put_bcl", "tsk_tile_put_bcl_gz", "tsk_tile_put_cif", "tsk_tile_end", "tsk_tile_stage_acquire", "tsk_tile_stage_release",
     "tsk_nccl_unique_id", "tsk_nccl_init_rank", "tsk_nccl_init_all", "tsk_nccl_destroy", "tsk_nccl_group_start",
     "tsk_nccl_group_end", "tsk_hist_allreduce", "tsk_merge_create", "tsk_merge_destroy", "tsk_merge_add_tile",
     "tsk_merge_add_totals", "tsk_merge_allreduce", "tsk_merge_get", "tsk_merge_reset", "tsk_merge_tile_count", "tsk_merge_fit",
@@ -110,6 +110,7 @@ def load():
     L.tsk_tile_put_bcl_gz.argtypes = [vp, i32, vp, sz, ctypes.c_uint64, ctypes.c_uint64]
     L.tsk_tile_put_cif.argtypes = [vp, i32, vp, sz]
     L.tsk_tile_end.argtypes = [vp]
+    L.tsk_encode_reserve.argtypes = [vp, u32]
     L.tsk_tile_stage_acquire.argtypes = [vp, sz, ctypes.POINTER(vp), ctypes.POINTER(i32)]
     L.tsk_tile_stage_release.argtypes = [vp, i32]
     L.tsk_bgzf_create.argtypes = [ctypes.POINTER(vp), i32]

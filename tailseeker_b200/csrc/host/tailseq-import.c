@@ -38,8 +38,19 @@ struct ctx_boot {
     pthread_t thread;
     const tsk_params *params;
     int device, rc, started;
+    int threaded;                       /* boot_context() runs on its own thread (set before it starts) */
     tsk_ctx *ctx;
     char error[512];
+    /* the thread goes on after the context is up: it sets up the output encoder and page-locks its
+     * host buffer (0.3 s) while the main thread uploads and processes the first block */
+    pthread_mutex_t lock;
+    pthread_cond_t changed;
+    int ctx_ready;                      /* tsk_ctx_create() has returned */
+    int hint_set;                       /* block_clusters is final (0: no encoder warm-up) */
+    uint32_t block_clusters;
+    const tsk_encode_layout *layout;    /* NULL: host writers */
+    int warm_rc;
+    char warm_error[512];
 };
 
 /* A process that handles several tiles keeps its context -- device buffers, the encoder's pinned
@@ -59,16 +70,51 @@ static void drop_kept_context(void)
 static void *boot_context(void *arg)
 {
     struct ctx_boot *b = arg;
+    uint32_t n;
     b->rc = tsk_ctx_create(&b->ctx, b->device, b->params);
     if (b->rc != 0) snprintf(b->error, sizeof(b->error), "%s", tsk_last_error());
+    if (!b->threaded) { b->ctx_ready = 1; return NULL; }       /* called in line: nothing to overlap with */
+    pthread_mutex_lock(&b->lock);
+    b->ctx_ready = 1;
+    pthread_cond_broadcast(&b->changed);
+    while (!b->hint_set) pthread_cond_wait(&b->changed, &b->lock);
+    n = b->block_clusters;
+    pthread_mutex_unlock(&b->lock);
+    if (b->rc == 0 && b->layout && n > 0) {
+        b->warm_rc = tsk_encode_configure(b->ctx, b->layout);
+        if (b->warm_rc == 0) b->warm_rc = tsk_encode_reserve(b->ctx, n);
+        if (b->warm_rc != 0) snprintf(b->warm_error, sizeof(b->warm_error), "%s", tsk_last_error());
+    }
     return NULL;
 }
 
+/* the size of the tile's read blocks is known (or there will be none): lets the start-up thread go on */
+static void boot_hint(struct ctx_boot *b, uint32_t block_clusters)
+{
+    pthread_mutex_lock(&b->lock);
+    if (!b->hint_set) { b->block_clusters = block_clusters; b->hint_set = 1; }
+    pthread_cond_broadcast(&b->changed);
+    pthread_mutex_unlock(&b->lock);
+}
+
+/* the context, as soon as it exists (the start-up thread may still be warming the encoder up) */
 static tsk_ctx *await_context(struct ctx_boot *b)
 {
-    if (b->started) { pthread_join(b->thread, NULL); b->started = 0; }
+    if (b->started) {
+        pthread_mutex_lock(&b->lock);
+        while (!b->ctx_ready) pthread_cond_wait(&b->changed, &b->lock);
+        pthread_mutex_unlock(&b->lock);
+    }
     if (b->rc != 0) { fprintf(stderr, "%s\n", b->error); return NULL; }
     return b->ctx;
+}
+
+/* the end of the start-up thread: before the encoder of its context is used, and before leaving */
+static int finish_boot(struct ctx_boot *b)
+{
+    if (b->started) { boot_hint(b, 0); pthread_join(b->thread, NULL); b->started = 0; }
+    if (b->warm_rc != 0) { fprintf(stderr, "%s\n", b->warm_error); b->warm_rc = 0; return -1; }
+    return 0;
 }
 
 /* --devices: one worker (host thread + CUDA context) per GPU, the configuration files dealt round
@@ -139,6 +185,7 @@ static int process(struct host_config *cfg, struct ctx_boot *boot, const float *
     if (blocksize > nclusters && nclusters > 0) blocksize = nclusters;
     totalblocks = nclusters / blocksize + ((nclusters % blocksize > 0) ? 1 : 0);
     printf("%sProcessing %u clusters.\n", msgprefix, nclusters);
+    boot_hint(boot, blocksize);
     if (tsk_write_signal_headers(cfg, nclusters) < 0) goto done;
 
     /* plain page-aligned buffers: pinning 2.5 GB for a single pass costs more than the staged copy */
@@ -176,6 +223,11 @@ static int process(struct host_config *cfg, struct ctx_boot *boot, const float *
         phase("wait for the CUDA context");
 
         printf("%sAnalyzing and writing out\n", msgprefix);
+        if ((!direct && tsk_tile_upload(ctx, bcl, count, cif, count, invmatrix, count, nclusters - togo, 0) != 0) ||
+            tsk_tile_process(ctx) != 0 || (!device_encode && tsk_tile_get_calls(ctx, calls) != 0)) {
+            fprintf(stderr, "%s\n", tsk_last_error());
+            goto done;
+        }
         if (device_encode && !encoder_ready) {
             tsk_encode_layout *layout = calloc(1, sizeof(*layout));
             if (!layout || tsk_build_encode_layout(cfg, layout) != 0) {
@@ -183,15 +235,15 @@ static int process(struct host_config *cfg, struct ctx_boot *boot, const float *
                 free(layout);
                 goto done;
             }
-            /* (a context kept from the previous tile is already set up: the call then returns at once) */
-            if (tsk_encode_configure(ctx, layout) != 0) { fprintf(stderr, "%s\n", tsk_last_error()); free(layout); goto done; }
+            /* the start-up thread of a new context has set the encoder up meanwhile, a context kept from
+             * the previous tile is set up already: the call then returns at once */
+            if (finish_boot(boot) != 0 || tsk_encode_configure(ctx, layout) != 0) {
+                fprintf(stderr, "%s\n", tsk_last_error());
+                free(layout);
+                goto done;
+            }
             free(layout);
             encoder_ready = 1;
-        }
-        if ((!direct && tsk_tile_upload(ctx, bcl, count, cif, count, invmatrix, count, nclusters - togo, 0) != 0) ||
-            tsk_tile_process(ctx) != 0 || (!device_encode && tsk_tile_get_calls(ctx, calls) != 0)) {
-            fprintf(stderr, "%s\n", tsk_last_error());
-            goto done;
         }
         phase("upload + kernels + calls");
         if (device_encode) {
@@ -255,6 +307,7 @@ static int run_tile(const char *inifile, int device, struct run_merge *rm)
     tsk_params *params;
     tsk_ctx *ctx = NULL;
     struct ctx_boot boot;
+    tsk_encode_layout *layout = NULL;
     float inv[16];
     int r;
 
@@ -265,17 +318,27 @@ static int run_tile(const char *inifile, int device, struct run_merge *rm)
     if (!params || tsk_build_params(cfg, params) < 0) { free(params); tsk_free_config(cfg); return -1; }
     memset(&boot, 0, sizeof(boot));
     boot.params = params; boot.device = device;
+    pthread_mutex_init(&boot.lock, NULL);
+    pthread_cond_init(&boot.changed, NULL);
     if (kept_ctx && kept_device == device && memcmp(kept_params, params, sizeof(*params)) == 0) {
         boot.ctx = kept_ctx;                        /* same parameters as the previous tile */
         if (tsk_counters_reset(kept_ctx) != 0) { fprintf(stderr, "%s\n", tsk_last_error()); free(params); tsk_free_config(cfg); return -1; }
     } else {
         drop_kept_context();
+        if (getenv("TSK_HOST_WRITERS") == NULL && (layout = calloc(1, sizeof(*layout))) != NULL &&
+            tsk_build_encode_layout(cfg, layout) == 0)
+            boot.layout = layout;                   /* else: process() reports what is wrong with it */
+        boot.threaded = 1;
         if (pthread_create(&boot.thread, NULL, boot_context, &boot) == 0) boot.started = 1;
-        else boot_context(&boot);
+        else { boot.threaded = 0; boot_context(&boot); }
     }
     r = process(cfg, &boot, inv, rm);
     phase("close files");
-    ctx = await_context(&boot);
+    if (finish_boot(&boot) != 0) r = -1;
+    ctx = boot.rc == 0 ? boot.ctx : NULL;
+    pthread_mutex_destroy(&boot.lock);
+    pthread_cond_destroy(&boot.changed);
+    free(layout);
     if (ctx && ctx != kept_ctx) {                   /* keep it for the next tile of this thread */
         kept_ctx = ctx; kept_device = device;
         kept_params = params; params = NULL;

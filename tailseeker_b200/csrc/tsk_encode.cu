@@ -893,6 +893,28 @@ extern "C" int tsk_encode_configure(tsk_ctx *ctx, const tsk_encode_layout *layou
     return 0;
 }
 
+/* The page-locked host buffer of the encoded streams, sized for a block of `nclusters` clusters, made NOW
+ * (e.g. on a start-up thread, beside the first tile's upload and kernels) instead of inside the first
+ * tsk_tile_encode(): page-locking ~0.8 GB is the largest first-use cost of a process (0.25 s).  Touches
+ * only the encoder's own state; must not run concurrently with tsk_encode_configure / tsk_tile_encode of
+ * the same context.  The size is an estimate (0.45 of the uncompressed bound; the streams deflate to
+ * ~0.36 of it); tsk_tile_encode() still grows the buffer when a tile needs more. */
+extern "C" int tsk_encode_reserve(tsk_ctx *ctx, uint32_t nclusters)
+{
+    if (!ctx || !ctx->enc) { tsk_set_error("tsk_encode_configure() has not been called"); return -1; }
+    TSK_CUDA(cudaSetDevice(ctx->device));
+    EncState *e = ctx->enc;
+    const double bound = (double)nclusters * ((double)(e->tagmax + e->sqmax) + 4.0 * (2 + ctx->maxdump));
+    const size_t want = (size_t)(0.45 * bound) + (1u << 20);
+    if (want > e->h_final_cap) {
+        if (e->h_final) cudaFreeHost(e->h_final);
+        e->h_final = NULL; e->h_final_cap = 0;
+        TSK_CUDA(cudaHostAlloc((void **)&e->h_final, want, cudaHostAllocDefault));
+        e->h_final_cap = want;
+    }
+    return 0;
+}
+
 static int enc_buffers(tsk_ctx *ctx)
 {
     EncState *e = ctx->enc;
