@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Wall time of the drop-in tailseq-import over several full tiles in one process, phase by phase
 (TSK_HOST_TIMING), beside the reference binary: bench.py's `e2e_cli` leg with more tiles.
-    python tools/cli_time.py [tiles] [clusters per tile]"""
+    python tools/cli_time.py [tiles] [clusters per tile]
+TSK_CLI_RAW_TIMING=1 also passes the program's own "[timing] phase seconds" lines through (stderr),
+tile by tile, instead of only their sums."""
 import json
 import os
 import sys
