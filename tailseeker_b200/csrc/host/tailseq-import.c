@@ -207,15 +207,16 @@ static int process(struct host_config *cfg, struct ctx_boot *boot, const float *
         const uint32_t count = togo >= blocksize ? blocksize : togo;
         snprintf(msgprefix, BUFSIZ, "[%s%d#%d/%d] ", cfg->laneid, cfg->tile, blockno + 1, totalblocks);
         printf("%sLoading CIF and BCL files\n", msgprefix);
-        /* With a context at hand (a later block, a later tile of this process, or
-         * TSK_DIRECT_INGEST=1) the cycle files go to the device row by row while they are read and
-         * .bcl.gz files are inflated there; the first tile of a process reads into host arrays
-         * while its context is still being created. */
+        /* The cycle files go to the device row by row while they are read (through the library's
+         * page-locked staging slots) and .bcl.gz files are inflated there.  On the first tile of a
+         * process that means waiting for the context first -- the files' read-ahead was started when
+         * they were opened -- which still beats reading into pageable arrays meanwhile and uploading
+         * those (0.76 s against 1.3 s for the first 1.07 M-cluster tile).  TSK_DIRECT_INGEST=0 keeps
+         * the whole-block host arrays (the reference's order of things, and what the host writers need). */
         int direct = 0;
-        const char *want_direct = getenv("TSK_DIRECT_INGEST");           /* "0": never, anything else: from the first block on */
+        const char *want_direct = getenv("TSK_DIRECT_INGEST");
         const int never_direct = want_direct && want_direct[0] == '0';
-        if (device_encode && !never_direct && !ctx && ((!boot->started && boot->ctx) || want_direct) &&
-            !(ctx = await_context(boot))) goto done;
+        if (device_encode && !never_direct && !ctx && !(ctx = await_context(boot))) goto done;
         direct = device_encode && !never_direct && ctx != NULL;
         if ((direct ? tsk_read_block_to_device(tf, count, bcl, cif, ctx, invmatrix) : tsk_read_block(tf, count, bcl, cif)) < 0) goto done;
         phase(direct ? "read CIF/BCL -> device" : "read CIF/BCL");

@@ -11,6 +11,7 @@
  * Colour matrix: 16 numbers, inverted like src/contrib/misc.c:11-58 (float cofactors, same order).
  */
 #include <endian.h>
+#include <fcntl.h>
 #include <limits.h>
 #include <stdlib.h>
 #include <string.h>
@@ -202,6 +203,9 @@ struct tile_files *tsk_open_tile(const struct host_config *cfg, const char *msgp
                  cfg->threep_start + i + 1, cfg->lane, cfg->tile);
         tf->cif[i] = open_cif(path, &n);
         if (!tf->cif[i]) { free(overridden); tsk_close_tile(tf); return NULL; }
+        /* 8 bytes per cluster and cycle: start the read-ahead now, the readers come later (after the
+         * CUDA context is up on the first tile of a process) */
+        posix_fadvise(fileno(tf->cif[i]), 0, 0, POSIX_FADV_WILLNEED);
         if (i == 0) tf->nclusters = n;
         else if (n != tf->nclusters) {
             fprintf(stderr, "Inconsistent number of clusters in CIF cycle %d.\n", cfg->threep_length + i + 1);

@@ -79,6 +79,26 @@ def test_programs_match_reference(tmp_path, control, bufsize):
         assert (refrun.read_sigdists(str(tmp_path / ("bpos_%s.gz" % s.name))) == want[s.name]["pos"]).all(), s.name
 
 
+@pytest.mark.parametrize("bufsize", [None, 4 * 1024 * 1024])
+def test_host_array_path_matches_reference(tmp_path, monkeypatch, bufsize):
+    """TSK_DIRECT_INGEST=0: the blocks are read into whole-block host arrays and uploaded with one
+    tsk_tile_upload() each (the default sends every cycle file from a page-locked staging slot as it is
+    read); same outputs."""
+    from tailseeker_b200.config import stock_config
+    from tailseeker_b200.synth import make_tile
+    cfg = stock_config("miseq", phix_match_name="PhiX")
+    tile = make_tile(cfg, 3300, seed=56, lowdiv_frac=0.05, dark_cluster_frac=0.01, spikein_weight=1.0,
+                     unknown_frac=0.15, phix_frac=0.6)
+    wref, wour = str(tmp_path / "ref"), str(tmp_path / "our")
+    os.makedirs(wref); os.makedirs(wour)
+    ref = refrun.run_import(cfg, tile, workdir=wref, read_buffer_size=bufsize)
+    monkeypatch.setenv("TSK_DIRECT_INGEST", "0")
+    monkeypatch.setenv("TSK_HOST_TIMING", "1")
+    our = refrun.run_import(cfg, tile, workdir=wour, read_buffer_size=bufsize, binary=OUR_IMPORT)
+    _same(ref, our)
+    assert "read CIF/BCL -> device" not in our["stderr"] and "read CIF/BCL" in our["stderr"]
+
+
 def test_ruler_exit_codes(tmp_path):
     import subprocess
     assert subprocess.run([OUR_RULER], capture_output=True).returncode == 1
